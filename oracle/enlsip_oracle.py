@@ -42,6 +42,14 @@ class ReferenceWouldThrow(Exception):
     """Raised where the Julia code would raise (BoundsError, destructuring error, ...)."""
 
 
+class ReferenceWouldHang(Exception):
+    """Raised where the Julia code provably never terminates (see evaluate_violated_constraints)."""
+
+
+EXIT_WOULD_THROW = -99   # engine/oracle convention: the reference raises an exception here
+EXIT_WOULD_HANG = -98    # engine/oracle convention: the reference loops forever here
+
+
 # --------------------------------------------------------------------------------------
 # Pivoted QR objects (Julia ``qr(M, ColumnNorm())`` -> LAPACK geqp3; SURVEY.md section 10)
 # --------------------------------------------------------------------------------------
@@ -434,11 +442,17 @@ def sub_search_direction(J1, rx, cx, F_A, F_L11, F_J2, n, t, rankA, dimA, dimJ2,
     elif code == -1:
         b_buff = -cx[F_A.p]
         b = F_L11.Qt_mul(b_buff)
+        if dimA > t or dimA > min(F_L11.R.shape):
+            raise ReferenceWouldThrow("BoundsError: R11[1:dimA,1:dimA]")
         dp1 = _solve_upper(F_L11.R[:dimA, :dimA], _jl_range(b, dimA))
         p1 = np.concatenate([dp1, np.zeros(t - dimA)])[F_L11.invperm()][:rankA]
         d_temp = -(J1 @ p1) - rx
         d = F_J2.Qt_mul(d_temp)
+        if dimA > t or dimA > F_L11.R.shape[0] or dimJ2 > F_J2.R.shape[0] or dimJ2 > F_J2.R.shape[1]:
+            raise ReferenceWouldThrow("BoundsError: R[1:dim,1:dim]")
         dp2 = _solve_upper(F_J2.R[:dimJ2, :dimJ2], _jl_range(d, dimJ2))
+        if n - rankA - dimJ2 < 0:
+            raise ReferenceWouldThrow("negative zeros() length")
         p2 = np.concatenate([dp2, np.zeros(n - rankA - dimJ2)])[F_J2.invperm()]
     else:
         raise ReferenceWouldThrow("sub_search_direction: code %r" % code)
@@ -634,6 +648,7 @@ def evaluate_violated_constraints(cx, W: WorkingSet, index_alpha_upp, n):
     delta = 0.1
     bnd = min(W.l, n)
     added = False
+    swaps = 0
     if W.l > W.t:
         i = 1
         while i <= W.l - W.t:
@@ -648,6 +663,13 @@ def evaluate_violated_constraints(cx, W: WorkingSet, index_alpha_upp, n):
                             worst_val = cx[jj - 1]
                             worst_k = j
                     if worst_k > 0 and worst_val > cx[k - 1]:
+                        # After the swap-out ``inactive`` is re-sorted, so position ``i`` may no longer
+                        # hold ``k``: the reference can re-add the constraint it just removed and then
+                        # repeats the same swap forever (observed on ~3% of the C2 HS65 instances).
+                        # The loop is deterministic, so exceeding this cap means it never ends.
+                        swaps += 1
+                        if swaps > 4 * W.l + 16:
+                            raise ReferenceWouldHang("evaluate_violated_constraints swap cycle")
                         W.remove_constraint(worst_k)
                     else:
                         i += 1
@@ -1664,6 +1686,7 @@ def enlsip(x0, prob: Problem, scaling=False, second_derivatives=True, weight_cod
     J, A = np.zeros((m, n)), np.zeros((l, n))
     new_point(ev, x0, rx, cx, J, A)
     x_opt = x0
+    x = x0
     f_opt = _dot(rx, rx)
     first = Iteration(x0, np.zeros(n), rx, cx, l, 1.0, 0, np.zeros(l), np.zeros(l), 0, 0, 0, 0, np.zeros(n), np.zeros(n),
                       0.0, 0.0, 0.0, 0.0, 0.0, False, True, False, False, 0, 1, 0)
@@ -1767,8 +1790,10 @@ def enlsip(x0, prob: Problem, scaling=False, second_derivatives=True, weight_cod
             details = [(0.0, 0.0, 0.0, 0.0, 0.0)]
         return Result(exit_code, convert_exit_code(exit_code), np.array(x_opt, dtype=F), float(f_opt), len(details),
                       nfe, njac, [int(v) for v in W.active[:W.t]], trace, details)
-    except ReferenceWouldThrow as e:
-        return Result(-99, -1, np.array(x_opt, dtype=F), float(f_opt), len(details), 0, 0,
+    except (ReferenceWouldThrow, ReferenceWouldHang) as e:
+        code = EXIT_WOULD_HANG if isinstance(e, ReferenceWouldHang) else EXIT_WOULD_THROW
+        # convention shared with the engine: report the last evaluated point and its objective
+        return Result(code, -1, np.array(x, dtype=F), _dot(rx, rx), len(details), 0, 0,
                       [int(v) for v in W.active[:W.t]], trace, details, threw=str(e))
 
 
