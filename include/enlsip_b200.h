@@ -1,0 +1,98 @@
+/* enlsip_b200.h -- C ABI of the B200-native ENLSIP Gauss-Newton engine (batched regime).
+ *
+ * Drop-in boundary for the reference call site
+ *     solve!(model) -> enlsip(x0, r, c, n, m, q, l; scaling, MAX_ITER, TIME_LIMIT, eps_rel, eps_x, eps_c, eps_rank)
+ *                   -> (exit_code, x_opt, f_opt, ExecutionInfo)
+ * (reference src/solver.jl:80-87, src/enlsip_functions.jl:2638-2655, 2879).  The Julia host layer
+ * (julia/EnlsipB200.jl) binds these symbols with `ccall`; tests bind them with ctypes.
+ *
+ * The reference's plugin surface -- four Julia closures wrapped by ResidualsFunction /
+ * ConstraintsFunction (src/cnls_model.jl:11-62) -- cannot cross a C ABI to a GPU.  It is replaced
+ * by a `family` id (a device functor compiled into the library) plus device/host data arrays.
+ * Constraint order and 1-based constraint ids are the reference's:
+ *     [equalities; inequalities; x - x_low (finite entries, index order); x_upp - x (finite entries)]
+ * (src/cnls_model.jl:402-403, 416).
+ *
+ * All functions return 0 on success or a negative ENLSIPB200_E* code; algorithmic outcomes are
+ * values in the per-problem `exit_code[]` (raw EF code, src/enlsip_functions.jl:2371-2396) and
+ * `status[]` (after convert_exit_code, src/cnls_model.jl:166-178).  Nothing throws.  There is no
+ * CPU fallback: every compute entry point fails with ENLSIPB200_ENOGPU when no CUDA device exists.
+ */
+#ifndef ENLSIP_B200_H
+#define ENLSIP_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENLSIPB200_FAMILY_HS65 0         /* test/problems/HS65.jl:7-17 ; n=3 m=3, 1 inequality       */
+#define ENLSIPB200_FAMILY_GAUSS_PEAKS 1  /* BASELINE.json config 3 ; n=6 m=128, 1 equality            */
+
+#define ENLSIPB200_JAC_ANALYTIC 0
+#define ENLSIPB200_JAC_FORWARD_DIFF 1    /* src/cnls_model.jl:65-82                                    */
+
+#define ENLSIPB200_EINVAL -1
+#define ENLSIPB200_ENOGPU -2
+#define ENLSIPB200_ECUDA -3
+#define ENLSIPB200_ENOMEM -4
+
+/* extra per-problem exit codes (besides the reference's, EF:2371-2396) */
+#define ENLSIPB200_EXIT_WOULD_THROW -99  /* the reference raises a Julia exception at this point      */
+#define ENLSIPB200_EXIT_WOULD_HANG -98   /* the reference loops forever at this point (EF:621-647)    */
+#define ENLSIPB200_EXIT_CAPACITY -97     /* initial working set larger than min(l, n)                 */
+
+#define ENLSIPB200_TRACE_HDR 16          /* doubles per trace row before the n iterate entries         */
+
+/* keyword arguments of solve! (src/solver.jl:62-63).  A NaN tolerance means "reference default":
+ * abs_tol = eps, rel_tol = sqrt(abs_tol), c_tol = x_tol = rel_tol.  As in the reference, abs_tol
+ * is used only to derive rel_tol (it is never forwarded to enlsip). */
+typedef struct enlsipb200_options {
+    int max_iter;        /* 100   */
+    int scaling;         /* 0     */
+    int jac_mode;        /* ENLSIPB200_JAC_*  (the reference's default is AD = analytic to rounding) */
+    int reserved;
+    double time_limit;   /* 1e3 seconds */
+    double abs_tol, rel_tol, c_tol, x_tol;
+} enlsipb200_options;
+
+typedef struct enlsipb200_handle_s* enlsipb200_handle;
+
+int enlsipb200_version(void);
+const char* enlsipb200_last_error(void);
+void enlsipb200_default_options(enlsipb200_options* opt);
+
+/* problem family + bounds (replaces CnlsModel(...) + instantiate_constraints_*; cnls_model.jl:345-496).
+ * x_low / x_upp: host arrays of length n, +-Inf = no bound.  device < 0 = current device. */
+int enlsipb200_create(int family, const double* x_low, const double* x_upp, int device, enlsipb200_handle* out);
+int enlsipb200_destroy(enlsipb200_handle h);
+int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_constraints, int* lmax);
+
+/* family data arrays (GAUSS_PEAKS: slot 0 = y [B,128], slot 1 = S [B]).  `on_device` != 0: ptr is a
+ * device pointer that must stay valid for the solve; otherwise the library copies host->device
+ * (asynchronously on `stream` when the host memory is pinned). */
+int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream);
+
+/* solve B independent problems (replaces B calls of solve!).  All array arguments are host or
+ * device pointers according to `on_device`; optional outputs may be NULL.
+ *   x0 [B,n] starting points;  x [B,n] x_opt;  f [B] sum of squared residuals (obj_value);
+ *   exit_code/status/iters/nact [B];  active [B,lmax] 1-based ids of the final working set;
+ *   counters [B,2] nb_function_evaluations, nb_jacobian_evaluations (reference counting formula);
+ *   trace [B,trace_cap,TRACE_HDR+n] per-iteration records (tests only).
+ * Blocking unless on_device != 0 and a stream is given (then enqueued on that stream). */
+int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, const enlsipb200_options* opt,
+                           double* x, double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
+                           int* counters, double* trace, int trace_cap, int on_device, void* stream);
+
+/* measurement hooks: device time of the last solve kernel (CUDA events on its stream), launch
+ * geometry, number of kernels launched by this handle so far */
+int enlsipb200_last_kernel_ms(enlsipb200_handle h, float* ms);
+int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_bytes_per_cta, int* threads_per_cta,
+                           int* ctas_per_sm, int* grid, int* lanes_per_problem);
+long long enlsipb200_launch_count(enlsipb200_handle h);
+
+/* deterministic exp used by the synthetic families, exposed for bit-parity tests vs oracle/detmath.c */
+int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
