@@ -23,9 +23,14 @@
 #if defined(__CUDACC__)
 #define ENL_FN __device__
 #define ENL_INL __device__ __forceinline__
+// Building blocks are deliberately NOT inlined: the first fully inlined build was 82 K SASS
+// instructions (1.3 MB) and spent 48 of 54 cycles per issued instruction waiting for instruction
+// fetch (ncu: smsp__average_warps_issue_stalled_no_instruction, profiles/r1_c3_v0_icache.md).
+#define ENL_NOINL __device__ __noinline__
 #else
 #define ENL_FN
 #define ENL_INL inline
+#define ENL_NOINL
 #endif
 
 namespace enl {
@@ -133,25 +138,57 @@ struct HostGroup {
 };
 
 // ---- strided views -----------------------------------------------------------------------
+// On the device a view is an element offset into the CTA's dynamic shared memory, so that every
+// access compiles to LDS/STS even across non-inlined calls; on the host it is a plain pointer.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) double enl_smem[];
+using vref = int;
+ENL_INL vref make_vref(double* p) { return (int)(p - enl_smem); }
+ENL_INL vref make_vref(int* p) { return (int)(p - reinterpret_cast<int*>(enl_smem)); }
+ENL_INL double& vderef_d(vref o) { return enl_smem[o]; }
+ENL_INL int& vderef_i(vref o) { return reinterpret_cast<int*>(enl_smem)[o]; }
+#else
+using vref = void*;
+ENL_INL vref make_vref(double* p) { return p; }
+ENL_INL vref make_vref(int* p) { return p; }
+#endif
+
 template <int S>
 struct SV {  // small-state vector of doubles, stride S
+#if defined(__CUDACC__)
+    int p;
+    ENL_INL double& operator[](int i) const { return enl_smem[p + i * S]; }
+#else
     double* p;
     ENL_INL double& operator[](int i) const { return p[i * S]; }
+#endif
     ENL_INL SV off(int k) const { return SV{p + k * S}; }
 };
 template <int S>
 struct SI {
+#if defined(__CUDACC__)
+    int p;
+    ENL_INL int& operator[](int i) const { return reinterpret_cast<int*>(enl_smem)[p + i * S]; }
+#else
     int* p;
     ENL_INL int& operator[](int i) const { return p[i * S]; }
+#endif
 };
 
 // row-distributed m x ncols matrix (column major by slots)
 template <int G, int MS, int NT>
 struct DM {
-    double* own;   // + tid
-    double* grp;   // + pid*G   (lane 0 of the group)
+#if defined(__CUDACC__)
+    int own;   // + tid
+    int grp;   // + pid*G   (lane 0 of the group)
+    ENL_INL double& at(int s, int c) const { return enl_smem[own + (c * MS + s) * NT]; }
+    ENL_INL double& row(int r, int c) const { return enl_smem[grp + (c * MS + r / G) * NT + (r % G)]; }
+#else
+    double* own;
+    double* grp;
     ENL_INL double& at(int s, int c) const { return own[(c * MS + s) * NT]; }
     ENL_INL double& row(int r, int c) const { return grp[(c * MS + r / G) * NT + (r % G)]; }
+#endif
     ENL_INL DM cols(int c0) const { return DM{own + c0 * MS * NT, grp + c0 * MS * NT}; }
 };
 

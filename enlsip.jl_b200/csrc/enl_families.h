@@ -94,7 +94,7 @@ struct FamGaussPeaks {
         }
         c.S = d.d1[b];
     }
-    ENL_FN static double peak(double b, double c, double t) {
+    ENL_NOINL static double peak(double b, double c, double t) {
         double d = sub_rn(t, c);
         return det_exp(mul_rn(-b, mul_rn(d, d)));
     }

@@ -15,15 +15,17 @@ namespace enl {
 // small (replicated) routines.  Matrices are column major: a(r,c) = a[c*ld + r].
 // ------------------------------------------------------------------------------------------
 template <class V>
-ENL_FN double nrm2_small(V a, int n) {
+ENL_NOINL double nrm2_small(V a, int n) {
     double s = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; ++i) s += a[i] * a[i];
     return sqrt(s);
 }
 
 // dlaqp2 on a rows x cols matrix; returns nothing, fills tau[min(rows,cols)], jpvt[cols] (0-based)
 template <class V, class VI>
-ENL_FN void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V vn2) {
+ENL_NOINL void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V vn2) {
+#pragma unroll 1
     for (int j = 0; j < cols; ++j) {
         jpvt[j] = j;
         double nj = nrm2_small(a.off(j * ld), rows);
@@ -31,13 +33,16 @@ ENL_FN void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V
         vn2[j] = nj;
     }
     int k = imin(rows, cols);
+#pragma unroll 1
     for (int i = 0; i < k; ++i) {
         // pivot: first index of the largest partial norm (idamax)
         int pvt = i;
         double best = vn1[i];
+#pragma unroll 1
         for (int j = i + 1; j < cols; ++j)
             if (vn1[j] > best) { best = vn1[j]; pvt = j; }
         if (pvt != i) {
+#pragma unroll 1
             for (int r = 0; r < rows; ++r) {
                 double tmp = a[pvt * ld + r];
                 a[pvt * ld + r] = a[i * ld + r];
@@ -56,6 +61,7 @@ ENL_FN void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V
                 double beta = -sign_of(lapy2(alpha, xn), alpha);
                 tau_i = (beta - alpha) / beta;
                 double sc = 1.0 / (alpha - beta);
+#pragma unroll 1
                 for (int r = i + 1; r < rows; ++r) a[i * ld + r] *= sc;
                 a[i * ld + i] = beta;
             }
@@ -63,15 +69,19 @@ ENL_FN void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V
         tau[i] = tau_i;
         // apply H(i)' to a(i:rows-1, i+1:cols-1)
         if (i < cols - 1 && tau_i != 0.0) {
+#pragma unroll 1
             for (int c = i + 1; c < cols; ++c) {
                 double wv = a[c * ld + i];
+#pragma unroll 1
                 for (int r = i + 1; r < rows; ++r) wv += a[i * ld + r] * a[c * ld + r];
                 wv *= tau_i;
                 a[c * ld + i] -= wv;
+#pragma unroll 1
                 for (int r = i + 1; r < rows; ++r) a[c * ld + r] -= wv * a[i * ld + r];
             }
         }
         // partial column norm update
+#pragma unroll 1
         for (int j = i + 1; j < cols; ++j) {
             double v1 = vn1[j];
             if (v1 != 0.0) {
@@ -98,37 +108,45 @@ ENL_FN void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V
 
 // v <- Q' v  (apply H(0), H(1), ..., H(k-1) in that order); factors a (rows x k), v length rows
 template <class V>
-ENL_FN void apply_qt_small(V a, int ld, int rows, int k, V tau, V v) {
+ENL_NOINL void apply_qt_small(V a, int ld, int rows, int k, V tau, V v) {
+#pragma unroll 1
     for (int i = 0; i < k; ++i) {
         double ti = tau[i];
         if (ti == 0.0) continue;
         double wv = v[i];
+#pragma unroll 1
         for (int r = i + 1; r < rows; ++r) wv += a[i * ld + r] * v[r];
         wv *= ti;
         v[i] -= wv;
+#pragma unroll 1
         for (int r = i + 1; r < rows; ++r) v[r] -= wv * a[i * ld + r];
     }
 }
 
 // v <- Q v  (apply H(k-1), ..., H(0))
 template <class V>
-ENL_FN void apply_q_small(V a, int ld, int rows, int k, V tau, V v) {
+ENL_NOINL void apply_q_small(V a, int ld, int rows, int k, V tau, V v) {
+#pragma unroll 1
     for (int i = k - 1; i >= 0; --i) {
         double ti = tau[i];
         if (ti == 0.0) continue;
         double wv = v[i];
+#pragma unroll 1
         for (int r = i + 1; r < rows; ++r) wv += a[i * ld + r] * v[r];
         wv *= ti;
         v[i] -= wv;
+#pragma unroll 1
         for (int r = i + 1; r < rows; ++r) v[r] -= wv * a[i * ld + r];
     }
 }
 
 // solve R[0:k,0:k] x = b (upper, back substitution).  returns false on an exactly zero diagonal
 template <class V, class V2>
-ENL_FN bool solve_upper_small(V R, int ld, int k, V2 x) {
+ENL_NOINL bool solve_upper_small(V R, int ld, int k, V2 x) {
+#pragma unroll 1
     for (int i = k - 1; i >= 0; --i) {
         double s = x[i];
+#pragma unroll 1
         for (int j = i + 1; j < k; ++j) s -= R[j * ld + i] * x[j];
         double d = R[i * ld + i];
         if (d == 0.0) return false;
@@ -139,9 +157,11 @@ ENL_FN bool solve_upper_small(V R, int ld, int k, V2 x) {
 
 // solve (R[0:k,0:k])' x = b (lower triangular = transpose of the stored upper factor)
 template <class V, class V2>
-ENL_FN bool solve_upperT_small(V R, int ld, int k, V2 x) {
+ENL_NOINL bool solve_upperT_small(V R, int ld, int k, V2 x) {
+#pragma unroll 1
     for (int i = 0; i < k; ++i) {
         double s = x[i];
+#pragma unroll 1
         for (int j = 0; j < i; ++j) s -= R[i * ld + j] * x[j];
         double d = R[i * ld + i];
         if (d == 0.0) return false;
@@ -152,10 +172,11 @@ ENL_FN bool solve_upperT_small(V R, int ld, int k, V2 x) {
 
 // EF:17-31 on diag(R) of a column-major factor with `len` diagonal entries
 template <class V>
-ENL_FN int pseudo_rank(V R, int ld, int len, double eps_rank) {
+ENL_NOINL int pseudo_rank(V R, int ld, int len, double eps_rank) {
     if (len <= 0 || fabs(R[0]) < eps_rank) return 0;
     double tol = fabs(R[0]) * sqrt((double)len) * eps_rank;
     int r = 1;
+#pragma unroll 1
     while (r < len && fabs(R[(r - 1) * ld + (r - 1)]) > tol) ++r;
     return r - ((r == len && fabs(R[(r - 1) * ld + (r - 1)]) > tol) ? 0 : 1);
 }
@@ -169,7 +190,7 @@ struct Dist {
     ENL_FN explicit Dist(const Grp& gg) : g(gg) {}
 
     // sum over rows >= r0 of a(:,c)^2
-    ENL_FN double colsq(DM<G, MS, NT> a, int c, int r0) const {
+    ENL_NOINL double colsq(DM<G, MS, NT> a, int c, int r0) const {
         double s = 0.0;
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) {
@@ -182,16 +203,19 @@ struct Dist {
 
     // J <- J * Q  where Q = H(0)...H(k-1) from small factors fa (n x k): per row, local
     template <class V>
-    ENL_FN void mul_q_right(DM<G, MS, NT> J, int n, V fa, int ld, int k, V tau) const {
+    ENL_NOINL void mul_q_right(DM<G, MS, NT> J, int n, V fa, int ld, int k, V tau) const {
+#pragma unroll 1
         for (int i = 0; i < k; ++i) {
             double ti = tau[i];
             if (ti == 0.0) continue;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) {
                 double wv = J.at(sl, i);
+#pragma unroll 1
                 for (int c = i + 1; c < n; ++c) wv += J.at(sl, c) * fa[i * ld + c];
                 wv *= ti;
                 J.at(sl, i) -= wv;
+#pragma unroll 1
                 for (int c = i + 1; c < n; ++c) J.at(sl, c) -= wv * fa[i * ld + c];
             }
         }
@@ -201,7 +225,8 @@ struct Dist {
     // Writes tau2[min(M,ncols)], jpvt[ncols]; copies the leading kk x ncols upper trapezoid to
     // Rout (column major, ld = ldr) where kk = min(M, ncols).
     template <class V, class VI>
-    ENL_FN void qrcp(DM<G, MS, NT> a, int M, int ncols, V tau2, VI jpvt, V vn1, V vn2, V Rout, int ldr) const {
+    ENL_NOINL void qrcp(DM<G, MS, NT> a, int M, int ncols, V tau2, VI jpvt, V vn1, V vn2, V Rout, int ldr) const {
+#pragma unroll 1
         for (int j = 0; j < ncols; ++j) {
             jpvt[j] = j;
             double nj = sqrt(colsq(a, j, 0));
@@ -209,9 +234,11 @@ struct Dist {
             vn2[j] = nj;
         }
         int k = imin(M, ncols);
+#pragma unroll 1
         for (int i = 0; i < k; ++i) {
             int pvt = i;
             double best = vn1[i];
+#pragma unroll 1
             for (int j = i + 1; j < ncols; ++j)
                 if (vn1[j] > best) { best = vn1[j]; pvt = j; }
             if (pvt != i) {
@@ -245,6 +272,7 @@ struct Dist {
             }
             tau2[i] = tau_i;
             if (i < ncols - 1 && tau_i != 0.0) {
+#pragma unroll 1
                 for (int c = i + 1; c < ncols; ++c) {
                     double part = 0.0;
 #pragma unroll
@@ -263,6 +291,7 @@ struct Dist {
                 }
             }
             g.sync();
+#pragma unroll 1
             for (int j = i + 1; j < ncols; ++j) {
                 double v1 = vn1[j];
                 if (v1 != 0.0) {
@@ -286,14 +315,17 @@ struct Dist {
             }
         }
         g.sync();
+#pragma unroll 1
         for (int c = 0; c < ncols; ++c)
+#pragma unroll 1
             for (int r = 0; r < k; ++r) Rout[c * ldr + r] = (r <= c) ? a.row(r, c) : 0.0;
     }
 
     // d <- Q' d for the distributed factor `a` with k reflectors; d is a distributed vector
     // (DM with one column)
     template <class V>
-    ENL_FN void apply_qt(DM<G, MS, NT> a, int k, V tau2, DM<G, MS, NT> d) const {
+    ENL_NOINL void apply_qt(DM<G, MS, NT> a, int k, V tau2, DM<G, MS, NT> d) const {
+#pragma unroll 1
         for (int i = 0; i < k; ++i) {
             double ti = tau2[i];
             if (ti == 0.0) continue;
@@ -316,7 +348,7 @@ struct Dist {
     }
 
     // sum_{row < len} d(row)^2
-    ENL_FN double prefix_sq(DM<G, MS, NT> d, int len) const {
+    ENL_NOINL double prefix_sq(DM<G, MS, NT> d, int len) const {
         double s = 0.0;
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) {

@@ -121,7 +121,11 @@ struct Solver {
     ENL_FN Solver(double* small, int* ints, double* distbase, int pid, int tid, const Grp& grp, const Options& o,
                   const Bounds& bb)
         : g(grp), dist(grp), opt(o), bnd(bb) {
+#if defined(__CUDACC__)
+        int s = (int)(small - enl_smem) + pid;
+#else
         double* s = small + pid;
+#endif
         auto mk = [&](int off) { return V{s + off * PPC}; };
         x = mk(LY::oX); xprev = mk(LY::oXPREV); xnew = mk(LY::oXNEW); cx = mk(LY::oCX); cnew = mk(LY::oCNEW);
         A = mk(LY::oA); gradf = mk(LY::oGRADF); w = mk(LY::oW); wnew = mk(LY::oWNEW); K = mk(LY::oK);
@@ -130,12 +134,21 @@ struct Solver {
         b = mk(LY::oB); p = mk(LY::oP); y = mk(LY::oY); Ap = mk(LY::oAP); aAp = mk(LY::oAAP); v1c = mk(LY::oV1C);
         vn1 = mk(LY::oVN1); vn2 = mk(LY::oVN2); s1 = mk(LY::oS1); s2 = mk(LY::oS2); s3 = mk(LY::oS3);
         s4 = mk(LY::oS4); s5 = mk(LY::oS5); nw = mk(LY::oNW);
+#if defined(__CUDACC__)
+        int ii = (int)(ints - reinterpret_cast<int*>(enl_smem)) + pid;
+#else
         int* ii = ints + pid;
+#endif
         auto mi = [&](int off) { return VI{ii + off * PPC}; };
         active = mi(LY::iACT); inactive = mi(LY::iINACT); permA = mi(LY::iPERMA); permL = mi(LY::iPERML);
         perm2 = mi(LY::iPERM2); posidx = mi(LY::iPOS);
+#if defined(__CUDACC__)
+        int own = (int)(distbase - enl_smem) + tid;
+        int grpb = (int)(distbase - enl_smem) + pid * G;
+#else
         double* own = distbase + tid;
         double* grpb = distbase + pid * G;
+#endif
         D all{own, grpb};
         dR = all; dJ = all.cols(1); dF = all.cols(1 + N); dD = all.cols(1 + 2 * N);
         l = NNL + bnd.nlo + bnd.nup;
@@ -150,12 +163,15 @@ struct Solver {
     }
 
     // r(xv) -> rn[MS] (registers), c(xv) -> cout[l]
-    ENL_FN void eval_point(const double* xv, double* rn, V cout) {
+    ENL_NOINL void eval_point(const double* xv, double* rn, V cout) {
         Fam::template residuals<Grp, MS>(ctx, g, xv, rn);
         double cnl[NNL > 0 ? NNL : 1];
         if (NNL > 0) Fam::template constraints<MS>(ctx, xv, cnl);
+#pragma unroll 1
         for (int i = 0; i < NNL; ++i) cout[i] = cnl[i];
+#pragma unroll 1
         for (int j = 0; j < bnd.nlo; ++j) cout[NNL + j] = sub_rn(xv[bnd.lo_idx[j]], bnd.lo_val[j]);
+#pragma unroll 1
         for (int j = 0; j < bnd.nup; ++j) cout[NNL + bnd.nlo + j] = sub_rn(bnd.up_val[j], xv[bnd.up_idx[j]]);
     }
 
@@ -167,7 +183,7 @@ struct Solver {
     }
 
     // J(x) -> dJ  (x in the small state, r(x) in dR)
-    ENL_FN void eval_res_jacobian() {
+    ENL_NOINL void eval_res_jacobian() {
         double xv[N];
         load_x(x, xv);
         double out[MS * N];
@@ -209,7 +225,7 @@ struct Solver {
     }
 
     // A(x) (l x n, row major) -> A
-    ENL_FN void eval_cons_jacobian() {
+    ENL_NOINL void eval_cons_jacobian() {
         double xv[N];
         load_x(x, xv);
         if (NNL > 0) {
@@ -218,27 +234,36 @@ struct Solver {
                 Fam::template jac_constraints<MS>(ctx, xv, An);
             } else {
                 double xf[N], cf[NNL > 0 ? NNL : 1];
+#pragma unroll 1
                 for (int j = 0; j < N; ++j) {
                     double dj = mul_rn(fmax(fabs(xv[j]), 1.0), SQRT_EPS);
+#pragma unroll 1
                     for (int i = 0; i < N; ++i) xf[i] = xv[i];
                     xf[j] = add_rn(xv[j], dj);
                     Fam::template constraints<MS>(ctx, xf, cf);
+#pragma unroll 1
                     for (int i = 0; i < NNL; ++i) An[i * N + j] = div_rn(sub_rn(cf[i], cx[i]), dj);
                 }
             }
+#pragma unroll 1
             for (int i = 0; i < NNL * N; ++i) A[i] = An[i];
         }
+#pragma unroll 1
         for (int j = 0; j < bnd.nlo; ++j)
+#pragma unroll 1
             for (int c = 0; c < N; ++c) A[(NNL + j) * N + c] = (c == bnd.lo_idx[j]) ? 1.0 : 0.0;
+#pragma unroll 1
         for (int j = 0; j < bnd.nup; ++j)
+#pragma unroll 1
             for (int c = 0; c < N; ++c) A[(NNL + bnd.nlo + j) * N + c] = (c == bnd.up_idx[j]) ? -1.0 : 0.0;
     }
 
     // gradient of the objective J' r and ||r||^2 (EF:2690, 2734-2735, 2829-2830)
-    ENL_FN void grad_and_sumsq() {
+    ENL_NOINL void grad_and_sumsq() {
         double rr[MS];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) rr[sl] = dR.at(sl, 0);
+#pragma unroll 1
         for (int j = 0; j < N; ++j) {
             double s = 0.0;
 #pragma unroll
@@ -255,8 +280,10 @@ struct Solver {
         int lt = l - t;
         int id = active[s - 1];
         int pos = lt;               // insert `id` into the sorted prefix inactive[0..lt)
+#pragma unroll 1
         while (pos > 0 && inactive[pos - 1] > id) { inactive[pos] = inactive[pos - 1]; --pos; }
         inactive[pos] = id;
+#pragma unroll 1
         for (int i = s; i <= t - 1; ++i) active[i - 1] = active[i];
         active[t - 1] = 0;
         t -= 1;
@@ -264,20 +291,23 @@ struct Solver {
     ENL_FN void ws_add(int s) {     // 1-based position in `inactive`
         int id = inactive[s - 1];
         int pos = t;
+#pragma unroll 1
         while (pos > 0 && active[pos - 1] > id) { active[pos] = active[pos - 1]; --pos; }
         active[pos] = id;
+#pragma unroll 1
         for (int i = s; i <= l - t - 1; ++i) inactive[i - 1] = inactive[i];
         inactive[l - t - 1] = 0;
         t += 1;
     }
 
-    ENL_FN bool evaluate_violated_constraints(int index_alpha_upp) {
+    ENL_NOINL bool evaluate_violated_constraints(int index_alpha_upp) {
         const double delta = 0.1;
         int cap = imin(l, N);
         bool added = false;
         int swaps = 0;
         if (l > t) {
             int i = 1;
+#pragma unroll 1
             while (i <= l - t) {
                 int kk = inactive[i - 1];
                 double ck = cx[kk - 1];
@@ -285,6 +315,7 @@ struct Solver {
                     if (t >= cap) {
                         int worst_k = 0;
                         double worst_val = -INFINITY;
+#pragma unroll 1
                         for (int j = Q + 1; j <= t; ++j) {
                             double cj = cx[active[j - 1] - 1];
                             if (cj > worst_val) { worst_val = cj; worst_k = j; }
@@ -309,21 +340,25 @@ struct Solver {
     }
 
     // active_C.cx = cx[active], active_C.A = A[active, :]  (EF:2683-2687, 2754-2755, 2854-2855)
-    ENL_FN void gather_active() {
+    ENL_NOINL void gather_active() {
+#pragma unroll 1
         for (int i = 0; i < t; ++i) {
             int id = active[i] - 1;
             acx[i] = cx[id];
+#pragma unroll 1
             for (int c = 0; c < N; ++c) aA[i * N + c] = A[id * N + c];
         }
     }
 
     // structures.jl:160-178
-    ENL_FN void evaluate_scaling() {
+    ENL_NOINL void evaluate_scaling() {
+#pragma unroll 1
         for (int i = 0; i < t; ++i) {
             double row = nrm2_small(aA.off(i * N), N);
             dsc[i] = row;
             if (opt.scaling) {
                 if (fabs(row) < EPS) row = 1.0;
+#pragma unroll 1
                 for (int c = 0; c < N; ++c) aA[i * N + c] = aA[i * N + c] / row;
                 acx[i] = acx[i] / row;
                 dsc[i] = 1.0 / row;
@@ -334,67 +369,84 @@ struct Solver {
     // =====================================================================================
     // multipliers (EF:461-603)
     // =====================================================================================
-    ENL_FN void factor_A() {
+    ENL_NOINL void factor_A() {
+#pragma unroll 1
         for (int c = 0; c < t; ++c)
+#pragma unroll 1
             for (int r = 0; r < N; ++r) FA[c * N + r] = aA[c * N + r];
         qrcp_small(FA, N, N, t, tauA, permA, vn1, vn2);
     }
-    ENL_FN void factor_L11() {
+    ENL_NOINL void factor_L11() {
+#pragma unroll 1
         for (int c = 0; c < t; ++c)
+#pragma unroll 1
             for (int r = 0; r < t; ++r) FL[c * T + r] = (c <= r) ? FA[r * N + c] : 0.0;
         qrcp_small(FL, T, t, t, tauL, permL, vn1, vn2);
     }
 
-    ENL_FN void first_lagrange() {
+    ENL_NOINL void first_lagrange() {
         int pr = pseudo_rank(FA, N, t, opt.eps_rank);
+#pragma unroll 1
         for (int i = 0; i < N; ++i) s1[i] = gradf[i];
         apply_qt_small(FA, N, N, t, tauA, s1);
+#pragma unroll 1
         for (int i = 0; i < t; ++i) s2[i] = (i < pr) ? s1[i] : 0.0;
         if (!solve_upper_small(FA, N, pr, s2)) threw = true;
         double gr = 0.0;
+#pragma unroll 1
         for (int i = pr; i < N; ++i) gr += s1[i] * s1[i];
         cur.grad_res = (N > pr) ? sqrt(gr) : 0.0;
+#pragma unroll 1
         for (int j = 0; j < t; ++j) s3[j] = (j < pr) ? -acx[permA[j]] : 0.0;
         if (!solve_upperT_small(FA, N, pr, s3)) threw = true;
         if (!solve_upper_small(FA, N, pr, s3)) threw = true;
+#pragma unroll 1
         for (int j = 0; j < t; ++j) lam[permA[j]] = s2[j] + s3[j];
         if (opt.scaling)
+#pragma unroll 1
             for (int i = 0; i < t; ++i) lam[i] = lam[i] * dsc[i];
     }
 
     // uses y = Q1' p_gn and J*Q1 in dJ
-    ENL_FN void second_lagrange() {
+    ENL_NOINL void second_lagrange() {
         int pr = pseudo_rank(FA, N, t, SQRT_EPS);
         double v[MS];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) {
             double acc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < N; ++c) acc += dJ.at(sl, c) * y[c];
             v[sl] = dR.at(sl, 0) + acc;
         }
+#pragma unroll 1
         for (int j = 0; j < t; ++j) {
             double s = 0.0;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) s += dJ.at(sl, j) * v[sl];
             s1[j] = g.sum(s);
         }
+#pragma unroll 1
         for (int j = pr; j < t; ++j) s1[j] = 0.0;
         if (!solve_upper_small(FA, N, pr, s1)) threw = true;
+#pragma unroll 1
         for (int j = 0; j < t; ++j) lam[permA[j]] = s1[j];
         if (opt.scaling)
+#pragma unroll 1
             for (int i = 0; i < t; ++i) lam[i] = lam[i] * dsc[i];
     }
 
-    ENL_FN int check_constraint_deletion(double grad_res) {
+    ENL_NOINL int check_constraint_deletion(double grad_res) {
         double lam_max = 1.0;
         if (t > 0) {
             lam_max = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) lam_max = fmax(lam_max, fabs(lam[i]));
         }
         double sq_rel = SQRT_EPS * lam_max;
         int s = 0;
         if (t > Q) {
             double e = sq_rel;
+#pragma unroll 1
             for (int i = Q + 1; i <= t; ++i) {
                 double row_i = opt.scaling ? 1.0 / dsc[i - 1] : dsc[i - 1];
                 double v = row_i * lam[i - 1];
@@ -409,7 +461,9 @@ struct Solver {
         lam_abs_max = 0.0;
         sigmin = INFINITY;
         if (t > Q) {
+#pragma unroll 1
             for (int i = 0; i < t; ++i) lam_abs_max = fmax(lam_abs_max, fabs(lam[i]));
+#pragma unroll 1
             for (int i = Q; i < t; ++i) {
                 double rows = opt.scaling ? 1.0 / dsc[i] : dsc[i];
                 double li = lam[i];
@@ -422,42 +476,53 @@ struct Solver {
     // search directions (EF:116-234)
     // =====================================================================================
     // writes y = [p1; p2], p = Q1 y, b (t entries), dD = Q3'(-J1 p1 - r)
-    ENL_FN void sub_search_direction(int rankA, int dimA, int dimJ2, int code) {
+    ENL_NOINL void sub_search_direction(int rankA, int dimA, int dimJ2, int code) {
         const int k2 = N - rankA;
         const int kq = imin(M, k2);
         if (code == 1) {
+#pragma unroll 1
             for (int j = 0; j < t; ++j) { double v = -acx[permA[j]]; b[j] = v; y[j] = v; }
             if (!solve_upperT_small(FA, N, t, y)) threw = true;
         } else {
+#pragma unroll 1
             for (int j = 0; j < t; ++j) s1[j] = -acx[permA[j]];
             apply_qt_small(FL, T, t, t, tauL, s1);
+#pragma unroll 1
             for (int j = 0; j < t; ++j) b[j] = s1[j];
             if (dimA > t || dimA < 0) { threw = true; dimA = imax(0, imin(dimA, t)); }
+#pragma unroll 1
             for (int j = 0; j < t; ++j) s2[j] = (j < dimA) ? s1[j] : 0.0;
             if (!solve_upper_small(FL, T, dimA, s2)) threw = true;
+#pragma unroll 1
             for (int j = 0; j < t; ++j) s3[permL[j]] = s2[j];
+#pragma unroll 1
             for (int j = 0; j < rankA; ++j) y[j] = s3[j];
         }
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) {
             double acc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < rankA; ++c) acc += dJ.at(sl, c) * y[c];
             dD.at(sl, 0) = -acc - dR.at(sl, 0);
         }
         g.sync();
         dist.apply_qt(dF, kq, tau2, dD);
         if (dimJ2 > kq || dimJ2 < 0) { threw = true; dimJ2 = imax(0, imin(dimJ2, kq)); }
+#pragma unroll 1
         for (int j = 0; j < dimJ2; ++j) s2[j] = dD.row(j, 0);
         if (!solve_upper_small(R2, N, dimJ2, s2)) threw = true;
+#pragma unroll 1
         for (int j = 0; j < k2; ++j) y[rankA + perm2[j]] = (j < dimJ2) ? s2[j] : 0.0;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) p[j] = y[j];
         apply_q_small(FA, N, N, t, tauA, p);
     }
 
-    ENL_FN void gn_search_direction(int rankA) {
+    ENL_NOINL void gn_search_direction(int rankA) {
         int code = (rankA == t) ? 1 : -1;
         dist.mul_q_right(dJ, N, FA, N, t, tauA);
         const int k2 = N - rankA;
+#pragma unroll 1
         for (int c = 0; c < k2; ++c)
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) dF.at(sl, c) = dJ.at(sl, rankA + c);
@@ -472,7 +537,7 @@ struct Solver {
     }
 
     // EF:686-795
-    ENL_FN void update_working_set() {
+    ENL_NOINL void update_working_set() {
         factor_A();
         first_lagrange();
         int s = check_constraint_deletion(cur.grad_res);
@@ -481,13 +546,16 @@ struct Solver {
             cur.index_del = 0;
             cur.del = false;
             if (opt.scaling) {
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) {
                     int id = active[i] - 1;
+#pragma unroll 1
                     for (int c = 0; c < N; ++c) aA[i * N + c] = A[id * N + c] * dsc[i];
                 }
                 factor_A();
             }
         }
+#pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             int rankA = pseudo_rank(FA, N, t, opt.eps_rank);
             factor_L11();
@@ -497,10 +565,12 @@ struct Solver {
                 int s2 = check_constraint_deletion(0.0);
                 if (s2 != 0) {
                     int id = active[s2 - 1];
+#pragma unroll 1
                     for (int i = s2; i <= t - 1; ++i) {
                         lam[i - 1] = lam[i];
                         dsc[i - 1] = dsc[i];
                         acx[i - 1] = acx[i];
+#pragma unroll 1
                         for (int c = 0; c < N; ++c) aA[(i - 1) * N + c] = aA[i * N + c];
                     }
                     ws_remove(s2);
@@ -523,11 +593,12 @@ struct Solver {
         int pm1 = prank - 1;
         if (mindim > pm1) return mindim;
         int kk = pm1;
+#pragma unroll 1
         while ((tau[kk - 1] >= tau_max * tau_prk || rho[kk - 1] <= rho_min * rho_prk) && kk > mindim) --kk;
         return (kk > mindim) ? kk : imax(mindim, pm1);
     }
 
-    ENL_FN int subspace_min_previous_step(V tau, V rho, int len, double rho_prk, double c1, int pseudo_rk, int pdim,
+    ENL_NOINL int subspace_min_previous_step(V tau, V rho, int len, double rho_prk, double c1, int pseudo_rk, int pdim,
                                           double progress, double plp, double prelin_prev, double prev_alpha) {
         const double stepb = 2e-1, pgb1 = 3e-1, pgb2 = 1e-1, predb = 7e-1, rlenb = 2.0, c2 = 1e2;
         auto ok = [&](int i) { if (i < 1 || i > len) { threw = true; return false; } return true; };
@@ -548,6 +619,7 @@ struct Solver {
         int i1 = pdim - 1;
         if (i1 <= 0) return pseudo_rk;
         int best = 0;
+#pragma unroll 1
         for (int i = i1; i <= pdim; ++i) {
             if (!ok(i)) return pseudo_rk;
             if (rho[i - 1] > predb * rho_prk) { if (best == 0) best = i; }
@@ -556,7 +628,7 @@ struct Solver {
     }
 
     // R: column major factor (ld), yv: first rankR entries of the right-hand side
-    ENL_FN int determine_solving_dim(int pdim, int rankR, double plp, double obj_progress, double prelin_prev, V R, int ld,
+    ENL_NOINL int determine_solving_dim(int pdim, int rankR, double plp, double obj_progress, double prelin_prev, V R, int ld,
                                      V yv, double prev_alpha, bool restart) {
         const double c1 = 0.1;
         int newdim = rankR;
@@ -565,6 +637,7 @@ struct Solver {
             V sd = s4, rh = s5;
             sd[0] = fabs(yv[0]);
             rh[0] = fabs(yv[0] / R[0]);
+#pragma unroll 1
             for (int i = 1; i < rankR; ++i) {
                 double a = yv[i], r = yv[i] / R[i * ld + i];
                 rh[i] = sqrt(rh[i - 1] * rh[i - 1] + r * r);
@@ -572,6 +645,7 @@ struct Solver {
             }
             double nrm_sd = sd[rankR - 1], nrm_rh = rh[rankR - 1];
             double dsum = 0.0, psimax = 0.0;
+#pragma unroll 1
             for (int i = 0; i < rankR; ++i) {
                 dsum += sd[i] * sd[i];
                 double psi = sqrt(dsum) * fabs(R[i * ld + i]);
@@ -593,7 +667,7 @@ struct Solver {
     }
 
     // bsub = Q2'(-c_act[P1]) in s1 on entry (t entries); returns dims; uses dD as scratch
-    ENL_FN void choose_subspace_dimensions(int rankA, int rankJ2, bool restart, int& dimA, int& dimJ2) {
+    ENL_NOINL void choose_subspace_dimensions(int rankA, int rankJ2, bool restart, int& dimA, int& dimJ2) {
         const double alpha_low = 0.2;
         double prev_alpha = prev.alpha;
         int pdA;
@@ -608,6 +682,7 @@ struct Solver {
             pdA = abs(prev.dimA) + t - prev.t;
             if (pdA > t) { threw = true; pdA = t; }
             double sb = 0.0, sa = 0.0;
+#pragma unroll 1
             for (int j = 0; j < t; ++j) {
                 sb += b[j] * b[j];
                 if (j < pdA) sa += b[j] * b[j];
@@ -616,10 +691,13 @@ struct Solver {
             double cprog = cdot_prev - active_cx_sum;
             dimA = determine_solving_dim(pdA, rankA, nrm_b, cprog, nrm_b_asprev, FL, T, b, prev_alpha, restart);
             if (dimA > t || rankA - dimA < 0) { threw = true; dimA = imin(dimA, rankA); }
+#pragma unroll 1
             for (int j = 0; j < rankA; ++j) s2[j] = (j < dimA) ? b[j] : 0.0;
             if (!solve_upper_small(FL, T, dimA, s2)) threw = true;
+#pragma unroll 1
             for (int i = 0; i < rankA; ++i) {
                 double acc = 0.0;
+#pragma unroll 1
                 for (int j = 0; j < rankA; ++j)
                     if (permL[j] == i) acc += s2[j];
                 s3[i] = acc;
@@ -627,6 +705,7 @@ struct Solver {
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) {
                 double acc = 0.0;
+#pragma unroll 1
                 for (int c = 0; c < rankA; ++c) acc += dJ.at(sl, c) * s3[c];
                 dD.at(sl, 0) = -(dR.at(sl, 0) + acc);
             }
@@ -639,6 +718,7 @@ struct Solver {
         double nrm_d = sqrt(dist.prefix_sq(dD, M));
         double rprog = rdot_prev - rx_sum;
         if (rankJ2 > M) { threw = true; }
+#pragma unroll 1
         for (int j = 0; j < rankJ2 && j < M; ++j) s2[j] = dD.row(j, 0);
         dimJ2 = determine_solving_dim(pdJ, rankJ2, nrm_d, rprog, nrm_d_asprev, R2, N, s2, prev_alpha, restart);
         if (!restart && prev_alpha >= alpha_low) {
@@ -648,7 +728,7 @@ struct Solver {
     }
 
     // EF:943-1030
-    ENL_FN int check_gn_direction(double b1nrm, double d1nrm, double d1nrm_as_km1, double dnrm, double active_c_sum,
+    ENL_NOINL int check_gn_direction(double b1nrm, double d1nrm, double d1nrm_as_km1, double dnrm, double active_c_sum,
                                   int rankA, bool restart, bool added, bool deleted, double& beta_k) {
         const double delta = 1e-1;
         const double c1 = 0.5, c2 = 0.1, c3 = 4.0, c4 = 10.0, c5 = 0.05;
@@ -667,6 +747,7 @@ struct Solver {
             bool to_reduce = false;
             if (Q < t) {
                 bool any_ge = false, any_neg = false;
+#pragma unroll 1
                 for (int i = Q; i < t; ++i) {
                     double rows = opt.scaling ? 1.0 / dsc[i] : dsc[i];
                     if (lam[i] * rows >= -SQRT_EPS) any_ge = true;
@@ -676,6 +757,7 @@ struct Solver {
             }
             if (l - t > 0) {
                 bool any_small = false;
+#pragma unroll 1
                 for (int j = 0; j < l - t; ++j)
                     if (cx[inactive[j] - 1] < delta) any_small = true;
                 to_reduce = to_reduce || any_small;
@@ -697,20 +779,25 @@ struct Solver {
     // =====================================================================================
     // Newton direction (EF:243-423)
     // =====================================================================================
-    ENL_FN bool newton_search_direction(int rankA) {
+    ENL_NOINL bool newton_search_direction(int rankA) {
         const double e1 = 6.055454452393343e-06;  // eps^(1/3)
         V Gm = nw, Em = nw.off(N * N), Wm = nw.off(2 * N * N);
         // p1 -> y[0..rankA)
         if (t == rankA) {
+#pragma unroll 1
             for (int j = 0; j < t; ++j) y[j] = -acx[permA[j]];
             if (!solve_upperT_small(FA, N, t, y)) threw = true;
         } else {
+#pragma unroll 1
             for (int j = 0; j < t; ++j) s1[j] = -acx[permA[j]];
             apply_qt_small(FL, T, t, t, tauL, s1);
+#pragma unroll 1
             for (int j = 0; j < rankA; ++j) s2[j] = s1[j];
             if (!solve_upper_small(FL, T, rankA, s2)) threw = true;
+#pragma unroll 1
             for (int i = 0; i < rankA; ++i) {
                 double acc = 0.0;
+#pragma unroll 1
                 for (int j = 0; j < rankA; ++j)
                     if (permL[j] == i) acc += s2[j];
                 y[i] = acc;
@@ -723,13 +810,17 @@ struct Solver {
         double rr[MS];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) rr[sl] = dR.at(sl, 0);
+#pragma unroll 1
         for (int kk = 0; kk < N; ++kk)
+#pragma unroll 1
             for (int j = 0; j <= kk; ++j) {
                 double ek = fmax(fabs(xv[kk]), 1.0) * e1;
                 double ej = fmax(fabs(xv[j]), 1.0) * e1;
                 double cacc[LMAX];
                 // four stencil points, order of EF:259-266 / 308-315
+#pragma unroll 1
                 for (int q4 = 0; q4 < 4; ++q4) {
+#pragma unroll 1
                     for (int i = 0; i < N; ++i) xw[i] = xv[i];
                     double sj = (q4 == 0 || q4 == 2) ? ej : -ej;
                     double sk = (q4 < 2) ? ek : -ek;
@@ -741,10 +832,12 @@ struct Solver {
                     if (q4 == 0) {
 #pragma unroll
                         for (int sl = 0; sl < MS; ++sl) fa[sl] = fb[sl];
+#pragma unroll 1
                         for (int i = 0; i < l; ++i) cacc[i] = cnew[i];
                     } else {
 #pragma unroll
                         for (int sl = 0; sl < MS; ++sl) fa[sl] = fa[sl] + sgn * fb[sl];
+#pragma unroll 1
                         for (int i = 0; i < l; ++i) cacc[i] = cacc[i] + sgn * cnew[i];
                     }
                 }
@@ -753,28 +846,38 @@ struct Solver {
                 for (int sl = 0; sl < MS; ++sl) sr += fa[sl] * rr[sl];
                 sr = g.sum(sr) / (4 * ej * ek);
                 double sc = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) sc += cacc[active[i] - 1] * lam[i];
                 sc = sc / (4.0 * ek * ej);
                 Gm[j * N + kk] = sr - sc;
                 Gm[kk * N + j] = sr - sc;
             }
         // E = Q1' * G * Q1
+#pragma unroll 1
         for (int c = 0; c < N; ++c) apply_qt_small(FA, N, N, t, tauA, Gm.off(c * N));   // Q1' G (columns)
+#pragma unroll 1
         for (int r = 0; r < N; ++r) {                                                    // (.) Q1 (rows)
+#pragma unroll 1
             for (int c = 0; c < N; ++c) s1[c] = Gm[c * N + r];
             // row * Q1 = (Q1' row')'
             apply_qt_small(FA, N, N, t, tauA, s1);
+#pragma unroll 1
             for (int c = 0; c < N; ++c) Em[c * N + r] = s1[c];
         }
         if (t > rankA) {
             if (t != N) { threw = true; return true; }   // E[P2,P2] is t x t, then E[rankA+1:n, .] -> BoundsError
+#pragma unroll 1
             for (int c = 0; c < N; ++c)
+#pragma unroll 1
                 for (int r = 0; r < N; ++r) Gm[c * N + r] = Em[permL[c] * N + permL[r]];
+#pragma unroll 1
             for (int i = 0; i < N * N; ++i) Em[i] = Gm[i];
         }
         const int k2 = N - rankA;
         // W22 = E22 + J2'J2 ; d = -(E21 + J2'J1) p1 - J2' r
+#pragma unroll 1
         for (int a = 0; a < k2; ++a) {
+#pragma unroll 1
             for (int c = 0; c < N; ++c) {
                 double s = 0.0;
 #pragma unroll
@@ -786,44 +889,57 @@ struct Solver {
             for (int sl = 0; sl < MS; ++sl) sjr += dJ.at(sl, rankA + a) * rr[sl];
             sjr = g.sum(sjr);
             double dacc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < rankA; ++c) dacc += (Em[c * N + (rankA + a)] + s1[c]) * y[c];
             s2[a] = -dacc - sjr;
+#pragma unroll 1
             for (int c2 = 0; c2 < k2; ++c2) Wm[c2 * N + a] = Em[(rankA + c2) * N + (rankA + a)] + s1[rankA + c2];
         }
         // symmetrise, Cholesky (upper, dpotrf), solve
+#pragma unroll 1
         for (int a = 0; a < k2; ++a)
+#pragma unroll 1
             for (int c = a; c < k2; ++c) {
                 double v = (Wm[c * N + a] + Wm[a * N + c]) * 0.5;
                 Gm[c * N + a] = v;   // upper part (row a, col c)
             }
+#pragma unroll 1
         for (int j = 0; j < k2; ++j) {
             double ajj = Gm[j * N + j];
+#pragma unroll 1
             for (int i = 0; i < j; ++i) ajj -= Gm[j * N + i] * Gm[j * N + i];
             if (!(ajj > 0.0)) {
+#pragma unroll 1
                 for (int i = 0; i < N; ++i) p[i] = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < N; ++i) y[i] = 0.0;
                 return true;
             }
             ajj = sqrt(ajj);
             Gm[j * N + j] = ajj;
+#pragma unroll 1
             for (int c = j + 1; c < k2; ++c) {
                 double v = Gm[c * N + j];
+#pragma unroll 1
                 for (int i = 0; i < j; ++i) v -= Gm[j * N + i] * Gm[c * N + i];
                 Gm[c * N + j] = v / ajj;
             }
         }
         solve_upperT_small(Gm, N, k2, s2);
         solve_upper_small(Gm, N, k2, s2);
+#pragma unroll 1
         for (int a = 0; a < k2; ++a) y[rankA + a] = s2[a];
+#pragma unroll 1
         for (int j = 0; j < N; ++j) p[j] = y[j];
         apply_q_small(FA, N, N, t, tauA, p);
         return false;
     }
 
     // EF:1191-1291
-    ENL_FN int search_direction_analys() {
+    ENL_NOINL int search_direction_analys() {
         const int rankA = cur.rankA, rankJ2 = cur.rankJ2;
         double sb = 0.0;
+#pragma unroll 1
         for (int j = 0; j < cur.dimA; ++j) sb += b[j] * b[j];
         double nrm_b1_gn = sqrt(sb);
         double nrm_d_gn = sqrt(dist.prefix_sq(dD, M));
@@ -838,8 +954,10 @@ struct Solver {
                                         cur.add, cur.del, beta);
         int dimA = rankA, dimJ2 = rankJ2;
         if (method == -1) {
+#pragma unroll 1
             for (int j = 0; j < t; ++j) s1[j] = -acx[permA[j]];
             apply_qt_small(FL, T, t, t, tauL, s1);
+#pragma unroll 1
             for (int j = 0; j < t; ++j) b[j] = s1[j];
             choose_subspace_dimensions(rankA, rankJ2, restart, dimA, dimJ2);
             if (!threw) sub_search_direction(rankA, dimA, dimJ2, -1);
@@ -867,14 +985,16 @@ struct Solver {
     // merit function, penalty weights (EF:1307-1629)
     // =====================================================================================
     // psi(x + alpha p): leaves r in rn (registers) and c in cnew
-    ENL_FN double psi(double alpha, V wv, double* rn) {
+    ENL_NOINL double psi(double alpha, V wv, double* rn) {
         double xv[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) xv[j] = add_rn(x[j], mul_rn(alpha, p[j]));
         eval_point(xv, rn, cnew);
         n_res += 1; n_cons += 1;
         double pen = 0.0;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) { int j = active[i] - 1; pen += wv[j] * (cnew[j] * cnew[j]); }
+#pragma unroll 1
         for (int i = 0; i < l - t; ++i) {
             int j = inactive[i] - 1;
             if (cnew[j] < 0.0) pen += wv[j] * (cnew[j] * cnew[j]);
@@ -883,10 +1003,13 @@ struct Solver {
     }
 
     ENL_FN void assort(V wv) {
+#pragma unroll 1
         for (int i = 0; i < t; ++i)
+#pragma unroll 1
             for (int ii = 0; ii < 4; ++ii) {
                 int kk = active[i] - 1;
                 if (wv[kk] > K[ii * LMAX + kk]) {
+#pragma unroll 1
                     for (int j = 3; j > ii; --j) K[j * LMAX + kk] = K[(j - 1) * LMAX + kk];
                     K[ii * LMAX + kk] = wv[kk];
                 }
@@ -894,26 +1017,32 @@ struct Solver {
     }
 
     // EF:1374-1423.  yv (nb_pos entries) and posidx are consumed.
-    ENL_FN void min_norm_w(int ctrl, V wv, V w_old, V yv, double tau, int nb_pos) {
+    ENL_NOINL void min_norm_w(int ctrl, V wv, V w_old, V yv, double tau, int nb_pos) {
+#pragma unroll 1
         for (int i = 0; i < l; ++i) wv[i] = w_old[i];
         if (nb_pos > 0) {
             double y_sum = 0.0;
+#pragma unroll 1
             for (int i = 0; i < nb_pos; ++i) y_sum += yv[i] * yv[i];
             double y_norm = sqrt(y_sum);
             if (y_norm != 0.0)
+#pragma unroll 1
                 for (int i = 0; i < nb_pos; ++i) yv[i] = yv[i] / y_norm;
             double tau_new = tau, s = 0.0;
             int n_runch = nb_pos;
             bool terminated = false;
+#pragma unroll 1
             while (!terminated) {
                 tau_new -= s;
                 double ymax = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < nb_pos; ++i) ymax = fmax(ymax, fabs(yv[i]));
                 double c = (ymax <= EPS) ? 1.0 : tau_new / y_sum;
                 y_sum = 0.0;
                 s = 0.0;
                 int i_stop = n_runch;
                 int kk = 1;
+#pragma unroll 1
                 while (kk <= n_runch) {
                     int i = posidx[kk - 1] - 1;
                     double buff = c * yv[kk - 1] * y_norm;
@@ -924,6 +1053,7 @@ struct Solver {
                     } else {
                         s += w_old[i] * yv[kk - 1] * y_norm;
                         n_runch -= 1;
+#pragma unroll 1
                         for (int j = kk; j <= n_runch; ++j) {
                             posidx[j - 1] = posidx[j];
                             yv[j - 1] = yv[j];
@@ -937,16 +1067,19 @@ struct Solver {
     }
 
     // EF:1429-1497.  vA = Ap*nrm_Ap (t), cxs = cx*nrm_cx (l)  ->  wnew
-    ENL_FN void euclidean_norm_weight_update(V vA, V cxs, double mu, int dimA) {
+    ENL_NOINL void euclidean_norm_weight_update(V vA, V cxs, double mu, int dimA) {
+#pragma unroll 1
         for (int i = 0; i < l; ++i) wnew[i] = w[i];
         if (t != 0) {
             V w_old = K.off(3 * LMAX);
             double ztw = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) ztw += (vA[i] * vA[i]) * w_old[active[i] - 1];
             V yv = s3;
             if (ztw >= mu && dimA < t) {
                 int nb_pos = 0;
                 double gamma = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) {
                     int kk = active[i];
                     double ye = vA[i] * (vA[i] + cxs[kk - 1]);
@@ -957,6 +1090,7 @@ struct Solver {
             } else if (ztw < mu && dimA < t) {
                 int nb_pos = 0;
                 double tau = mu;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) {
                     int kk = active[i];
                     double ee = -vA[i] * cxs[kk - 1];
@@ -965,6 +1099,7 @@ struct Solver {
                 }
                 min_norm_w(2, wnew, w_old, yv, tau, nb_pos);
             } else if (ztw < mu && dimA == t) {
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) { posidx[i] = active[i]; yv[i] = vA[i] * vA[i]; }
                 min_norm_w(1, wnew, w_old, yv, mu, t);
             }
@@ -973,13 +1108,15 @@ struct Solver {
     }
 
     // EF:1545-1629 (weight_code == 2).  jp = J p rows (registers). returns dpsi0, fills wnew
-    ENL_FN double penalty_weight_update(const double* jp, int dimA) {
+    ENL_NOINL double penalty_weight_update(const double* jp, int dimA) {
         const double delta = 0.25;
         if (dimA < 0 || dimA > t) { threw = true; dimA = imax(0, imin(dimA, t)); }
         double sAp = 0.0;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) sAp += aAp[i] * aAp[i];
         double nrm_Ap = sqrt(sAp);
         double nrm_cx = 0.0;
+#pragma unroll 1
         for (int i = 0; i < dimA; ++i) nrm_cx = fmax(nrm_cx, fabs(cx[active[i] - 1]));
         double nrm_Jp = sqrt(jp_jp);
         double nrm_rx = sqrt(rx_sum);
@@ -993,9 +1130,12 @@ struct Solver {
         }
         double Jp_rx = g.sum(part) * nrm_Jp * nrm_rx;
         V Apn = s1, cxn = s2;  // normalised copies
+#pragma unroll 1
         for (int i = 0; i < t; ++i) Apn[i] = (nrm_Ap != 0) ? aAp[i] / nrm_Ap : aAp[i];
+#pragma unroll 1
         for (int i = 0; i < l; ++i) cxn[i] = (nrm_cx != 0) ? cx[i] / nrm_cx : cx[i];
         double AtwA = 0.0, BtwA = 0.0;
+#pragma unroll 1
         for (int i = 0; i < dimA; ++i) {
             int kk = active[i] - 1;
             AtwA += w[kk] * (Apn[i] * Apn[i]);
@@ -1006,11 +1146,14 @@ struct Solver {
         double rmy = (fabs(Jp_rx + nrm_Jp * nrm_Jp) / delta) - nrm_Jp * nrm_Jp;
         // euclidean update on the re-multiplied vectors (EF:1610)
         V vA = s4, cxs = s5;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) vA[i] = Apn[i] * nrm_Ap;
+#pragma unroll 1
         for (int i = 0; i < l; ++i) cxs[i] = cxn[i] * nrm_cx;
         euclidean_norm_weight_update(vA, cxs, rmy, dimA);
         BtwA = 0.0;
         AtwA = 0.0;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) {
             int kk = active[i] - 1;
             AtwA += wnew[kk] * (Apn[i] * Apn[i]);
@@ -1028,16 +1171,19 @@ struct Solver {
         int len;
         ENL_FN double operator()(double xx) const {
             double acc = c[len - 1];
+#pragma unroll 1
             for (int i = len - 2; i >= 0; --i) acc = fma(acc, xx, c[i]);
             return acc;
         }
         ENL_FN void chop() {
+#pragma unroll 1
             while (len > 1 && c[len - 1] == 0.0) --len;
         }
         ENL_FN Quartic derivative() const {
             Quartic d;
             if (len <= 1) { d.len = 1; d.c[0] = 0.0; return d; }
             d.len = len - 1;
+#pragma unroll 1
             for (int i = 1; i < len; ++i) d.c[i - 1] = (double)i * c[i];
             d.chop();
             return d;
@@ -1051,7 +1197,7 @@ struct Solver {
         return x1 - s / q;
     }
 
-    ENL_FN static void minrn(double x1, double y1, double x2, double y2, double x3, double y3, double amin, double amax,
+    ENL_NOINL static void minrn(double x1, double y1, double x2, double y2, double x3, double y3, double amin, double amax,
                              double p_max, double& a, double& pa) {
         double eps_ = SQRT_EPS / p_max;
         if (fabs(x1 - x2) < eps_ || fabs(x3 - x1) < eps_ || fabs(x3 - x2) < eps_) { a = 0.0; pa = 0.0; return; }
@@ -1063,10 +1209,11 @@ struct Solver {
         pa = t1 + t2 + t3;
     }
 
-    ENL_FN static double newton_raphson(double x_min, double Dm, const Quartic& ds, const Quartic& dds) {
+    ENL_NOINL static double newton_raphson(double x_min, double Dm, const Quartic& ds, const Quartic& dds) {
         double alpha = x_min;
         int it = 0;
         double err = 1.0;
+#pragma unroll 1
         while ((err > 1e-4 || it < 3) && it < 50) {
             double c = dds(alpha);
             if (fabs(c) < EPS) break;
@@ -1078,7 +1225,7 @@ struct Solver {
         return alpha;
     }
 
-    ENL_FN void parameters_rm(double dot_v1v2, double normv2, double x_min, const Quartic& ds, const Quartic& dds,
+    ENL_NOINL void parameters_rm(double dot_v1v2, double normv2, double x_min, const Quartic& ds, const Quartic& dds,
                               double& alpha_hat, double& beta_hat) {
         double dds_best = dds(x_min);
         const double eta = 0.1;
@@ -1122,7 +1269,7 @@ struct Solver {
     }
 
     // the six dot products of v0, v1, v2 (EF:1665-1689, 1849) from r, r(alpha), cx, c(alpha)
-    ENL_FN void minrm(const double* jp, const double* rn, double alpha_k, double x_min, double amin, double amax,
+    ENL_NOINL void minrm(const double* jp, const double* rn, double alpha_k, double x_min, double amin, double amax,
                       double& a_hat, double& s_a, double& b_hat, double& s_b) {
         double d00 = 0, d01 = 0, d02 = 0, d11 = 0, d12 = 0, d22 = 0;
 #pragma unroll
@@ -1132,8 +1279,11 @@ struct Solver {
             d00 += v0 * v0; d01 += v0 * v1; d02 += v0 * v2; d11 += v1 * v1; d12 += v1 * v2; d22 += v2 * v2;
         }
         d00 = g.sum(d00); d01 = g.sum(d01); d02 = g.sum(d02); d11 = g.sum(d11); d12 = g.sum(d12); d22 = g.sum(d22);
+#pragma unroll 1
         for (int i = 0; i < l; ++i) s1[i] = 0.0;   // membership: 1 active, 0 inactive
+#pragma unroll 1
         for (int i = 0; i < t; ++i) s1[active[i] - 1] = 1.0;
+#pragma unroll 1
         for (int kk = 0; kk < l; ++kk) {
             double sw = sqrt(wnew[kk]);
             double v0, vb;
@@ -1164,7 +1314,7 @@ struct Solver {
         return false;
     }
 
-    ENL_FN double linesearch(const double* jp, double alpha0, double psi0, double dpsi0, double alpha_low, double alpha_upp,
+    ENL_NOINL double linesearch(const double* jp, double alpha0, double psi0, double dpsi0, double alpha_low, double alpha_upp,
                              bool& gac_error) {
         const double eta = 0.3, tau = 0.25, gamma = 0.4;
         double rn[MS];
@@ -1172,11 +1322,15 @@ struct Solver {
         double alpha_k = fmin(alpha0, amax);
         double alpha_km1 = 0.0, psi_km1 = psi0;
         double p_max = 0.0;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) p_max = fmax(p_max, fabs(p[j]));
         gac_error = false;
         // v1 constraint part (EF:1986-1998)
+#pragma unroll 1
         for (int i = 0; i < l; ++i) s1[i] = 0.0;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) s1[active[i] - 1] = 1.0;
+#pragma unroll 1
         for (int kk = 0; kk < l; ++kk) {
             double sw = sqrt(wnew[kk]);
             v1c[kk] = (s1[kk] != 0.0) ? sw * Ap[kk] : ((cx[kk] > 0) ? 0.0 : sw * Ap[kk]);
@@ -1197,6 +1351,7 @@ struct Solver {
         if ((-diff_psi <= tau * dpsi0 * alpha_km1) || (psi_km1 < gamma * psi0)) {
             diff_psi = psi0 - psi_k;
             bool likely = check_reduction(psi_km1, psi_k, pk, eta, diff_psi);
+#pragma unroll 1
             while (likely) {
                 minrn(alpha_k, psi_k, alpha_km1, psi_km1, alpha_km2, psi_km2, amin, amax, p_max, alpha_kp1, pk);
                 alpha_km2 = alpha_km1; psi_km2 = psi_km1;
@@ -1227,6 +1382,7 @@ struct Solver {
                 alpha_k = alpha_kp1;
                 psi_k = psi(alpha_k, wnew, rn);
                 bool likely = check_reduction(psi_km1, psi_k, pk, eta, diff_psi);
+#pragma unroll 1
                 while (likely) {
                     minrn(alpha_k, psi_k, alpha_km1, psi_km1, alpha_km2, psi_km2, amin, amax, p_max, alpha_kp1, pk);
                     alpha_km2 = alpha_km1; psi_km2 = psi_km1;
@@ -1242,6 +1398,7 @@ struct Solver {
                 double u = alpha_k;
                 bool ex = (p_max * u < SQRT_EPS) || (u <= amin);
                 double psi_u = psi(u, wnew, rn);
+#pragma unroll 1
                 while (!ex && (psi_u > psi0 + tau * u * dpsi0)) {
                     u *= 0.5;
                     psi_u = psi(u, wnew, rn);
@@ -1258,6 +1415,7 @@ struct Solver {
     ENL_FN double upper_bound_steplength(int index_del, int& index_alpha_upp) {
         double alpha_upper = INFINITY;
         index_alpha_upp = 0;
+#pragma unroll 1
         for (int i = 0; i < l - t; ++i) {
             int j = inactive[i];
             if (j != index_del) {
@@ -1270,11 +1428,12 @@ struct Solver {
     }
 
     // EF:2197-2293.  On return r(x+alpha p), c(x+alpha p) are in rfin / cnew when `have_final`.
-    ENL_FN double compute_steplength(int& Psi_error, double* rfin, bool& have_final) {
+    ENL_NOINL double compute_steplength(int& Psi_error, double* rfin, bool& have_final) {
         double jp[MS];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) {
             double acc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < N; ++c) acc += dJ.at(sl, c) * y[c];   // J p = (J Q1)(Q1' p)
             jp[sl] = acc;
         }
@@ -1285,13 +1444,17 @@ struct Solver {
             jp_r = g.sum(a);
             jp_jp = g.sum(bq);
         }
+#pragma unroll 1
         for (int i = 0; i < l; ++i) {
             double acc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < N; ++c) acc += A[i * N + c] * p[c];
             Ap[i] = acc;
         }
+#pragma unroll 1
         for (int i = 0; i < t; ++i) {
             double acc = 0.0;
+#pragma unroll 1
             for (int c = 0; c < N; ++c) acc += aA[i * N + c] * p[c];
             aAp[i] = opt.scaling ? acc / dsc[i] : acc;
         }
@@ -1301,6 +1464,7 @@ struct Solver {
         if (cur.code != 2) {
             double dpsi0 = penalty_weight_update(jp, cur.dimA);
             double pen = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) { int kk = active[i] - 1; pen += wnew[kk] * (cx[kk] * cx[kk]); }
             double psi0 = 0.5 * (rx_sum + pen);
             if (dpsi0 >= 0) {
@@ -1326,6 +1490,7 @@ struct Solver {
                 }
                 double upp = fmin(1.0, alpha_upp);
                 double atwa = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) atwa += wnew[active[i] - 1] * (aAp[i] * aAp[i]);
                 cur.predicted_reduction = upp * (-2.0 * jp_r - upp * jp_jp + (2.0 - upp * upp) * atwa);
                 // progress: r, c at x + alpha p (EF:2274-2280); the same point as new_point! (EF:2825-2828)
@@ -1336,11 +1501,13 @@ struct Solver {
                 n_res += 1; n_cons += 1;
                 have_final = true;
                 double whsum = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) { int kk = active[i] - 1; whsum += wnew[kk] * (cnew[kk] * cnew[kk]); }
                 cur.progress = 2 * psi0 - sumsq_regs(rfin) - whsum;
                 cur.index_alpha_upp = (idx_upp != 0 && fabs(alpha - alpha_upp) > 0.1) ? 0 : idx_upp;
             }
         } else {
+#pragma unroll 1
             for (int i = 0; i < l; ++i) wnew[i] = w[i];
             cur.index_alpha_upp = 0;
             alpha = 1.0;
@@ -1351,22 +1518,27 @@ struct Solver {
     // =====================================================================================
     // termination (EF:2399-2517); x is still x_k, xnew = x_{k+1}; cx/gradf/rx_sum at x_{k+1}
     // =====================================================================================
-    ENL_FN int check_termination(int error_code, bool time_up, double sigma_min, double lam_abs_max, int Psi_error) {
+    ENL_NOINL int check_termination(int error_code, bool time_up, double sigma_min, double lam_abs_max, int Psi_error) {
         int ec = 0;
         double pn = 0.0;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) pn += p[j] * p[j];
         double alfnoi = EPS / (sqrt(pn) + EPS);
         bool preliminary = !(cur.restart || (cur.code == -1 && alfnoi <= 0.25));
         double xd = 0.0, xn2 = 0.0;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) { double dd = xprev[j] - xnew[j]; xd += dd * dd; xn2 += xnew[j] * xnew[j]; }
         double x_diff = sqrt(xd);
         if (preliminary) {
             double ca = 0.0, gn = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) ca += acx[i] * acx[i];
+#pragma unroll 1
             for (int j = 0; j < N; ++j) gn += gradf[j] * gradf[j];
             bool necessary = (!cur.del) && (sqrt(ca) < opt.eps_c) && (cur.grad_res < sqrt(opt.eps_rel) * (1 + sqrt(gn)));
             if (l - t > 0) {
                 bool allpos = true;
+#pragma unroll 1
                 for (int i = 0; i < l - t; ++i)
                     if (!(cx[inactive[i] - 1] > 0)) allpos = false;
                 necessary = necessary && allpos;
@@ -1385,6 +1557,7 @@ struct Solver {
                 if (alfnoi > 0.25) ec += 40;
                 if (ec > 0 && l - t > 0) {
                     int feas = 1;
+#pragma unroll 1
                     for (int i = 0; i < l - t; ++i)
                         if (cx[inactive[i] - 1] <= 0.0) { feas = -1; break; }
                     ec *= feas;
@@ -1393,13 +1566,16 @@ struct Solver {
         }
         if (ec == 0) {
             double an = 0.0;
+#pragma unroll 1
             for (int c = 0; c < N; ++c) {
                 double acc = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < t; ++i) acc += aA[i * N + c] * acx[i];
                 an += acc * acc;
             }
             double Atcx_nrm = sqrt(an);
             double aps = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) { double wi = wnew[active[i] - 1]; aps += wi * wi; }
             if (k_iter >= opt.max_iter) ec = -2;
             else if (error_code >= -5 && error_code <= -3) ec = error_code;
@@ -1415,8 +1591,9 @@ struct Solver {
     // driver (EF:2638-2880)
     // =====================================================================================
     // start a solve: x0 -> state at iteration 0
-    ENL_FN void init(const double* x0, const FamilyData& fd, long long bidx, double now) {
+    ENL_NOINL void init(const double* x0, const FamilyData& fd, long long bidx, double now) {
         Fam::template load<Grp, MS>(ctx, fd, bidx, g);
+#pragma unroll 1
         for (int j = 0; j < N; ++j) { double v = x0[j]; x[j] = v; xprev[j] = v; }
         l = NNL + bnd.nlo + bnd.nup;
         k_iter = 0; ndetail = 0; exit_code = 0; threw = false; hang = false;
@@ -1434,12 +1611,17 @@ struct Solver {
         grad_and_sumsq();
         f_detail = rx_sum;
         // init_working_set (EF:826-859)
+#pragma unroll 1
         for (int i = 0; i < 4 * LMAX; ++i) K[i] = 0.1;
+#pragma unroll 1
         for (int i = 0; i < l; ++i) w[i] = fmin(fabs(cx[i]) + 0.01, 0.1);
         t = Q;
         int lmt = 0;
+#pragma unroll 1
         for (int i = 0; i < LMAX; ++i) { active[i] = 0; inactive[i] = 0; }
+#pragma unroll 1
         for (int i = 1; i <= Q; ++i) active[i - 1] = i;
+#pragma unroll 1
         for (int i = Q + 1; i <= l; ++i) {
             if (cx[i - 1] <= 0.0) {
                 if (t < T) active[t] = i;
@@ -1459,13 +1641,15 @@ struct Solver {
     }
 
     // one ENLSIP iteration; sets exit_code != 0 when the solve is over
-    ENL_FN void step(double now, double* trace_row) {
+    ENL_NOINL void step(double now, double* trace_row) {
         evaluate_scaling();
         update_working_set();
         active_cx_sum = 0.0;
+#pragma unroll 1
         for (int i = 0; i < t; ++i) { double v = cx[active[i] - 1]; active_cx_sum += v * v; }
         cur.t = t;
         double cdot_now = 0.0;
+#pragma unroll 1
         for (int i = 0; i < l; ++i) cdot_now += cx[i] * cx[i];
         if (k_iter == 0) {
             prev = cur;   // EF:2703
@@ -1485,6 +1669,7 @@ struct Solver {
         if (threw || hang) { finish_abnormal(); return; }
         cur.alpha = alpha;
         double pn = 0.0;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) pn += p[j] * p[j];
         // x_{k+1}
         double xv[N];
@@ -1494,10 +1679,12 @@ struct Solver {
         if (!have_final) eval_point(xv, rfin, cnew);
         n_res += 1; n_cons += 1; n_jres += 1; n_jcons += 1;
         // termination needs active c / A at x_k (acx, aA) and everything else at x_{k+1}
+#pragma unroll 1
         for (int i = 0; i < l; ++i) cx[i] = cnew[i];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) dR.at(sl, 0) = rfin[sl];
         g.sync();
+#pragma unroll 1
         for (int j = 0; j < N; ++j) { s5[j] = x[j]; x[j] = xnew[j]; }   // s5 = x_k
         eval_res_jacobian();
         eval_cons_jacobian();
@@ -1514,8 +1701,10 @@ struct Solver {
             trace_row[8] = sqrt(pn); trace_row[9] = cur.index_del; trace_row[10] = ec; trace_row[11] = active_cx_sum;
             trace_row[12] = cur.progress; trace_row[13] = k_iter;
             double mask = 0.0;
+#pragma unroll 1
             for (int i = 0; i < t; ++i) mask += ldexp(1.0, active[i] - 1);
             trace_row[14] = mask; trace_row[15] = cur.grad_res;
+#pragma unroll 1
             for (int j = 0; j < N; ++j) trace_row[TRACE_HDR + j] = xnew[j];
         }
         if (ec == 0) {
@@ -1524,6 +1713,7 @@ struct Solver {
             if (hang) { finish_abnormal(); return; }
             gather_active();
             k_iter += 1;
+#pragma unroll 1
             for (int i = 0; i < l; ++i) w[i] = wnew[i];   // iter.w = w ; prev = copy(iter)
             prev = cur;
             // previous_iter.x: snapshot taken before iter.x is rebound (EF:2860-2861)
@@ -1534,6 +1724,7 @@ struct Solver {
             exit_code = ec;
             if (k_iter == 0) {
                 // T5: the loop body never ran: x_opt = x0, ExecutionInfo() default
+#pragma unroll 1
                 for (int j = 0; j < N; ++j) x[j] = s5[j];
                 ndetail = 1;
                 n_res = n_cons = n_jres = n_jcons = 0;
@@ -1557,8 +1748,9 @@ struct Solver {
     }
 
     // lane 0 of the group writes the results of problem `bidx`
-    ENL_FN void store(const Outputs& o, long long bidx) {
+    ENL_NOINL void store(const Outputs& o, long long bidx) {
         if (g.lane != 0) return;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) o.x[bidx * N + j] = x[j];
         o.f[bidx] = rx_sum;
         o.exit_code[bidx] = exit_code;
@@ -1566,6 +1758,7 @@ struct Solver {
         o.iters[bidx] = ndetail;
         o.nact[bidx] = t;
         if (o.active)
+#pragma unroll 1
             for (int i = 0; i < LMAX; ++i) o.active[bidx * LMAX + i] = (i < t) ? active[i] : 0;
         if (o.counters) {
             o.counters[bidx * 2 + 0] = n_res + n_cons;

@@ -50,9 +50,8 @@ __device__ __forceinline__ double now_seconds() {
 template <class Fam, int G, int NT>
 __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_constant__ KernelArgs a) {
     using LY = Layout<Fam, G, NT>;
-    extern __shared__ __align__(16) double smem[];
-    double* small = smem;
-    double* distb = smem + (size_t)LY::nD * LY::PPC;
+    double* small = enl_smem;
+    double* distb = enl_smem + (size_t)LY::nD * LY::PPC;
     int* ints = reinterpret_cast<int*>(distb + (size_t)LY::DCOLS * LY::MS * NT);
     DevGroup<G> g;
     const int tid = threadIdx.x;
