@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched ENLSIP engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (compiled port of the oracle)
+
+Workload (config.workload): BASELINE.json config 3 -- batched bound + equality constrained
+Gaussian-peak curve fits, n=6, m=128, 1 equality + 12 bounds, forward-difference Jacobians,
+B problems per GPU (4M at the named size), synthetic data of SURVEY.md section 8d (seed 128).
+A "step" is one complete solve of the whole batch.  `value` times the solve with inputs already
+resident in HBM; `e2e` times the C-ABI call with pinned HOST buffers (H2D of y, S, x0 and D2H of
+x, f, exit codes, iteration counts inside the timed region).  Multi-GPU: the batch is sharded, one
+process per GPU, no collective on the solve path (weak scaling: B problems per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched CNLS solves/s (n=6,m=128)"
+UNIT = "solves/s"
+ALG_BYTES_PER_SOLVE = 128 * 8 + 48 + 8 + 48 + 8 + 12   # y, x0, S in; x, f, (exit, iters, t) out = 1148 B
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port(B, nthreads, seed_start=0):
+    """Compiled scalar port of the solver core (oracle/hostport) on the host cores: solves/s."""
+    import ctypes
+    import math
+    import __graft_entry__ as ge
+    import enlsip_jl_b200 as E
+    lib = ctypes.CDLL(ge.build_hostport())
+
+    class Opt(ctypes.Structure):
+        _fields_ = [("max_iter", ctypes.c_int), ("scaling", ctypes.c_int), ("jac_mode", ctypes.c_int),
+                    ("second_derivatives", ctypes.c_int), ("time_limit", ctypes.c_double), ("eps_abs", ctypes.c_double),
+                    ("eps_rel", ctypes.c_double), ("eps_x", ctypes.c_double), ("eps_c", ctypes.c_double),
+                    ("eps_rank", ctypes.c_double)]
+
+    se = math.sqrt(np.finfo(float).eps)
+    opt = Opt(100, 0, 1, 1, 1e3, 1e-10, se, se, se, se)
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B, start=seed_start)
+    n, lmax = 6, 13
+    x = np.zeros((B, n)); f = np.zeros(B)
+    ints = [np.zeros(B, np.int32) for _ in range(4)]
+    act = np.zeros((B, lmax), np.int32); cnt = np.zeros((B, 2), np.int32)
+    vp = ctypes.c_void_p
+    lib.hostport_solve.argtypes = [ctypes.c_int, ctypes.c_longlong] + [vp] * 5 + [ctypes.POINTER(Opt)] + [vp] * 9 + \
+                                  [ctypes.c_int, ctypes.c_int]
+    p = lambda a: a.ctypes.data_as(vp)
+    lo, up = np.ascontiguousarray(E.synth.GP_LOW), np.ascontiguousarray(E.synth.GP_UPP)
+    y = np.ascontiguousarray(y)
+
+    def run():
+        t0 = time.perf_counter()
+        lib.hostport_solve(1, B, p(x0), p(y), p(S), p(lo), p(up), ctypes.byref(opt), p(x), p(f), p(ints[0]), p(ints[1]),
+                           p(ints[2]), p(ints[3]), p(act), p(cnt), None, 0, nthreads)
+        return time.perf_counter() - t0
+
+    return run, ints[2]
+
+
+def reference_arm(args):
+    """`--impl reference`: the CPU implementation of the path on the host cores.
+
+    Enlsip.jl is pure Julia and no Julia binary exists in this image, so oracle/_ref cannot be built;
+    the arm times the compiled C++ port of the oracle restatement (oracle/hostport), all host threads.
+    """
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample
+    run, iters = cpu_port(sample, cores)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    v = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 gauss-peaks n=6 m=128 q=1 l=13 FD-jacobian (BASELINE.json config 3)",
+                       "problems_per_step": sample, "note": "bounded sample of the 4M-problem workload"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d problems (seed 128 stream, first chunk), compiled C++ port of the oracle, "
+                                       "OpenMP over problems" % sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mean_iterations": float(np.mean(iters))}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--problems", type=int, default=int(os.environ.get("ENLSIP_BENCH_PROBLEMS", 4_000_000)),
+                    help="problems per GPU per step (named size: 4,000,000)")
+    ap.add_argument("--cpu-sample", type=int, default=60_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import enlsip_jl_b200 as E
+    from enlsip_jl_b200.model import last_kernel_ms
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.problems
+
+    # ---- synthetic inputs of this rank's shard, pinned on the host ---------------------------------
+    y_np, S_np, x0_np, _ = E.synth.gen_gauss_peaks_batch(B, start=rank * B)
+    y_h = torch.from_numpy(np.ascontiguousarray(y_np)).pin_memory()
+    S_h = torch.from_numpy(np.ascontiguousarray(S_np)).pin_memory()
+    x0_h = torch.from_numpy(np.ascontiguousarray(x0_np)).pin_memory()
+    del y_np, S_np, x0_np
+    y_d, S_d, x0_d = y_h.to(dev), S_h.to(dev), x0_h.to(dev)
+
+    model = E.CnlsModel("gauss_peaks", x0_d, data={"y": y_d, "S": S_d}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP,
+                        jacobian="forward_diff", device=local)
+    out = {"x": torch.empty(B, 6, dtype=torch.float64, device=dev), "f": torch.empty(B, dtype=torch.float64, device=dev)}
+    for k in ("exit_code", "status", "iters", "nact"):
+        out[k] = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def step():
+        E.solve(model, want_active=False, want_counters=False, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = model.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(None)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kms = last_kernel_ms(model)    # the dominant (only) kernel: CUDA events on its launch stream, last timed step
+    clocks = sampler.stop() if rank == 0 else None
+    launches = model.launch_count() - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    status = out["status"].cpu().numpy()
+    iters = out["iters"].cpu().numpy()
+    conv = float(np.mean(status == 1))
+
+    # ---- end to end through the C ABI with pinned host buffers -------------------------------------
+    x_h = torch.empty(B, 6, dtype=torch.float64).pin_memory()
+    f_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    ints_h = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(4)]
+    hmodel = E.CnlsModel("gauss_peaks", x0_h.numpy(), data={"y": y_h.numpy(), "S": S_h.numpy()}, x_low=E.synth.GP_LOW,
+                         x_upp=E.synth.GP_UPP, jacobian="forward_diff", device=local)
+    hout = {"x": x_h.numpy(), "f": f_h.numpy(), "exit_code": ints_h[0].numpy(), "status": ints_h[1].numpy(),
+            "iters": ints_h[2].numpy(), "nact": ints_h[3].numpy()}
+
+    def e2e_step():
+        hmodel.set_data(0, y_h.numpy())          # H2D of the step's inputs, inside the timed region
+        hmodel.set_data(1, S_h.numpy())
+        E.solve(hmodel, want_active=False, want_counters=False, out=hout)   # H2D x0, kernel, D2H results (blocking)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / float(t.item())
+    h2d = B * (128 + 1 + 6) * 8
+    d2h = B * (6 * 8 + 8 + 4 * 4)
+    same = bool(np.array_equal(hout["status"], status)) and bool(np.array_equal(hout["iters"], iters))
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = ALG_BYTES_PER_SOLVE * B / (kms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C3 gauss-peaks n=6 m=128 q=1 l=13 FD-jacobian (BASELINE.json config 3)",
+                           "problems_per_gpu": B, "seed": 128, "sharding": "contiguous shards, no collective",
+                           "l2": "inputs (%.2f GB/GPU) larger than L2" % (B * 135 * 8 / 1e9)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "same_results_as_device_path": same},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "enlsip_solve_batch_kernel<GaussPeaks>",
+                             "kernel_ms": kms, "algorithmic_bytes_per_solve": ALG_BYTES_PER_SOLVE,
+                             "note": "fused whole-solve kernel: FP64-latency bound, not HBM bound (see DESIGN.md)"},
+                "quality": {"converged_fraction": conv, "mean_iterations": float(iters.mean()),
+                            "kernel_info": model.kernel_info()}}
+        if not args.skip_cpu:
+            cores = os.cpu_count() or 1
+            run, cit = cpu_port(args.cpu_sample, cores)
+            run()
+            dt = min(run() for _ in range(2))
+            line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d problems of the same stream, compiled C++ port of the oracle "
+                                              "(oracle/hostport), OpenMP over problems; Enlsip.jl itself needs Julia, "
+                                              "absent from this image" % args.cpu_sample,
+                                    "mean_iterations": float(np.mean(cit))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

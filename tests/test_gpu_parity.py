@@ -1,0 +1,161 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against the oracle fixtures.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+Nothing here reads /root/reference; the oracle (oracle/) is used only as the checker.
+"""
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import enlsip_jl_b200 as E
+    E.capi.lib()
+    return E
+
+
+def _outputs(m):
+    return dict(x=np.asarray(m.sol), f=np.asarray(m.obj_value), exit_code=np.asarray(m.exit_code), status=np.asarray(m.status_code),
+                iters=np.asarray(m.iterations), active=np.asarray(m.active), trace=np.asarray(m.trace), counters=np.asarray(m.counters))
+
+
+def test_det_exp_bit_parity(E):
+    """The CUDA det_exp and oracle/detmath.c produce identical bits (the synthetic families are defined through it)."""
+    from oracle import problems as P
+    x = np.concatenate([np.random.default_rng(1).uniform(-750, 710, 1_000_000), np.linspace(-3, 3, 100001),
+                        [0.0, -0.0, 709.78, -745.1, -744.0, -708.4, 1e-300, np.inf, -np.inf]])
+    y = np.empty_like(x)
+    E.capi.check(E.capi.lib().enlsipb200_det_exp(x.ctypes.data, y.ctypes.data, x.size, 0))
+    assert np.array_equal(y.view(np.uint64), P.det_exp(x).view(np.uint64))
+
+
+def test_c1_hs65_single_solve(E):
+    """BASELINE config 1: the README / test/problems/HS65.jl solve."""
+    from oracle import enlsip_oracle as O, problems as P
+    m = E.CnlsModel("hs65", E.synth.HS65_X0[None, :].copy(), x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    assert E.total_nb_constraints(m) == 7 and E.status(m) == ["unsolved"]
+    E.solve(m, trace_cap=40)
+    o = O.solve(P.hs65(), wallclock=False)
+    assert E.status(m) == ["found_first_order_stationary_point"] and int(m.exit_code[0]) == o.exit_code
+    assert int(m.iterations[0]) == o.iterations and [int(v) for v in m.active[0] if v > 0] == o.active
+    assert abs(E.sum_sq_residuals(m)[0] - 0.9535288567) < 1.5e-8          # docs/src/tutorial.md:128, 209-211
+    assert abs(m.obj_value[0] - o.f) <= 1e-12 * o.f
+    for k, tr in enumerate(o.trace):
+        row = m.trace[0, k]
+        assert (tr.t, tr.rankA, tr.rankJ2, tr.dimA, tr.dimJ2, tr.code, tr.exit_code) == tuple(int(v) for v in (row[1], row[2], row[3], row[4], row[5], row[6], row[10]))
+        if k < len(o.trace) - 1:
+            assert np.allclose(row[16:19], tr.x_new, rtol=1e-10, atol=0)
+    assert m.trace[0, 0, 2] == 2 and m.trace[0, 0, 1] == 3               # starts rank deficient
+    cv = E.constraints_values(m)[0]
+    assert np.allclose(cv, np.concatenate([m.sol[0] - E.synth.HS65_LOW, E.synth.HS65_UPP - m.sol[0]]))
+
+
+def test_c2_hs65_batch_vs_golden(E, golden_dir):
+    gold = np.load(golden_dir + "/c2_hs65.npz")
+    B = gold["x"].shape[0]
+    m = E.CnlsModel("hs65", E.synth.gen_hs65_batch(B), x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(m, trace_cap=40)
+    out = _outputs(m)
+    st = parity.compare(gold, out, "analytic", 3)
+    print("C2 parity", st)
+    assert (out["exit_code"] == -98).sum() == (gold["exit_code"] == -98).sum() > 0
+    ok = (out["exit_code"] == gold["exit_code"]) & (out["iters"] == gold["iters"])
+    assert np.array_equal(out["counters"][ok][:, 1], gold["njac"][ok])
+
+
+@pytest.mark.parametrize("mode,fixture,jac", [("analytic", "c3_gp_analytic.npz", "analytic"), ("fd", "c3_gp_fd.npz", "forward_diff")])
+def test_c3_gauss_peaks_vs_golden(E, golden_dir, mode, fixture, jac):
+    gold = np.load(golden_dir + "/" + fixture)
+    B = gold["x"].shape[0]
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B)
+    m = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian=jac)
+    E.solve(m, trace_cap=40)
+    st = parity.compare(gold, _outputs(m), mode, 6)
+    print("C3 parity", mode, st)
+
+
+def test_c3_fresh_samples_vs_live_oracle(E):
+    """Problems beyond the committed fixtures, checked against the oracle run on the box."""
+    from oracle import enlsip_oracle as O, problems as P
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(24, start=1_000_000)
+    m = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="analytic")
+    E.solve(m, trace_cap=40)
+    for b in range(24):
+        o = O.solve(P.gauss_peaks(y[b], S[b], x0[b], fd=False), wallclock=False)
+        assert int(m.status_code[b]) == o.status and int(m.iterations[b]) == o.iterations
+        assert [int(v) for v in m.active[b] if v > 0] == o.active
+        assert abs(m.obj_value[b] - o.f) <= 1e-10 * abs(o.f)
+        if len(o.trace) >= 2:
+            xp = m.trace[b, len(o.trace) - 2, 16:22]
+            assert np.linalg.norm(xp - o.trace[-2].x_new) <= 1e-10 * np.linalg.norm(xp)
+
+
+def test_options_time_limit_max_iter_scaling(E):
+    x0 = E.synth.gen_hs65_batch(64)
+    m = E.CnlsModel("hs65", x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(m, time_limit=-1.0)                       # test/problems/chained_rosenbrock.jl:71-73 behaviour
+    assert set(E.status(m)) == {"time_limit_exceeded"} and np.array_equal(m.sol, x0) and np.all(m.iterations == 1)
+    E.solve(m, max_iter=3)
+    assert set(E.status(m)) == {"maximum_iterations_exceeded"} and np.all(m.iterations == 3)
+    E.solve(m, scaling=True)
+    assert np.mean(np.asarray(m.status_code) == 1) > 0.85
+
+
+def test_device_buffers_and_determinism(E):
+    """torch CUDA tensors (zero copy) give bit-identical results to host buffers; re-solving is idempotent; results do
+    not depend on the position of a problem in the batch (the work queue hands problems to arbitrary warps)."""
+    import torch
+    B = 4096
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B)
+    mh = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(mh)
+    dev = torch.device("cuda", 0)
+    md = E.CnlsModel("gauss_peaks", torch.from_numpy(x0).to(dev), data={"y": torch.from_numpy(y).to(dev), "S": torch.from_numpy(S).to(dev)},
+                     x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(md)
+    torch.cuda.synchronize()
+    assert np.array_equal(md.sol.cpu().numpy().view(np.uint64), np.asarray(mh.sol).view(np.uint64))
+    assert np.array_equal(md.exit_code.cpu().numpy(), mh.exit_code) and np.array_equal(md.iterations.cpu().numpy(), mh.iterations)
+    x1 = md.sol.clone()
+    E.solve(md)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, md.sol)
+    perm = np.random.default_rng(3).permutation(B)
+    mp = E.CnlsModel("gauss_peaks", x0[perm], data={"y": y[perm], "S": S[perm]}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(mp)
+    assert np.array_equal(np.asarray(mp.sol).view(np.uint64), np.asarray(mh.sol)[perm].view(np.uint64))
+
+
+def test_full_size_properties(E):
+    """Size-independent properties at a large batch (1M HS65 = BASELINE config 2; 262144 Gaussian-peak fits)."""
+    B = 1_000_000
+    x0 = E.synth.gen_hs65_batch(B)
+    m = E.CnlsModel("hs65", x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(m)
+    ec, st = np.asarray(m.exit_code), np.asarray(m.status_code)
+    assert set(np.unique(st)) <= {1, -1, -2, -11}
+    conv = st == 1
+    assert conv.mean() > 0.9
+    assert np.all(np.abs(np.asarray(m.obj_value)[conv] - 0.9535288567) < 1e-6)
+    lo, up = E.synth.HS65_LOW, E.synth.HS65_UPP
+    xs = np.asarray(m.sol)[conv]
+    assert np.all(xs >= lo - 1e-6) and np.all(xs <= up + 1e-6) and np.all(48 - (xs ** 2).sum(1) > -1e-6)
+    assert 0.04 < np.mean(ec == -98) < 0.08          # the reference's endless working-set swap (EF:621-647)
+    Bg = 262144
+    y, S, x0g, truth = E.synth.gen_gauss_peaks_batch(Bg)
+    g = E.CnlsModel("gauss_peaks", x0g, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(g)
+    stg = np.asarray(g.status_code)
+    assert np.mean(stg == 1) > 0.9
+    xs = np.asarray(g.sol)[stg == 1]
+    assert np.all(xs >= E.synth.GP_LOW - 1e-9) and np.all(xs <= E.synth.GP_UPP + 1e-9)
+    h = xs[:, 0] / np.sqrt(xs[:, 1]) + xs[:, 3] / np.sqrt(xs[:, 4]) - S[stg == 1]
+    assert np.max(np.abs(h)) < 1e-6                  # the equality constraint holds at the solutions
+    f = np.asarray(g.obj_value)[stg == 1]
+    assert np.median(f) < 128 * 0.01 ** 2 * 3        # residual level of the 0.01-sigma noise
