@@ -1,0 +1,124 @@
+# EnlsipB200.jl -- Julia host layer over the C ABI of include/enlsip_b200.h.
+#
+# Keeps the exported names of the reference (src/cnls_model.jl:1-3, src/solver.jl:1):
+#     CnlsModel, solve!, status, solution, sum_sq_residuals, total_nb_constraints, dict_status_codes
+# and calls the B200 engine with `ccall`.  The reference's closures (residuals, jacobians,
+# constraints) cannot cross to the GPU, so a model names a device problem `family` compiled into
+# libenlsip_b200.so and carries its data arrays; one model object is a BATCH of B independent
+# problems (row b of `starting_point` is the starting point of problem b).
+#
+# NOT EXECUTED in the build container (no Julia binary in the image; see DESIGN.md).  The ctypes
+# binding in enlsip.jl_b200/capi.py binds the same symbols with the same argument lists and is what
+# the tests exercise.
+module EnlsipB200
+
+export CnlsModel, solve!, status, solution, sum_sq_residuals, total_nb_constraints, dict_status_codes
+
+const libenlsip = get(ENV, "ENLSIP_B200_LIB", joinpath(@__DIR__, "..", "lib", "libenlsip_b200.so"))
+
+const FAMILY_HS65 = Cint(0)
+const FAMILY_GAUSS_PEAKS = Cint(1)
+const JAC_ANALYTIC = Cint(0)
+const JAC_FORWARD_DIFF = Cint(1)
+
+# struct enlsipb200_options (include/enlsip_b200.h) == keyword arguments of solve! (solver.jl:62-63)
+struct Options
+    max_iter::Cint
+    scaling::Cint
+    jac_mode::Cint
+    reserved::Cint
+    time_limit::Cdouble
+    abs_tol::Cdouble
+    rel_tol::Cdouble
+    c_tol::Cdouble
+    x_tol::Cdouble
+end
+
+const dict_status_codes = Dict(          # cnls_model.jl:180-186
+    0 => :unsolved,
+    1 => :found_first_order_stationary_point,
+    -1 => :failed,
+    -2 => :maximum_iterations_exceeded,
+    -11 => :time_limit_exceeded,
+)
+
+last_error() = unsafe_string(ccall((:enlsipb200_last_error, libenlsip), Cstring, ()))
+check(rc::Cint) = rc == 0 || error("enlsip_b200 error $rc: $(last_error())")
+
+mutable struct CnlsModel{T<:Float64}
+    handle::Ptr{Cvoid}
+    family::Symbol
+    nb_parameters::Int
+    nb_residuals::Int
+    nb_eqcons::Int
+    nb_constraints::Int
+    lmax::Int
+    starting_point::Matrix{T}        # n x B  (column b = problem b; column major == the ABI's [B,n] row major)
+    x_low::Vector{T}
+    x_upp::Vector{T}
+    jacobian::Symbol                 # :analytic | :forward_diff  (cnls_model.jl:65-82)
+    status_code::Vector{Cint}
+    exit_code::Vector{Cint}
+    sol::Matrix{T}
+    obj_value::Vector{T}
+    iterations::Vector{Cint}
+    nb_active::Vector{Cint}
+    active::Matrix{Cint}             # lmax x B, 1-based constraint ids of the final working set, 0 padded
+end
+
+"""
+    CnlsModel(family, starting_point; data=(), x_low, x_upp, jacobian=:analytic)
+
+`family` is `:hs65` or `:gauss_peaks`; `data` are the family's arrays in slot order
+(`:gauss_peaks`: `y` (128 x B) and `S` (B)).  Mirrors the assertions of cnls_model.jl:363-369.
+"""
+function CnlsModel(family::Symbol, starting_point::Matrix{Float64}; data=(), x_low=fill(-Inf, size(starting_point, 1)),
+                   x_upp=fill(Inf, size(starting_point, 1)), jacobian::Symbol=:analytic, device::Integer=-1)
+    fam = family === :hs65 ? FAMILY_HS65 : family === :gauss_peaks ? FAMILY_GAUSS_PEAKS :
+          error("A device problem family must be provided")
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:enlsipb200_create, libenlsip), Cint, (Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Ptr{Cvoid}}),
+                fam, x_low, x_upp, Cint(device), h))
+    n, m, q, l, lmax = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    check(ccall((:enlsipb200_dims, libenlsip), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}),
+                h[], n, m, q, l, lmax))
+    @assert size(starting_point, 1) == n[] "starting_point must be n x B"
+    B = size(starting_point, 2)
+    for (slot, arr) in enumerate(data)
+        check(ccall((:enlsipb200_set_data, libenlsip), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint, Ptr{Cvoid}),
+                    h[], Cint(slot - 1), arr, length(arr), Cint(0), C_NULL))
+    end
+    model = CnlsModel{Float64}(h[], family, n[], m[], q[], l[], lmax[], starting_point, x_low, x_upp, jacobian,
+                               zeros(Cint, B), zeros(Cint, B), copy(starting_point), fill(NaN, B), zeros(Cint, B),
+                               zeros(Cint, B), zeros(Cint, lmax[], B))
+    finalizer(m -> ccall((:enlsipb200_destroy, libenlsip), Cint, (Ptr{Cvoid},), m.handle), model)
+    return model
+end
+
+"""
+    solve!(model; silent=true, max_iter=100, scaling=false, time_limit=1e3, abs_tol=eps(), rel_tol=√abs_tol,
+           c_tol=rel_tol, x_tol=rel_tol)
+
+Same keyword arguments and defaults as the reference (solver.jl:62-63); fills `status_code`, `sol`,
+`obj_value` like solver.jl:84-87 and returns `nothing`.
+"""
+function solve!(model::CnlsModel; silent::Bool=true, max_iter::Int=100, scaling::Bool=false, time_limit::Float64=1e3,
+                abs_tol::Float64=eps(Float64), rel_tol::Float64=sqrt(abs_tol), c_tol::Float64=rel_tol, x_tol::Float64=rel_tol)
+    B = size(model.starting_point, 2)
+    opt = Ref(Options(max_iter, scaling, model.jacobian === :forward_diff ? JAC_FORWARD_DIFF : JAC_ANALYTIC, 0,
+                      time_limit, abs_tol, rel_tol, c_tol, x_tol))
+    check(ccall((:enlsipb200_solve_batch, libenlsip), Cint,
+                (Ptr{Cvoid}, Clonglong, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
+                 Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
+                model.handle, B, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,
+                model.iterations, model.nb_active, model.active, C_NULL, C_NULL, Cint(0), Cint(0), C_NULL))
+    silent || println("solved $B problems: ", count(==(1), model.status_code), " converged")
+    return
+end
+
+status(model::CnlsModel) = [dict_status_codes[Int(c)] for c in model.status_code]     # cnls_model.jl:206
+solution(model::CnlsModel) = model.sol                                                # cnls_model.jl:213
+sum_sq_residuals(model::CnlsModel) = model.obj_value                                  # cnls_model.jl:221
+total_nb_constraints(model::CnlsModel) = model.nb_constraints                         # cnls_model.jl:238
+
+end # module
