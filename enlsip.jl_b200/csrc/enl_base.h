@@ -67,15 +67,17 @@ ENL_INL double pow2i(int k) {
 }
 
 ENL_INL double det_exp(double x) {
+    // Branch-free restatement of oracle/detmath.c::det_exp (bit-identical results):
+    //  * x < -745.2 -> 0 and x > 709.7827 -> +Inf fall out of the IEEE scaling below once x is clamped
+    //    to [-800, 710] (the true exp under/overflows on the whole clamped-away range);
+    //  * NaN is restored by the final select.
     const double LOG2E = 1.44269504088896338700e+00;
     const double LN2_HI = 6.93147180369123816490e-01;
     const double LN2_LO = 1.90821492927058770002e-10;
-    if (x != x) return x;
-    if (x > 709.782712893384) return INFINITY;
-    if (x < -745.2) return 0.0;
-    double kd = rint(mul_rn(x, LOG2E));
+    double xc = fmin(fmax(x, -800.0), 710.0);
+    double kd = rint(mul_rn(xc, LOG2E));
     int k = (int)kd;
-    double r = fma_rn(-kd, LN2_HI, x);
+    double r = fma_rn(-kd, LN2_HI, xc);
     r = fma_rn(-kd, LN2_LO, r);
     double acc = 1.0 / 6227020800.0;
     acc = fma_rn(acc, r, 1.0 / 479001600.0);
@@ -93,7 +95,10 @@ ENL_INL double det_exp(double x) {
     acc = fma_rn(acc, r, 1.0);
     int k1 = k >> 1;
     int k2 = k - k1;
-    return mul_rn(mul_rn(acc, pow2i(k1)), pow2i(k2));
+    double res = mul_rn(mul_rn(acc, pow2i(k1)), pow2i(k2));
+    if (x < -745.2) res = 0.0;          // same cut as the oracle (the natural result is 0 here as well)
+    if (x > 709.782712893384) res = INFINITY;
+    return (x != x) ? x : res;
 }
 
 ENL_INL double det_tanh(double z) {
@@ -175,21 +180,21 @@ struct SI {
 #endif
 };
 
-// row-distributed m x ncols matrix (column major by slots)
+// row-distributed m x ncols matrix (column major by slots).  The view itself is per-problem (the
+// lane offset is added at access time), so it can live in the problem's shared-memory state.
 template <int G, int MS, int NT>
 struct DM {
 #if defined(__CUDACC__)
-    int own;   // + tid
-    int grp;   // + pid*G   (lane 0 of the group)
-    ENL_INL double& at(int s, int c) const { return enl_smem[own + (c * MS + s) * NT]; }
+    int grp;   // element offset of (slot 0, column 0, lane 0 of the group)
+    ENL_INL static int lane() { return (int)(threadIdx.x & (G - 1)); }
+    ENL_INL double& at(int s, int c) const { return enl_smem[grp + lane() + (c * MS + s) * NT]; }
     ENL_INL double& row(int r, int c) const { return enl_smem[grp + (c * MS + r / G) * NT + (r % G)]; }
 #else
-    double* own;
     double* grp;
-    ENL_INL double& at(int s, int c) const { return own[(c * MS + s) * NT]; }
+    ENL_INL double& at(int s, int c) const { return grp[(c * MS + s) * NT]; }
     ENL_INL double& row(int r, int c) const { return grp[(c * MS + r / G) * NT + (r % G)]; }
 #endif
-    ENL_INL DM cols(int c0) const { return DM{own + c0 * MS * NT, grp + c0 * MS * NT}; }
+    ENL_INL DM cols(int c0) const { return DM{grp + c0 * MS * NT}; }
 };
 
 ENL_INL double sq(double v) { return v * v; }

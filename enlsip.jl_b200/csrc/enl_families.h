@@ -28,13 +28,15 @@ struct FamHS65 {
     static constexpr int N = 3, M = 3, Q = 0, NI = 1;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = false;
-    template <int MS>
-    struct Ctx {};
-    template <class Grp, int MS>
-    ENL_FN static void load(Ctx<MS>&, const FamilyData&, long long, const Grp&) {}
+    static constexpr int NDCOLS = 0;   // per-row data columns kept in distributed shared memory
+    static constexpr int NSCAL = 0;    // per-problem data scalars kept in the small state
+    template <class DMt, class Vt>
+    struct Ctx { DMt d; Vt s; };
+    template <class Grp, int MS, class C>
+    ENL_FN static void load(const C&, const FamilyData&, long long, const Grp&) {}
 
-    template <class Grp, int MS>
-    ENL_FN static void residuals(const Ctx<MS>&, const Grp& g, const double* x, double* out) {
+    template <class Grp, int MS, class C>
+    ENL_FN static void residuals(const C&, const Grp& g, const double* x, double* out) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
@@ -45,13 +47,13 @@ struct FamHS65 {
             out[s] = v;
         }
     }
-    template <int MS>
-    ENL_FN static void constraints(const Ctx<MS>&, const double* x, double* c) {
+    template <int MS, class C>
+    ENL_FN static void constraints(const C&, const double* x, double* c) {
         c[0] = sub_rn(sub_rn(sub_rn(48.0, mul_rn(x[0], x[0])), mul_rn(x[1], x[1])), mul_rn(x[2], x[2]));
     }
     // analytic Jacobian of the residual rows owned by this lane: out[s*N + j]
-    template <class Grp, int MS>
-    ENL_FN static void jac_residuals(const Ctx<MS>&, const Grp& g, const double*, double* out) {
+    template <class Grp, int MS, class C>
+    ENL_FN static void jac_residuals(const C&, const Grp& g, const double*, double* out) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
@@ -62,8 +64,8 @@ struct FamHS65 {
             out[s * N + 0] = a; out[s * N + 1] = b; out[s * N + 2] = c;
         }
     }
-    template <int MS>
-    ENL_FN static void jac_constraints(const Ctx<MS>&, const double* x, double* A /* [ (Q+NI) x N ] row major */) {
+    template <int MS, class C>
+    ENL_FN static void jac_constraints(const C&, const double* x, double* A /* [ (Q+NI) x N ] row major */) {
         A[0] = mul_rn(-2.0, x[0]); A[1] = mul_rn(-2.0, x[1]); A[2] = mul_rn(-2.0, x[2]);
     }
 };
@@ -78,49 +80,53 @@ struct FamGaussPeaks {
     static constexpr int N = 6, M = 128, Q = 1, NI = 0;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = true;
-    template <int MS>
+    static constexpr int NDCOLS = 2;   // y_i, t_i
+    static constexpr int NSCAL = 1;    // S
+    template <class DMt, class Vt>
     struct Ctx {
-        double y[MS];
-        double t[MS];
-        double S;
+        DMt d;    // column 0 = y, column 1 = t (row-distributed shared memory)
+        Vt s;     // s[0] = S
+        ENL_INL double y(int sl) const { return d.at(sl, 0); }
+        ENL_INL double t(int sl) const { return d.at(sl, 1); }
+        ENL_INL double S() const { return s[0]; }
     };
-    template <class Grp, int MS>
-    ENL_FN static void load(Ctx<MS>& c, const FamilyData& d, long long b, const Grp& g) {
+    template <class Grp, int MS, class C>
+    ENL_FN static void load(const C& c, const FamilyData& d, long long b, const Grp& g) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
-            c.y[s] = (row < M) ? d.d0[b * M + row] : 0.0;
-            c.t[s] = div_rn(mul_rn(10.0, (double)row), 127.0);
+            c.d.at(s, 0) = (row < M) ? d.d0[b * M + row] : 0.0;       // coalesced: lane l reads rows l, l+G, ...
+            c.d.at(s, 1) = div_rn(mul_rn(10.0, (double)row), 127.0);
         }
-        c.S = d.d1[b];
+        c.s[0] = d.d1[b];
     }
-    ENL_NOINL static double peak(double b, double c, double t) {
+    ENL_INL static double peak(double b, double c, double t) {
         double d = sub_rn(t, c);
         return det_exp(mul_rn(-b, mul_rn(d, d)));
     }
-    template <class Grp, int MS>
-    ENL_FN static void residuals(const Ctx<MS>& c, const Grp& g, const double* x, double* out) {
+    template <class Grp, int MS, class C>
+    ENL_FN static void residuals(const C& c, const Grp& g, const double* x, double* out) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
-            double e1 = peak(x[1], x[2], c.t[s]);
-            double e2 = peak(x[4], x[5], c.t[s]);
-            double v = sub_rn(c.y[s], add_rn(mul_rn(x[0], e1), mul_rn(x[3], e2)));
+            double e1 = peak(x[1], x[2], c.t(s));
+            double e2 = peak(x[4], x[5], c.t(s));
+            double v = sub_rn(c.y(s), add_rn(mul_rn(x[0], e1), mul_rn(x[3], e2)));
             out[s] = (row < M) ? v : 0.0;
         }
     }
-    template <int MS>
-    ENL_FN static void constraints(const Ctx<MS>& c, const double* x, double* h) {
+    template <int MS, class C>
+    ENL_FN static void constraints(const C& c, const double* x, double* h) {
         double i1 = div_rn(1.0, sqrt_rn(x[1]));
         double i2 = div_rn(1.0, sqrt_rn(x[4]));
-        h[0] = sub_rn(add_rn(mul_rn(x[0], i1), mul_rn(x[3], i2)), c.S);
+        h[0] = sub_rn(add_rn(mul_rn(x[0], i1), mul_rn(x[3], i2)), c.S());
     }
-    template <class Grp, int MS>
-    ENL_FN static void jac_residuals(const Ctx<MS>& c, const Grp& g, const double* x, double* out) {
+    template <class Grp, int MS, class C>
+    ENL_FN static void jac_residuals(const C& c, const Grp& g, const double* x, double* out) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
-            double d1 = sub_rn(c.t[s], x[2]), d2 = sub_rn(c.t[s], x[5]);
+            double d1 = sub_rn(c.t(s), x[2]), d2 = sub_rn(c.t(s), x[5]);
             double q1 = mul_rn(d1, d1), q2 = mul_rn(d2, d2);
             double e1 = det_exp(mul_rn(-x[1], q1)), e2 = det_exp(mul_rn(-x[4], q2));
             bool ok = row < M;
@@ -132,8 +138,8 @@ struct FamGaussPeaks {
             out[s * N + 5] = ok ? -mul_rn(mul_rn(x[3], e2), mul_rn(mul_rn(2.0, x[4]), d2)) : 0.0;
         }
     }
-    template <int MS>
-    ENL_FN static void jac_constraints(const Ctx<MS>&, const double* x, double* A) {
+    template <int MS, class C>
+    ENL_FN static void jac_constraints(const C&, const double* x, double* A) {
         double s1 = sqrt_rn(x[1]), s2 = sqrt_rn(x[4]);
         A[0] = div_rn(1.0, s1);
         A[1] = div_rn(mul_rn(-0.5, x[0]), mul_rn(x[1], s1));
@@ -147,14 +153,14 @@ struct FamGaussPeaks {
     // b2/c2 only the second.  Every value is computed by the same rounded operations as a plain
     // re-evaluation of r(x + delta_j e_j), so the result is bit-identical to the generic path
     // with 6 instead of 14 det_exp per row.   r0[s] = r(x) rows, dl[j] = delta_j.
-    template <class Grp, int MS>
-    ENL_FN static void fd_jac_residuals(const Ctx<MS>& c, const Grp& g, const double* x, const double* r0,
+    template <class Grp, int MS, class C>
+    ENL_FN static void fd_jac_residuals(const C& c, const Grp& g, const double* x, const double* r0,
                                         const double* dl, double* out) {
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
             bool ok = row < M;
-            double t = c.t[s], y = c.y[s];
+            double t = c.t(s), y = c.y(s);
             double e1 = peak(x[1], x[2], t), e2 = peak(x[4], x[5], t);
             double g1 = mul_rn(x[0], e1), g2 = mul_rn(x[3], e2);
             double base = r0[s];

@@ -186,8 +186,7 @@ ENL_NOINL int pseudo_rank(V R, int ld, int len, double eps_rank) {
 // ------------------------------------------------------------------------------------------
 template <class Grp, int G, int MS, int NT>
 struct Dist {
-    const Grp& g;
-    ENL_FN explicit Dist(const Grp& gg) : g(gg) {}
+    Grp g;   // lane / mask are recomputed from threadIdx: nothing per-lane is stored across calls
 
     // sum over rows >= r0 of a(:,c)^2
     ENL_NOINL double colsq(DM<G, MS, NT> a, int c, int r0) const {
@@ -345,6 +344,30 @@ struct Dist {
             }
         }
         g.sync();
+    }
+
+    // v <- Q v for a register-resident distributed vector (v[s] = row s*G+lane): H(k-1) ... H(0)
+    template <class V>
+    ENL_NOINL void apply_q_regs(DM<G, MS, NT> a, int k, V tau2, double* v) const {
+#pragma unroll 1
+        for (int i = k - 1; i >= 0; --i) {
+            double ti = tau2[i];
+            if (ti == 0.0) continue;
+            double part = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                int row = sl * G + g.lane;
+                double vv = (row > i) ? a.at(sl, i) : ((row == i) ? 1.0 : 0.0);
+                part += vv * v[sl];
+            }
+            double wv = g.sum(part) * ti;
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                int row = sl * G + g.lane;
+                double vv = (row > i) ? a.at(sl, i) : ((row == i) ? 1.0 : 0.0);
+                v[sl] -= wv * vv;
+            }
+        }
     }
 
     // sum_{row < len} d(row)^2

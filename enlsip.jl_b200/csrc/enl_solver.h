@@ -59,11 +59,12 @@ struct Layout {
         oTAUL = oFL + T * T, oR2 = oTAUL + T, oTAU2 = oR2 + N * N, oLAM = oTAU2 + N, oB = oLAM + T, oP = oB + T,
         oY = oP + N, oAP = oY + N, oAAP = oAP + LMAX, oV1C = oAAP + T, oVN1 = oV1C + LMAX, oVN2 = oVN1 + N,
         oS1 = oVN2 + N, oS2 = oS1 + NS, oS3 = oS2 + NS, oS4 = oS3 + NS, oS5 = oS4 + NS, oNW = oS5 + NS,
-        nD = oNW + 3 * N * N
+        oFS = oNW + 3 * N * N, nD = oFS + Fam::NSCAL
     };
     enum : int { iACT = 0, iINACT = iACT + LMAX, iPERMA = iINACT + LMAX, iPERML = iPERMA + T, iPERM2 = iPERML + T,
                  iPOS = iPERM2 + N, nI = iPOS + T };
-    static constexpr int DCOLS = 2 * N + 2;   // r | J (n cols) | F (n cols) | d
+    // r | J (n cols; J*Q1, then J1 | QR factor of J2 in place) | d | family row data
+    static constexpr int DCOLS = N + 2 + Fam::NDCOLS;
     static constexpr size_t smem_bytes() {
         return (size_t)nD * PPC * 8 + (size_t)DCOLS * MS * NT * 8 + (size_t)nI * PPC * 4;
     }
@@ -102,10 +103,14 @@ struct Solver {
     V x, xprev, xnew, cx, cnew, A, gradf, w, wnew, K, acx, aA, dsc, FA, tauA, FL, tauL, R2, tau2, lam, b, p, y, Ap, aAp,
         v1c, vn1, vn2, s1, s2, s3, s4, s5, nw;
     VI active, inactive, permA, permL, perm2, posidx;
-    D dR, dJ, dF, dD;
-    const Grp& g;
-    Dist<Grp, G, MS, NT> dist;
-    typename Fam::template Ctx<MS> ctx;
+    D dR, dJ, dF, dD, dY;
+    V fs;
+    using FCtx = typename Fam::template Ctx<D, V>;
+    // Nothing per-lane is stored in this object: it is one per PROBLEM and lives in shared memory, so
+    // the non-inlined member functions reach it with shared loads instead of a per-thread stack copy.
+    ENL_INL Grp grp() const { return Grp(); }
+    ENL_INL Dist<Grp, G, MS, NT> dst() const { return Dist<Grp, G, MS, NT>(); }
+    ENL_INL FCtx fctx() const { return FCtx{dY, fs}; }
     const Options& opt;
     const Bounds& bnd;
 
@@ -113,14 +118,14 @@ struct Solver {
     int l, t, k_iter, ndetail, exit_code;
     int n_res, n_cons, n_jres, n_jcons;
     bool threw, hang;
+    bool j2_factored;              // columns rankA.. of dJ hold the QR factor of J2 (else J2 itself)
     IterRec cur, prev;
     double rx_sum, active_cx_sum, f_detail, rdot_x1, cdot_x1, rdot_prev, cdot_prev;
     double jp_r, jp_jp;            // dot(Jp, rx), dot(Jp, Jp)
     double t_start;
 
-    ENL_FN Solver(double* small, int* ints, double* distbase, int pid, int tid, const Grp& grp, const Options& o,
-                  const Bounds& bb)
-        : g(grp), dist(grp), opt(o), bnd(bb) {
+    ENL_FN Solver(double* small, int* ints, double* distbase, int pid, const Options& o, const Bounds& bb)
+        : opt(o), bnd(bb) {
 #if defined(__CUDACC__)
         int s = (int)(small - enl_smem) + pid;
 #else
@@ -133,7 +138,7 @@ struct Solver {
         FL = mk(LY::oFL); tauL = mk(LY::oTAUL); R2 = mk(LY::oR2); tau2 = mk(LY::oTAU2); lam = mk(LY::oLAM);
         b = mk(LY::oB); p = mk(LY::oP); y = mk(LY::oY); Ap = mk(LY::oAP); aAp = mk(LY::oAAP); v1c = mk(LY::oV1C);
         vn1 = mk(LY::oVN1); vn2 = mk(LY::oVN2); s1 = mk(LY::oS1); s2 = mk(LY::oS2); s3 = mk(LY::oS3);
-        s4 = mk(LY::oS4); s5 = mk(LY::oS5); nw = mk(LY::oNW);
+        s4 = mk(LY::oS4); s5 = mk(LY::oS5); nw = mk(LY::oNW); fs = mk(LY::oFS);
 #if defined(__CUDACC__)
         int ii = (int)(ints - reinterpret_cast<int*>(enl_smem)) + pid;
 #else
@@ -143,14 +148,12 @@ struct Solver {
         active = mi(LY::iACT); inactive = mi(LY::iINACT); permA = mi(LY::iPERMA); permL = mi(LY::iPERML);
         perm2 = mi(LY::iPERM2); posidx = mi(LY::iPOS);
 #if defined(__CUDACC__)
-        int own = (int)(distbase - enl_smem) + tid;
         int grpb = (int)(distbase - enl_smem) + pid * G;
 #else
-        double* own = distbase + tid;
         double* grpb = distbase + pid * G;
 #endif
-        D all{own, grpb};
-        dR = all; dJ = all.cols(1); dF = all.cols(1 + N); dD = all.cols(1 + 2 * N);
+        D all{grpb};
+        dR = all; dJ = all.cols(1); dF = dJ; dD = all.cols(1 + N); dY = all.cols(2 + N);
         l = NNL + bnd.nlo + bnd.nup;
     }
 
@@ -164,9 +167,9 @@ struct Solver {
 
     // r(xv) -> rn[MS] (registers), c(xv) -> cout[l]
     ENL_NOINL void eval_point(const double* xv, double* rn, V cout) {
-        Fam::template residuals<Grp, MS>(ctx, g, xv, rn);
+        Fam::template residuals<Grp, MS>(fctx(), grp(), xv, rn);
         double cnl[NNL > 0 ? NNL : 1];
-        if (NNL > 0) Fam::template constraints<MS>(ctx, xv, cnl);
+        if (NNL > 0) Fam::template constraints<MS>(fctx(), xv, cnl);
 #pragma unroll 1
         for (int i = 0; i < NNL; ++i) cout[i] = cnl[i];
 #pragma unroll 1
@@ -179,7 +182,7 @@ struct Solver {
         double s = 0.0;
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) s += rn[sl] * rn[sl];
-        return g.sum(s);
+        return grp().sum(s);
     }
 
     // J(x) -> dJ  (x in the small state, r(x) in dR)
@@ -188,7 +191,7 @@ struct Solver {
         load_x(x, xv);
         double out[MS * N];
         if (opt.jac_mode == 0) {
-            Fam::template jac_residuals<Grp, MS>(ctx, g, xv, out);
+            Fam::template jac_residuals<Grp, MS>(fctx(), grp(), xv, out);
         } else {
             double r0[MS], dl[N];
 #pragma unroll
@@ -201,13 +204,14 @@ struct Solver {
         for (int sl = 0; sl < MS; ++sl)
 #pragma unroll
             for (int j = 0; j < N; ++j) dJ.at(sl, j) = out[sl * N + j];
-        g.sync();
+        j2_factored = false;
+        grp().sync();
     }
 
     template <class F2 = Fam>
     ENL_FN typename std::enable_if<F2::HAS_FAST_FD>::type fd_res(const double* xv, const double* r0, const double* dl,
                                                                  double* out) {
-        F2::template fd_jac_residuals<Grp, MS>(ctx, g, xv, r0, dl, out);
+        F2::template fd_jac_residuals<Grp, MS>(fctx(), grp(), xv, r0, dl, out);
     }
     template <class F2 = Fam>
     ENL_FN typename std::enable_if<!F2::HAS_FAST_FD>::type fd_res(const double* xv, const double* r0, const double* dl,
@@ -218,7 +222,7 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < N; ++i) xf[i] = xv[i];
             xf[j] = add_rn(xv[j], dl[j]);
-            F2::template residuals<Grp, MS>(ctx, g, xf, rf);
+            F2::template residuals<Grp, MS>(fctx(), grp(), xf, rf);
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) out[sl * N + j] = div_rn(sub_rn(rf[sl], r0[sl]), dl[j]);
         }
@@ -231,7 +235,7 @@ struct Solver {
         if (NNL > 0) {
             double An[(NNL > 0 ? NNL : 1) * N];
             if (opt.jac_mode == 0) {
-                Fam::template jac_constraints<MS>(ctx, xv, An);
+                Fam::template jac_constraints<MS>(fctx(), xv, An);
             } else {
                 double xf[N], cf[NNL > 0 ? NNL : 1];
 #pragma unroll 1
@@ -240,7 +244,7 @@ struct Solver {
 #pragma unroll 1
                     for (int i = 0; i < N; ++i) xf[i] = xv[i];
                     xf[j] = add_rn(xv[j], dj);
-                    Fam::template constraints<MS>(ctx, xf, cf);
+                    Fam::template constraints<MS>(fctx(), xf, cf);
 #pragma unroll 1
                     for (int i = 0; i < NNL; ++i) An[i * N + j] = div_rn(sub_rn(cf[i], cx[i]), dj);
                 }
@@ -248,6 +252,10 @@ struct Solver {
 #pragma unroll 1
             for (int i = 0; i < NNL * N; ++i) A[i] = An[i];
         }
+    }
+
+    // rows of A for the bounds are constant (+-e_j, cnls_model.jl:393-403): written once per solve
+    ENL_NOINL void init_bound_rows() {
 #pragma unroll 1
         for (int j = 0; j < bnd.nlo; ++j)
 #pragma unroll 1
@@ -268,7 +276,7 @@ struct Solver {
             double s = 0.0;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) s += dJ.at(sl, j) * rr[sl];
-            gradf[j] = g.sum(s);
+            gradf[j] = grp().sum(s);
         }
         rx_sum = sumsq_regs(rr);
     }
@@ -410,20 +418,24 @@ struct Solver {
     // uses y = Q1' p_gn and J*Q1 in dJ
     ENL_NOINL void second_lagrange() {
         int pr = pseudo_rank(FA, N, t, SQRT_EPS);
+        // r + J p_gn = r + J1 p1 + J2 p2 with J2 p2 = Q3 [d(0:kq); 0]  =>  r + J p_gn = -Q3 [0; d(kq:)]
+        // (J2 itself has been overwritten by its QR factor; here rankJ2 == kq == min(m, n - rankA))
         double v[MS];
+        {
+            const int kq = imin(M, N - cur.rankA);
 #pragma unroll
-        for (int sl = 0; sl < MS; ++sl) {
-            double acc = 0.0;
-#pragma unroll 1
-            for (int c = 0; c < N; ++c) acc += dJ.at(sl, c) * y[c];
-            v[sl] = dR.at(sl, 0) + acc;
+            for (int sl = 0; sl < MS; ++sl) {
+                int row = sl * G + grp().lane;
+                v[sl] = (row >= kq) ? -dD.at(sl, 0) : 0.0;
+            }
+            dst().apply_q_regs(dF, kq, tau2, v);
         }
 #pragma unroll 1
         for (int j = 0; j < t; ++j) {
             double s = 0.0;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) s += dJ.at(sl, j) * v[sl];
-            s1[j] = g.sum(s);
+            s1[j] = grp().sum(s);
         }
 #pragma unroll 1
         for (int j = pr; j < t; ++j) s1[j] = 0.0;
@@ -505,8 +517,8 @@ struct Solver {
             for (int c = 0; c < rankA; ++c) acc += dJ.at(sl, c) * y[c];
             dD.at(sl, 0) = -acc - dR.at(sl, 0);
         }
-        g.sync();
-        dist.apply_qt(dF, kq, tau2, dD);
+        grp().sync();
+        dst().apply_qt(dF, kq, tau2, dD);
         if (dimJ2 > kq || dimJ2 < 0) { threw = true; dimJ2 = imax(0, imin(dimJ2, kq)); }
 #pragma unroll 1
         for (int j = 0; j < dimJ2; ++j) s2[j] = dD.row(j, 0);
@@ -520,14 +532,12 @@ struct Solver {
 
     ENL_NOINL void gn_search_direction(int rankA) {
         int code = (rankA == t) ? 1 : -1;
-        dist.mul_q_right(dJ, N, FA, N, t, tauA);
+        dst().mul_q_right(dJ, N, FA, N, t, tauA);
         const int k2 = N - rankA;
-#pragma unroll 1
-        for (int c = 0; c < k2; ++c)
-#pragma unroll
-            for (int sl = 0; sl < MS; ++sl) dF.at(sl, c) = dJ.at(sl, rankA + c);
-        g.sync();
-        dist.qrcp(dF, M, k2, tau2, perm2, vn1, vn2, R2, N);
+        dF = dJ.cols(rankA);          // J2 is factored in place; J1 = columns [0, rankA) stays intact
+        grp().sync();
+        dst().qrcp(dF, M, k2, tau2, perm2, vn1, vn2, R2, N);
+        j2_factored = true;
         int rankJ2 = pseudo_rank(R2, N, imin(M, k2), opt.eps_rank);
         sub_search_direction(rankA, rankA, rankJ2, code);
         cur.rankA = rankA;
@@ -710,12 +720,12 @@ struct Solver {
                 dD.at(sl, 0) = -(dR.at(sl, 0) + acc);
             }
         }
-        g.sync();
-        if (rankJ2 > 0) dist.apply_qt(dF, kq, tau2, dD);
+        grp().sync();
+        if (rankJ2 > 0) dst().apply_qt(dF, kq, tau2, dD);
         int pdJ = abs(prev.dimJ2) + prev.t - t;
         if (pdJ > M) { threw = true; pdJ = M; }
-        double nrm_d_asprev = sqrt(dist.prefix_sq(dD, pdJ));
-        double nrm_d = sqrt(dist.prefix_sq(dD, M));
+        double nrm_d_asprev = sqrt(dst().prefix_sq(dD, pdJ));
+        double nrm_d = sqrt(dst().prefix_sq(dD, M));
         double rprog = rdot_prev - rx_sum;
         if (rankJ2 > M) { threw = true; }
 #pragma unroll 1
@@ -804,7 +814,10 @@ struct Solver {
             }
         }
         if (rankA == N) { threw = true; return true; }   // EF:379-381 returns a bare vector -> TypeError
-        // dJ holds J*Q1 with J1 | J2 intact
+        // J2 was overwritten by its QR factor: re-evaluate J(x) (deterministic) and form J*Q1 again
+        eval_res_jacobian();
+        dst().mul_q_right(dJ, N, FA, N, t, tauA);
+        grp().sync();
         double xv[N], xw[N], fa[MS], fb[MS];
         load_x(x, xv);
         double rr[MS];
@@ -844,7 +857,7 @@ struct Solver {
                 double sr = 0.0;
 #pragma unroll
                 for (int sl = 0; sl < MS; ++sl) sr += fa[sl] * rr[sl];
-                sr = g.sum(sr) / (4 * ej * ek);
+                sr = grp().sum(sr) / (4 * ej * ek);
                 double sc = 0.0;
 #pragma unroll 1
                 for (int i = 0; i < t; ++i) sc += cacc[active[i] - 1] * lam[i];
@@ -882,12 +895,12 @@ struct Solver {
                 double s = 0.0;
 #pragma unroll
                 for (int sl = 0; sl < MS; ++sl) s += dJ.at(sl, rankA + a) * dJ.at(sl, c);
-                s1[c] = g.sum(s);
+                s1[c] = grp().sum(s);
             }
             double sjr = 0.0;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) sjr += dJ.at(sl, rankA + a) * rr[sl];
-            sjr = g.sum(sjr);
+            sjr = grp().sum(sjr);
             double dacc = 0.0;
 #pragma unroll 1
             for (int c = 0; c < rankA; ++c) dacc += (Em[c * N + (rankA + a)] + s1[c]) * y[c];
@@ -942,11 +955,11 @@ struct Solver {
 #pragma unroll 1
         for (int j = 0; j < cur.dimA; ++j) sb += b[j] * b[j];
         double nrm_b1_gn = sqrt(sb);
-        double nrm_d_gn = sqrt(dist.prefix_sq(dD, M));
-        double nrm_d1_gn = sqrt(dist.prefix_sq(dD, cur.dimJ2));
+        double nrm_d_gn = sqrt(dst().prefix_sq(dD, M));
+        double nrm_d1_gn = sqrt(dst().prefix_sq(dD, cur.dimJ2));
         int pd = prev.dimJ2 + prev.t - t - 1;
         if (pd > M) { threw = true; pd = M; }
-        double nrm_d1_asprev = sqrt(dist.prefix_sq(dD, pd));
+        double nrm_d1_asprev = sqrt(dst().prefix_sq(dD, pd));
         bool restart = cur.restart;
         int error_code = 0;
         double beta;
@@ -1128,7 +1141,7 @@ struct Solver {
             double r = (nrm_rx != 0) ? dR.at(sl, 0) / nrm_rx : dR.at(sl, 0);
             part += a * r;
         }
-        double Jp_rx = g.sum(part) * nrm_Jp * nrm_rx;
+        double Jp_rx = grp().sum(part) * nrm_Jp * nrm_rx;
         V Apn = s1, cxn = s2;  // normalised copies
 #pragma unroll 1
         for (int i = 0; i < t; ++i) Apn[i] = (nrm_Ap != 0) ? aAp[i] / nrm_Ap : aAp[i];
@@ -1278,7 +1291,7 @@ struct Solver {
             double v2 = ((rn[sl] - v0) / alpha_k - v1) / alpha_k;
             d00 += v0 * v0; d01 += v0 * v1; d02 += v0 * v2; d11 += v1 * v1; d12 += v1 * v2; d22 += v2 * v2;
         }
-        d00 = g.sum(d00); d01 = g.sum(d01); d02 = g.sum(d02); d11 = g.sum(d11); d12 = g.sum(d12); d22 = g.sum(d22);
+        d00 = grp().sum(d00); d01 = grp().sum(d01); d02 = grp().sum(d02); d11 = grp().sum(d11); d12 = grp().sum(d12); d22 = grp().sum(d22);
 #pragma unroll 1
         for (int i = 0; i < l; ++i) s1[i] = 0.0;   // membership: 1 active, 0 inactive
 #pragma unroll 1
@@ -1430,19 +1443,44 @@ struct Solver {
     // EF:2197-2293.  On return r(x+alpha p), c(x+alpha p) are in rfin / cnew when `have_final`.
     ENL_NOINL double compute_steplength(int& Psi_error, double* rfin, bool& have_final) {
         double jp[MS];
-#pragma unroll
-        for (int sl = 0; sl < MS; ++sl) {
-            double acc = 0.0;
+        if (j2_factored) {
+            // J p = (J Q1) y = J1 y1 + J2 y2,  J2 = Q3 [R22 P3'; 0]  =>  J2 y2 = Q3 [R22 (P3' y2); 0]
+            const int rankA = cur.rankA, k2 = N - cur.rankA, kq = imin(M, N - cur.rankA);
 #pragma unroll 1
-            for (int c = 0; c < N; ++c) acc += dJ.at(sl, c) * y[c];   // J p = (J Q1)(Q1' p)
-            jp[sl] = acc;
+            for (int i = 0; i < kq; ++i) {
+                double acc = 0.0;
+#pragma unroll 1
+                for (int j = i; j < k2; ++j) acc += R2[j * N + i] * y[rankA + perm2[j]];
+                s1[i] = acc;
+            }
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                int row = sl * G + grp().lane;
+                jp[sl] = (row < kq) ? s1[row < kq ? row : 0] : 0.0;
+            }
+            dst().apply_q_regs(dF, kq, tau2, jp);
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                double acc = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < rankA; ++c) acc += dJ.at(sl, c) * y[c];
+                jp[sl] += acc;
+            }
+        } else {
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                double acc = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < N; ++c) acc += dJ.at(sl, c) * y[c];   // J p = (J Q1)(Q1' p)
+                jp[sl] = acc;
+            }
         }
         {
             double a = 0.0, bq = 0.0;
 #pragma unroll
             for (int sl = 0; sl < MS; ++sl) { a += jp[sl] * dR.at(sl, 0); bq += jp[sl] * jp[sl]; }
-            jp_r = g.sum(a);
-            jp_jp = g.sum(bq);
+            jp_r = grp().sum(a);
+            jp_jp = grp().sum(bq);
         }
 #pragma unroll 1
         for (int i = 0; i < l; ++i) {
@@ -1550,7 +1588,7 @@ struct Solver {
             if (necessary) {
                 int dj = cur.dimJ2;
                 if (dj > M) { threw = true; dj = M; }
-                double d1 = dist.prefix_sq(dD, dj);
+                double d1 = dst().prefix_sq(dD, dj);
                 if (d1 <= rx_sum * opt.eps_rel * opt.eps_rel) ec += 10000;
                 if (rx_sum <= opt.eps_abs * opt.eps_abs) ec += 2000;
                 if (x_diff < opt.eps_x * sqrt(xn2)) ec += 300;
@@ -1592,7 +1630,7 @@ struct Solver {
     // =====================================================================================
     // start a solve: x0 -> state at iteration 0
     ENL_NOINL void init(const double* x0, const FamilyData& fd, long long bidx, double now) {
-        Fam::template load<Grp, MS>(ctx, fd, bidx, g);
+        Fam::template load<Grp, MS>(fctx(), fd, bidx, grp());
 #pragma unroll 1
         for (int j = 0; j < N; ++j) { double v = x0[j]; x[j] = v; xprev[j] = v; }
         l = NNL + bnd.nlo + bnd.nup;
@@ -1604,7 +1642,8 @@ struct Solver {
         eval_point(xv, rn, cx);
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) dR.at(sl, 0) = rn[sl];
-        g.sync();
+        grp().sync();
+        init_bound_rows();
         eval_res_jacobian();
         eval_cons_jacobian();
         n_res += 1; n_cons += 1; n_jres += 1; n_jcons += 1;
@@ -1683,7 +1722,7 @@ struct Solver {
         for (int i = 0; i < l; ++i) cx[i] = cnew[i];
 #pragma unroll
         for (int sl = 0; sl < MS; ++sl) dR.at(sl, 0) = rfin[sl];
-        g.sync();
+        grp().sync();
 #pragma unroll 1
         for (int j = 0; j < N; ++j) { s5[j] = x[j]; x[j] = xnew[j]; }   // s5 = x_k
         eval_res_jacobian();
@@ -1749,7 +1788,7 @@ struct Solver {
 
     // lane 0 of the group writes the results of problem `bidx`
     ENL_NOINL void store(const Outputs& o, long long bidx) {
-        if (g.lane != 0) return;
+        if (grp().lane != 0) return;
 #pragma unroll 1
         for (int j = 0; j < N; ++j) o.x[bidx * N + j] = x[j];
         o.f[bidx] = rx_sum;

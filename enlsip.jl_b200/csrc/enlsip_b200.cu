@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -50,38 +52,56 @@ __device__ __forceinline__ double now_seconds() {
 template <class Fam, int G, int NT>
 __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_constant__ KernelArgs a) {
     using LY = Layout<Fam, G, NT>;
-    double* small = enl_smem;
-    double* distb = enl_smem + (size_t)LY::nD * LY::PPC;
-    int* ints = reinterpret_cast<int*>(distb + (size_t)LY::DCOLS * LY::MS * NT);
-    DevGroup<G> g;
+    constexpr bool SYNC_ITER = (NT > 32);
+    using SolverT = Solver<Fam, DevGroup<G>, NT>;
+    constexpr int SOLVER_DOUBLES = (int)((sizeof(SolverT) + 7) / 8) | 1;   // odd stride: no bank conflicts for G == 1
     const int tid = threadIdx.x;
     const int pid = tid / G;
-    Solver<Fam, DevGroup<G>, NT> S(small, ints, distb, pid, tid, g, a.opt, a.bnd);
+    double* objs = enl_smem;
+    double* small = enl_smem + (size_t)SOLVER_DOUBLES * LY::PPC;
+    double* distb = small + (size_t)LY::nD * LY::PPC;
+    int* ints = reinterpret_cast<int*>(distb + (size_t)LY::DCOLS * LY::MS * NT);
+    DevGroup<G> g;
+    // the per-problem solver object lives in shared memory; every lane of the group writes identical values
+    SolverT& S = *new (objs + (size_t)SOLVER_DOUBLES * pid) SolverT(small, ints, distb, pid, a.opt, a.bnd);
+    g.sync();
     const int row_w = TRACE_HDR + Fam::N;
-    bool have = false;
+    bool have = false, exhausted = false;
     long long b = 0;
     int row = 0;
     for (;;) {
-        if (!have) {
+        if (!have && !exhausted) {
             unsigned long long nb = 0;
             if (g.lane == 0) nb = atomicAdd(a.counter, 1ULL);
             if (G > 1) nb = __shfl_sync(g.mask, nb, 0, G);
             b = (long long)nb;
-            if (b >= a.B) break;
-            S.init(a.x0 + b * Fam::N, a.fd, b, now_seconds());
-            have = true;
-            row = 0;
+            if (b >= a.B) {
+                exhausted = true;
+            } else {
+                S.init(a.x0 + b * Fam::N, a.fd, b, now_seconds());
+                have = true;
+                row = 0;
+            }
         }
-        if (S.exit_code == 0) {
-            double* tr = nullptr;
-            if (a.out.trace && row < a.out.trace_cap && g.lane == 0)
-                tr = a.out.trace + ((size_t)b * a.out.trace_cap + row) * row_w;
-            S.step(now_seconds(), tr);
-            ++row;
+        // Multi-warp CTAs re-align their warps once per iteration: co-resident warps then run the same
+        // routines at the same time and share instruction-cache lines (the kernel is fetch-bound).
+        if (SYNC_ITER) {
+            if (!__syncthreads_or(have ? 1 : 0)) break;
+        } else if (!have) {
+            break;
         }
-        if (S.exit_code != 0) {
-            S.store(a.out, b);
-            have = false;
+        if (have) {
+            if (S.exit_code == 0) {
+                double* tr = nullptr;
+                if (a.out.trace && row < a.out.trace_cap && g.lane == 0)
+                    tr = a.out.trace + ((size_t)b * a.out.trace_cap + row) * row_w;
+                S.step(now_seconds(), tr);
+                ++row;
+            }
+            if (S.exit_code != 0) {
+                S.store(a.out, b);
+                have = false;
+            }
         }
     }
 }
@@ -119,10 +139,17 @@ struct enlsipb200_handle_s {
 namespace {
 
 template <class Fam, int G, int NT>
+size_t smem_total() {
+    using LY = Layout<Fam, G, NT>;
+    size_t sd = ((sizeof(Solver<Fam, DevGroup<G>, NT>) + 7) / 8) | 1;
+    return LY::smem_bytes() + sd * 8 * LY::PPC;
+}
+
+template <class Fam, int G, int NT>
 int configure(enlsipb200_handle h) {
     using LY = Layout<Fam, G, NT>;
     auto kern = enlsip_solve_batch_kernel<Fam, G, NT>;
-    size_t smem = LY::smem_bytes();
+    size_t smem = smem_total<Fam, G, NT>();
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kern));
@@ -147,7 +174,7 @@ int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     CU(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
     CU(cudaEventRecord(h->ev0, st));
-    enlsip_solve_batch_kernel<Fam, G, NT><<<grid, NT, LY::smem_bytes(), st>>>(a);
+    enlsip_solve_batch_kernel<Fam, G, NT><<<grid, NT, smem_total<Fam, G, NT>(), st>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
@@ -157,7 +184,8 @@ int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st) {
 
 // lanes per problem / threads per CTA of each family
 constexpr int HS_G = 1, HS_NT = 64;
-constexpr int GP_G = 32, GP_NT = 32;
+constexpr int GP_G = 32;
+static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 448; return (v == 224 || v == 128 || v == 64) ? v : 448; }
 
 Options make_options(const enlsipb200_options* o, int n, int m) {
     enlsipb200_options d;
@@ -235,7 +263,15 @@ int enlsipb200_create(int family, const double* x_low, const double* x_upp, int 
     if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) { delete h; return fail(ENLSIPB200_ENOMEM, "cudaMalloc"); }
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { delete h; return fail(ENLSIPB200_ECUDA, "cudaEventCreate"); }
     if (family == ENLSIPB200_FAMILY_HS65) rc = configure<FamHS65, HS_G, HS_NT>(h);
-    else rc = configure<FamGaussPeaks, GP_G, GP_NT>(h);
+    else {
+        switch (gp_nt()) {
+            case 64: rc = configure<FamGaussPeaks, GP_G, 64>(h); break;
+            case 224: rc = configure<FamGaussPeaks, GP_G, 224>(h); break;
+
+            case 128: rc = configure<FamGaussPeaks, GP_G, 128>(h); break;
+            default: rc = configure<FamGaussPeaks, GP_G, 448>(h);
+        }
+    }
     if (rc != 0) { enlsipb200_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -334,7 +370,15 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     }
     int rc;
     if (h->family == ENLSIPB200_FAMILY_HS65) rc = launch<FamHS65, HS_G, HS_NT>(h, a, st);
-    else rc = launch<FamGaussPeaks, GP_G, GP_NT>(h, a, st);
+    else {
+        switch (h->nt) {
+            case 64: rc = launch<FamGaussPeaks, GP_G, 64>(h, a, st); break;
+            case 224: rc = launch<FamGaussPeaks, GP_G, 224>(h, a, st); break;
+
+            case 128: rc = launch<FamGaussPeaks, GP_G, 128>(h, a, st); break;
+            default: rc = launch<FamGaussPeaks, GP_G, 448>(h, a, st);
+        }
+    }
     if (rc != 0) return rc;
     if (!on_device) {
         CU(cudaMemcpyAsync(x, a.out.x, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));

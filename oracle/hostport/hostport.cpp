@@ -31,7 +31,7 @@ static void solve_range(long long b0, long long b1, const double* x0, const Fami
         std::fill(small.begin(), small.end(), 0.0);
         std::fill(dist.begin(), dist.end(), 0.0);
         std::fill(ints.begin(), ints.end(), 0);
-        Solver<Fam, HostGroup, 1> S(small.data(), ints.data(), dist.data(), 0, 0, g, opt, bnd);
+        Solver<Fam, HostGroup, 1> S(small.data(), ints.data(), dist.data(), 0, opt, bnd);
         S.init(x0 + b * Fam::N, fd, b, now());
         int row = 0;
         while (S.exit_code == 0) {
@@ -64,4 +64,8 @@ extern "C" int hostport_solve(int family, long long B, const double* x0, const d
         else solve_range<FamGaussPeaks>(b0, b1, x0, fd, *opt, bnd, out);
     }
     return 0;
+}
+
+extern "C" void hostport_det_exp(const double* x, double* y, long long n) {
+    for (long long i = 0; i < n; ++i) y[i] = enl::det_exp(x[i]);
 }
