@@ -53,6 +53,12 @@ ENL_INL double div_rn(double a, double b) { return a / b; }
 ENL_INL double sqrt_rn(double a) { return sqrt(a); }
 #endif
 
+// a / b with a shortcut for a == 0 (b finite, non-zero): the hardware-assisted double division falls
+// into a ~100-instruction slow path for zero / denormal numerators, which are very common here
+// (FD differences of residual rows far from a peak, inactive constraints in the linesearch model).
+// The result is bit-identical to IEEE a / b for b > 0; for b < 0 the sign of a zero result may differ.
+ENL_INL double div_z(double a, double b) { return (a == 0.0) ? a : div_rn(a, b); }
+
 // Deterministic exp: the synthetic families are DEFINED through this function (same operation
 // sequence as oracle/detmath.c, so CPU oracle and GPU engine see bit-identical residuals).
 ENL_INL double pow2i(int k) {

@@ -166,17 +166,17 @@ struct FamGaussPeaks {
             double base = r0[s];
             double rf;
             rf = sub_rn(y, add_rn(mul_rn(add_rn(x[0], dl[0]), e1), g2));
-            out[s * N + 0] = ok ? div_rn(sub_rn(rf, base), dl[0]) : 0.0;
+            out[s * N + 0] = ok ? div_z(sub_rn(rf, base), dl[0]) : 0.0;
             rf = sub_rn(y, add_rn(mul_rn(x[0], peak(add_rn(x[1], dl[1]), x[2], t)), g2));
-            out[s * N + 1] = ok ? div_rn(sub_rn(rf, base), dl[1]) : 0.0;
+            out[s * N + 1] = ok ? div_z(sub_rn(rf, base), dl[1]) : 0.0;
             rf = sub_rn(y, add_rn(mul_rn(x[0], peak(x[1], add_rn(x[2], dl[2]), t)), g2));
-            out[s * N + 2] = ok ? div_rn(sub_rn(rf, base), dl[2]) : 0.0;
+            out[s * N + 2] = ok ? div_z(sub_rn(rf, base), dl[2]) : 0.0;
             rf = sub_rn(y, add_rn(g1, mul_rn(add_rn(x[3], dl[3]), e2)));
-            out[s * N + 3] = ok ? div_rn(sub_rn(rf, base), dl[3]) : 0.0;
+            out[s * N + 3] = ok ? div_z(sub_rn(rf, base), dl[3]) : 0.0;
             rf = sub_rn(y, add_rn(g1, mul_rn(x[3], peak(add_rn(x[4], dl[4]), x[5], t))));
-            out[s * N + 4] = ok ? div_rn(sub_rn(rf, base), dl[4]) : 0.0;
+            out[s * N + 4] = ok ? div_z(sub_rn(rf, base), dl[4]) : 0.0;
             rf = sub_rn(y, add_rn(g1, mul_rn(x[3], peak(x[4], add_rn(x[5], dl[5]), t))));
-            out[s * N + 5] = ok ? div_rn(sub_rn(rf, base), dl[5]) : 0.0;
+            out[s * N + 5] = ok ? div_z(sub_rn(rf, base), dl[5]) : 0.0;
         }
     }
 };

@@ -224,7 +224,7 @@ struct Solver {
             xf[j] = add_rn(xv[j], dl[j]);
             F2::template residuals<Grp, MS>(fctx(), grp(), xf, rf);
 #pragma unroll
-            for (int sl = 0; sl < MS; ++sl) out[sl * N + j] = div_rn(sub_rn(rf[sl], r0[sl]), dl[j]);
+            for (int sl = 0; sl < MS; ++sl) out[sl * N + j] = div_z(sub_rn(rf[sl], r0[sl]), dl[j]);
         }
     }
 
@@ -246,7 +246,7 @@ struct Solver {
                     xf[j] = add_rn(xv[j], dj);
                     Fam::template constraints<MS>(fctx(), xf, cf);
 #pragma unroll 1
-                    for (int i = 0; i < NNL; ++i) An[i * N + j] = div_rn(sub_rn(cf[i], cx[i]), dj);
+                    for (int i = 0; i < NNL; ++i) An[i * N + j] = div_z(sub_rn(cf[i], cx[i]), dj);
                 }
             }
 #pragma unroll 1
@@ -1298,12 +1298,15 @@ struct Solver {
         for (int i = 0; i < t; ++i) s1[active[i] - 1] = 1.0;
 #pragma unroll 1
         for (int kk = 0; kk < l; ++kk) {
+            const bool act = s1[kk] != 0.0;
+            // inactive and satisfied at both points: v0 = v1 = v(alpha) = 0 exactly, the row adds nothing
+            if (!act && cx[kk] > 0 && cnew[kk] > 0) continue;
             double sw = sqrt(wnew[kk]);
             double v0, vb;
-            if (s1[kk] != 0.0) { v0 = sw * cx[kk]; vb = sw * cnew[kk]; }
+            if (act) { v0 = sw * cx[kk]; vb = sw * cnew[kk]; }
             else { v0 = (cx[kk] > 0) ? 0.0 : sw * cx[kk]; vb = (cnew[kk] > 0) ? 0.0 : sw * cnew[kk]; }
             double v1 = v1c[kk];
-            double v2 = ((vb - v0) / alpha_k - v1) / alpha_k;
+            double v2 = (div_z(vb - v0, alpha_k) - v1) / alpha_k;
             d00 += v0 * v0; d01 += v0 * v1; d02 += v0 * v2; d11 += v1 * v1; d12 += v1 * v2; d22 += v2 * v2;
         }
         Quartic s;
@@ -1345,8 +1348,8 @@ struct Solver {
         for (int i = 0; i < t; ++i) s1[active[i] - 1] = 1.0;
 #pragma unroll 1
         for (int kk = 0; kk < l; ++kk) {
-            double sw = sqrt(wnew[kk]);
-            v1c[kk] = (s1[kk] != 0.0) ? sw * Ap[kk] : ((cx[kk] > 0) ? 0.0 : sw * Ap[kk]);
+            if (s1[kk] == 0.0 && cx[kk] > 0) { v1c[kk] = 0.0; continue; }
+            v1c[kk] = sqrt(wnew[kk]) * Ap[kk];
         }
         double psi_k = psi(alpha_k, wnew, rn);
         double diff_psi = psi0 - psi_k;
@@ -1483,12 +1486,17 @@ struct Solver {
             jp_jp = grp().sum(bq);
         }
 #pragma unroll 1
-        for (int i = 0; i < l; ++i) {
+        for (int i = 0; i < NNL; ++i) {
             double acc = 0.0;
 #pragma unroll 1
             for (int c = 0; c < N; ++c) acc += A[i * N + c] * p[c];
             Ap[i] = acc;
         }
+        // rows of the bounds are +e_j / -e_j (cnls_model.jl:393-403): the dot product is +-p_j
+#pragma unroll 1
+        for (int j = 0; j < bnd.nlo; ++j) Ap[NNL + j] = p[bnd.lo_idx[j]];
+#pragma unroll 1
+        for (int j = 0; j < bnd.nup; ++j) Ap[NNL + bnd.nlo + j] = -p[bnd.up_idx[j]];
 #pragma unroll 1
         for (int i = 0; i < t; ++i) {
             double acc = 0.0;

@@ -57,13 +57,20 @@ __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_con
     constexpr int SOLVER_DOUBLES = (int)((sizeof(SolverT) + 7) / 8) | 1;   // odd stride: no bank conflicts for G == 1
     const int tid = threadIdx.x;
     const int pid = tid / G;
-    double* objs = enl_smem;
-    double* small = enl_smem + (size_t)SOLVER_DOUBLES * LY::PPC;
+    // CTA-shared copy of the options and bounds: reading kernel parameters through the generic pointers held
+    // by the solver object costs a long-scoreboard stall per access (ncu: eval_point 50 % long_sb)
+    constexpr int CFG_DOUBLES = (int)((sizeof(Options) + sizeof(Bounds) + 15) / 16) * 2;
+    Options* s_opt = reinterpret_cast<Options*>(enl_smem);
+    Bounds* s_bnd = reinterpret_cast<Bounds*>(reinterpret_cast<char*>(enl_smem) + sizeof(Options));
+    if (tid == 0) { *s_opt = a.opt; *s_bnd = a.bnd; }
+    __syncthreads();
+    double* objs = enl_smem + CFG_DOUBLES;
+    double* small = objs + (size_t)SOLVER_DOUBLES * LY::PPC;
     double* distb = small + (size_t)LY::nD * LY::PPC;
     int* ints = reinterpret_cast<int*>(distb + (size_t)LY::DCOLS * LY::MS * NT);
     DevGroup<G> g;
     // the per-problem solver object lives in shared memory; every lane of the group writes identical values
-    SolverT& S = *new (objs + (size_t)SOLVER_DOUBLES * pid) SolverT(small, ints, distb, pid, a.opt, a.bnd);
+    SolverT& S = *new (objs + (size_t)SOLVER_DOUBLES * pid) SolverT(small, ints, distb, pid, *s_opt, *s_bnd);
     g.sync();
     const int row_w = TRACE_HDR + Fam::N;
     bool have = false, exhausted = false;
@@ -142,7 +149,8 @@ template <class Fam, int G, int NT>
 size_t smem_total() {
     using LY = Layout<Fam, G, NT>;
     size_t sd = ((sizeof(Solver<Fam, DevGroup<G>, NT>) + 7) / 8) | 1;
-    return LY::smem_bytes() + sd * 8 * LY::PPC;
+    size_t cfg = ((sizeof(Options) + sizeof(Bounds) + 15) / 16) * 16;
+    return LY::smem_bytes() + sd * 8 * LY::PPC + cfg;
 }
 
 template <class Fam, int G, int NT>
