@@ -181,6 +181,7 @@ def main():
     from enlsip_jl_b200.model import last_kernel_ms
 
     rank, world, local = dist_env()
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the single JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
