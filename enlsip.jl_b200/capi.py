@@ -13,6 +13,9 @@ HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_linalg.h"
 
 FAMILY_HS65 = 0
 FAMILY_GAUSS_PEAKS = 1
+FAMILY_OSBORNE2 = 2
+FAMILY_CHAINED_ROSENBROCK10 = 3
+FAMILY_CHAINED_WOOD20 = 4
 JAC_ANALYTIC = 0
 JAC_FORWARD_DIFF = 1
 TRACE_HDR = 16

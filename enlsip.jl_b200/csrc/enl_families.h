@@ -25,7 +25,7 @@ struct FamilyData {
 // HS65 (test/problems/HS65.jl:7-17, README.md:89-116): n = 3, m = 3, one nonlinear inequality
 // ---------------------------------------------------------------------------------------------
 struct FamHS65 {
-    static constexpr int N = 3, M = 3, Q = 0, NI = 1;
+    static constexpr int N = 3, M = 3, Q = 0, NI = 1, MAXB = 2 * N;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = false;
     static constexpr int NDCOLS = 0;   // per-row data columns kept in distributed shared memory
@@ -77,7 +77,7 @@ struct FamHS65 {
 //   h   = a1*(1/sqrt(b1)) + a2*(1/sqrt(b2)) - S
 // ---------------------------------------------------------------------------------------------
 struct FamGaussPeaks {
-    static constexpr int N = 6, M = 128, Q = 1, NI = 0;
+    static constexpr int N = 6, M = 128, Q = 1, NI = 0, MAXB = 2 * N;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = true;
     static constexpr int NDCOLS = 2;   // y_i, t_i
@@ -177,6 +177,234 @@ struct FamGaussPeaks {
             out[s * N + 4] = ok ? div_z(sub_rn(rf, base), dl[4]) : 0.0;
             rf = sub_rn(y, add_rn(g1, mul_rn(x[3], peak(x[4], add_rn(x[5], dl[5]), t))));
             out[s * N + 5] = ok ? div_z(sub_rn(rf, base), dl[5]) : 0.0;
+        }
+    }
+};
+
+}  // namespace enl
+
+namespace enl {
+
+// ---------------------------------------------------------------------------------------------
+// The reference's own test problems (test/problems/*.jl) as device families, so that parity can be
+// checked on the suite the north star names.  Operation order follows oracle/problems.py.
+// ---------------------------------------------------------------------------------------------
+
+// Osborne 2 (test/problems/osborne2.jl:10-102): n = 11, m = 65, 22 bounds, no other constraints.
+// data slot 0 = t[65], slot 1 = y[65] (shared by every problem of the batch).
+struct FamOsborne2 {
+    static constexpr int N = 11, M = 65, Q = 0, NI = 0, MAXB = 2 * N;
+    static constexpr bool HAS_ANALYTIC = true;
+    static constexpr bool HAS_FAST_FD = false;
+    static constexpr int NDCOLS = 2, NSCAL = 0;
+    template <class DMt, class Vt>
+    struct Ctx {
+        DMt d;
+        Vt s;
+        ENL_INL double t(int sl) const { return d.at(sl, 0); }
+        ENL_INL double y(int sl) const { return d.at(sl, 1); }
+    };
+    template <class Grp, int MS, class C>
+    ENL_FN static void load(const C& c, const FamilyData& d, long long, const Grp& g) {
+#pragma unroll
+        for (int s = 0; s < MS; ++s) {
+            int row = s * Grp::G + g.lane;
+            c.d.at(s, 0) = (row < M) ? d.d0[row] : 0.0;
+            c.d.at(s, 1) = (row < M) ? d.d1[row] : 0.0;
+        }
+    }
+    template <class Grp, int MS, class C>
+    ENL_FN static void residuals(const C& c, const Grp& g, const double* x, double* out) {
+#pragma unroll 1
+        for (int s = 0; s < MS; ++s) {
+            int row = s * Grp::G + g.lane;
+            double t = c.t(s);
+            double d2 = sub_rn(t, x[8]), d3 = sub_rn(t, x[9]), d4 = sub_rn(t, x[10]);
+            double e1 = det_exp(mul_rn(-x[4], t));
+            double e2 = det_exp(mul_rn(-x[5], mul_rn(d2, d2)));
+            double e3 = det_exp(mul_rn(-x[6], mul_rn(d3, d3)));
+            double e4 = det_exp(mul_rn(-x[7], mul_rn(d4, d4)));
+            double mdl = add_rn(add_rn(add_rn(mul_rn(x[0], e1), mul_rn(x[1], e2)), mul_rn(x[2], e3)), mul_rn(x[3], e4));
+            out[s] = (row < M) ? sub_rn(c.y(s), mdl) : 0.0;
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void constraints(const C&, const double*, double*) {}
+    template <class Grp, int MS, class C>
+    ENL_FN static void jac_residuals(const C& c, const Grp& g, const double* x, double* out) {
+#pragma unroll 1
+        for (int s = 0; s < MS; ++s) {
+            int row = s * Grp::G + g.lane;
+            bool ok = row < M;
+            double t = c.t(s);
+            double d2 = sub_rn(t, x[8]), d3 = sub_rn(t, x[9]), d4 = sub_rn(t, x[10]);
+            double e1 = det_exp(mul_rn(-x[4], t));
+            double e2 = det_exp(mul_rn(-x[5], mul_rn(d2, d2)));
+            double e3 = det_exp(mul_rn(-x[6], mul_rn(d3, d3)));
+            double e4 = det_exp(mul_rn(-x[7], mul_rn(d4, d4)));
+            double* o = out + s * N;
+            o[0] = ok ? -e1 : 0.0; o[1] = ok ? -e2 : 0.0; o[2] = ok ? -e3 : 0.0; o[3] = ok ? -e4 : 0.0;
+            o[4] = ok ? mul_rn(mul_rn(x[0], t), e1) : 0.0;
+            o[5] = ok ? mul_rn(mul_rn(x[1], mul_rn(d2, d2)), e2) : 0.0;
+            o[6] = ok ? mul_rn(mul_rn(x[2], mul_rn(d3, d3)), e3) : 0.0;
+            o[7] = ok ? mul_rn(mul_rn(x[3], mul_rn(d4, d4)), e4) : 0.0;
+            o[8] = ok ? mul_rn(mul_rn(mul_rn(mul_rn(-x[1], e2), 2.0), x[5]), d2) : 0.0;
+            o[9] = ok ? mul_rn(mul_rn(mul_rn(mul_rn(-x[2], e3), 2.0), x[6]), d3) : 0.0;
+            o[10] = ok ? mul_rn(mul_rn(mul_rn(mul_rn(-x[3], e4), 2.0), x[7]), d4) : 0.0;
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void jac_constraints(const C&, const double*, double*) {}
+};
+
+// Chained Rosenbrock (test/problems/chained_rosenbrock.jl:8-53) with n = NN parameters:
+// m = 2(n-1) residuals, q = n-2 nonlinear equalities, no bounds.
+template <int NN>
+struct FamChainedRosenbrock {
+    static constexpr int N = NN, M = 2 * (NN - 1), Q = NN - 2, NI = 0, MAXB = 0;
+    static constexpr bool HAS_ANALYTIC = true;
+    static constexpr bool HAS_FAST_FD = false;
+    static constexpr int NDCOLS = 0, NSCAL = 0;
+    template <class DMt, class Vt>
+    struct Ctx { DMt d; Vt s; };
+    template <class Grp, int MS, class C>
+    ENL_FN static void load(const C&, const FamilyData&, long long, const Grp&) {}
+    template <class Grp, int MS, class C>
+    ENL_FN static void residuals(const C&, const Grp& g, const double* x, double* out) {
+#pragma unroll 1
+        for (int s = 0; s < MS; ++s) {
+            int row = s * Grp::G + g.lane;
+            double v = 0.0;
+            if (row < N - 1) v = mul_rn(10.0, sub_rn(mul_rn(x[row], x[row]), x[row + 1]));
+            else if (row < M) v = sub_rn(x[row - (N - 1)], 1.0);
+            out[s] = v;
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void constraints(const C&, const double* x, double* c) {
+#pragma unroll 1
+        for (int k = 0; k < Q; ++k) {
+            double a = x[k], b = x[k + 1], cc = x[k + 2];
+            double v = add_rn(mul_rn(3.0, mul_rn(mul_rn(b, b), b)), mul_rn(2.0, cc));
+            v = sub_rn(v, 5.0);
+            v = add_rn(v, mul_rn(sin(sub_rn(b, cc)), sin(add_rn(b, cc))));
+            v = add_rn(v, mul_rn(4.0, b));
+            v = sub_rn(v, mul_rn(a, exp(sub_rn(a, b))));
+            c[k] = sub_rn(v, 3.0);
+        }
+    }
+    template <class Grp, int MS, class C>
+    ENL_FN static void jac_residuals(const C&, const Grp& g, const double* x, double* out) {
+#pragma unroll 1
+        for (int s = 0; s < MS; ++s) {
+            int row = s * Grp::G + g.lane;
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+                double v = 0.0;
+                if (row < N - 1) { if (j == row) v = mul_rn(20.0, x[row]); else if (j == row + 1) v = -10.0; }
+                else if (row < M) { if (j == row - (N - 1)) v = 1.0; }
+                out[s * N + j] = v;
+            }
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void jac_constraints(const C&, const double* x, double* A) {
+#pragma unroll 1
+        for (int i = 0; i < Q * N; ++i) A[i] = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < Q; ++k) {
+            double a = x[k], b = x[k + 1], cc = x[k + 2];
+            double e = exp(sub_rn(a, b));
+            double sm = sin(sub_rn(b, cc)), cm = cos(sub_rn(b, cc)), sp = sin(add_rn(b, cc)), cp = cos(add_rn(b, cc));
+            A[k * N + k] = mul_rn(-add_rn(a, 1.0), e);
+            double v = add_rn(mul_rn(9.0, mul_rn(b, b)), mul_rn(cm, sp));
+            v = add_rn(v, mul_rn(sm, cp));
+            v = add_rn(v, 4.0);
+            A[k * N + k + 1] = add_rn(v, mul_rn(a, e));
+            A[k * N + k + 2] = add_rn(sub_rn(2.0, mul_rn(cm, sp)), mul_rn(sm, cp));
+        }
+    }
+};
+
+// Chained Wood (test/problems/chained_wood.jl:4-35), n = NN (even, >= 8): m = 6(n/2-1), q = n-7.
+// Polynomial only: residuals, constraints and Jacobians are bit-identical to the numpy oracle.
+template <int NN>
+struct FamChainedWood {
+    static constexpr int N = NN, NB = NN / 2 - 1, M = 6 * NB, Q = NN - 7, NI = 0, MAXB = 0;
+    static constexpr bool HAS_ANALYTIC = true;
+    static constexpr bool HAS_FAST_FD = false;
+    static constexpr int NDCOLS = 0, NSCAL = 0;
+    template <class DMt, class Vt>
+    struct Ctx { DMt d; Vt s; };
+    template <class Grp, int MS, class C>
+    ENL_FN static void load(const C&, const FamilyData&, long long, const Grp&) {}
+    // row -> (block, i) ; o = 2i, e = 2i+1, o2 = 2i+2, e2 = 2i+3 (0-based, i = 0..NB-1)
+    ENL_FN static double res_row(int row, const double* x) {
+        const double s = sqrt_rn(10.0);
+        int blk = row / NB, i = row % NB;
+        double xo = x[2 * i], xe = x[2 * i + 1], xo2 = x[2 * i + 2], xe2 = x[2 * i + 3];
+        switch (blk) {
+            case 0: return mul_rn(10.0, sub_rn(mul_rn(xo, xo), xe));
+            case 1: return sub_rn(xo, 1.0);
+            case 2: return mul_rn(mul_rn(3.0, s), sub_rn(mul_rn(xo2, xo2), xe2));
+            case 3: return sub_rn(xo2, 1.0);
+            case 4: return mul_rn(s, sub_rn(add_rn(xe, xe2), 2.0));
+            default: return mul_rn(sub_rn(xe, xe2), div_rn(1.0, s));
+        }
+    }
+    template <class Grp, int MS, class C>
+    ENL_FN static void residuals(const C&, const Grp& g, const double* x, double* out) {
+#pragma unroll 1
+        for (int sl = 0; sl < MS; ++sl) {
+            int row = sl * Grp::G + g.lane;
+            out[sl] = (row < M) ? res_row(row, x) : 0.0;
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void constraints(const C&, const double* x, double* c) {
+#pragma unroll 1
+        for (int k = 1; k <= Q; ++k) {
+            double xk5 = x[k + 4];
+            double acc = 0.0;
+            int lo = (k - 5 > 1) ? k - 5 : 1;
+#pragma unroll 1
+            for (int ii = lo; ii <= k + 1; ++ii) acc = add_rn(acc, mul_rn(x[ii - 1], add_rn(1.0, x[ii - 1])));
+            double v = mul_rn(add_rn(2.0, mul_rn(5.0, mul_rn(xk5, xk5))), xk5);
+            c[k - 1] = add_rn(add_rn(v, 1.0), acc);
+        }
+    }
+    template <class Grp, int MS, class C>
+    ENL_FN static void jac_residuals(const C&, const Grp& g, const double* x, double* out) {
+        const double s = sqrt_rn(10.0);
+#pragma unroll 1
+        for (int sl = 0; sl < MS; ++sl) {
+            int row = sl * Grp::G + g.lane;
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) out[sl * N + j] = 0.0;
+            if (row >= M) continue;
+            int blk = row / NB, i = row % NB;
+            double* o = out + sl * N;
+            switch (blk) {
+                case 0: o[2 * i] = mul_rn(20.0, x[2 * i]); o[2 * i + 1] = -10.0; break;
+                case 1: o[2 * i] = 1.0; break;
+                case 2: o[2 * i + 2] = mul_rn(mul_rn(6.0, s), x[2 * i + 2]); o[2 * i + 3] = mul_rn(-3.0, s); break;
+                case 3: o[2 * i + 2] = 1.0; break;
+                case 4: o[2 * i + 1] = s; o[2 * i + 3] = s; break;
+                default: o[2 * i + 1] = div_rn(1.0, s); o[2 * i + 3] = div_rn(-1.0, s); break;
+            }
+        }
+    }
+    template <int MS, class C>
+    ENL_FN static void jac_constraints(const C&, const double* x, double* A) {
+#pragma unroll 1
+        for (int i = 0; i < Q * N; ++i) A[i] = 0.0;
+#pragma unroll 1
+        for (int k = 1; k <= Q; ++k) {
+            A[(k - 1) * N + k + 4] = add_rn(A[(k - 1) * N + k + 4], add_rn(2.0, mul_rn(15.0, mul_rn(x[k + 4], x[k + 4]))));
+            int lo = (k - 5 > 1) ? k - 5 : 1;
+#pragma unroll 1
+            for (int ii = lo; ii <= k + 1; ++ii)
+                A[(k - 1) * N + ii - 1] = add_rn(A[(k - 1) * N + ii - 1], add_rn(1.0, mul_rn(2.0, x[ii - 1])));
         }
     }
 };

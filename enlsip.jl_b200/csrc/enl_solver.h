@@ -47,7 +47,7 @@ constexpr int TRACE_HDR = 16;
 template <class Fam, int G, int NT>
 struct Layout {
     static constexpr int N = Fam::N, M = Fam::M, Q = Fam::Q, NNL = Fam::Q + Fam::NI;
-    static constexpr int LMAX = NNL + 2 * N;
+    static constexpr int LMAX = NNL + Fam::MAXB;   // MAXB: bound rows the family may carry (0 or 2n)
     static constexpr int T = (LMAX < N) ? LMAX : N;
     static constexpr int PPC = NT / G;
     static constexpr int MS = (M + G - 1) / G;

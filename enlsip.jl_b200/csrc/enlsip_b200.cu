@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <math.h>
 #include <new>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -118,7 +119,7 @@ __global__ void det_exp_kernel(const double* x, double* y, long long n) {
     if (i < n) y[i] = det_exp(x[i]);
 }
 
-struct FamilyInfo { int n, m, q, ni; };
+struct FamilyInfo { int n, m, q, ni, maxb; };
 
 }  // namespace
 
@@ -190,6 +191,28 @@ int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st) {
     return 0;
 }
 
+template <int V>
+using ic = std::integral_constant<int, V>;
+
+// family id (+ CTA size for the tuned family) -> template instantiation
+template <class F>
+int with_family(int family, int nt, F&& f) {
+    switch (family) {
+        case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<64>{});
+        case ENLSIPB200_FAMILY_GAUSS_PEAKS:
+            switch (nt) {
+                case 64: return f(FamGaussPeaks{}, ic<32>{}, ic<64>{});
+                case 128: return f(FamGaussPeaks{}, ic<32>{}, ic<128>{});
+                case 224: return f(FamGaussPeaks{}, ic<32>{}, ic<224>{});
+                default: return f(FamGaussPeaks{}, ic<32>{}, ic<448>{});
+            }
+        case ENLSIPB200_FAMILY_OSBORNE2: return f(FamOsborne2{}, ic<32>{}, ic<32>{});
+        case ENLSIPB200_FAMILY_CHAINED_ROSENBROCK10: return f(FamChainedRosenbrock<10>{}, ic<32>{}, ic<32>{});
+        case ENLSIPB200_FAMILY_CHAINED_WOOD20: return f(FamChainedWood<20>{}, ic<32>{}, ic<32>{});
+    }
+    return fail(ENLSIPB200_EINVAL, "unknown family id");
+}
+
 // lanes per problem / threads per CTA of each family
 constexpr int HS_G = 1, HS_NT = 64;
 constexpr int GP_G = 32;
@@ -241,10 +264,16 @@ void enlsipb200_default_options(enlsipb200_options* o) {
 int enlsipb200_create(int family, const double* x_low, const double* x_upp, int device, enlsipb200_handle* out) {
     if (!out) return fail(ENLSIPB200_EINVAL, "out is NULL");
     *out = nullptr;
-    FamilyInfo fi;
-    if (family == ENLSIPB200_FAMILY_HS65) fi = {FamHS65::N, FamHS65::M, FamHS65::Q, FamHS65::NI};
-    else if (family == ENLSIPB200_FAMILY_GAUSS_PEAKS) fi = {FamGaussPeaks::N, FamGaussPeaks::M, FamGaussPeaks::Q, FamGaussPeaks::NI};
-    else return fail(ENLSIPB200_EINVAL, "unknown family id");
+    FamilyInfo fi{0, 0, 0, 0, 0};
+    int known = with_family(family, 0, [&](auto fam, auto, auto) {
+        using Fm = decltype(fam);
+        fi = {Fm::N, Fm::M, Fm::Q, Fm::NI, Fm::MAXB};
+        return 0;
+    });
+    if (known != 0) return known;
+    if (fi.maxb == 0 && ((x_low && [&] { for (int j = 0; j < fi.n; ++j) if (isfinite(x_low[j])) return true; return false; }()) ||
+                         (x_upp && [&] { for (int j = 0; j < fi.n; ++j) if (isfinite(x_upp[j])) return true; return false; }())))
+        return fail(ENLSIPB200_EINVAL, "this family is compiled without bound rows");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -270,16 +299,9 @@ int enlsipb200_create(int family, const double* x_low, const double* x_upp, int 
     int rc = 0;
     if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) { delete h; return fail(ENLSIPB200_ENOMEM, "cudaMalloc"); }
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { delete h; return fail(ENLSIPB200_ECUDA, "cudaEventCreate"); }
-    if (family == ENLSIPB200_FAMILY_HS65) rc = configure<FamHS65, HS_G, HS_NT>(h);
-    else {
-        switch (gp_nt()) {
-            case 64: rc = configure<FamGaussPeaks, GP_G, 64>(h); break;
-            case 224: rc = configure<FamGaussPeaks, GP_G, 224>(h); break;
-
-            case 128: rc = configure<FamGaussPeaks, GP_G, 128>(h); break;
-            default: rc = configure<FamGaussPeaks, GP_G, 448>(h);
-        }
-    }
+    rc = with_family(family, gp_nt(), [&](auto fam, auto g_, auto nt_) {
+        return configure<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h);
+    });
     if (rc != 0) { enlsipb200_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -304,7 +326,7 @@ int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_con
     if (m) *m = h->fi.m;
     if (nb_eq) *nb_eq = h->fi.q;
     if (nb_constraints) *nb_constraints = h->l;
-    if (lmax) *lmax = h->fi.q + h->fi.ni + 2 * h->fi.n;
+    if (lmax) *lmax = h->fi.q + h->fi.ni + h->fi.maxb;
     return 0;
 }
 
@@ -329,12 +351,12 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     if (!h) return fail(ENLSIPB200_EINVAL, "null handle");
     if (B < 0 || !x0 || !x || !f || !exit_code || !status || !iters || !nact)
         return fail(ENLSIPB200_EINVAL, "x0, x, f, exit_code, status, iters, nact are required");
-    if (h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS && (!h->data[0] || !h->data[1]))
-        return fail(ENLSIPB200_EINVAL, "GAUSS_PEAKS needs data slots 0 (y) and 1 (S)");
+    if ((h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS || h->family == ENLSIPB200_FAMILY_OSBORNE2) && (!h->data[0] || !h->data[1]))
+        return fail(ENLSIPB200_EINVAL, "this family needs data slots 0 and 1 (GAUSS_PEAKS: y, S; OSBORNE2: t, y)");
     if (B == 0) return 0;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int n = h->fi.n, lmax = h->fi.q + h->fi.ni + 2 * n;
+    const int n = h->fi.n, lmax = h->fi.q + h->fi.ni + h->fi.maxb;
     const int row_w = TRACE_HDR + n;
     KernelArgs a;
     memset(&a, 0, sizeof(a));
@@ -376,17 +398,9 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
         if (trace) CU(cudaMemsetAsync(a.out.trace, 0, (size_t)B * trace_cap * row_w * 8, st));
         a.x0 = d_x0;
     }
-    int rc;
-    if (h->family == ENLSIPB200_FAMILY_HS65) rc = launch<FamHS65, HS_G, HS_NT>(h, a, st);
-    else {
-        switch (h->nt) {
-            case 64: rc = launch<FamGaussPeaks, GP_G, 64>(h, a, st); break;
-            case 224: rc = launch<FamGaussPeaks, GP_G, 224>(h, a, st); break;
-
-            case 128: rc = launch<FamGaussPeaks, GP_G, 128>(h, a, st); break;
-            default: rc = launch<FamGaussPeaks, GP_G, 448>(h, a, st);
-        }
-    }
+    int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
+        return launch<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h, a, st);
+    });
     if (rc != 0) return rc;
     if (!on_device) {
         CU(cudaMemcpyAsync(x, a.out.x, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));

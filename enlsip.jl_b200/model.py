@@ -30,8 +30,10 @@ from . import capi
 dict_status_codes = {0: "unsolved", 1: "found_first_order_stationary_point", -1: "failed",
                      -2: "maximum_iterations_exceeded", -11: "time_limit_exceeded"}   # cnls_model.jl:180-186
 
-_FAMILIES = {"hs65": capi.FAMILY_HS65, "gauss_peaks": capi.FAMILY_GAUSS_PEAKS}
-_FAMILY_DATA = {"hs65": (), "gauss_peaks": ("y", "S")}
+_FAMILIES = {"hs65": capi.FAMILY_HS65, "gauss_peaks": capi.FAMILY_GAUSS_PEAKS, "osborne2": capi.FAMILY_OSBORNE2,
+             "chained_rosenbrock10": capi.FAMILY_CHAINED_ROSENBROCK10, "chained_wood20": capi.FAMILY_CHAINED_WOOD20}
+_FAMILY_DATA = {"hs65": (), "gauss_peaks": ("y", "S"), "osborne2": ("t", "y"), "chained_rosenbrock10": (),
+                "chained_wood20": ()}
 _JAC = {"analytic": capi.JAC_ANALYTIC, "forward_diff": capi.JAC_FORWARD_DIFF}
 
 

@@ -26,6 +26,9 @@ extern "C" {
 
 #define ENLSIPB200_FAMILY_HS65 0         /* test/problems/HS65.jl:7-17 ; n=3 m=3, 1 inequality       */
 #define ENLSIPB200_FAMILY_GAUSS_PEAKS 1  /* BASELINE.json config 3 ; n=6 m=128, 1 equality            */
+#define ENLSIPB200_FAMILY_OSBORNE2 2     /* test/problems/osborne2.jl ; n=11 m=65, bounds only          */
+#define ENLSIPB200_FAMILY_CHAINED_ROSENBROCK10 3 /* test/problems/chained_rosenbrock.jl with n=10 (m=18, q=8) */
+#define ENLSIPB200_FAMILY_CHAINED_WOOD20 4       /* test/problems/chained_wood.jl, n=20 (m=54, q=13)          */
 
 #define ENLSIPB200_JAC_ANALYTIC 0
 #define ENLSIPB200_JAC_FORWARD_DIFF 1    /* src/cnls_model.jl:65-82                                    */
@@ -66,7 +69,8 @@ int enlsipb200_create(int family, const double* x_low, const double* x_upp, int 
 int enlsipb200_destroy(enlsipb200_handle h);
 int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_constraints, int* lmax);
 
-/* family data arrays (GAUSS_PEAKS: slot 0 = y [B,128], slot 1 = S [B]).  `on_device` != 0: ptr is a
+/* family data arrays (GAUSS_PEAKS: slot 0 = y [B,128], slot 1 = S [B]; OSBORNE2: slot 0 = t [65], slot 1 = y [65],
+ * shared by the whole batch).  `on_device` != 0: ptr is a
  * device pointer that must stay valid for the solve; otherwise the library copies host->device
  * (asynchronously on `stream` when the host memory is pinned). */
 int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream);

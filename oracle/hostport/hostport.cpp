@@ -48,7 +48,7 @@ extern "C" int hostport_solve(int family, long long B, const double* x0, const d
                               const double* x_low, const double* x_upp, const Options* opt, double* x, double* f,
                               int* exit_code, int* status, int* iters, int* nact, int* active, int* counters,
                               double* trace, int trace_cap, int nthreads) {
-    int n = (family == 0) ? FamHS65::N : FamGaussPeaks::N;
+    int n = family == 0 ? FamHS65::N : family == 1 ? FamGaussPeaks::N : family == 2 ? FamOsborne2::N : family == 3 ? 10 : 20;
     Bounds bnd{};
     for (int j = 0; j < n; ++j)
         if (std::isfinite(x_low[j])) { bnd.lo_idx[bnd.nlo] = j; bnd.lo_val[bnd.nlo] = x_low[j]; bnd.nlo++; }
@@ -60,8 +60,13 @@ extern "C" int hostport_solve(int family, long long B, const double* x0, const d
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
     for (int c = 0; c < nthreads * 8; ++c) {
         long long b0 = B * c / (nthreads * 8), b1 = B * (c + 1) / (nthreads * 8);
-        if (family == 0) solve_range<FamHS65>(b0, b1, x0, fd, *opt, bnd, out);
-        else solve_range<FamGaussPeaks>(b0, b1, x0, fd, *opt, bnd, out);
+        switch (family) {
+            case 0: solve_range<FamHS65>(b0, b1, x0, fd, *opt, bnd, out); break;
+            case 1: solve_range<FamGaussPeaks>(b0, b1, x0, fd, *opt, bnd, out); break;
+            case 2: solve_range<FamOsborne2>(b0, b1, x0, fd, *opt, bnd, out); break;
+            case 3: solve_range<FamChainedRosenbrock<10>>(b0, b1, x0, fd, *opt, bnd, out); break;
+            default: solve_range<FamChainedWood<20>>(b0, b1, x0, fd, *opt, bnd, out); break;
+        }
     }
     return 0;
 }

@@ -89,10 +89,11 @@ def osborne2(golden_dir=None) -> Problem:
     y = np.array(d["y"])
 
     def model_terms(x):
-        e1 = np.exp(-x[4] * t)
-        e2 = np.exp(-x[5] * (t - x[8]) ** 2)
-        e3 = np.exp(-x[6] * (t - x[9]) ** 2)
-        e4 = np.exp(-x[7] * (t - x[10]) ** 2)
+        # det_exp (oracle/detmath.c) instead of libm so that the CUDA family reproduces the bits
+        e1 = det_exp(-x[4] * t)
+        e2 = det_exp(-x[5] * (t - x[8]) ** 2)
+        e3 = det_exp(-x[6] * (t - x[9]) ** 2)
+        e4 = det_exp(-x[7] * (t - x[10]) ** 2)
         return e1, e2, e3, e4
 
     def r(x):
@@ -138,7 +139,7 @@ def chained_rosenbrock(n=1000) -> Problem:
 
     def c(x):
         a, b, cc = x[: n - 2], x[1: n - 1], x[2:n]
-        return 3 * b ** 3 + 2 * cc - 5 + np.sin(b - cc) * np.sin(b + cc) + 4 * b - a * np.exp(a - b) - 3
+        return 3 * (b * b * b) + 2 * cc - 5 + np.sin(b - cc) * np.sin(b + cc) + 4 * b - a * np.exp(a - b) - 3
 
     def jac_c(x):
         A = np.zeros((n - 2, n))

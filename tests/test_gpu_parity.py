@@ -161,3 +161,21 @@ def test_full_size_properties(E):
     assert np.max(np.abs(h)) < 1e-6                  # the equality constraint holds at the solutions
     f = np.asarray(g.obj_value)[stg == 1]
     assert np.median(f) < 128 * 0.01 ** 2 * 3        # residual level of the 0.01-sigma noise
+
+
+def test_reference_suite_on_gpu(E):
+    """test/problems/{osborne2, chained_rosenbrock (n=10), chained_wood (n=20)} + perturbed starts: identical
+    termination, iteration counts, working sets and per-iteration method/rank/dimension trace; 1e-10 iterates."""
+    from oracle import enlsip_oracle as O
+    from tests.test_hostport import reference_suite_cases, check_against_oracle
+    for fam, name, mk, xs, data, (lo, up), kw in reference_suite_cases():
+        m = E.CnlsModel(name, np.ascontiguousarray(xs), data=data, x_low=lo, x_upp=up)
+        E.solve(m, trace_cap=60, **kw)
+        out = _outputs(m)
+        for b in range(xs.shape[0]):
+            o = O.solve(mk(xs[b]), wallclock=False, **kw)
+            check_against_oracle(out, b, o, xs.shape[1], name)
+        if name == "chained_wood20":
+            assert np.any(out["trace"][:, :, 6] == 2)          # Newton steps taken
+        assert set(E.status(m)) <= {"found_first_order_stationary_point", "failed", "maximum_iterations_exceeded"}
+        print(name, "statuses", sorted(set(E.status(m))), "iters", list(np.asarray(m.iterations)), m.kernel_info())
