@@ -58,3 +58,38 @@ def gen_gauss_peaks_batch(B, seed=128, start=0, chunk=1 << 18):
         x0[out] = np.clip(xs * (1.0 + 0.1 * u2[sl]), GP_LOW + 1e-3 * span, GP_UPP - 1e-3 * span)
         truth[out] = xs
     return y, S, x0, truth
+
+
+def gen_single_index(m, n, nb, seed=4, start=0, rows=None, ineq=False, chunk=1 << 16):
+    """C4 / C5: W_ij ~ N(0,1)/sqrt(n), y = tanh(W x*) + 0.01 eps, x* ~ U(-1,1)^n,
+    block constraints on groups of 4 parameters (rho from x*), x0 = x* (1 + 0.05 u).
+
+    Returns dict(W [rows,n], y [rows], rho [nb], x0 [n], truth [n]).  ``start``/``rows`` select the
+    row shard [start, start+rows) of the global m-row problem (row chunks have their own child
+    generators, so a shard is reproducible without generating its predecessors); x*, x0, rho are
+    global and identical on every shard.
+    """
+    rows = m - start if rows is None else rows
+    root = np.random.SeedSequence(seed)
+    g = np.random.default_rng(root.spawn(1)[0])
+    truth = g.uniform(-1.0, 1.0, size=n)
+    x0 = truth * (1.0 + 0.05 * g.uniform(-1.0, 1.0, size=n))
+    blocks = (truth[: 4 * nb] ** 2).reshape(nb, 4).sum(axis=1)
+    if ineq:   # half the blocks active at the solution (0.9), the rest slack (1.5)
+        rho = np.where(np.arange(nb) % 2 == 0, 0.9, 1.5) * blocks
+    else:
+        rho = blocks.copy()
+    W = np.empty((rows, n))
+    y = np.empty(rows)
+    first, last = start // chunk, (start + rows - 1) // chunk
+    children = np.random.SeedSequence([seed, 1]).spawn(last + 1)
+    for c in range(first, last + 1):
+        rng = np.random.default_rng(children[c])
+        lo, hi = max(start, c * chunk), min(start + rows, (c + 1) * chunk)
+        Wc = rng.standard_normal(size=(chunk, n)) / np.sqrt(n)
+        ec = rng.standard_normal(size=chunk)
+        sl = slice(lo - c * chunk, hi - c * chunk)
+        out = slice(lo - start, hi - start)
+        W[out] = Wc[sl]
+        y[out] = np.tanh(Wc[sl] @ truth) + 0.01 * ec[sl]
+    return dict(W=W, y=y, rho=rho, x0=x0, truth=truth)

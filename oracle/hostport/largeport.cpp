@@ -1,0 +1,163 @@
+// largeport.cpp -- CPU backend of enl_large::LargeOps for the single-index family.
+//
+// TEST INFRASTRUCTURE / CPU BASELINE ONLY (same role as hostport.cpp for the batched core):
+//   (1) checks the large-regime ENLSIP driver (enlsip.jl_b200/csrc/enl_large_host.h) against the
+//       Python oracle in the build container, which has no GPU;
+//   (2) gives bench.py a compiled CPU implementation of one Gauss-Newton iteration of config 4
+//       (OpenMP Householder QR of [J r]) to time as the `cpu_baseline` of the large regime.
+// Never linked into libenlsip_b200.so; the product has no CPU fallback.
+//
+// Build: g++ -O2 -ffp-contract=off -mfma -std=c++17 -shared -fPIC -fopenmp largeport.cpp -o ../_build/liblargeport.so
+#include <cstring>
+#include <vector>
+#define ENL_HOST_BUILD 1
+#include "../../enlsip.jl_b200/csrc/enl_base.h"
+#include "../../enlsip.jl_b200/csrc/enl_large_family.h"
+#include "../../enlsip.jl_b200/csrc/enl_large_host.h"
+
+using namespace enl_large;
+
+namespace {
+
+struct CpuOps : LargeOps {
+    const double* W;    // m x n row major
+    const double* y;
+    SingleIndexConstraints sc;
+    int nthreads = 1;
+    std::vector<double> u, r, s, v, Jp;
+
+    void eval_u(const double* x, std::vector<double>& out) const {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (long long i = 0; i < m; ++i) out[i] = dot_n(W + (size_t)i * n, x, n);
+    }
+    int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
+        const int nc = n + 1;
+        u.resize(m); r.resize(m); s.resize(m);
+        eval_u(x, u);
+        // augmented matrix [diag(s) W | r], column major for the Householder sweep
+        std::vector<double> M((size_t)m * nc);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (long long i = 0; i < m; ++i) {
+            double th = enl::det_tanh(u[i]);
+            r[i] = th - y[i];
+            s[i] = 1.0 - th * th;
+            for (int j = 0; j < n; ++j) M[(size_t)j * m + i] = s[i] * W[(size_t)i * n + j];
+            M[(size_t)n * m + i] = r[i];
+        }
+        // unpivoted Householder QR (dgeqr2 order), R only
+        for (int i = 0; i < nc && i < m; ++i) {
+            double* ci = M.data() + (size_t)i * m;
+            double alpha = ci[i];
+            double xn = norm_n(ci + i + 1, (int)(m - i - 1));
+            double tau = 0.0;
+            if (xn != 0.0) {
+                double beta = -copysign(lapy2(alpha, xn), alpha);
+                tau = (beta - alpha) / beta;
+                double sc_ = 1.0 / (alpha - beta);
+                for (long long rr = i + 1; rr < m; ++rr) ci[rr] *= sc_;
+                ci[i] = beta;
+            }
+            if (tau != 0.0) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+                for (int c = i + 1; c < nc; ++c) {
+                    double* cc = M.data() + (size_t)c * m;
+                    double w = (cc[i] + dot_n(ci + i + 1, cc + i + 1, (int)(m - i - 1))) * tau;
+                    cc[i] -= w;
+                    for (long long rr = i + 1; rr < m; ++rr) cc[rr] -= w * ci[rr];
+                }
+            }
+        }
+        const int mt = n + 1;
+        for (int c = 0; c < n; ++c)
+            for (int rr = 0; rr < mt; ++rr) Jt[(size_t)c * mt + rr] = (rr <= c && rr < m) ? M[(size_t)c * m + rr] : 0.0;
+        for (int rr = 0; rr < mt; ++rr) rt[rr] = (rr < m) ? M[(size_t)n * m + rr] : 0.0;
+        sc.cons(x, cx);
+        sc.jac(x, A);
+        return 0;
+    }
+    int set_direction(const double*, const double* p, double sums[3]) override {
+        v.resize(m); Jp.resize(m);
+        eval_u(p, v);
+        double a = 0, b = 0, c = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a, b, c)
+        for (long long i = 0; i < m; ++i) {
+            Jp[i] = s[i] * v[i];
+            a += r[i] * r[i]; b += r[i] * Jp[i]; c += Jp[i] * Jp[i];
+        }
+        sums[0] = a; sums[1] = b; sums[2] = c;
+        return 0;
+    }
+    int res_sq(double alpha, double* out) override {
+        double a = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a)
+        for (long long i = 0; i < m; ++i) {
+            double ra = enl::det_tanh(__builtin_fma(alpha, v[i], u[i])) - y[i];
+            a += ra * ra;
+        }
+        *out = a;
+        return 0;
+    }
+    int ls_coeffs(double alpha, double out[4]) override {
+        double a = 0, b = 0, c = 0, d = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a, b, c, d)
+        for (long long i = 0; i < m; ++i) {
+            double ra = enl::det_tanh(__builtin_fma(alpha, v[i], u[i])) - y[i];
+            double v2 = ((ra - r[i]) / alpha - Jp[i]) / alpha;
+            a += ra * ra; b += r[i] * v2; c += Jp[i] * v2; d += v2 * v2;
+        }
+        out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+        return 0;
+    }
+    int cons(const double* x, double* cx) override { sc.cons(x, cx); return 0; }
+};
+
+}  // namespace
+
+// Solve one single-index problem on the CPU.  trace: [trace_cap][16 + n] rows, layout of enlsip_b200.h.
+extern "C" int largeport_solve(int n, long long m, int nb, int ineq, const double* W, const double* y,
+                               const double* rho, const double* x_low, const double* x_upp, const double* x0,
+                               int max_iter, int scaling, double rel_tol, double x_tol, double c_tol, double* x,
+                               double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
+                               double* trace, int trace_cap, int nthreads) {
+    CpuOps ops;
+    ops.n = n; ops.m = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
+    ops.sc.n = n; ops.sc.nb = nb; ops.sc.ineq = ineq != 0;
+    ops.sc.rho.assign(rho, rho + nb);
+    ops.sc.set_bounds(x_low, x_upp);
+    ops.l = ops.sc.l(); ops.q = ops.sc.q();
+    LargeOptions opt;
+    opt.max_iter = max_iter; opt.scaling = scaling;
+    opt.eps_rel = rel_tol; opt.eps_x = x_tol; opt.eps_c = c_tol;
+    LargeSolver S(ops, opt);
+    LargeResult R = S.solve(x0, trace != nullptr);
+    std::memcpy(x, R.x.data(), sizeof(double) * n);
+    *f = R.f; *exit_code = R.exit_code; *status = R.status; *iters = R.iterations; *nact = R.nact;
+    for (int i = 0; i < ops.l; ++i) active[i] = i < R.nact ? R.active[i] : 0;
+    if (trace) {
+        int rows = (int)R.trace.size();
+        for (int k = 0; k < rows && k < trace_cap; ++k) {
+            double* tr = trace + (size_t)k * (16 + n);
+            const IterTraceL& t = R.trace[k];
+            // same row layout as the batched engine (enl_solver.h Solver::step)
+            tr[0] = t.f_new; tr[1] = t.t; tr[2] = t.rankA; tr[3] = t.rankJ2; tr[4] = t.dimA; tr[5] = t.dimJ2;
+            tr[6] = t.code; tr[7] = t.alpha; tr[8] = t.p_norm; tr[9] = t.index_del; tr[10] = t.exit_code;
+            tr[11] = t.active_cx_sum; tr[12] = t.progress; tr[13] = t.k; tr[14] = 0; tr[15] = 0;
+            std::memcpy(tr + 16, R.trace_x.data() + (size_t)k * n, sizeof(double) * n);
+        }
+    }
+    return 0;
+}
+
+// One Gauss-Newton iteration's dominant work on the CPU (the reference's `new_point!` + QR of J): used by
+// bench.py as the large-regime cpu_baseline.  Returns seconds through *secs.
+extern "C" int largeport_new_point(int n, long long m, const double* W, const double* y, const double* x, int nthreads,
+                                   double* rho_out) {
+    CpuOps ops;
+    ops.n = n; ops.m = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
+    ops.sc.n = n; ops.sc.nb = 0;
+    std::vector<double> Jt((size_t)(n + 1) * n), rt(n + 1), cx(1), A(1);
+    ops.l = 0; ops.q = 0;
+    ops.new_point(x, Jt.data(), rt.data(), cx.data(), A.data());
+    *rho_out = rt[n];
+    return 0;
+}
