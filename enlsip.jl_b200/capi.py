@@ -10,6 +10,13 @@ LIB_PATH = os.path.join(_HERE, "lib", "libenlsip_b200.so")
 SRC = os.path.join(_HERE, "csrc", "enlsip_b200.cu")
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_linalg.h", "enl_families.h", "enl_solver.h")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "enlsip_b200.h")]
+# second translation unit: the large-Jacobian regime (TSQR + host-driven iteration)
+SRC_LARGE = os.path.join(_HERE, "csrc", "enl_large.cu")
+HEADERS_LARGE = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_tsqr.cuh", "enl_large_host.h",
+                                                          "enl_large_family.h")] + \
+                [os.path.join(os.path.dirname(_HERE), "include", "enlsip_b200.h")]
+OBJ_DIR = os.path.join(_HERE, "lib", "obj")
+FAMILY_SINGLE_INDEX = 16
 
 FAMILY_HS65 = 0
 FAMILY_GAUSS_PEAKS = 1
@@ -23,7 +30,10 @@ EXIT_WOULD_THROW, EXIT_WOULD_HANG, EXIT_CAPACITY = -99, -98, -97
 
 EXPORTS = ["enlsipb200_version", "enlsipb200_last_error", "enlsipb200_default_options", "enlsipb200_create",
            "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data", "enlsipb200_solve_batch",
-           "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count", "enlsipb200_det_exp"]
+           "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count", "enlsipb200_det_exp",
+           "enlsipb200_large_last_error", "enlsipb200_large_create", "enlsipb200_large_destroy",
+           "enlsipb200_large_set_data", "enlsipb200_large_comm_id", "enlsipb200_large_comm_init",
+           "enlsipb200_large_solve", "enlsipb200_large_factor", "enlsipb200_large_stats"]
 
 
 class Options(ctypes.Structure):
@@ -33,17 +43,26 @@ class Options(ctypes.Structure):
 
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp"]
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/enlsip_b200.cu for sm_100a into lib/libenlsip_b200.so (in-tree)."""
-    newest = max(os.path.getmtime(p) for p in [SRC] + HEADERS)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", LIB_PATH]
-    subprocess.check_call(cmd)
+    """Compile csrc/enlsip_b200.cu and csrc/enl_large.cu for sm_100a into lib/libenlsip_b200.so (in-tree).
+
+    Each translation unit is compiled to lib/obj/*.o only when one of its sources is newer, then linked."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs, relink = [], force or not os.path.exists(LIB_PATH)
+    for src, hdrs in ((SRC, HEADERS), (SRC_LARGE, HEADERS_LARGE)):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        newest = max(os.path.getmtime(p) for p in [src] + hdrs)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            subprocess.check_call(cmd)
+            relink = True
+        objs.append(obj)
+    if relink or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs +
+                              ["-o", LIB_PATH, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl"])
     return LIB_PATH
 
 
@@ -74,6 +93,16 @@ def lib():
         L.enlsipb200_launch_count.argtypes = [vp]
         L.enlsipb200_launch_count.restype = ctypes.c_longlong
         L.enlsipb200_det_exp.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_int]
+        ll, ci = ctypes.c_longlong, ctypes.c_int
+        L.enlsipb200_large_last_error.restype = ctypes.c_char_p
+        L.enlsipb200_large_create.argtypes = [ci, ci, ll, ll, ci, ci, vp, vp, vp, ci, ctypes.POINTER(vp)]
+        L.enlsipb200_large_destroy.argtypes = [vp]
+        L.enlsipb200_large_set_data.argtypes = [vp, ci, vp, ll, ci]
+        L.enlsipb200_large_comm_id.argtypes = [vp]
+        L.enlsipb200_large_comm_init.argtypes = [vp, vp, ci, ci]
+        L.enlsipb200_large_solve.argtypes = [vp, vp, ctypes.POINTER(Options)] + [vp] * 8 + [ci]
+        L.enlsipb200_large_factor.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+        L.enlsipb200_large_stats.argtypes = [vp, vp, ci]
         _lib = L
     return _lib
 
@@ -85,6 +114,11 @@ class EngineError(RuntimeError):
 def check(rc):
     if rc != 0:
         raise EngineError("enlsip_b200 error %d: %s" % (rc, lib().enlsipb200_last_error().decode()))
+
+
+def check_large(rc):
+    if rc != 0:
+        raise EngineError("enlsip_b200 (large regime) error %d: %s" % (rc, lib().enlsipb200_large_last_error().decode()))
 
 
 def default_options() -> Options:

@@ -1,0 +1,344 @@
+// enl_tsqr.cuh -- tall-skinny Householder QR (R factor only) of a row-major FP64 matrix on sm_100a.
+//
+// Replaces, for the large-Jacobian regime, the reference's `qr(J2, ColumnNorm())` + `F.Q' * v` on the
+// m x n residual Jacobian (src/enlsip_functions.jl:219-223, 135-151): the engine reduces the augmented
+// matrix [J | r] (m x (n+1), m ~ 4e6) to its (n+1) x (n+1) triangular factor and runs the pivoted
+// small-matrix stage on that (pivot choices are invariant under the left orthogonal transform).
+//
+// Algorithm: communication-avoiding blocked Householder QR, panel width 32.
+//   for each 32-column panel j:
+//     level 0, 1, 2, ...: the rows are cut into blocks of 32; a "subtile" is 8 blocks (stride 8^level
+//       blocks apart, i.e. at level >= 1 the top blocks of the subtiles of the level below).
+//       tsqr_panel_kernel  : one CTA per subtile; Householder QR of its 256 x 32 panel held in
+//                            registers (lane = column, 8 warps x 32 rows), compact-WY T by
+//                            T = (striu(V'V) + diag(1/tau))^-1; V is stored in place, T in a side buffer
+//       tsqr_trail_kernel  : one CTA per (subtile, 32-column block of the trailing matrix):
+//                            B <- (I - V T' V')B with three FP64 tensor-core products
+//                            (mma.sync.m8n8k4.f64 = DMMA.8x8x4): G = V'B, W = -T'G, B += V W
+//     the top 32 rows of the last level are the finished rows 32j..32j+31 of R: copied out, then
+//     zeroed in place so later panels see them as empty rows.
+//   the final column (the residual column of [J | r]) needs only its norm.
+// Every subtile is independent inside a level, so each kernel is a plain grid over subtiles; the
+// price is 1/7 more flops than a flat tree (each level re-factors 1/8 of the rows).
+// Algorithmic flops: 2 m n^2 (n = number of columns).  See DESIGN.md for the roofline accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace enl_large {
+
+constexpr int TS_B = 32;     // block rows = panel width
+constexpr int TS_FAN = 8;    // blocks per subtile
+constexpr int TS_LDS = 36;   // shared-memory leading dimension (doubles): conflict-free m8n8k4 fragment loads
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel factorisation of one subtile
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int upper_only,
+                  double* __restrict__ Tbuf) {
+    __shared__ double red[TS_FAN];
+    __shared__ double s_alpha;
+    __shared__ double vbuf[TS_FAN][TS_B];
+    __shared__ double dots[TS_FAN][TS_B];
+    __shared__ double Gs[TS_B][TS_B + 1];   // Gs[c][i] = v_c . v_i, c < i
+    __shared__ double taus[TS_B];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long sub = blockIdx.x;
+    const long long blk = (sub * TS_FAN + w) * stride;
+    const bool valid = blk < nblk;
+    double* base = A + (blk * TS_B) * (long long)ld + col0 + lane;
+    double a[TS_B];
+#pragma unroll
+    for (int r = 0; r < TS_B; ++r) {
+        double v = valid ? base[(long long)r * ld] : 0.0;
+        if (upper_only && r > lane) v = 0.0;   // level >= 1: below the diagonal lie stale reflectors of the level below
+        a[r] = v;
+    }
+#pragma unroll 1
+    for (int i = 0; i < TS_B; ++i) {
+        // (1) squared norm of column i below the pivot (every lane does its own column; lane i's is used)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < TS_B; r += 4) {
+            double v0 = (w > 0 || r + 0 > i) ? a[r + 0] : 0.0;
+            double v1 = (w > 0 || r + 1 > i) ? a[r + 1] : 0.0;
+            double v2 = (w > 0 || r + 2 > i) ? a[r + 2] : 0.0;
+            double v3 = (w > 0 || r + 3 > i) ? a[r + 3] : 0.0;
+            s0 = fma(v0, v0, s0); s1 = fma(v1, v1, s1); s2 = fma(v2, v2, s2); s3 = fma(v3, v3, s3);
+        }
+        if (lane == i) {
+            red[w] = (s0 + s1) + (s2 + s3);
+            if (w == 0) {
+                double al = 0.0;
+#pragma unroll
+                for (int r = 0; r < TS_B; ++r) al = (r == i) ? a[r] : al;
+                s_alpha = al;
+            }
+        }
+        __syncthreads();
+        const double sigma = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+        const double alpha = s_alpha;
+        double tau = 0.0, scale = 0.0, beta = alpha;
+        if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||
+            beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        // (2) lane i turns its column into the reflector and publishes it to its warp
+        if (lane == i) {
+#pragma unroll
+            for (int r = 0; r < TS_B; ++r) {
+                double v;
+                if (w == 0 && r < i) v = 0.0;
+                else if (w == 0 && r == i) v = 1.0;
+                else { v = a[r] * scale; a[r] = v; }
+                vbuf[w][r] = v;
+            }
+            if (w == 0) {
+#pragma unroll
+                for (int r = 0; r < TS_B; ++r) a[r] = (r == i) ? beta : a[r];
+                taus[i] = tau;
+            }
+        }
+        __syncwarp();
+        // (3) v_i . (every column): columns > i get updated, columns < i feed the Gram matrix of V
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < TS_B; r += 4) {
+            d0 = fma(vbuf[w][r + 0], a[r + 0], d0); d1 = fma(vbuf[w][r + 1], a[r + 1], d1);
+            d2 = fma(vbuf[w][r + 2], a[r + 2], d2); d3 = fma(vbuf[w][r + 3], a[r + 3], d3);
+        }
+        dots[w][lane] = (d0 + d1) + (d2 + d3);
+        __syncthreads();
+        const double dsum = ((dots[0][lane] + dots[1][lane]) + (dots[2][lane] + dots[3][lane])) +
+                            ((dots[4][lane] + dots[5][lane]) + (dots[6][lane] + dots[7][lane]));
+        if (w == 0 && lane < i) Gs[lane][i] = dsum;
+        if (tau != 0.0 && lane > i) {
+            const double wc = tau * dsum;
+#pragma unroll
+            for (int r = 0; r < TS_B; ++r) a[r] = fma(-wc, vbuf[w][r], a[r]);
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int r = 0; r < TS_B; ++r) base[(long long)r * ld] = a[r];
+    }
+    __syncthreads();
+    // compact-WY factor: T = U^-1 with U = striu(V'V) + diag(1/tau); column `lane` by back substitution.
+    // tau_r = 0 (H_r = I) gives a zero row/column r, as in dlarft.
+    if (w == 0) {
+        double t[TS_B];
+#pragma unroll
+        for (int r = TS_B - 1; r >= 0; --r) {
+            double sa = (r == lane) ? 1.0 : 0.0, sb = 0.0;
+#pragma unroll
+            for (int k = r + 1; k < TS_B; k += 2) {
+                sa = fma(-Gs[r][k], t[k], sa);
+                if (k + 1 < TS_B) sb = fma(-Gs[r][k + 1], t[k + 1], sb);
+            }
+            t[r] = (r <= lane) ? (sa + sb) * taus[r] : 0.0;
+        }
+        double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+        for (int r = 0; r < TS_B; ++r) Tg[r * TS_B + lane] = t[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trailing update of one (subtile, column block)
+// ---------------------------------------------------------------------------------------------
+template <int CB>
+__device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, long long nblk, long long stride,
+                                                int col0, int ccol0, long long sub, const double* __restrict__ Tbuf,
+                                                double* smem) {
+    constexpr int NT = CB / 8;          // 8-column tiles per block row
+    constexpr int CBP = CB + 4;         // padded leading dimension of the CB-wide shared tiles
+    double (*Ts)[TS_LDS] = reinterpret_cast<double (*)[TS_LDS]>(smem);
+    double (*Gs)[CBP] = reinterpret_cast<double (*)[CBP]>(smem + TS_B * TS_LDS);
+    double (*Ws)[CBP] = reinterpret_cast<double (*)[CBP]>(smem + TS_B * TS_LDS + TS_B * CBP);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const long long blk = (sub * TS_FAN + w) * stride;
+    const bool valid = blk < nblk;
+    const double* Vb = A + (blk * TS_B) * (long long)ld + col0;
+    double* Bb = A + (blk * TS_B) * (long long)ld + ccol0;
+    const double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int idx = tid + 256 * q;
+        Ts[idx >> 5][idx & 31] = Tg[idx];
+    }
+    for (int idx = tid; idx < TS_B * CB; idx += 256) Gs[idx / CB][idx % CB] = 0.0;
+    // reflector block element (row, c) of this warp's block: unit lower trapezoid for the top block
+    auto vload = [&](int row, int c) -> double {
+        double v = Vb[(long long)row * ld + c];
+        if (w == 0) v = (row < c) ? 0.0 : ((row == c) ? 1.0 : v);
+        return v;
+    };
+    // pass 1: partial G = V_w' B_w over this warp's 32 rows
+    double acc[4][NT][2];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < NT; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+    if (valid) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int row = kk * 4 + t;
+            double av[4], bv[NT];
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti) av[ti] = vload(row, ti * 8 + g);
+#pragma unroll
+            for (int tj = 0; tj < NT; ++tj) bv[tj] = Bb[(long long)row * ld + tj * 8 + g];
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < NT; ++tj) dmma884(acc[ti][tj][0], acc[ti][tj][1], av[ti], bv[tj]);
+        }
+    }
+    __syncthreads();
+    // ordered (deterministic) sum of the 8 partial products
+#pragma unroll 1
+    for (int ww = 0; ww < TS_FAN; ++ww) {
+        if (w == ww && valid) {
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < NT; ++tj) {
+                    Gs[ti * 8 + g][tj * 8 + 2 * t] += acc[ti][tj][0];
+                    Gs[ti * 8 + g][tj * 8 + 2 * t + 1] += acc[ti][tj][1];
+                }
+        }
+        __syncthreads();
+    }
+    // W = -T' G  (4 x NT tiles over the 8 warps)
+    for (int id = w; id < 4 * NT; id += TS_FAN) {
+        const int ti = id / NT, tj = id % NT;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) dmma884(c0, c1, Ts[kk * 4 + t][ti * 8 + g], Gs[kk * 4 + t][tj * 8 + g]);
+        Ws[ti * 8 + g][tj * 8 + 2 * t] = -c0;
+        Ws[ti * 8 + g][tj * 8 + 2 * t + 1] = -c1;
+    }
+    __syncthreads();
+    // pass 2: B_w += V_w W
+    if (valid) {
+        double b2[4][NT][2];
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < NT; ++cj) {
+                double2 v = *reinterpret_cast<const double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t);
+                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
+            }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            double av[4], bw[NT];
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) av[ri] = vload(ri * 8 + g, kk * 4 + t);
+#pragma unroll
+            for (int cj = 0; cj < NT; ++cj) bw[cj] = Ws[kk * 4 + t][cj * 8 + g];
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+                for (int cj = 0; cj < NT; ++cj) dmma884(b2[ri][cj][0], b2[ri][cj][1], av[ri], bw[cj]);
+        }
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < NT; ++cj)
+                *reinterpret_cast<double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t) =
+                    make_double2(b2[ri][cj][0], b2[ri][cj][1]);
+    }
+}
+
+// 1-D grid of nsub * (ncb32 + 1) CTAs, column block fastest (CTAs sharing a reflector block V run together, so V
+// is read from HBM once): cb < ncb32 -> the 32-column block col0 + 32 (cb + 1); cb == ncb32 -> the 8-column block
+// at column `lastcol` holding the residual column of [J | r] (and 7 zero padding columns)
+__global__ void __launch_bounds__(256, 2)
+tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb32, int lastcol,
+                  const double* __restrict__ Tbuf) {
+    __shared__ __align__(16) double smem[TS_B * TS_LDS + 2 * TS_B * (TS_B + 4)];
+    const long long sub = blockIdx.x / (unsigned)(ncb32 + 1);
+    const int cb = (int)(blockIdx.x % (unsigned)(ncb32 + 1));
+    if (cb < ncb32)
+        tsqr_trail_body<32>(A, ld, nblk, stride, col0, col0 + TS_B * (cb + 1), sub, Tbuf, smem);
+    else
+        tsqr_trail_body<8>(A, ld, nblk, stride, col0, lastcol, sub, Tbuf, smem);
+}
+
+// rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
+__global__ void tsqr_extract_kernel(double* __restrict__ A, int ld, int col0, int ncols, double* __restrict__ Rout,
+                                    int ldr) {
+    for (int idx = threadIdx.x; idx < TS_B * (ld - col0); idx += blockDim.x) {
+        int r = idx / (ld - col0), c = col0 + idx % (ld - col0);
+        double v = A[(long long)r * ld + c];
+        if (c < col0 + TS_B && c - col0 < r) v = 0.0;
+        if (c < ncols) Rout[(long long)(col0 + r) * ldr + c] = v;
+        A[(long long)r * ld + c] = 0.0;
+    }
+}
+
+// sum of squares of one column: stage 1 (fixed grid, fixed tree) and stage 2
+__global__ void __launch_bounds__(256) tsqr_colsq_kernel(const double* __restrict__ A, int ld, long long rows, int col,
+                                                          double* __restrict__ part) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows; i += (long long)gridDim.x * 256) {
+        double v = A[i * ld + col];
+        s = fma(v, v, s);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void tsqr_colsq_finish_kernel(const double* __restrict__ part, int nparts, double* __restrict__ Rout,
+                                         int ldr, int col) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nparts; ++i) s += part[i];
+        Rout[(long long)col * ldr + col] = sqrt(s);
+    }
+}
+
+// Host-side launcher.  A: rows_pad x ld row major, rows_pad a multiple of 32, pad rows zero.
+// ncols = n + 1 with n a multiple of 32 (columns n+1 .. ld-1 must be zero; ld = n + 8).
+// Rout: (n + 1) x ldr row major, zero-initialised by the caller.  Tbuf: ceil(nblk / 8) * 1024 doubles.
+// part: >= 512 doubles.  Returns the number of kernels launched.
+inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rout, int ldr, double* Tbuf, double* part,
+                       cudaStream_t st) {
+    const long long nblk = rows_pad / TS_B;
+    const int npanels = n / TS_B;
+    int launches = 0;
+    for (int j = 0; j < npanels; ++j) {
+        const int col0 = j * TS_B;
+        const int ncb32 = npanels - 1 - j;
+        long long stride = 1;
+        for (int level = 0;; ++level) {
+            long long nb_level = (nblk + stride - 1) / stride;
+            if (level > 0 && nb_level <= 1) break;
+            long long nsub = (nb_level + TS_FAN - 1) / TS_FAN;
+            tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, Tbuf);
+            tsqr_trail_kernel<<<(unsigned)(nsub * (ncb32 + 1)), 256, 0, st>>>(A, ld, nblk, stride, col0, ncb32, n, Tbuf);
+            launches += 2;
+            stride *= TS_FAN;
+        }
+        tsqr_extract_kernel<<<1, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);
+        ++launches;
+    }
+    const int nparts = 296;
+    tsqr_colsq_kernel<<<nparts, 256, 0, st>>>(A, ld, rows_pad, n, part);
+    tsqr_colsq_finish_kernel<<<1, 32, 0, st>>>(part, nparts, Rout, ldr, n);
+    return launches + 2;
+}
+
+}  // namespace enl_large

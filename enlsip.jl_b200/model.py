@@ -26,6 +26,7 @@ import math
 import numpy as np
 
 from . import capi
+from .model_large import LargeCnlsModel, solve_large
 
 dict_status_codes = {0: "unsolved", 1: "found_first_order_stationary_point", -1: "failed",
                      -2: "maximum_iterations_exceeded", -11: "time_limit_exceeded"}   # cnls_model.jl:180-186
@@ -141,6 +142,11 @@ def solve(model: CnlsModel, silent=True, max_iter=100, scaling=False, time_limit
     ``out`` (optional) supplies preallocated result arrays (dict with x, f, exit_code, status, iters, nact and
     optionally active, counters) so that repeated solves allocate nothing.
     """
+    if isinstance(model, LargeCnlsModel):   # one large problem: TSQR engine (model_large.py)
+        if out is not None:
+            raise ValueError("`out` is a batched-regime argument")
+        return solve_large(model, silent=silent, max_iter=max_iter, scaling=scaling, time_limit=time_limit,
+                           abs_tol=abs_tol, rel_tol=rel_tol, c_tol=c_tol, x_tol=x_tol, trace_cap=trace_cap)
     B, n = model.B, model.nb_parameters
     o = capi.default_options()
     o.max_iter = int(max_iter)

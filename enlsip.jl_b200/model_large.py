@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's model API for the LARGE-JACOBIAN regime (one problem, m >> n).
+
+reference                                   here
+---------                                   ----
+CnlsModel(residuals, n, m; starting_point,  LargeCnlsModel("single_index", starting_point[n], data={"W","y","rho"},
+          eq_constraints, nb_eqcons, ...)                  ineq=False, x_low, x_upp, m_global=None)
+   (cnls_model.jl:345-378)                     the rows of W / y held by THIS process (a row shard when m_global > rows)
+solve!(model; ...)     (solver.jl:62-91)    solve(model, ...)   (same function as the batched regime: it dispatches)
+status / solution / sum_sq_residuals        same accessors (cnls_model.jl:206-221), B = 1
+
+Row sharding over the GPUs of one box (BASELINE.json config 4): one process per GPU, each builds a model
+from its own rows and calls ``model.join(rank, world)`` once (NCCL unique id broadcast through
+``torch.distributed``); afterwards every rank calls ``solve`` with identical arguments and gets identical results.
+There is no CPU execution path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class LargeCnlsModel:
+    def __init__(self, family, starting_point, data, ineq=False, x_low=None, x_upp=None, m_global=None, device=-1):
+        if family != "single_index":
+            raise AssertionError("large-regime families: ['single_index']")
+        self.family = family
+        self.B = 1
+        self.starting_point = np.ascontiguousarray(starting_point, dtype=np.float64).reshape(-1)
+        n = self.starting_point.size
+        W, y = data["W"], data["y"]
+        rho = np.ascontiguousarray(data["rho"], dtype=np.float64)
+        rows = int(W.shape[0])
+        if int(W.shape[1]) != n or int(y.shape[0]) != rows:
+            raise ValueError("W must be [rows, n] and y [rows]")
+        self.nb_parameters, self.rows = n, rows
+        self.nb_residuals = int(rows if m_global is None else m_global)
+        self.x_low = np.full(n, -np.inf) if x_low is None else np.ascontiguousarray(x_low, dtype=np.float64)
+        self.x_upp = np.full(n, np.inf) if x_upp is None else np.ascontiguousarray(x_upp, dtype=np.float64)
+        nb = rho.size
+        self.nb_eqcons = 0 if ineq else nb
+        self.nb_constraints = nb + int(np.isfinite(self.x_low).sum()) + int(np.isfinite(self.x_upp).sum())
+        self.lmax = self.nb_constraints
+        h = ctypes.c_void_p()
+        capi.check_large(capi.lib().enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, n, rows, self.nb_residuals, nb,
+                                                            1 if ineq else 0, rho.ctypes.data, self.x_low.ctypes.data,
+                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)))
+        self._h = h
+        self._keep = []
+        for slot, arr in ((0, W), (1, y)):
+            dev = _is_torch(arr) and arr.is_cuda
+            if _is_torch(arr):
+                if not dev:
+                    raise ValueError("torch tensors must live on a CUDA device; pass numpy arrays for host buffers")
+                arr = arr.contiguous()
+                ptr, count = arr.data_ptr(), arr.numel()
+            else:
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                ptr, count = arr.ctypes.data, arr.size
+            if dev:
+                self._keep.append(arr)
+            capi.check_large(capi.lib().enlsipb200_large_set_data(h, slot, ctypes.c_void_p(ptr), count, 1 if dev else 0))
+        self.status_code = None
+        self.sol = self.starting_point
+        self.obj_value = None
+        self.exit_code = None
+        self.iterations = None
+        self.nb_active = None
+        self.active = None
+        self.trace = None
+
+    def join(self, rank, world, broadcast=None):
+        """Join the row shards of `world` processes (one per GPU).  `broadcast(buf: np.uint8[128])` must
+        overwrite buf on every rank with rank 0's content; default: torch.distributed.broadcast."""
+        buf = np.zeros(128, dtype=np.uint8)
+        if rank == 0 and world > 1:
+            capi.check_large(capi.lib().enlsipb200_large_comm_id(buf.ctypes.data))
+        if world > 1:
+            if broadcast is None:
+                import torch
+                import torch.distributed as dist
+                if dist.get_backend() == "nccl":
+                    t = torch.from_numpy(buf).cuda()
+                    dist.broadcast(t, 0)
+                    buf[:] = t.cpu().numpy()
+                else:
+                    t = torch.from_numpy(buf)
+                    dist.broadcast(t, 0)
+            else:
+                broadcast(buf)
+        capi.check_large(capi.lib().enlsipb200_large_comm_init(self._h, buf.ctypes.data, int(rank), int(world)))
+
+    def factor(self, x, want_R=True):
+        """Measurement / test hook: one evaluation + QR of [J | r] at x.  Returns (R or None, build_ms, tsqr_ms)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = self.nb_parameters
+        R = np.zeros((n + 1, n + 1)) if want_R else None
+        b, t = ctypes.c_float(), ctypes.c_float()
+        capi.check_large(capi.lib().enlsipb200_large_factor(self._h, x.ctypes.data, None if R is None else R.ctypes.data,
+                                                            ctypes.byref(b), ctypes.byref(t)))
+        return R, float(b.value), float(t.value)
+
+    def stats(self):
+        v = np.zeros(8)
+        capi.check_large(capi.lib().enlsipb200_large_stats(self._h, v.ctypes.data, 8))
+        keys = ("factorisations", "build_ms", "tsqr_ms", "linesearch_ms", "solve_wall_ms", "linesearch_evals",
+                "launches", "rows_pad")
+        return dict(zip(keys, [float(a) for a in v]))
+
+    def launch_count(self):
+        return int(self.stats()["launches"])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().enlsipb200_large_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False, time_limit=1e3, abs_tol=None,
+                rel_tol=None, c_tol=None, x_tol=None, trace_cap=0):
+    """solve!(model; ...) (solver.jl:62-91) for the large regime; results land in the model (B = 1 arrays)."""
+    n = model.nb_parameters
+    o = capi.default_options()
+    o.max_iter = int(max_iter)
+    o.scaling = 1 if scaling else 0
+    o.time_limit = float(time_limit)
+    nan = float("nan")
+    o.abs_tol = nan if abs_tol is None else float(abs_tol)
+    o.rel_tol = nan if rel_tol is None else float(rel_tol)
+    o.c_tol = nan if c_tol is None else float(c_tol)
+    o.x_tol = nan if x_tol is None else float(x_tol)
+    x = np.zeros((1, n))
+    f = np.zeros(1)
+    ec, st, it, na = (np.zeros(1, dtype=np.int32) for _ in range(4))
+    act = np.zeros((1, max(model.lmax, 1)), dtype=np.int32)
+    tr = np.zeros((1, trace_cap, capi.TRACE_HDR + n)) if trace_cap > 0 else None
+    p = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
+    capi.check_large(capi.lib().enlsipb200_large_solve(model._h, p(model.starting_point), ctypes.byref(o), p(x), p(f),
+                                                       p(ec), p(st), p(it), p(na), p(act), p(tr), int(trace_cap)))
+    model.status_code, model.exit_code, model.sol, model.obj_value = st, ec, x, f
+    model.iterations, model.nb_active, model.active, model.trace = it, na, act, tr
+    if not silent:
+        print("single_index problem (n=%d, m=%d, constraints=%d): exit code %d after %d iterations, objective %.6e"
+              % (n, model.nb_residuals, model.nb_constraints, int(ec[0]), int(it[0]), float(f[0])))
+    return None

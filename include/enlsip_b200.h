@@ -96,6 +96,49 @@ long long enlsipb200_launch_count(enlsipb200_handle h);
 /* deterministic exp used by the synthetic families, exposed for bit-parity tests vs oracle/detmath.c */
 int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
 
+/* ===========================================================================================
+ * Large-Jacobian regime (BASELINE.json configs 4/5): ONE problem whose m x n residual Jacobian is
+ * too large for a CTA.  Replaces the same reference call site (solve! -> enlsip, src/solver.jl:80-87);
+ * per iterate the engine factors [J | r] with a tall-skinny Householder QR on the GPU
+ * (replacing `qr(J2, ColumnNorm())` and `F.Q' * v`, src/enlsip_functions.jl:135-151, 219-223) and
+ * runs the pivoted small-matrix stage on the (n+1) x (n+1) triangular factor.
+ *
+ * Rows may be sharded over several GPUs / processes (one handle per GPU): every rank passes its own
+ * m_local rows of W and y and the global m; the ranks are joined by enlsipb200_large_comm_init
+ * (NCCL: all-gather of the per-GPU R factors, all-reduce of the linesearch sums).  Every rank then
+ * calls enlsipb200_large_solve with the same x0 / options and receives the same results.
+ * =========================================================================================== */
+#define ENLSIPB200_FAMILY_SINGLE_INDEX 16 /* r_i = det_tanh(w_i.x) - y_i ; block constraints on groups of 4
+                                             parameters: equalities sum x_j^2 - rho_k (ineq = 0) or
+                                             inequalities rho_k - sum x_j^2 >= 0 (ineq = 1); optional bounds */
+
+typedef struct enlsipb200_large_s* enlsipb200_large;
+
+const char* enlsipb200_large_last_error(void);
+
+/* n: parameters (multiple of 32); m_local: residual rows held by this handle; m_global: all rows;
+ * nb: number of 4-parameter blocks with a constraint; rho [nb]; x_low / x_upp [n] or NULL (+-Inf = none). */
+int enlsipb200_large_create(int family, int n, long long m_local, long long m_global, int nb, int ineq,
+                            const double* rho, const double* x_low, const double* x_upp, int device,
+                            enlsipb200_large* out);
+int enlsipb200_large_destroy(enlsipb200_large h);
+/* slot 0 = W [m_local, n] row major, slot 1 = y [m_local].  on_device != 0: device pointer that must stay
+ * valid (and resident on the handle's device) for the solves; otherwise copied host -> device. */
+int enlsipb200_large_set_data(enlsipb200_large h, int slot, const double* ptr, long long count, int on_device);
+/* multi-GPU: rank 0 creates a 128-byte NCCL unique id, the host layer distributes it, every rank joins */
+int enlsipb200_large_comm_id(void* id128);
+int enlsipb200_large_comm_init(enlsipb200_large h, const void* id128, int rank, int nranks);
+/* blocking solve; outputs as in enlsipb200_solve_batch for B = 1 (active [l], trace [trace_cap, TRACE_HDR + n]) */
+int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb200_options* opt, double* x, double* f,
+                           int* exit_code, int* status, int* iters, int* nact, int* active, double* trace,
+                           int trace_cap);
+/* measurement / test hook: evaluate [J | r] at x and factor it; R [(n+1) x (n+1)] row major (may be NULL);
+ * device times of the two stages (CUDA events on the handle's stream) */
+int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
+/* cumulative counters: {factorisations, build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
+ * evaluations, kernels launched, padded local rows} */
+int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
+
 #ifdef __cplusplus
 }
 #endif
