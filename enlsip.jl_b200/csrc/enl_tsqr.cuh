@@ -28,6 +28,7 @@ namespace enl_large {
 
 constexpr int TS_B = 32;     // block rows = panel width
 constexpr int TS_FAN = 8;    // blocks per subtile
+constexpr int TS_CG = 4;     // panel columns per unrolled group (code size: the group body must stay in the 32 KB L1.5 I-cache)
 constexpr int TS_LDS = 36;   // shared-memory leading dimension (doubles): conflict-free m8n8k4 fragment loads
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -42,10 +43,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __global__ void __launch_bounds__(256, 2)
 tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int upper_only,
                   double* __restrict__ Tbuf) {
-    __shared__ double red[TS_FAN];
-    __shared__ double s_alpha;
-    __shared__ double vbuf[TS_FAN][TS_B];
-    __shared__ double dots[TS_FAN][TS_B];
+    // One block-wide barrier per column: the raw column i is published (per warp), ONE pass of dot products
+    // g_c = sum_{rows below the pivot} a_i[r] a_c[r] gives both the norm (g_i) and, because the reflector
+    // v_i = e_i + scale * a_i[below] is linear in the raw column, every v_i . a_c = a_c[i] + scale * g_c.
+    __shared__ __align__(16) double vbuf[TS_FAN][TS_B];
+    __shared__ double dots[2][TS_FAN][TS_B];
+    __shared__ double rowi[2][TS_B];        // row i of the top block (warp 0), double-buffered like dots
     __shared__ double Gs[TS_B][TS_B + 1];   // Gs[c][i] = v_c . v_i, c < i
     __shared__ double taus[TS_B];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,72 +63,90 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
         if (upper_only && r > lane) v = 0.0;   // level >= 1: below the diagonal lie stale reflectors of the level below
         a[r] = v;
     }
+    // Columns are processed in groups of TS_CG: the group body is unrolled (compile-time register indices), the
+    // loop over groups is not (the fully unrolled kernel is 160 KB of code and starves on instruction fetch).
+    // After a group the top block (warp 0) stores its TS_CG finished rows and zeroes them, and every warp rotates
+    // its register rows by TS_CG, so that the pivot rows of the next group are again rows 0..TS_CG-1.
 #pragma unroll 1
-    for (int i = 0; i < TS_B; ++i) {
-        // (1) squared norm of column i below the pivot (every lane does its own column; lane i's is used)
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int ib = 0; ib < TS_B / TS_CG; ++ib) {
 #pragma unroll
-        for (int r = 0; r < TS_B; r += 4) {
-            double v0 = (w > 0 || r + 0 > i) ? a[r + 0] : 0.0;
-            double v1 = (w > 0 || r + 1 > i) ? a[r + 1] : 0.0;
-            double v2 = (w > 0 || r + 2 > i) ? a[r + 2] : 0.0;
-            double v3 = (w > 0 || r + 3 > i) ? a[r + 3] : 0.0;
-            s0 = fma(v0, v0, s0); s1 = fma(v1, v1, s1); s2 = fma(v2, v2, s2); s3 = fma(v3, v3, s3);
-        }
-        if (lane == i) {
-            red[w] = (s0 + s1) + (s2 + s3);
+        for (int k = 0; k < TS_CG; ++k) {
+            const int i = ib * TS_CG + k;
+            const int buf = k & 1;
+            __syncwarp();
+            // (1) lane i publishes its raw column (pivot row and the rows above it masked in the top block)
+            if (lane == i) {
+#pragma unroll
+                for (int r = 0; r < TS_B; r += 2) {
+                    double2 v = make_double2(a[r], a[r + 1]);
+                    if (w == 0) {
+                        if (r <= k) v.x = 0.0;
+                        if (r + 1 <= k) v.y = 0.0;
+                    }
+                    *reinterpret_cast<double2*>(&vbuf[w][r]) = v;
+                }
+            }
+            if (w == 0) rowi[buf][lane] = a[k];
+            __syncwarp();
+            // (2) g_c over this warp's 32 rows
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < TS_B; r += 4) {
+                const double2 v01 = *reinterpret_cast<const double2*>(&vbuf[w][r]);
+                const double2 v23 = *reinterpret_cast<const double2*>(&vbuf[w][r + 2]);
+                d0 = fma(v01.x, a[r + 0], d0); d1 = fma(v01.y, a[r + 1], d1);
+                d2 = fma(v23.x, a[r + 2], d2); d3 = fma(v23.y, a[r + 3], d3);
+            }
+            dots[buf][w][lane] = (d0 + d1) + (d2 + d3);
+            __syncthreads();
+            const double g = ((dots[buf][0][lane] + dots[buf][1][lane]) + (dots[buf][2][lane] + dots[buf][3][lane])) +
+                             ((dots[buf][4][lane] + dots[buf][5][lane]) + (dots[buf][6][lane] + dots[buf][7][lane]));
+            const double sigma = ((dots[buf][0][i] + dots[buf][1][i]) + (dots[buf][2][i] + dots[buf][3][i])) +
+                                 ((dots[buf][4][i] + dots[buf][5][i]) + (dots[buf][6][i] + dots[buf][7][i]));
+            const double alpha = rowi[buf][i];
+            double tau = 0.0, scale = 0.0, beta = alpha;
+            if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||
+                beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            // (3) v_i . (column of this lane): columns > i get updated, columns < i feed the Gram matrix of V
+            const double gv = fma(scale, g, rowi[buf][lane]);
+            const double wc = (lane > i) ? tau * gv : 0.0;
             if (w == 0) {
-                double al = 0.0;
+                if (lane < i) Gs[lane][i] = gv;
+                if (lane == i) taus[i] = tau;
+                a[k] = (lane == i) ? beta : a[k] - wc;
+            }
+            const double cs = wc * scale;
 #pragma unroll
-                for (int r = 0; r < TS_B; ++r) al = (r == i) ? a[r] : al;
-                s_alpha = al;
+            for (int r = 0; r < TS_B; r += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&vbuf[w][r]);
+                a[r] = fma(-cs, v.x, a[r]);
+                a[r + 1] = fma(-cs, v.y, a[r + 1]);
+            }
+            if (lane == i) {   // the column becomes the reflector (unit diagonal implied)
+#pragma unroll
+                for (int r = 0; r < TS_B; ++r)
+                    if (r > k || w > 0) a[r] *= scale;
             }
         }
-        __syncthreads();
-        const double sigma = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-        const double alpha = s_alpha;
-        double tau = 0.0, scale = 0.0, beta = alpha;
-        if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||
-            beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        // (2) lane i turns its column into the reflector and publishes it to its warp
-        if (lane == i) {
+        if (w == 0) {
 #pragma unroll
-            for (int r = 0; r < TS_B; ++r) {
-                double v;
-                if (w == 0 && r < i) v = 0.0;
-                else if (w == 0 && r == i) v = 1.0;
-                else { v = a[r] * scale; a[r] = v; }
-                vbuf[w][r] = v;
-            }
-            if (w == 0) {
-#pragma unroll
-                for (int r = 0; r < TS_B; ++r) a[r] = (r == i) ? beta : a[r];
-                taus[i] = tau;
+            for (int r = 0; r < TS_CG; ++r) {
+                base[(long long)(ib * TS_CG + r) * ld] = a[r];
+                a[r] = 0.0;
             }
         }
-        __syncwarp();
-        // (3) v_i . (every column): columns > i get updated, columns < i feed the Gram matrix of V
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        double tmp[TS_CG];
 #pragma unroll
-        for (int r = 0; r < TS_B; r += 4) {
-            d0 = fma(vbuf[w][r + 0], a[r + 0], d0); d1 = fma(vbuf[w][r + 1], a[r + 1], d1);
-            d2 = fma(vbuf[w][r + 2], a[r + 2], d2); d3 = fma(vbuf[w][r + 3], a[r + 3], d3);
-        }
-        dots[w][lane] = (d0 + d1) + (d2 + d3);
-        __syncthreads();
-        const double dsum = ((dots[0][lane] + dots[1][lane]) + (dots[2][lane] + dots[3][lane])) +
-                            ((dots[4][lane] + dots[5][lane]) + (dots[6][lane] + dots[7][lane]));
-        if (w == 0 && lane < i) Gs[lane][i] = dsum;
-        if (tau != 0.0 && lane > i) {
-            const double wc = tau * dsum;
+        for (int r = 0; r < TS_CG; ++r) tmp[r] = a[r];
 #pragma unroll
-            for (int r = 0; r < TS_B; ++r) a[r] = fma(-wc, vbuf[w][r], a[r]);
-        }
+        for (int r = 0; r < TS_B - TS_CG; ++r) a[r] = a[r + TS_CG];
+#pragma unroll
+        for (int r = 0; r < TS_CG; ++r) a[TS_B - TS_CG + r] = tmp[r];
     }
-    if (valid) {
+    if (valid && w > 0) {
 #pragma unroll
         for (int r = 0; r < TS_B; ++r) base[(long long)r * ld] = a[r];
     }
@@ -159,9 +180,11 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
                                                 double* smem) {
     constexpr int NT = CB / 8;          // 8-column tiles per block row
     constexpr int CBP = CB + 4;         // padded leading dimension of the CB-wide shared tiles
+    constexpr int NV = 4 * NT * 2;      // accumulator values per thread
     double (*Ts)[TS_LDS] = reinterpret_cast<double (*)[TS_LDS]>(smem);
     double (*Gs)[CBP] = reinterpret_cast<double (*)[CBP]>(smem + TS_B * TS_LDS);
     double (*Ws)[CBP] = reinterpret_cast<double (*)[CBP]>(smem + TS_B * TS_LDS + TS_B * CBP);
+    double* Ps = smem + TS_B * TS_LDS + 2 * TS_B * (TS_B + 4);   // 4 partial-sum buffers, [value][lane]
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const long long blk = (sub * TS_FAN + w) * stride;
     const bool valid = blk < nblk;
@@ -173,7 +196,6 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
         int idx = tid + 256 * q;
         Ts[idx >> 5][idx & 31] = Tg[idx];
     }
-    for (int idx = tid; idx < TS_B * CB; idx += 256) Gs[idx / CB][idx % CB] = 0.0;
     // reflector block element (row, c) of this warp's block: unit lower trapezoid for the top block
     auto vload = [&](int row, int c) -> double {
         double v = Vb[(long long)row * ld + c];
@@ -201,21 +223,55 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
                 for (int tj = 0; tj < NT; ++tj) dmma884(acc[ti][tj][0], acc[ti][tj][1], av[ti], bv[tj]);
         }
     }
+    // deterministic pairwise tree over the 8 warps: (w, w + 4), then (w, w + 2), then (0, 1)
+    auto put = [&](int b) {
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < NT; ++tj) {
+                Ps[(b * NV + (ti * NT + tj) * 2) * 32 + lane] = acc[ti][tj][0];
+                Ps[(b * NV + (ti * NT + tj) * 2 + 1) * 32 + lane] = acc[ti][tj][1];
+            }
+    };
+    auto take = [&](int b) {
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < NT; ++tj) {
+                acc[ti][tj][0] += Ps[(b * NV + (ti * NT + tj) * 2) * 32 + lane];
+                acc[ti][tj][1] += Ps[(b * NV + (ti * NT + tj) * 2 + 1) * 32 + lane];
+            }
+    };
+    if (w >= 4) put(w - 4);
     __syncthreads();
-    // ordered (deterministic) sum of the 8 partial products
-#pragma unroll 1
-    for (int ww = 0; ww < TS_FAN; ++ww) {
-        if (w == ww && valid) {
+    if (w < 4) take(w);
+    if (w == 2 || w == 3) put(w);      // its own buffer: nobody else reads it before the next barrier
+    __syncthreads();
+    if (w < 2) take(w + 2);
+    if (w == 1) put(1);
+    __syncthreads();
+    if (w == 0) {
+        take(1);
 #pragma unroll
-            for (int ti = 0; ti < 4; ++ti)
+        for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
-                for (int tj = 0; tj < NT; ++tj) {
-                    Gs[ti * 8 + g][tj * 8 + 2 * t] += acc[ti][tj][0];
-                    Gs[ti * 8 + g][tj * 8 + 2 * t + 1] += acc[ti][tj][1];
-                }
-        }
-        __syncthreads();
+            for (int tj = 0; tj < NT; ++tj) {
+                Gs[ti * 8 + g][tj * 8 + 2 * t] = acc[ti][tj][0];
+                Gs[ti * 8 + g][tj * 8 + 2 * t + 1] = acc[ti][tj][1];
+            }
     }
+    // the block of B in accumulator layout for pass 2: issued here so that the loads fly during the W stage
+    double b2[4][NT][2];
+    if (valid) {
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < NT; ++cj) {
+                double2 v = *reinterpret_cast<const double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t);
+                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
+            }
+    }
+    __syncthreads();
     // W = -T' G  (4 x NT tiles over the 8 warps)
     for (int id = w; id < 4 * NT; id += TS_FAN) {
         const int ti = id / NT, tj = id % NT;
@@ -228,14 +284,6 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
     __syncthreads();
     // pass 2: B_w += V_w W
     if (valid) {
-        double b2[4][NT][2];
-#pragma unroll
-        for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-            for (int cj = 0; cj < NT; ++cj) {
-                double2 v = *reinterpret_cast<const double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t);
-                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
-            }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             double av[4], bw[NT];
@@ -257,13 +305,15 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
     }
 }
 
+constexpr int TS_TRAIL_SMEM = (TS_B * TS_LDS + 2 * TS_B * (TS_B + 4) + 4 * 32 * 32) * (int)sizeof(double);
+
 // 1-D grid of nsub * (ncb32 + 1) CTAs, column block fastest (CTAs sharing a reflector block V run together, so V
 // is read from HBM once): cb < ncb32 -> the 32-column block col0 + 32 (cb + 1); cb == ncb32 -> the 8-column block
 // at column `lastcol` holding the residual column of [J | r] (and 7 zero padding columns)
 __global__ void __launch_bounds__(256, 2)
 tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb32, int lastcol,
                   const double* __restrict__ Tbuf) {
-    __shared__ __align__(16) double smem[TS_B * TS_LDS + 2 * TS_B * (TS_B + 4)];
+    extern __shared__ __align__(16) double smem[];
     const long long sub = blockIdx.x / (unsigned)(ncb32 + 1);
     const int cb = (int)(blockIdx.x % (unsigned)(ncb32 + 1));
     if (cb < ncb32)
@@ -319,6 +369,8 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     const long long nblk = rows_pad / TS_B;
     const int npanels = n / TS_B;
     int launches = 0;
+    // > 48 KB of dynamic shared memory needs the opt-in (per device, so it is simply set on every call)
+    cudaFuncSetAttribute(tsqr_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
@@ -328,7 +380,7 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             if (level > 0 && nb_level <= 1) break;
             long long nsub = (nb_level + TS_FAN - 1) / TS_FAN;
             tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, Tbuf);
-            tsqr_trail_kernel<<<(unsigned)(nsub * (ncb32 + 1)), 256, 0, st>>>(A, ld, nblk, stride, col0, ncb32, n, Tbuf);
+            tsqr_trail_kernel<<<(unsigned)(nsub * (ncb32 + 1)), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32, n, Tbuf);
             launches += 2;
             stride *= TS_FAN;
         }
