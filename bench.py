@@ -27,7 +27,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "batched CNLS solves/s (n=6,m=128)"
+METRIC = "batched CNLS solves/s (n=6,m=128)"      # first half of BASELINE.json's metric; the second half (GN iters/s,
+                                                  # m=4M, n=256) is the "large" object of the same JSON line
 UNIT = "solves/s"
 ALG_BYTES_PER_SOLVE = 128 * 8 + 48 + 8 + 48 + 8 + 12   # y, x0, S in; x, f, (exit, iters, t) out = 1148 B
 
@@ -129,6 +130,154 @@ def cpu_port(B, nthreads, seed_start=0):
     return run, ints[2]
 
 
+# =================================================================================================
+# large-Jacobian regime (BASELINE.json config 4): GN iterations/s at m = 4M, n = 256, 64 equalities
+# =================================================================================================
+LARGE_METRIC = "GN iters/s (m=4M,n=256)"
+LARGE_N, LARGE_NB = 256, 64
+
+
+def fp64_tensor_peak():
+    """Measured FP64 DMMA peak of this pool's B200s (tools/fp64_peaks.cu; MEASURED_PEAKS.json has no FP64 entry)."""
+    p = os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["fp64_dmma_m8n8k4_tflops"]), "measured mma.sync.m8n8k4.f64 peak (tools/fp64_peaks.cu, profiles/r1_fp64_peaks.json)"
+    return 40.0, "fallback: B200 FP64 tensor datasheet figure"
+
+
+def gen_large_shard(torch, dev, m_global, row0, rows, n=LARGE_N, nb=LARGE_NB, chunk=1 << 18):
+    """Device-side synthetic single-index problem; rows [row0, row0 + rows) of the global matrix.
+    Chunks of 2^18 rows own their generator seed, so every world size sees the same global W and y."""
+    g0 = torch.Generator(device=dev).manual_seed(4)
+    truth = torch.rand(n, dtype=torch.float64, device=dev, generator=g0) * 2 - 1
+    x0 = truth * (1 + 0.05 * (torch.rand(n, dtype=torch.float64, device=dev, generator=g0) * 2 - 1))
+    W = torch.empty(rows, n, dtype=torch.float64, device=dev)
+    y = torch.empty(rows, dtype=torch.float64, device=dev)
+    for c in range(row0 // chunk, (row0 + rows - 1) // chunk + 1):
+        g = torch.Generator(device=dev).manual_seed(4000 + c)
+        Wc = torch.randn(chunk, n, dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+        yc = torch.tanh(Wc @ truth) + 0.01 * torch.randn(chunk, dtype=torch.float64, device=dev, generator=g)
+        lo, hi = max(row0, c * chunk), min(row0 + rows, (c + 1) * chunk)
+        W[lo - row0:hi - row0] = Wc[lo - c * chunk:hi - c * chunk]
+        y[lo - row0:hi - row0] = yc[lo - c * chunk:hi - c * chunk]
+        del Wc, yc
+    tr = truth.cpu().numpy()
+    rho = (tr[:4 * nb] ** 2).reshape(nb, 4).sum(axis=1)
+    return W, y, x0.cpu().numpy(), rho
+
+
+def large_cpu_baseline(sample_rows, m_global):
+    """The reference's dense path for one C4-shaped problem on the host cores: the oracle restatement (numpy + the
+    same LAPACK dgeqp3/dormqr/dtrtrs Julia calls, OpenBLAS threads = all cores) on a row sample; the cost of an
+    iteration is linear in m, so iterations/s at m_global = (sample iterations/s) * sample_rows / m_global."""
+    import enlsip_jl_b200 as E
+    from oracle import enlsip_oracle as O, problems as P
+    d = E.synth.gen_single_index(sample_rows, LARGE_N, LARGE_NB, seed=4)
+    t0 = time.perf_counter()
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock=False)
+    dt = time.perf_counter() - t0
+    v = r.iterations / dt * sample_rows / m_global
+    return {"value": v, "unit": "iters/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d of the %d rows (n=256, 64 equalities): %d oracle iterations in %.2f s, scaled linearly in m; "
+                      "oracle = numpy + SciPy LAPACK restatement of Enlsip.jl (Julia itself is absent from this image)"
+                      % (sample_rows, m_global, r.iterations, dt)}
+
+
+def large_arm(args, torch, dist, E, rank, world, local, dev):
+    """One step = one complete solve of the row-sharded problem from x0 (every rank holds m/world rows; R factors
+    all-gathered, linesearch sums all-reduced over NCCL).  Strong scaling: the problem size is fixed."""
+    m_global = args.large_rows
+    rows = m_global // world
+    row0 = rank * rows
+    if rank == world - 1:
+        rows = m_global - row0
+    W, y, x0, rho = gen_large_shard(torch, dev, m_global, row0, rows)
+    mod = E.LargeCnlsModel("single_index", x0, {"W": W, "y": y, "rho": rho}, m_global=m_global, device=local)
+    mod.join(rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.large_warmup)):
+        E.solve(mod)
+    st0 = mod.stats()
+    barrier()
+    t0 = time.perf_counter()
+    iters_solver = 0
+    for _ in range(args.large_steps):
+        E.solve(mod)
+        iters_solver += int(mod.iterations[0])
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    st1 = mod.stats()
+    dst = {k: st1[k] - st0[k] for k in st1 if k != "rows_pad"}
+    nfac = max(dst["factorisations"], 1.0)
+    # executed Gauss-Newton iterations: every pass of the `while exit_code == 0` loop (EF:2776-2878) ends with one
+    # new_point!, and one more precedes the loop; the solver's own counter does not count the terminating pass
+    iters = int(nfac) - args.large_steps
+    tsqr_ms = dst["tsqr_ms"] / nfac
+    flops = 2.0 * m_global * (LARGE_N + 1) ** 2          # Householder R factor of the augmented [J | r] (SURVEY.md 8d)
+    peak, peak_src = fp64_tensor_peak()
+    achieved = flops / world / (tsqr_ms * 1e-3) / 1e12  # per GPU: its m/world rows in its own tsqr time
+    res = {"metric": LARGE_METRIC, "value": iters / dt, "unit": "iters/s", "n_gpus": world, "steps": args.large_steps,
+           "warmup": max(1, args.large_warmup), "scaling": "strong", "higher_is_better": True, "dtype": "f64",
+           "ms_per_iteration": dt * 1e3 / iters, "iterations_per_solve": iters / args.large_steps,
+           "iterations_reported_by_solver_per_solve": iters_solver / args.large_steps,
+           "exit_code": int(mod.exit_code[0]), "status": int(mod.status_code[0]), "objective": float(mod.obj_value[0]),
+           "config": {"workload": "C4 single-index m=%d n=256 q=64 (BASELINE.json config 4), analytic Jacobian" % m_global,
+                      "rows_per_gpu": rows, "sharding": "row blocks; all-gather of R factors + all-reduce of linesearch sums (NCCL)",
+                      "l2": "[J | r] is %.1f GB per GPU, larger than L2" % (rows * (LARGE_N + 8) * 8 / 1e9)},
+           "phases_ms_per_factorisation": {"build_J_r": dst["build_ms"] / nfac, "tsqr": tsqr_ms},
+           "phases_ms_per_solve": {"linesearch_kernels": dst["linesearch_ms"] / args.large_steps,
+                                   "total": dst["solve_wall_ms"] / args.large_steps,
+                                   "factorisations": nfac / args.large_steps,
+                                   "linesearch_evals": dst["linesearch_evals"] / args.large_steps},
+           "gpu_launches": int(dst["launches"]),
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src, "kernel": "tsqr_panel_kernel + tsqr_trail_kernel (one TSQR of [J | r])",
+                        "kernel_ms": tsqr_ms, "algorithmic_flops_per_launch": flops / world,
+                        "note": "2 m (n+1)^2 flops per factorisation; trailing updates on mma.sync.m8n8k4.f64, panels on the FP64 FMA pipe"}}
+    # ---- end to end: W and y start in pinned HOST memory every step, result read back ---------------
+    if args.large_e2e_steps > 0:
+        W_h = torch.empty(W.shape, dtype=torch.float64).pin_memory()
+        y_h = torch.empty(y.shape, dtype=torch.float64).pin_memory()
+        W_h.copy_(W); y_h.copy_(y)
+        mod.close()
+        del W, y, mod
+        torch.cuda.empty_cache()
+        hm = E.LargeCnlsModel("single_index", x0, {"W": W_h.numpy(), "y": y_h.numpy(), "rho": rho}, m_global=m_global,
+                              device=local)
+        hm.join(rank, world)
+        E.solve(hm)
+        barrier()
+        t0 = time.perf_counter()
+        f0 = hm.stats()["factorisations"]
+        for _ in range(args.large_e2e_steps):
+            hm.set_data(0, W_h.numpy())          # H2D of the step's inputs inside the timed region
+            hm.set_data(1, y_h.numpy())
+            E.solve(hm)                          # x, f, exit code come back to host arrays
+        barrier()
+        it2 = int(hm.stats()["factorisations"] - f0) - args.large_e2e_steps
+        dt2 = time.perf_counter() - t0
+        t = torch.tensor([dt2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["e2e"] = {"value": it2 / float(t.item()), "unit": "iters/s",
+                      "h2d_bytes_per_step": int(rows * (LARGE_N + 1) * 8 + LARGE_N * 8), "d2h_bytes_per_step": LARGE_N * 8 + 8 + 16,
+                      "note": "per GPU; W (%.1f GB) and y copied from pinned host memory every step" % (rows * LARGE_N * 8 / 1e9)}
+        hm.close()
+    else:
+        mod.close()
+    return res
+
+
 def reference_arm(args):
     """`--impl reference`: the CPU implementation of the path on the host cores.
 
@@ -156,6 +305,11 @@ def reference_arm(args):
                                        "OpenMP over problems" % sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mean_iterations": float(np.mean(iters))}
+    if not args.skip_large:
+        lb = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
+        line["large"] = {"impl": "reference", "metric": LARGE_METRIC, "value": lb["value"], "unit": "iters/s",
+                         "higher_is_better": True, "cpu_baseline": lb,
+                         "config": {"workload": "C4 single-index m=%d n=256 q=64 (BASELINE.json config 4)" % args.large_rows}}
     print(json.dumps(line))
 
 
@@ -170,6 +324,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=60_000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-large", action="store_true", help="skip the large-Jacobian half of the metric (config 4)")
+    ap.add_argument("--large-rows", type=int, default=int(os.environ.get("ENLSIP_BENCH_LARGE_ROWS", 1 << 22)))
+    ap.add_argument("--large-steps", type=int, default=3)
+    ap.add_argument("--large-warmup", type=int, default=1)
+    ap.add_argument("--large-e2e-steps", type=int, default=1)
+    ap.add_argument("--large-cpu-rows", type=int, default=65536)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -272,6 +432,14 @@ def main():
     d2h = B * (6 * 8 + 8 + 4 * 4)
     same = bool(np.array_equal(hout["status"], status)) and bool(np.array_equal(hout["iters"], iters))
 
+    # ---- the other half of the metric: GN iterations/s of the large-Jacobian regime (config 4) -------
+    kernel_info = model.kernel_info()
+    large = None
+    if not args.skip_large:
+        del hmodel, model, y_d, S_d, x0_d, y_h, S_h, x0_h, x_h, f_h, out, hout
+        torch.cuda.empty_cache()
+        large = large_arm(args, torch, dist, E, rank, world, local, dev)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = ALG_BYTES_PER_SOLVE * B / (kms * 1e-3) / 1e9
@@ -290,8 +458,8 @@ def main():
                              "kernel_ms": kms, "algorithmic_bytes_per_solve": ALG_BYTES_PER_SOLVE,
                              "note": "fused whole-solve kernel: FP64-latency bound, not HBM bound (see DESIGN.md)"},
                 "quality": {"converged_fraction": conv, "mean_iterations": float(iters.mean()),
-                            "kernel_info": model.kernel_info()}}
-        if not args.skip_cpu:
+                            "kernel_info": kernel_info}}
+        if not args.skip_cpu and world == 1:      # cpu_baseline: rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             run, cit = cpu_port(args.cpu_sample, cores)
             run()
@@ -301,6 +469,11 @@ def main():
                                               "(oracle/hostport), OpenMP over problems; Enlsip.jl itself needs Julia, "
                                               "absent from this image" % args.cpu_sample,
                                     "mean_iterations": float(np.mean(cit))}
+        if large is not None:
+            if not args.skip_cpu and world == 1:
+                large["cpu_baseline"] = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
+            line["large"] = large
+            line["gpu_launches"] = int(launches) + large["gpu_launches"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

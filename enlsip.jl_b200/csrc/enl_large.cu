@@ -207,6 +207,7 @@ struct LargeHandle : LargeOps {
     const double* dW = nullptr;
     const double* dy = nullptr;
     double *ownW = nullptr, *owny = nullptr;
+    long long own_count[2] = {0, 0};
     double *dA = nullptr, *du = nullptr, *dr = nullptr, *ds = nullptr, *dv = nullptr, *dJp = nullptr;
     double *dx = nullptr, *dp = nullptr, *dT = nullptr, *dpart = nullptr, *dout = nullptr;
     double *dR = nullptr, *dStack = nullptr, *dR2 = nullptr;
@@ -418,8 +419,9 @@ int enlsipb200_large_set_data(enlsipb200_large hh, int slot, const double* ptr, 
     const double** dst = slot == 0 ? &h->dW : &h->dy;
     double** own = slot == 0 ? &h->ownW : &h->owny;
     if (on_device) { *dst = ptr; return 0; }
-    if (*own) { cudaFree(*own); *own = nullptr; }
-    LCU(cudaMalloc(own, sizeof(double) * (count > 0 ? count : 1)));
+    if (*own && h->own_count[slot] != count) { cudaFree(*own); *own = nullptr; }
+    if (!*own) LCU(cudaMalloc(own, sizeof(double) * (count > 0 ? count : 1)));
+    h->own_count[slot] = count;
     LCU(cudaMemcpy(*own, ptr, sizeof(double) * count, cudaMemcpyHostToDevice));
     *dst = *own;
     return 0;

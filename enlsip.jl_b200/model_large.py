@@ -52,20 +52,9 @@ class LargeCnlsModel:
                                                             1 if ineq else 0, rho.ctypes.data, self.x_low.ctypes.data,
                                                             self.x_upp.ctypes.data, device, ctypes.byref(h)))
         self._h = h
-        self._keep = []
-        for slot, arr in ((0, W), (1, y)):
-            dev = _is_torch(arr) and arr.is_cuda
-            if _is_torch(arr):
-                if not dev:
-                    raise ValueError("torch tensors must live on a CUDA device; pass numpy arrays for host buffers")
-                arr = arr.contiguous()
-                ptr, count = arr.data_ptr(), arr.numel()
-            else:
-                arr = np.ascontiguousarray(arr, dtype=np.float64)
-                ptr, count = arr.ctypes.data, arr.size
-            if dev:
-                self._keep.append(arr)
-            capi.check_large(capi.lib().enlsipb200_large_set_data(h, slot, ctypes.c_void_p(ptr), count, 1 if dev else 0))
+        self._keep = {}
+        self.set_data(0, W)
+        self.set_data(1, y)
         self.status_code = None
         self.sol = self.starting_point
         self.obj_value = None
@@ -74,6 +63,21 @@ class LargeCnlsModel:
         self.nb_active = None
         self.active = None
         self.trace = None
+
+    def set_data(self, slot, arr):
+        """Bind family data: slot 0 = W [rows, n], slot 1 = y [rows].  CUDA torch tensors are used in place
+        (zero copy); numpy arrays are copied host -> device by the library (reusing its buffer)."""
+        dev = _is_torch(arr) and arr.is_cuda
+        if _is_torch(arr):
+            if not dev:
+                raise ValueError("torch tensors must live on a CUDA device; pass numpy arrays for host buffers")
+            arr = arr.contiguous()
+            ptr, count = arr.data_ptr(), arr.numel()
+        else:
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            ptr, count = arr.ctypes.data, arr.size
+        self._keep[slot] = arr if dev else None
+        capi.check_large(capi.lib().enlsipb200_large_set_data(self._h, slot, ctypes.c_void_p(ptr), count, 1 if dev else 0))
 
     def join(self, rank, world, broadcast=None):
         """Join the row shards of `world` processes (one per GPU).  `broadcast(buf: np.uint8[128])` must

@@ -91,5 +91,5 @@ def gen_single_index(m, n, nb, seed=4, start=0, rows=None, ineq=False, chunk=1 <
         sl = slice(lo - c * chunk, hi - c * chunk)
         out = slice(lo - start, hi - start)
         W[out] = Wc[sl]
-        y[out] = np.tanh(Wc[sl] @ truth) + 0.01 * ec[sl]
+        y[out] = (np.tanh(Wc @ truth) + 0.01 * ec)[sl]      # whole-chunk product: a shard sees the same bits as the full run
     return dict(W=W, y=y, rho=rho, x0=x0, truth=truth)

@@ -19,32 +19,28 @@ using namespace enl_large;
 
 namespace {
 
+// collectives of the row-sharded run, supplied by the test (torch.distributed gloo) -- the CPU stand-ins for the
+// ncclAllGather / ncclAllReduce calls of enl_large.cu
+typedef void (*allgather_fn)(const double* send, double* recv, long long count);   // recv: world * count
+typedef void (*allreduce_fn)(double* buf, int count);                              // in-place sum
+
 struct CpuOps : LargeOps {
-    const double* W;    // m x n row major
+    const double* W;    // rows x n row major (this shard's rows)
     const double* y;
+    long long rows = 0;  // rows held here (== m when not sharded)
+    int world = 1;
+    allgather_fn ag = nullptr;
+    allreduce_fn ar = nullptr;
     SingleIndexConstraints sc;
     int nthreads = 1;
     std::vector<double> u, r, s, v, Jp;
 
     void eval_u(const double* x, std::vector<double>& out) const {
 #pragma omp parallel for num_threads(nthreads) schedule(static)
-        for (long long i = 0; i < m; ++i) out[i] = dot_n(W + (size_t)i * n, x, n);
+        for (long long i = 0; i < rows; ++i) out[i] = dot_n(W + (size_t)i * n, x, n);
     }
-    int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
-        const int nc = n + 1;
-        u.resize(m); r.resize(m); s.resize(m);
-        eval_u(x, u);
-        // augmented matrix [diag(s) W | r], column major for the Householder sweep
-        std::vector<double> M((size_t)m * nc);
-#pragma omp parallel for num_threads(nthreads) schedule(static)
-        for (long long i = 0; i < m; ++i) {
-            double th = enl::det_tanh(u[i]);
-            r[i] = th - y[i];
-            s[i] = 1.0 - th * th;
-            for (int j = 0; j < n; ++j) M[(size_t)j * m + i] = s[i] * W[(size_t)i * n + j];
-            M[(size_t)n * m + i] = r[i];
-        }
-        // unpivoted Householder QR (dgeqr2 order), R only
+    // unpivoted Householder QR (dgeqr2 order) of the column-major m x nc matrix M, in place (R in the upper triangle)
+    void qr_inplace(std::vector<double>& M, long long m, int nc) const {
         for (int i = 0; i < nc && i < m; ++i) {
             double* ci = M.data() + (size_t)i * m;
             double alpha = ci[i];
@@ -67,6 +63,36 @@ struct CpuOps : LargeOps {
                 }
             }
         }
+    }
+    int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
+        const int nc = n + 1;
+        long long m = rows;
+        u.resize(m); r.resize(m); s.resize(m);
+        eval_u(x, u);
+        // augmented matrix [diag(s) W | r], column major for the Householder sweep
+        std::vector<double> M((size_t)m * nc);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (long long i = 0; i < m; ++i) {
+            double th = enl::det_tanh(u[i]);
+            r[i] = th - y[i];
+            s[i] = 1.0 - th * th;
+            for (int j = 0; j < n; ++j) M[(size_t)j * m + i] = s[i] * W[(size_t)i * n + j];
+            M[(size_t)n * m + i] = r[i];
+        }
+        qr_inplace(M, m, nc);
+        if (world > 1) {
+            // row-sharded TSQR: all-gather the nc x nc factors, every rank re-factors the same stack
+            std::vector<double> Rl((size_t)nc * nc, 0.0), Rall((size_t)world * nc * nc);
+            for (int c = 0; c < nc; ++c)
+                for (int rr = 0; rr <= c && rr < m; ++rr) Rl[(size_t)rr * nc + c] = M[(size_t)c * m + rr];
+            ag(Rl.data(), Rall.data(), (long long)nc * nc);
+            m = (long long)world * nc;
+            M.assign((size_t)m * nc, 0.0);
+            for (int g = 0; g < world; ++g)
+                for (int rr = 0; rr < nc; ++rr)
+                    for (int c = rr; c < nc; ++c) M[(size_t)c * m + (size_t)g * nc + rr] = Rall[((size_t)g * nc + rr) * nc + c];
+            qr_inplace(M, m, nc);
+        }
         const int mt = n + 1;
         for (int c = 0; c < n; ++c)
             for (int rr = 0; rr < mt; ++rr) Jt[(size_t)c * mt + rr] = (rr <= c && rr < m) ? M[(size_t)c * m + rr] : 0.0;
@@ -76,6 +102,7 @@ struct CpuOps : LargeOps {
         return 0;
     }
     int set_direction(const double*, const double* p, double sums[3]) override {
+        const long long m = rows;
         v.resize(m); Jp.resize(m);
         eval_u(p, v);
         double a = 0, b = 0, c = 0;
@@ -85,19 +112,23 @@ struct CpuOps : LargeOps {
             a += r[i] * r[i]; b += r[i] * Jp[i]; c += Jp[i] * Jp[i];
         }
         sums[0] = a; sums[1] = b; sums[2] = c;
+        if (world > 1) ar(sums, 3);
         return 0;
     }
     int res_sq(double alpha, double* out) override {
+        const long long m = rows;
         double a = 0;
 #pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a)
         for (long long i = 0; i < m; ++i) {
             double ra = enl::det_tanh(__builtin_fma(alpha, v[i], u[i])) - y[i];
             a += ra * ra;
         }
+        if (world > 1) ar(&a, 1);
         *out = a;
         return 0;
     }
     int ls_coeffs(double alpha, double out[4]) override {
+        const long long m = rows;
         double a = 0, b = 0, c = 0, d = 0;
 #pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a, b, c, d)
         for (long long i = 0; i < m; ++i) {
@@ -106,6 +137,7 @@ struct CpuOps : LargeOps {
             a += ra * ra; b += r[i] * v2; c += Jp[i] * v2; d += v2 * v2;
         }
         out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+        if (world > 1) ar(out, 4);
         return 0;
     }
     int cons(const double* x, double* cx) override { sc.cons(x, cx); return 0; }
@@ -114,13 +146,16 @@ struct CpuOps : LargeOps {
 }  // namespace
 
 // Solve one single-index problem on the CPU.  trace: [trace_cap][16 + n] rows, layout of enlsip_b200.h.
-extern "C" int largeport_solve(int n, long long m, int nb, int ineq, const double* W, const double* y,
-                               const double* rho, const double* x_low, const double* x_upp, const double* x0,
-                               int max_iter, int scaling, double rel_tol, double x_tol, double c_tol, double* x,
-                               double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
-                               double* trace, int trace_cap, int nthreads) {
+// Row-sharded variant (world > 1): W / y hold `rows` of the m_global rows; `ag` / `ar` are the collectives.
+extern "C" int largeport_solve_sharded(int n, long long m, long long rows, int world, allgather_fn ag, allreduce_fn ar,
+                                       int nb, int ineq, const double* W, const double* y,
+                                       const double* rho, const double* x_low, const double* x_upp, const double* x0,
+                                       int max_iter, int scaling, double rel_tol, double x_tol, double c_tol, double* x,
+                                       double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
+                                       double* trace, int trace_cap, int nthreads) {
     CpuOps ops;
-    ops.n = n; ops.m = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
+    ops.n = n; ops.m = m; ops.rows = rows; ops.world = world; ops.ag = ag; ops.ar = ar;
+    ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
     ops.sc.n = n; ops.sc.nb = nb; ops.sc.ineq = ineq != 0;
     ops.sc.rho.assign(rho, rho + nb);
     ops.sc.set_bounds(x_low, x_upp);
@@ -148,12 +183,22 @@ extern "C" int largeport_solve(int n, long long m, int nb, int ineq, const doubl
     return 0;
 }
 
+extern "C" int largeport_solve(int n, long long m, int nb, int ineq, const double* W, const double* y,
+                               const double* rho, const double* x_low, const double* x_upp, const double* x0,
+                               int max_iter, int scaling, double rel_tol, double x_tol, double c_tol, double* x,
+                               double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
+                               double* trace, int trace_cap, int nthreads) {
+    return largeport_solve_sharded(n, m, m, 1, nullptr, nullptr, nb, ineq, W, y, rho, x_low, x_upp, x0, max_iter, scaling,
+                                   rel_tol, x_tol, c_tol, x, f, exit_code, status, iters, nact, active, trace, trace_cap,
+                                   nthreads);
+}
+
 // One Gauss-Newton iteration's dominant work on the CPU (the reference's `new_point!` + QR of J): used by
 // bench.py as the large-regime cpu_baseline.  Returns seconds through *secs.
 extern "C" int largeport_new_point(int n, long long m, const double* W, const double* y, const double* x, int nthreads,
                                    double* rho_out) {
     CpuOps ops;
-    ops.n = n; ops.m = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
+    ops.n = n; ops.m = m; ops.rows = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
     ops.sc.n = n; ops.sc.nb = 0;
     std::vector<double> Jt((size_t)(n + 1) * n), rt(n + 1), cx(1), A(1);
     ops.l = 0; ops.q = 0;
