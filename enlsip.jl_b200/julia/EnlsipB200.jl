@@ -12,7 +12,7 @@
 # the tests exercise.
 module EnlsipB200
 
-export CnlsModel, solve!, status, solution, sum_sq_residuals, total_nb_constraints, dict_status_codes
+export CnlsModel, LargeCnlsModel, solve!, status, solution, sum_sq_residuals, total_nb_constraints, dict_status_codes
 
 const libenlsip = get(ENV, "ENLSIP_B200_LIB", joinpath(@__DIR__, "..", "lib", "libenlsip_b200.so"))
 
@@ -120,5 +120,80 @@ status(model::CnlsModel) = [dict_status_codes[Int(c)] for c in model.status_code
 solution(model::CnlsModel) = model.sol                                                # cnls_model.jl:213
 sum_sq_residuals(model::CnlsModel) = model.obj_value                                  # cnls_model.jl:221
 total_nb_constraints(model::CnlsModel) = model.nb_constraints                         # cnls_model.jl:238
+
+# ---------------------------------------------------------------------------------------------------
+# Large-Jacobian regime (one problem, m >> n; include/enlsip_b200.h, "Large-Jacobian regime"):
+# the same `solve!` / `status` / `solution` / `sum_sq_residuals` surface for B = 1.
+# ---------------------------------------------------------------------------------------------------
+const FAMILY_SINGLE_INDEX = Cint(16)
+
+mutable struct LargeCnlsModel{T<:AbstractFloat}
+    handle::Ptr{Cvoid}
+    nb_parameters::Int
+    nb_residuals::Int               # global m (all row shards)
+    nb_eqcons::Int
+    nb_constraints::Int
+    starting_point::Vector{T}
+    status_code::Base.RefValue{Cint}
+    exit_code::Base.RefValue{Cint}
+    sol::Vector{T}
+    obj_value::Base.RefValue{T}
+    iterations::Base.RefValue{Cint}
+    nb_active::Base.RefValue{Cint}
+    active::Vector{Cint}
+end
+
+"""
+    LargeCnlsModel(:single_index, starting_point; W, y, rho, ineq=false, x_low, x_upp, m_global=size(W,2))
+
+`W` is `n x rows` (column major = the ABI's row-major `[rows, n]`), `y` has `rows` entries: the rows held by THIS
+process (a row shard when `m_global > rows`).  Constraints: `rho[k]` for the k-th block of 4 parameters
+(equalities, or inequalities with `ineq=true`), plus finite bounds -- ordered as cnls_model.jl:402-403.
+"""
+function LargeCnlsModel(family::Symbol, starting_point::Vector{Float64}; W::Matrix{Float64}, y::Vector{Float64},
+                        rho::Vector{Float64}, ineq::Bool=false, x_low=fill(-Inf, length(starting_point)),
+                        x_upp=fill(Inf, length(starting_point)), m_global::Integer=size(W, 2), device::Integer=-1)
+    family === :single_index || error("A device problem family must be provided")
+    n, rows = length(starting_point), size(W, 2)
+    @assert size(W, 1) == n && length(y) == rows "W must be n x rows and y of length rows"
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    checkl(ccall((:enlsipb200_large_create, libenlsip), Cint,
+                 (Cint, Cint, Clonglong, Clonglong, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Ptr{Cvoid}}),
+                 FAMILY_SINGLE_INDEX, n, rows, m_global, length(rho), ineq, rho, x_low, x_upp, Cint(device), h))
+    for (slot, arr) in ((0, W), (1, y))
+        checkl(ccall((:enlsipb200_large_set_data, libenlsip), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint),
+                     h[], Cint(slot), arr, length(arr), Cint(0)))
+    end
+    l = length(rho) + count(isfinite, x_low) + count(isfinite, x_upp)
+    model = LargeCnlsModel{Float64}(h[], n, m_global, ineq ? 0 : length(rho), l, starting_point, Ref(Cint(0)), Ref(Cint(0)),
+                                    copy(starting_point), Ref(NaN), Ref(Cint(0)), Ref(Cint(0)), zeros(Cint, max(l, 1)))
+    finalizer(m -> ccall((:enlsipb200_large_destroy, libenlsip), Cint, (Ptr{Cvoid},), m.handle), model)
+    return model
+end
+
+checkl(rc) = rc == 0 ? nothing :
+    error("enlsip_b200 (large regime) error $rc: ", unsafe_string(ccall((:enlsipb200_large_last_error, libenlsip), Cstring, ())))
+
+"Join the row shards of `nranks` processes (one per GPU): `id` is the 128-byte NCCL id made by rank 0 (`large_comm_id()`), distributed by the caller (MPI.jl / Distributed)."
+large_comm_id() = (id = zeros(UInt8, 128); checkl(ccall((:enlsipb200_large_comm_id, libenlsip), Cint, (Ptr{UInt8},), id)); id)
+join!(model::LargeCnlsModel, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    checkl(ccall((:enlsipb200_large_comm_init, libenlsip), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), model.handle, id, rank, nranks))
+
+function solve!(model::LargeCnlsModel; silent::Bool=true, max_iter::Int=100, scaling::Bool=false, time_limit::Float64=1e3,
+                abs_tol::Float64=eps(Float64), rel_tol::Float64=sqrt(abs_tol), c_tol::Float64=rel_tol, x_tol::Float64=rel_tol)
+    opt = Ref(Options(max_iter, scaling, JAC_ANALYTIC, 0, time_limit, abs_tol, rel_tol, c_tol, x_tol))
+    checkl(ccall((:enlsipb200_large_solve, libenlsip), Cint,
+                 (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
+                  Ptr{Cint}, Ptr{Cdouble}, Cint),
+                 model.handle, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,
+                 model.iterations, model.nb_active, model.active, C_NULL, Cint(0)))
+    silent || println("exit code ", model.exit_code[], " after ", model.iterations[], " iterations")
+    return
+end
+
+status(model::LargeCnlsModel) = dict_status_codes[Int(model.status_code[])]
+solution(model::LargeCnlsModel) = model.sol
+sum_sq_residuals(model::LargeCnlsModel) = model.obj_value[]
+total_nb_constraints(model::LargeCnlsModel) = model.nb_constraints
 
 end # module
