@@ -25,6 +25,7 @@
 #include "enl_large_family.h"
 #include "enl_large_host.h"
 #include "enl_tsqr.cuh"
+#include "enl_dense.cuh"
 
 using namespace enl_large;
 
@@ -194,11 +195,142 @@ __global__ void li_finish_kernel(const double* __restrict__ part, int nparts, do
     if (lane == 0) out[k] = t;
 }
 
+// R (row major, leading dimension ld, upper triangle valid) -> column-major nc x nc with explicit zeros below the
+// diagonal: the layout of the compressed problem [J~ | r~] the host driver and enl_dense.cuh work on
+__global__ void r_to_colmajor_kernel(const double* __restrict__ R, int ld, int nc, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < nc && c < nc && r <= c) ? R[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < nc && c < nc) out[(size_t)c * nc + r] = tile[threadIdx.x][i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // device implementation of LargeOps
 // ---------------------------------------------------------------------------------------------
-struct LargeHandle : LargeOps {
+// Work below this many matrix entries stays on the host (launch latency of 2 kernels per column dominates)
+constexpr long long DENSE_ACCEL_MIN = 384LL * 384LL;
+
+struct LargeHandle : LargeOps, DenseAccel {
     int device = 0;
+    // ---- DenseAccel: device QRCP / M*Q of the compressed problem when it is large (config 5) ----
+    double *dq_f = nullptr, *dq_m = nullptr, *dq_small = nullptr;
+    int* dq_p = nullptr;
+    size_t dq_f_cap = 0, dq_m_cap = 0, dq_small_cap = 0, dq_p_cap = 0;
+    long long n_dev_qrcp = 0, n_dev_mulq = 0;
+    double ms_dense = 0;
+    bool grow(double** p, size_t* cap, size_t want) {
+        if (*cap >= want) return true;
+        if (*p) cudaFree(*p);
+        *p = nullptr; *cap = 0;
+        if (cudaMalloc(p, sizeof(double) * want) != cudaSuccess) return false;
+        *cap = want;
+        return true;
+    }
+    bool qrcp(double* f, int rows, int cols, double* tau, int* jpvt) override {
+        if ((long long)rows * cols < DENSE_ACCEL_MIN) return false;
+        auto t0 = std::chrono::steady_clock::now();
+        const int k = rows < cols ? rows : cols;
+        if (cudaSetDevice(device) != cudaSuccess) return false;
+        if (!grow(&dq_f, &dq_f_cap, (size_t)rows * cols)) return false;
+        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * cols + enl_dense::MULQ_CHUNKS * (size_t)(rows + 1))) return false;
+        if (dq_p_cap < (size_t)cols) {
+            if (dq_p) cudaFree(dq_p);
+            dq_p = nullptr; dq_p_cap = 0;
+            if (cudaMalloc(&dq_p, sizeof(int) * cols) != cudaSuccess) return false;
+            dq_p_cap = cols;
+        }
+        double* dtau = dq_small;            // [cols]
+        double* dvn = dq_small + cols;      // [2 cols]
+        bool ok = cudaMemcpyAsync(dq_f, f, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        launches += enl_dense::qrcp_device(dq_f, rows, cols, dtau, dq_p, dvn, st);
+        ok = ok && cudaMemcpyAsync(f, dq_f, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(jpvt, dq_p, sizeof(int) * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        if (!ok) throw std::runtime_error("device QRCP failed");
+        ++n_dev_qrcp;
+        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+    bool jq1(const double* fA, int nq, int k, const double* tauA, double* JQ1_host, int mr, int ncols_host) override {
+        if ((long long)mr * nq < DENSE_ACCEL_MIN || nq != n || mr != n + 1) return false;
+        auto t0 = std::chrono::steady_clock::now();
+        if (cudaSetDevice(device) != cudaSuccess) return false;
+        if (!grow(&dq_m, &dq_m_cap, (size_t)mr * nq)) return false;
+        if (k > 0 && !grow(&dq_f, &dq_f_cap, (size_t)nq * k)) return false;
+        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * (k + 1) + enl_dense::MULQ_CHUNKS * (size_t)(mr + 1))) return false;
+        double* dtau = dq_small;
+        double* dw = dq_small + 3 * (size_t)(k + 1);
+        bool ok = cudaMemcpyAsync(dq_m, dJc, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+        if (k > 0) {
+            ok = ok && cudaMemcpyAsync(dq_f, fA, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(dtau, tauA, sizeof(double) * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            launches += enl_dense::mulq_device(dq_m, mr, nq, dq_f, nq, k, dtau, dw, st);
+        }
+        if (ncols_host > 0)
+            ok = ok && cudaMemcpyAsync(JQ1_host, dq_m, sizeof(double) * (size_t)mr * ncols_host, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        if (!ok) throw std::runtime_error("device J*Q1 failed");
+        jq1_resident = true;
+        ++n_dev_mulq;
+        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+    bool qrcp_tail(int c0, int rows, int cols, double* f_host, double* tau, int* jpvt) override {
+        if (!jq1_resident || rows != n + 1 || c0 + cols != n) return false;
+        auto t0 = std::chrono::steady_clock::now();
+        const int k = rows < cols ? rows : cols;
+        if (cudaSetDevice(device) != cudaSuccess) return false;
+        if (!grow(&dq_f, &dq_f_cap, (size_t)rows * cols)) return false;
+        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * cols + enl_dense::MULQ_CHUNKS * (size_t)(rows + 1))) return false;
+        if (dq_p_cap < (size_t)cols) {
+            if (dq_p) cudaFree(dq_p);
+            dq_p = nullptr; dq_p_cap = 0;
+            if (cudaMalloc(&dq_p, sizeof(int) * cols) != cudaSuccess) return false;
+            dq_p_cap = cols;
+        }
+        double* dtau = dq_small;
+        double* dvn = dq_small + cols;
+        bool ok = cudaMemcpyAsync(dq_f, dq_m + (size_t)c0 * rows, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+        launches += enl_dense::qrcp_device(dq_f, rows, cols, dtau, dq_p, dvn, st);
+        ok = ok && cudaMemcpyAsync(f_host, dq_f, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(jpvt, dq_p, sizeof(int) * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        if (!ok) throw std::runtime_error("device QRCP (tail) failed");
+        ++n_dev_qrcp;
+        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+    bool mul_Q(const double* f, int nq, int k, const double* tau, double* M, int mr) override {
+        if ((long long)mr * nq < DENSE_ACCEL_MIN || k < 16) return false;
+        auto t0 = std::chrono::steady_clock::now();
+        if (cudaSetDevice(device) != cudaSuccess) return false;
+        if (!grow(&dq_f, &dq_f_cap, (size_t)nq * k)) return false;
+        if (!grow(&dq_m, &dq_m_cap, (size_t)mr * nq)) return false;
+        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * k + enl_dense::MULQ_CHUNKS * (size_t)(mr + 1))) return false;
+        jq1_resident = false;                     // dq_m is overwritten
+        double* dtau = dq_small;                  // [k]
+        double* dw = dq_small + 3 * (size_t)k;    // [16 mr]
+        bool ok = cudaMemcpyAsync(dq_f, f, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(dtau, tau, sizeof(double) * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(dq_m, M, sizeof(double) * (size_t)mr * nq, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        launches += enl_dense::mulq_device(dq_m, mr, nq, dq_f, nq, k, dtau, dw, st);
+        ok = ok && cudaMemcpyAsync(M, dq_m, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        if (!ok) throw std::runtime_error("device M*Q failed");
+        ++n_dev_mulq;
+        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+
     long long m_local = 0, rows_pad = 0;
     int ld = 0, rr_rows = 0;
     SingleIndexConstraints sc;
@@ -211,7 +343,9 @@ struct LargeHandle : LargeOps {
     double *dA = nullptr, *du = nullptr, *dr = nullptr, *ds = nullptr, *dv = nullptr, *dJp = nullptr;
     double *dx = nullptr, *dp = nullptr, *dT = nullptr, *dpart = nullptr, *dout = nullptr;
     double *dR = nullptr, *dStack = nullptr, *dR2 = nullptr;
-    std::vector<double> hR;
+    double* dJc = nullptr;          // [J~ | r~] column major (n+1) x (n+1): stays resident for enl_dense.cuh
+    bool jq1_resident = false;      // dq_m holds J~ * Q1 of the current working set
+    std::vector<double> hR;         // host copy of dJc
     // comm
     NcclApi::Comm comm = nullptr;
     int rank = 0, nranks = 1;
@@ -224,8 +358,12 @@ struct LargeHandle : LargeOps {
     ~LargeHandle() override { release(); }
     void release() {
         cudaSetDevice(device);
-        for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2})
+        for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2, dq_f, dq_m, dq_small, dJc})
             if (p) cudaFree(p);
+        if (dq_p) cudaFree(dq_p);
+        dq_p = nullptr;
+        dq_f = dq_m = dq_small = dJc = nullptr;
+        dq_f_cap = dq_m_cap = dq_small_cap = dq_p_cap = 0;
         ownW = owny = dA = du = dr = ds = dv = dJp = dx = dp = dT = dpart = dout = dR = dStack = dR2 = nullptr;
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -255,7 +393,8 @@ struct LargeHandle : LargeOps {
         LCU(cudaMalloc(&dpart, sizeof(double) * LI_PARTS * 4));
         LCU(cudaMalloc(&dout, sizeof(double) * 8));
         LCU(cudaMalloc(&dR, sizeof(double) * rr_rows * ld));
-        hR.resize((size_t)rr_rows * ld);
+        LCU(cudaMalloc(&dJc, sizeof(double) * (size_t)(n + 1) * (n + 1)));
+        hR.resize((size_t)(n + 1) * (n + 1));
         return 0;
     }
     int grid_rows() const {   // CTAs for the warp-per-row kernels
@@ -277,7 +416,7 @@ struct LargeHandle : LargeOps {
     int cur_parts = LI_PARTS;
 
     // factor [J | r] at x into hR (row major (n+1) x ld), identical on every rank
-    int factor_at(const double* x) {
+    int factor_at(const double* x, bool want_host_R = true) {
         LCU(cudaSetDevice(device));
         LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         LCU(cudaEventRecord(e0, st));
@@ -296,8 +435,15 @@ struct LargeHandle : LargeOps {
             launches += tsqr_factor(dStack, ld, (long long)nranks * rr_rows, n, dR2, ld, dT, dpart, st);
             dfinal = dR2;
         }
+        {
+            const int nc = n + 1;
+            dim3 grid((nc + 31) / 32, (nc + 31) / 32), block(32, 8);
+            r_to_colmajor_kernel<<<grid, block, 0, st>>>(dfinal, ld, nc, dJc);
+            ++launches;
+        }
+        jq1_resident = false;
         LCU(cudaEventRecord(e2, st));
-        LCU(cudaMemcpyAsync(hR.data(), dfinal, sizeof(double) * (n + 1) * ld, cudaMemcpyDeviceToHost, st));
+        if (want_host_R) LCU(cudaMemcpyAsync(hR.data(), dJc, sizeof(double) * (size_t)(n + 1) * (n + 1), cudaMemcpyDeviceToHost, st));
         LCU(cudaStreamSynchronize(st));
         LCU(cudaGetLastError());
         LCU(cudaEventElapsedTime(&last_build_ms, e0, e1));
@@ -310,12 +456,12 @@ struct LargeHandle : LargeOps {
 
     // ---- LargeOps ----
     int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
-        int rc = factor_at(x);
+        int rc = factor_at(x, false);
         if (rc != 0) return rc;
-        const int mt = n + 1;
-        for (int c = 0; c < n; ++c)
-            for (int r = 0; r < mt; ++r) Jt[(size_t)c * mt + r] = (r <= c) ? hR[(size_t)r * ld + c] : 0.0;
-        for (int r = 0; r < mt; ++r) rt[r] = hR[(size_t)r * ld + n];
+        const size_t mt = (size_t)n + 1;
+        LCU(cudaMemcpyAsync(Jt, dJc, sizeof(double) * mt * n, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(rt, dJc + mt * n, sizeof(double) * mt, cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
         sc.cons(x, cx);
         sc.jac(x, A);
         return 0;
@@ -469,13 +615,16 @@ int enlsipb200_large_solve(enlsipb200_large hh, const double* x0, const enlsipb2
     opt.eps_x = (o->x_tol == o->x_tol) ? o->x_tol : rel_tol;
     auto t0 = std::chrono::steady_clock::now();
     LargeResult R;
+    dense_accel() = h;        // large compressed problems (n >= 384) factor on the device (enl_dense.cuh)
     try {
         LargeSolver S(*h, opt);
         R = S.solve(x0, trace != nullptr && trace_cap > 0);
     } catch (const std::exception& e) {
+        dense_accel() = nullptr;
         if (g_lerr.empty()) g_lerr = e.what();
         return ENLSIPB200_ECUDA;
     }
+    dense_accel() = nullptr;
     double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     h->ms_total += total;
     memcpy(x, R.x.data(), sizeof(double) * h->n);
@@ -510,7 +659,7 @@ int enlsipb200_large_factor(enlsipb200_large hh, const double* x, double* R, flo
     const int nc = h->n + 1;
     if (R)
         for (int r = 0; r < nc; ++r)
-            for (int c = 0; c < nc; ++c) R[(size_t)r * nc + c] = (c >= r) ? h->hR[(size_t)r * h->ld + c] : 0.0;
+            for (int c = 0; c < nc; ++c) R[(size_t)r * nc + c] = h->hR[(size_t)c * nc + r];
     if (build_ms) *build_ms = h->last_build_ms;
     if (tsqr_ms) *tsqr_ms = h->last_tsqr_ms;
     return 0;
@@ -519,9 +668,9 @@ int enlsipb200_large_factor(enlsipb200_large hh, const double* x, double* R, flo
 int enlsipb200_large_stats(enlsipb200_large hh, double* out, int count) {
     LargeHandle* h = LH(hh);
     if (!h || !out) return lfail(ENLSIPB200_EINVAL, "NULL argument");
-    double v[8] = {(double)h->n_newpoint, h->ms_build, h->ms_tsqr, h->ms_ls, h->ms_total, (double)h->n_ls,
-                   (double)h->launches, (double)h->rows_pad};
-    for (int i = 0; i < count && i < 8; ++i) out[i] = v[i];
+    double v[11] = {(double)h->n_newpoint, h->ms_build, h->ms_tsqr, h->ms_ls, h->ms_total, (double)h->n_ls,
+                    (double)h->launches, (double)h->rows_pad, (double)h->n_dev_qrcp, (double)h->n_dev_mulq, h->ms_dense};
+    for (int i = 0; i < count && i < 11; ++i) out[i] = v[i];
     return 0;
 }
 

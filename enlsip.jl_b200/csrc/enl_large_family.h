@@ -46,9 +46,14 @@ struct SingleIndexConstraints {
         for (size_t i = 0; i < up_idx.size(); ++i) c[o++] = up_val[i] - x[up_idx[i]];
     }
     // A: l x n column major
+    // The sparsity pattern is fixed, so a buffer that was filled by the previous call (same address) only needs its
+    // structural non-zeros rewritten; anything else (a fresh zero-initialised Mat included) gets the full fill.
+    mutable const double* last_A = nullptr;
     void jac(const double* x, double* A) const {
         int L = l();
-        for (size_t i = 0; i < (size_t)L * n; ++i) A[i] = 0.0;
+        if (A != last_A)
+            for (size_t i = 0; i < (size_t)L * n; ++i) A[i] = 0.0;
+        last_A = A;
         for (int k = 0; k < nb; ++k)
             for (int j = 0; j < 4; ++j) {
                 double v = 2.0 * x[4 * k + j];

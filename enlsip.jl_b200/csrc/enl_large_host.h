@@ -24,6 +24,8 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -81,6 +83,52 @@ inline double norm_range(const Vec& v, int k) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Optional device acceleration of the two O(n^3) primitives below (enl_dense.cuh).  When the compressed problem
+// is itself large (config 5: n = 4096) the product installs an accelerator; the CPU test backend never does.
+// Both calls return false when they decline (small matrix), and the host code path runs.
+// ------------------------------------------------------------------------------------------
+// Wall-clock profile of the host driver (development aid, printed when ENLSIP_PROF is set)
+struct HostProf {
+    static constexpr int N = 16;
+    double ms[N] = {0};
+    long long calls[N] = {0};
+    const char* names[N] = {"new_point", "gather_active", "factor_A", "factor_L11", "ensure_JQ1", "gn_search_direction",
+                            "first_lagrange", "second_lagrange", "update_working_set", "search_direction_analys",
+                            "compute_steplength", "upper_bound_steplength", "evaluate_violated", "termination", "compute_gradf", "other"};
+    void dump() const {
+        for (int i = 0; i < N; ++i)
+            if (calls[i]) fprintf(stderr, "  [enlsip host prof] %-26s %6lld calls %10.2f ms\n", names[i], calls[i], ms[i]);
+    }
+};
+inline HostProf& host_prof() { static thread_local HostProf p; return p; }
+struct ProfScope {
+    int id;
+    std::chrono::steady_clock::time_point t0;
+    explicit ProfScope(int i) : id(i), t0(std::chrono::steady_clock::now()) {}
+    ~ProfScope() {
+        host_prof().ms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        host_prof().calls[id]++;
+    }
+};
+
+struct DenseAccel {
+    virtual ~DenseAccel() {}
+    // f: rows x cols column major, factored in place; tau [min(rows, cols)]; jpvt [cols], 0-based
+    virtual bool qrcp(double* f, int rows, int cols, double* tau, int* jpvt) = 0;
+    // M (mr x nq, column major) <- M * Q, Q = H(0) ... H(k-1) stored in f (nq x k, column major) / tau
+    virtual bool mul_Q(const double* f, int nq, int k, const double* tau, double* M, int mr) = 0;
+    // Device-resident variants: the compressed Jacobian J~ ((n+1) x n) of the last new_point never left the device.
+    //   jq1:       JQ1 = J~ * Q (kept on the device); its leading `ncols_host` columns are copied to JQ1_host
+    //   qrcp_tail: QRCP of the columns c0.. of that device-resident JQ1 ((n+1) x (n - c0)), factors to f_host
+    virtual bool jq1(const double* fA, int nq, int k, const double* tauA, double* JQ1_host, int mr, int ncols_host) = 0;
+    virtual bool qrcp_tail(int c0, int rows, int cols, double* f_host, double* tau, int* jpvt) = 0;
+};
+inline DenseAccel*& dense_accel() {
+    static thread_local DenseAccel* a = nullptr;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
 // qr(M, ColumnNorm()) = LAPACK dgeqp3 (restated as the unblocked dlaqp2: first-max pivot, dlarfg
 // with beta = -sign(alpha)*dlapy2, partial-norm downdate with the tol3z recompute rule)
 // ------------------------------------------------------------------------------------------
@@ -95,6 +143,7 @@ struct QRP {
         rows = M.rows; cols = M.cols; k = std::min(rows, cols);
         tau.assign(k, 0.0);
         p.resize(cols);
+        if (dense_accel() && k > 0 && dense_accel()->qrcp(f.a.data(), rows, cols, tau.data(), p.data())) return;
         Vec vn1(cols), vn2(cols);
         for (int j = 0; j < cols; ++j) {
             p[j] = j;
@@ -156,6 +205,15 @@ struct QRP {
             }
         }
     }
+    // QRCP of the columns c0.. of the device-resident J*Q1 (DenseAccel::qrcp_tail); false -> caller uses factor()
+    bool factor_device_tail(int c0, int rows_, int cols_) {
+        if (!dense_accel() || cols_ <= 0) return false;
+        f = Mat(rows_, cols_);
+        rows = rows_; cols = cols_; k = std::min(rows, cols);
+        tau.assign(k, 0.0);
+        p.resize(cols);
+        return dense_accel()->qrcp_tail(c0, rows, cols, f.a.data(), tau.data(), p.data());
+    }
     double R(int r, int c) const { return (r <= c) ? f(r, c) : 0.0; }
     double diag(int i) const { return f(i, i); }
     std::vector<int> invperm() const {
@@ -189,6 +247,7 @@ struct QRP {
     // reflector is a rank-one update of the columns i.. of M
     void mul_Q(Mat& M) const {
         const int mr = M.rows;
+        if (dense_accel() && k > 0 && dense_accel()->mul_Q(f.a.data(), rows, k, tau.data(), M.a.data(), mr)) return;
         Vec w(mr);
         for (int i = 0; i < k; ++i) {
             double ti = tau[i];
@@ -356,22 +415,23 @@ public:
     // ---- small helpers ------------------------------------------------------------------
     void check(int rc) { if (rc != 0) throw std::runtime_error("LargeOps failure"); }
 
-    void do_new_point(const Vec& x) {   // EF:34-52
+    void do_new_point(const Vec& x) { ProfScope prof_(0);   // EF:34-52
         check(ops.new_point(x.data(), J.a.data(), rx.data(), cx.data(), A.a.data()));
         ++n_new_point;
         jq1_valid = false;
     }
-    void compute_gradf() {   // J' * rx
+    void compute_gradf() { ProfScope prof_(14);   // J' * rx
         for (int j = 0; j < n; ++j) gradf[j] = dot_n(J.col(j), rx.data(), mt);
     }
-    void gather_active() {   // C.cx = cx[active], C.A = A[active, :]
+    void gather_active() { ProfScope prof_(1);   // C.cx = cx[active], C.A = A[active, :]
         int t = W.t;
         C.cx.resize(t);
         C.A = Mat(t, n);
-        for (int i = 0; i < t; ++i) {
-            int k = W.active[i] - 1;
-            C.cx[i] = cx[k];
-            for (int j = 0; j < n; ++j) C.A(i, j) = A(k, j);
+        for (int i = 0; i < t; ++i) C.cx[i] = cx[W.active[i] - 1];
+        for (int j = 0; j < n; ++j) {
+            const double* aj = A.col(j);
+            double* cj = C.A.col(j);
+            for (int i = 0; i < t; ++i) cj[i] = aj[W.active[i] - 1];
         }
     }
     void evaluate_scaling() {   // structures.jl:160-178
@@ -390,7 +450,7 @@ public:
             }
         }
     }
-    void factor_A() {   // F_A = qr(C.A', ColumnNorm())
+    void factor_A() { ProfScope prof_(2);   // F_A = qr(C.A', ColumnNorm())
         int t = C.A.rows;
         Mat At(n, t);
         for (int i = 0; i < t; ++i)
@@ -398,17 +458,29 @@ public:
         F_A.factor(At);
         jq1_valid = false;
     }
-    void factor_L11() {   // F_L11 = qr(F_A.R', ColumnNorm()); F_A.R is min(n,t) x t
+    void factor_L11() { ProfScope prof_(3);   // F_L11 = qr(F_A.R', ColumnNorm()); F_A.R is min(n,t) x t
         int kr = F_A.k, t = F_A.cols;
         Mat Rt(t, kr);
         for (int r = 0; r < kr; ++r)
             for (int c = 0; c < t; ++c) Rt(c, r) = F_A.R(r, c);
         F_L11.factor(Rt);
     }
-    void ensure_JQ1() {
+    bool jq1_on_device = false;   // JQ1 lives on the device; the host copy holds only its leading min(t, n) columns
+    void ensure_JQ1() { ProfScope prof_(4);
         if (!jq1_valid) {
-            JQ1 = J;
-            F_A.mul_Q(JQ1);
+            const int lead = std::min(F_A.cols, n);
+            jq1_on_device = false;
+            if (dense_accel()) {
+                Mat lead_cols(mt, lead);
+                if (dense_accel()->jq1(F_A.f.a.data(), F_A.rows, F_A.k, F_A.tau.data(), lead_cols.a.data(), mt, lead)) {
+                    JQ1 = std::move(lead_cols);
+                    jq1_on_device = true;
+                }
+            }
+            if (!jq1_on_device) {
+                JQ1 = J;
+                F_A.mul_Q(JQ1);
+            }
             jq1_valid = true;
         }
     }
@@ -478,12 +550,15 @@ public:
     }
 
     // EF:206-234
-    void gn_search_direction(int rankA, int t, IterL& it, Vec& p_gn) {
+    void gn_search_direction(int rankA, int t, IterL& it, Vec& p_gn) { ProfScope prof_(5);
         int code = (rankA == t) ? 1 : -1;
         ensure_JQ1();
-        Mat J2(mt, n - rankA);
-        for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
-        F_J2.factor(J2);
+        if (!(jq1_on_device && F_J2.factor_device_tail(rankA, mt, n - rankA))) {
+            if (jq1_on_device) throw std::runtime_error("device-resident J*Q1 lost");
+            Mat J2(mt, n - rankA);
+            for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
+            F_J2.factor(J2);
+        }
         int rankJ2 = pseudo_rank(F_J2, opt.eps_rank);
         Vec b, d;
         sub_search_direction(t, rankA, rankA, rankJ2, code, p_gn, b, d);
@@ -496,7 +571,7 @@ public:
     }
 
     // EF:461-508
-    void first_lagrange_mult_estimate(Vec& lam, IterL& it) {
+    void first_lagrange_mult_estimate(Vec& lam, IterL& it) { ProfScope prof_(6);
         int t = C.A.rows;
         std::vector<int> inv_p = F_A.invperm();
         int prankA = pseudo_rank(F_A, opt.eps_rank);
@@ -520,7 +595,7 @@ public:
     }
 
     // EF:514-537
-    void second_lagrange_mult_estimate(Vec& lam, const Vec& p_gn, int t) {
+    void second_lagrange_mult_estimate(Vec& lam, const Vec& p_gn, int t) { ProfScope prof_(7);
         int prankA = pseudo_rank(F_A, SQRT_EPS);
         ensure_JQ1();
         // b = J1' (rx + J p_gn), J1 = JQ1[:, 0:t]
@@ -578,7 +653,7 @@ public:
     }
 
     // EF:608-650
-    bool evaluate_violated_constraints(int index_alpha_upp) {
+    bool evaluate_violated_constraints(int index_alpha_upp) { ProfScope prof_(12);
         const double eps_ = SQRT_EPS, delta = 0.1;
         int bnd = std::min(W.l, n);
         bool added = false;
@@ -614,7 +689,7 @@ public:
     }
 
     // EF:686-795 (first-order deletion detour skipped: it is always reverted)
-    void update_working_set(IterL& it, Vec& p_gn) {
+    void update_working_set(IterL& it, Vec& p_gn) { ProfScope prof_(8);
         Vec lam;
         factor_A();
         first_lagrange_mult_estimate(lam, it);
@@ -863,7 +938,7 @@ public:
     }
 
     // EF:1191-1291
-    int search_direction_analys(const IterL& prev, IterL& cur, int iter_number, double active_cx_sum, const Vec& p_gn) {
+    int search_direction_analys(const IterL& prev, IterL& cur, int iter_number, double active_cx_sum, const Vec& p_gn) { ProfScope prof_(9);
         double rx_sum = dotv(rx, rx);
         double nrm_b1_gn = norm_range(cur.b_gn, cur.dimA);
         int rankA = cur.rankA;
@@ -1320,17 +1395,24 @@ public:
     }
 
     // EF:2149-2178
-    double upper_bound_steplength(const Vec& p, int index_del, int& index_alpha_upp) {
+    double upper_bound_steplength(const Vec& p, int index_del, int& index_alpha_upp) { ProfScope prof_(11);
         double alpha_upper = INFINITY;
         index_alpha_upp = 0;
         int mx = 0;
         for (int v : W.inactive) mx = std::max(mx, abs(v));
         if (!W.inactive.empty() && mx > 0) {
+            // A * p for every row, columns outermost (A is column major): per row the same summation order
+            // c = 0..n-1 as the row-wise dot product of the reference, so the values are bit-identical
+            Vec g_all(l, 0.0);
+            for (int c = 0; c < n; ++c) {
+                const double pc = p[c];
+                const double* ac = A.col(c);
+                for (int r = 0; r < l; ++r) g_all[r] += ac[r] * pc;
+            }
             for (int i = 0; i < W.l - W.t; ++i) {
                 int j = W.inactive[i];
                 if (j != index_del) {
-                    double g = 0.0;
-                    for (int c = 0; c < n; ++c) g += A(j - 1, c) * p[c];
+                    const double g = g_all[j - 1];
                     double a_j = -cx[j - 1] / g;
                     if (cx[j - 1] > 0 && g < 0 && a_j < alpha_upper) { alpha_upper = a_j; index_alpha_upp = j; }
                 }
@@ -1340,7 +1422,7 @@ public:
     }
 
     // EF:2197-2293
-    double compute_steplength(IterL& it, const IterL& prev, const Vec& x, Vec& w_out, int& Psi_error) {
+    double compute_steplength(IterL& it, const IterL& prev, const Vec& x, Vec& w_out, int& Psi_error) { ProfScope prof_(10);
         const Vec& p = it.p;
         int dimA = it.dimA;
         // Jp (compressed), Ap, active_Ap
@@ -1626,6 +1708,7 @@ public:
         res.active.assign(W.active.begin(), W.active.begin() + W.t);
         res.n_new_point = n_new_point;
         res.n_res_eval = n_res_eval;
+        if (getenv("ENLSIP_PROF")) { host_prof().dump(); host_prof() = HostProf(); }
         return res;
     }
 };

@@ -118,3 +118,48 @@ def test_large_full_size_properties(E):
     assert np.linalg.norm(x - truth.cpu().numpy()) <= 1e-2 * np.linalg.norm(x)          # noise 0.01, m/n = 16384
     assert abs(float(mod.obj_value[0]) / m - 1e-4) < 2e-6                                # sum r^2 ~ m * sigma^2
     mod.close()
+
+
+@pytest.mark.parametrize("m,n,nb,seed", [(4096, 512, 128, 31), (3000, 384, 64, 32)])
+def test_wide_problem_device_small_stage_vs_oracle(E, m, n, nb, seed):
+    """BASELINE config 5 shape at reduced size (inequalities + bounds on every parameter, l = nb + 2n): the compressed
+    problem is large enough for the device QRCP / M*Q of enl_dense.cuh (src/enlsip_functions.jl:219-223, 700)."""
+    from oracle import enlsip_oracle as O, problems as P
+    from tests.test_large_host import compare_with_oracle
+    d = E.synth.gen_single_index(m, n, nb, seed=seed, ineq=True)
+    lo, up = np.full(n, -2.0), np.full(n, 2.0)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d, ineq=True, x_low=lo, x_upp=up)
+    E.solve(mod, trace_cap=60)
+    st = mod.stats()
+    assert st["device_mulq"] > 0 and (n < 512 or st["device_qrcp"] > 0)      # the device path really ran
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"], ineq=True, bounds=(-2.0, 2.0)), wallclock=False)
+    out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, status=mod.status_code, iters=mod.iterations,
+               nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
+    compare_with_oracle(out, r, n)
+    mod.close()
+
+
+def test_c5_full_size_properties(E):
+    """BASELINE config 5 at the named size: n = 4096, m = 16384, 1024 nonlinear inequalities + 8192 bounds.
+    Size-independent properties only (the oracle needs ~1 h of CPU at this size): convergence, feasibility,
+    the working set found (the blocks with rho = 0.9 * truth are the active ones), determinism of the objective."""
+    m, n, nb = 16384, 4096, 1024
+    d = E.synth.gen_single_index(m, n, nb, seed=5, ineq=True)
+    lo, up = np.full(n, -2.0), np.full(n, 2.0)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d, ineq=True, x_low=lo, x_upp=up)
+    E.solve(mod)
+    st = mod.stats()
+    assert int(mod.status_code[0]) == 1 and int(mod.exit_code[0]) > 0
+    assert st["device_qrcp"] > 0 and st["device_mulq"] > 0
+    x = mod.sol[0]
+    g = d["rho"] - (x[:4 * nb] ** 2).reshape(nb, 4).sum(axis=1)
+    assert g.min() >= -1e-7 and np.all(np.abs(x) <= 2.0 + 1e-12)
+    act = np.sort(mod.active[0][: int(mod.nb_active[0])])
+    assert np.all(act <= nb)                                   # no bound is active (|x*| <= 1 < 2)
+    assert np.all((act - 1) % 2 == 0)                          # only the tightened blocks (even k) can be active
+    assert np.abs(g[act - 1]).max() <= 1e-7                     # active constraints hold with equality
+    assert 400 <= act.size <= 512
+    f1 = float(mod.obj_value[0])
+    E.solve(mod)
+    assert float(mod.obj_value[0]) == f1
+    mod.close()
