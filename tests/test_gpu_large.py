@@ -139,27 +139,56 @@ def test_wide_problem_device_small_stage_vs_oracle(E, m, n, nb, seed):
     mod.close()
 
 
-def test_c5_full_size_properties(E):
-    """BASELINE config 5 at the named size: n = 4096, m = 16384, 1024 nonlinear inequalities + 8192 bounds.
-    Size-independent properties only (the oracle needs ~1 h of CPU at this size): convergence, feasibility,
-    the working set found (the blocks with rho = 0.9 * truth are the active ones), determinism of the objective."""
+def test_c5_full_size_vs_golden(E, golden_dir):
+    """BASELINE config 5 at the named size: n = 4096, m = 16384, 1024 nonlinear inequalities + 8192 bounds, against
+    the committed oracle solve of the same problem (tests/golden/c5_full_oracle.npz, made by make_c5_fixture.py:
+    606 s on 8 cores): identical exit code, iteration count and per-iteration (t, rankA, rankJ2, dimA, dimJ2, method),
+    identical final working set, objective to 1e-10; plus size-independent properties."""
+    import os
     m, n, nb = 16384, 4096, 1024
+    gold = np.load(os.path.join(golden_dir, "c5_full_oracle.npz"))
     d = E.synth.gen_single_index(m, n, nb, seed=5, ineq=True)
     lo, up = np.full(n, -2.0), np.full(n, 2.0)
     mod = E.LargeCnlsModel("single_index", d["x0"], d, ineq=True, x_low=lo, x_upp=up)
-    E.solve(mod)
+    E.solve(mod, trace_cap=40)
     st = mod.stats()
-    assert int(mod.status_code[0]) == 1 and int(mod.exit_code[0]) > 0
     assert st["device_qrcp"] > 0 and st["device_mulq"] > 0
+    assert int(mod.exit_code[0]) == int(gold["exit_code"]) and int(mod.iterations[0]) == int(gold["iterations"])
+    assert int(mod.status_code[0]) == 1
+    k = gold["trace"].shape[0]
+    assert np.array_equal(mod.trace[0][:k, 1:7].astype(np.int32), gold["trace"])
+    assert abs(float(mod.obj_value[0]) - float(gold["f"])) <= 1e-10 * float(gold["f"])
     x = mod.sol[0]
+    assert np.linalg.norm(x - gold["x"]) <= 1e-8 * np.linalg.norm(gold["x"])
+    act = np.sort(mod.active[0][: int(mod.nb_active[0])])
+    assert np.array_equal(act, gold["active"])
     g = d["rho"] - (x[:4 * nb] ** 2).reshape(nb, 4).sum(axis=1)
     assert g.min() >= -1e-7 and np.all(np.abs(x) <= 2.0 + 1e-12)
-    act = np.sort(mod.active[0][: int(mod.nb_active[0])])
-    assert np.all(act <= nb)                                   # no bound is active (|x*| <= 1 < 2)
     assert np.all((act - 1) % 2 == 0)                          # only the tightened blocks (even k) can be active
-    assert np.abs(g[act - 1]).max() <= 1e-7                     # active constraints hold with equality
-    assert 400 <= act.size <= 512
     f1 = float(mod.obj_value[0])
     E.solve(mod)
-    assert float(mod.obj_value[0]) == f1
+    assert float(mod.obj_value[0]) == f1                       # deterministic
+    mod.close()
+
+
+def test_c4_1M_rows_vs_golden(E, golden_dir):
+    """BASELINE config 4 at a quarter of the named row count (m = 2^20, n = 256, 64 equalities) against the
+    committed oracle solve on the full m x n Jacobian (tests/golden/c4_1M_oracle.npz, make_c4_fixture.py: 149 s
+    on 8 cores): identical exit code / iterations / per-iteration trace, objective 1e-10, every iterate 1e-10
+    except the last (flat merit function)."""
+    import os
+    gold = np.load(os.path.join(golden_dir, "c4_1M_oracle.npz"))
+    m, n, nb = int(gold["m"]), 256, 64
+    d = E.synth.gen_single_index(m, n, nb, seed=4)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d)
+    E.solve(mod, trace_cap=40)
+    assert int(mod.exit_code[0]) == int(gold["exit_code"]) and int(mod.iterations[0]) == int(gold["iterations"])
+    k = gold["trace"].shape[0]
+    assert np.array_equal(mod.trace[0][:k, 1:7].astype(np.int32), gold["trace"])
+    assert abs(float(mod.obj_value[0]) - float(gold["f"])) <= 1e-10 * float(gold["f"])
+    for i in range(k - 1):
+        xi = gold["x_iter"][i]
+        assert np.linalg.norm(mod.trace[0][i, 16:16 + n] - xi) <= 1e-10 * np.linalg.norm(xi), i
+    assert np.linalg.norm(mod.sol[0] - gold["x"]) <= 1e-8 * np.linalg.norm(gold["x"])
+    assert np.array_equal(np.sort(mod.active[0][: int(mod.nb_active[0])]), gold["active"])
     mod.close()
