@@ -341,7 +341,12 @@ def main():
     from enlsip_jl_b200.model import last_kernel_ms
 
     rank, world, local = dist_env()
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the single JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) are pointed at
+    # stderr for the whole run, the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -474,7 +479,8 @@ def main():
                 large["cpu_baseline"] = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
             line["large"] = large
             line["gpu_launches"] = int(launches) + large["gpu_launches"]
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

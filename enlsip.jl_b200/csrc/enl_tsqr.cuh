@@ -105,10 +105,16 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
                                  ((dots[buf][4][i] + dots[buf][5][i]) + (dots[buf][6][i] + dots[buf][7][i]));
             const double alpha = rowi[buf][i];
             double tau = 0.0, scale = 0.0, beta = alpha;
-            if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||
-                beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+            if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta
+                // one rsqrt and one reciprocal instead of sqrt + two divisions (the scalar chain is on the critical
+                // path of every column): ||.|| = s * rsqrt(s), 1/beta = -sign(alpha) * rsqrt(s); each within ~1 ulp,
+                // which perturbs H by O(eps) exactly like the rounding of tau itself
+                const double s2 = fma(alpha, alpha, sigma);
+                const double rs = rsqrt(s2);
+                beta = -copysign(s2 * rs, alpha);
+                const double dab = alpha - beta;
+                scale = __drcp_rn(dab);
+                tau = dab * copysign(rs, alpha);
             }
             // (3) v_i . (column of this lane): columns > i get updated, columns < i feed the Gram matrix of V
             const double gv = fma(scale, g, rowi[buf][lane]);

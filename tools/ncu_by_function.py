@@ -1,6 +1,6 @@
 """Development aid: aggregate an ncu report's SASS-level samples per device function.
 
-    python tools_ncu_by_function.py gpurun_out/prof.ncu-rep [kernel-substring] [lib.so]
+    python tools/ncu_by_function.py gpurun_out/prof.ncu-rep [kernel-substring] [lib.so]
 
 Uses `ncu --page source --csv` for per-instruction counters and the cubin's symbol table (cuobjdump
 -xelf + readelf) to attribute each SASS address to the (non-inlined) device function containing it.
@@ -19,7 +19,7 @@ import tempfile
 def main():
     rep = sys.argv[1]
     kern_sub = sys.argv[2] if len(sys.argv) > 2 else "GaussPeaks"
-    so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.abspath(__file__)),
+    so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                             "enlsip.jl_b200", "lib", "libenlsip_b200.so")
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
