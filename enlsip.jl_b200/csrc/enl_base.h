@@ -72,7 +72,12 @@ ENL_INL double pow2i(int k) {
 #endif
 }
 
-ENL_INL double det_exp(double x) {
+#if defined(ENL_COMPACT_CODE) && defined(__CUDA_ARCH__)
+#define ENL_DET_EXP_ATTR ENL_NOINL      // one copy: the batched kernel is bound by instruction fetch, not by issue
+#else
+#define ENL_DET_EXP_ATTR ENL_INL
+#endif
+ENL_DET_EXP_ATTR double det_exp(double x) {
     // Branch-free restatement of oracle/detmath.c::det_exp (bit-identical results):
     //  * x < -745.2 -> 0 and x > 709.7827 -> +Inf fall out of the IEEE scaling below once x is clamped
     //    to [-800, 710] (the true exp under/overflows on the whole clamped-away range);
@@ -193,10 +198,12 @@ struct DM {
 #if defined(__CUDACC__)
     int grp;   // element offset of (slot 0, column 0, lane 0 of the group)
     ENL_INL static int lane() { return (int)(threadIdx.x & (G - 1)); }
+    ENL_INL static int row_of(int s) { return s * G + lane(); }   // matrix row held in slot s by this lane
     ENL_INL double& at(int s, int c) const { return enl_smem[grp + lane() + (c * MS + s) * NT]; }
     ENL_INL double& row(int r, int c) const { return enl_smem[grp + (c * MS + r / G) * NT + (r % G)]; }
 #else
     double* grp;
+    ENL_INL static int row_of(int s) { return s * G; }
     ENL_INL double& at(int s, int c) const { return grp[(c * MS + s) * NT]; }
     ENL_INL double& row(int r, int c) const { return grp[(c * MS + r / G) * NT + (r % G)]; }
 #endif

@@ -76,27 +76,45 @@ struct FamHS65 {
 //   r_i = y_i - (a1*det_exp(-b1*(t_i-c1)^2) + a2*det_exp(-b2*(t_i-c2)^2))
 //   h   = a1*(1/sqrt(b1)) + a2*(1/sqrt(b2)) - S
 // ---------------------------------------------------------------------------------------------
+#if defined(ENL_COMPACT_CODE)
+#define ENL_GP_UNROLL _Pragma("unroll 1")
+#else
+#define ENL_GP_UNROLL _Pragma("unroll")
+#endif
+#if defined(__CUDACC__) && !defined(ENL_HOST_BUILD)
+// abscissae t_i = 10 i / 127 of the Gaussian-peak family: identical for every problem, so one 1 KB table for the
+// whole device (filled by enlsipb200_create with the same two IEEE operations the oracle uses) instead of one
+// shared-memory column per problem -- that kilobyte is what lets a 15th problem fit into an SM.
+__device__ double g_gp_t[128];
+#endif
+
 struct FamGaussPeaks {
     static constexpr int N = 6, M = 128, Q = 1, NI = 0, MAXB = 2 * N;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = true;
-    static constexpr int NDCOLS = 2;   // y_i, t_i
+    static constexpr int NDCOLS = 1;   // y_i
     static constexpr int NSCAL = 1;    // S
+    static double abscissa(int row) { return (10.0 * (double)row) / 127.0; }
     template <class DMt, class Vt>
     struct Ctx {
-        DMt d;    // column 0 = y, column 1 = t (row-distributed shared memory)
+        DMt d;    // column 0 = y (row-distributed shared memory)
         Vt s;     // s[0] = S
         ENL_INL double y(int sl) const { return d.at(sl, 0); }
-        ENL_INL double t(int sl) const { return d.at(sl, 1); }
+        ENL_INL double t(int sl) const {
+#if defined(__CUDA_ARCH__)
+            return g_gp_t[DMt::row_of(sl) & 127];
+#else
+            return div_rn(mul_rn(10.0, (double)DMt::row_of(sl)), 127.0);
+#endif
+        }
         ENL_INL double S() const { return s[0]; }
     };
     template <class Grp, int MS, class C>
     ENL_FN static void load(const C& c, const FamilyData& d, long long b, const Grp& g) {
-#pragma unroll
+ENL_GP_UNROLL
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
             c.d.at(s, 0) = (row < M) ? d.d0[b * M + row] : 0.0;       // coalesced: lane l reads rows l, l+G, ...
-            c.d.at(s, 1) = div_rn(mul_rn(10.0, (double)row), 127.0);
         }
         c.s[0] = d.d1[b];
     }
@@ -106,7 +124,7 @@ struct FamGaussPeaks {
     }
     template <class Grp, int MS, class C>
     ENL_FN static void residuals(const C& c, const Grp& g, const double* x, double* out) {
-#pragma unroll
+ENL_GP_UNROLL
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
             double e1 = peak(x[1], x[2], c.t(s));
@@ -123,7 +141,7 @@ struct FamGaussPeaks {
     }
     template <class Grp, int MS, class C>
     ENL_FN static void jac_residuals(const C& c, const Grp& g, const double* x, double* out) {
-#pragma unroll
+ENL_GP_UNROLL
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
             double d1 = sub_rn(c.t(s), x[2]), d2 = sub_rn(c.t(s), x[5]);
@@ -156,7 +174,7 @@ struct FamGaussPeaks {
     template <class Grp, int MS, class C>
     ENL_FN static void fd_jac_residuals(const C& c, const Grp& g, const double* x, const double* r0,
                                         const double* dl, double* out) {
-#pragma unroll
+ENL_GP_UNROLL
         for (int s = 0; s < MS; ++s) {
             int row = s * Grp::G + g.lane;
             bool ok = row < M;

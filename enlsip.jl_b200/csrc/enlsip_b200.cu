@@ -50,6 +50,10 @@ __device__ __forceinline__ double now_seconds() {
     return (double)t * 1e-9;
 }
 
+#ifndef ENL_SYNC_GROUPS
+#define ENL_SYNC_GROUPS 1
+#endif
+
 template <class Fam, int G, int NT>
 __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_constant__ KernelArgs a) {
     using LY = Layout<Fam, G, NT>;
@@ -94,7 +98,18 @@ __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_con
         // Multi-warp CTAs re-align their warps once per iteration: co-resident warps then run the same
         // routines at the same time and share instruction-cache lines (the kernel is fetch-bound).
         if (SYNC_ITER) {
+#if ENL_SYNC_GROUPS > 1
+            // warps re-align in ENL_SYNC_GROUPS independent groups (named barriers 1..): less waiting for the
+            // slowest problem of the iteration, at the price of ENL_SYNC_GROUPS instruction streams per CTA
+            constexpr int WPG = (NT / 32) / ENL_SYNC_GROUPS;
+            const unsigned bar_id = 1 + (tid >> 5) / WPG;
+            unsigned any;
+            asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(any) : "r"(have ? 1u : 0u), "r"(bar_id), "r"((unsigned)(WPG * 32)) : "memory");
+            if (!any) break;
+#else
             if (!__syncthreads_or(have ? 1 : 0)) break;
+#endif
         } else if (!have) {
             break;
         }
@@ -204,7 +219,8 @@ int with_family(int family, int nt, F&& f) {
                 case 64: return f(FamGaussPeaks{}, ic<32>{}, ic<64>{});
                 case 128: return f(FamGaussPeaks{}, ic<32>{}, ic<128>{});
                 case 224: return f(FamGaussPeaks{}, ic<32>{}, ic<224>{});
-                default: return f(FamGaussPeaks{}, ic<32>{}, ic<448>{});
+                case 448: return f(FamGaussPeaks{}, ic<32>{}, ic<448>{});
+                default: return f(FamGaussPeaks{}, ic<32>{}, ic<480>{});   // 15 problems per SM: all the shared memory
             }
         case ENLSIPB200_FAMILY_OSBORNE2: return f(FamOsborne2{}, ic<32>{}, ic<32>{});
         case ENLSIPB200_FAMILY_CHAINED_ROSENBROCK10: return f(FamChainedRosenbrock<10>{}, ic<32>{}, ic<32>{});
@@ -216,7 +232,7 @@ int with_family(int family, int nt, F&& f) {
 // lanes per problem / threads per CTA of each family
 constexpr int HS_G = 1, HS_NT = 64;
 constexpr int GP_G = 32;
-static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 448; return (v == 224 || v == 128 || v == 64) ? v : 448; }
+static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 480; return (v == 448 || v == 224 || v == 128 || v == 64) ? v : 480; }
 
 Options make_options(const enlsipb200_options* o, int n, int m) {
     enlsipb200_options d;
@@ -299,6 +315,11 @@ int enlsipb200_create(int family, const double* x_low, const double* x_upp, int 
     int rc = 0;
     if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) { delete h; return fail(ENLSIPB200_ENOMEM, "cudaMalloc"); }
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { delete h; return fail(ENLSIPB200_ECUDA, "cudaEventCreate"); }
+    if (family == ENLSIPB200_FAMILY_GAUSS_PEAKS) {   // the family's shared abscissa table (enl_families.h)
+        double tt[128];
+        for (int i = 0; i < 128; ++i) tt[i] = FamGaussPeaks::abscissa(i);
+        if (cudaMemcpyToSymbol(g_gp_t, tt, sizeof(tt)) != cudaSuccess) { enlsipb200_destroy(h); return fail(ENLSIPB200_ECUDA, "cudaMemcpyToSymbol"); }
+    }
     rc = with_family(family, gp_nt(), [&](auto fam, auto g_, auto nt_) {
         return configure<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h);
     });
