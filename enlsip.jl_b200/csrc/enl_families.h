@@ -92,14 +92,20 @@ struct FamGaussPeaks {
     static constexpr int N = 6, M = 128, Q = 1, NI = 0, MAXB = 2 * N;
     static constexpr bool HAS_ANALYTIC = true;
     static constexpr bool HAS_FAST_FD = true;
-    static constexpr int NDCOLS = 1;   // y_i
-    static constexpr int NSCAL = 1;    // S
+    static constexpr int NDCOLS = 0;   // the data row y is re-read from global memory (L1/L2 resident, 1 KB per problem):
+                                       // the kilobyte of shared memory it would take is the 16th problem of an SM
+    static constexpr int NSCAL = 2;    // S, and the address of this problem's y row (bit pattern in a double slot)
     static double abscissa(int row) { return (10.0 * (double)row) / 127.0; }
     template <class DMt, class Vt>
     struct Ctx {
-        DMt d;    // column 0 = y (row-distributed shared memory)
-        Vt s;     // s[0] = S
-        ENL_INL double y(int sl) const { return d.at(sl, 0); }
+        DMt d;    // (no row-distributed family data)
+        Vt s;     // s[0] = S, s[1] = bits of (const double*) y row
+        ENL_INL double y(int sl) const {
+            double bits = s[1];
+            const double* yp;
+            __builtin_memcpy(&yp, &bits, sizeof(yp));
+            return yp[DMt::row_of(sl) & (M - 1)];
+        }
         ENL_INL double t(int sl) const {
 #if defined(__CUDA_ARCH__)
             return g_gp_t[DMt::row_of(sl) & 127];
@@ -110,13 +116,12 @@ struct FamGaussPeaks {
         ENL_INL double S() const { return s[0]; }
     };
     template <class Grp, int MS, class C>
-    ENL_FN static void load(const C& c, const FamilyData& d, long long b, const Grp& g) {
-ENL_GP_UNROLL
-        for (int s = 0; s < MS; ++s) {
-            int row = s * Grp::G + g.lane;
-            c.d.at(s, 0) = (row < M) ? d.d0[b * M + row] : 0.0;       // coalesced: lane l reads rows l, l+G, ...
-        }
+    ENL_FN static void load(const C& c, const FamilyData& d, long long b, const Grp&) {
+        const double* yp = d.d0 + b * M;
+        double bits;
+        __builtin_memcpy(&bits, &yp, sizeof(yp));
         c.s[0] = d.d1[b];
+        c.s[1] = bits;
     }
     ENL_INL static double peak(double b, double c, double t) {
         double d = sub_rn(t, c);

@@ -50,10 +50,6 @@ __device__ __forceinline__ double now_seconds() {
     return (double)t * 1e-9;
 }
 
-#ifndef ENL_SYNC_GROUPS
-#define ENL_SYNC_GROUPS 1
-#endif
-
 template <class Fam, int G, int NT>
 __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_constant__ KernelArgs a) {
     using LY = Layout<Fam, G, NT>;
@@ -98,18 +94,9 @@ __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_con
         // Multi-warp CTAs re-align their warps once per iteration: co-resident warps then run the same
         // routines at the same time and share instruction-cache lines (the kernel is fetch-bound).
         if (SYNC_ITER) {
-#if ENL_SYNC_GROUPS > 1
-            // warps re-align in ENL_SYNC_GROUPS independent groups (named barriers 1..): less waiting for the
-            // slowest problem of the iteration, at the price of ENL_SYNC_GROUPS instruction streams per CTA
-            constexpr int WPG = (NT / 32) / ENL_SYNC_GROUPS;
-            const unsigned bar_id = 1 + (tid >> 5) / WPG;
-            unsigned any;
-            asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(any) : "r"(have ? 1u : 0u), "r"(bar_id), "r"((unsigned)(WPG * 32)) : "memory");
-            if (!any) break;
-#else
+            // (measured alternatives, all slower: re-aligning in 2 / 7 independent groups 1.26 / 0.60 M solves/s,
+            //  every 2nd / 3rd pass 1.65 / 1.35 M, 1-3 extra barriers inside Solver::step 1.93-1.94 M, vs 1.96 M)
             if (!__syncthreads_or(have ? 1 : 0)) break;
-#endif
         } else if (!have) {
             break;
         }
@@ -220,7 +207,8 @@ int with_family(int family, int nt, F&& f) {
                 case 128: return f(FamGaussPeaks{}, ic<32>{}, ic<128>{});
                 case 224: return f(FamGaussPeaks{}, ic<32>{}, ic<224>{});
                 case 448: return f(FamGaussPeaks{}, ic<32>{}, ic<448>{});
-                default: return f(FamGaussPeaks{}, ic<32>{}, ic<480>{});   // 15 problems per SM: all the shared memory
+                case 480: return f(FamGaussPeaks{}, ic<32>{}, ic<480>{});
+                default: return f(FamGaussPeaks{}, ic<32>{}, ic<512>{});   // 16 problems per SM: all the shared memory and registers
             }
         case ENLSIPB200_FAMILY_OSBORNE2: return f(FamOsborne2{}, ic<32>{}, ic<32>{});
         case ENLSIPB200_FAMILY_CHAINED_ROSENBROCK10: return f(FamChainedRosenbrock<10>{}, ic<32>{}, ic<32>{});
@@ -232,7 +220,7 @@ int with_family(int family, int nt, F&& f) {
 // lanes per problem / threads per CTA of each family
 constexpr int HS_G = 1, HS_NT = 64;
 constexpr int GP_G = 32;
-static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 480; return (v == 448 || v == 224 || v == 128 || v == 64) ? v : 480; }
+static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 512; return (v == 480 || v == 448 || v == 224 || v == 128 || v == 64) ? v : 512; }
 
 Options make_options(const enlsipb200_options* o, int n, int m) {
     enlsipb200_options d;
