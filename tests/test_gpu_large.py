@@ -192,3 +192,25 @@ def test_c4_1M_rows_vs_golden(E, golden_dir):
     assert np.linalg.norm(mod.sol[0] - gold["x"]) <= 1e-8 * np.linalg.norm(gold["x"])
     assert np.array_equal(np.sort(mod.active[0][: int(mod.nb_active[0])]), gold["active"])
     mod.close()
+
+
+@pytest.mark.parametrize("kw", [dict(max_iter=2), dict(scaling=True), dict(time_limit=-1.0)])
+def test_large_options_vs_oracle(E, kw):
+    """solve!(model; max_iter, scaling, time_limit) in the large regime (solver.jl:62-63): -2 / -11 statuses as in the
+    reference (test/problems/chained_rosenbrock.jl:71-73 pins :time_limit_exceeded for time_limit = -1)."""
+    from oracle import enlsip_oracle as O, problems as P
+    from tests.test_large_host import compare_with_oracle
+    d = E.synth.gen_single_index(1500, 32, 8, seed=4)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d)
+    E.solve(mod, trace_cap=60, **kw)
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock="time_limit" in kw, **kw)
+    assert int(mod.exit_code[0]) == r.exit_code and int(mod.status_code[0]) == r.status
+    assert int(mod.iterations[0]) == r.iterations
+    if "time_limit" in kw:
+        assert str(E.status(mod)[0]).lstrip(":") == "time_limit_exceeded"
+        assert np.array_equal(mod.sol[0], d["x0"])          # x_opt stays x0 (SURVEY.md T5)
+    else:
+        out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, status=mod.status_code, iters=mod.iterations,
+                   nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
+        compare_with_oracle(out, r, 32)
+    mod.close()

@@ -24,7 +24,7 @@ AR = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.c_int)
 
 
 def run_large(d, ineq=False, bounds=None, rows=None, m_global=None, world=1, ag=None, ar=None, trace_cap=60, nthreads=2,
-              max_iter=100):
+              max_iter=100, scaling=False):
     """largeport_solve_sharded on the dict produced by synth.gen_single_index."""
     lib = ctypes.CDLL(ge.build_largeport())
     W = np.ascontiguousarray(d["W"]); y = np.ascontiguousarray(d["y"]); rho = np.ascontiguousarray(d["rho"])
@@ -42,7 +42,7 @@ def run_large(d, ineq=False, bounds=None, rows=None, m_global=None, world=1, ag=
     lib.largeport_solve_sharded.argtypes = [ci, ll, ll, ci, AG, AR, ci, ci] + [vp] * 6 + [ci, ci, cd, cd, cd] + [vp] * 8 + [ci, ci]
     p = lambda a: a.ctypes.data_as(vp)
     rc = lib.largeport_solve_sharded(n, m, rows_, world, ag if ag else AG(), ar if ar else AR(), rho.size, 1 if ineq else 0,
-                                     p(W), p(y), p(rho), p(lo), p(up), p(x0), max_iter, 0, se, se, se, p(out["x"]),
+                                     p(W), p(y), p(rho), p(lo), p(up), p(x0), max_iter, 1 if scaling else 0, se, se, se, p(out["x"]),
                                      p(out["f"]), p(out["exit_code"]), p(out["status"]), p(out["iters"]), p(out["nact"]),
                                      p(out["active"]), p(out["trace"]), trace_cap, nthreads)
     assert rc == 0
@@ -75,6 +75,20 @@ def test_large_host_driver_vs_oracle(m, n, nb, seed, ineq, bounds):
     out = run_large(d, ineq=ineq, bounds=bounds)
     r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"], ineq=ineq, bounds=bounds), wallclock=False)
     compare_with_oracle(out, r, n)
+
+
+@pytest.mark.parametrize("kw", [dict(max_iter=2), dict(scaling=True)])
+def test_large_host_driver_options_vs_oracle(kw):
+    """solve!(model; max_iter, scaling) (solver.jl:62-63): iteration cap -> exit code -2 (:maximum_iterations_exceeded),
+    row scaling of the active constraints (structures.jl:168-175) -> same trace machinery."""
+    import enlsip_jl_b200 as E
+    from oracle import enlsip_oracle as O, problems as P
+    d = E.synth.gen_single_index(1500, 32, 8, seed=4)
+    out = run_large(d, **kw)
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock=False, **kw)
+    compare_with_oracle(out, r, 32)
+    if "max_iter" in kw:
+        assert int(out["exit_code"][0]) == -2 and int(out["status"][0]) == -2
 
 
 def test_single_index_shards_are_position_independent():
