@@ -29,6 +29,7 @@ namespace enl_large {
 constexpr int TS_B = 32;     // block rows = panel width
 constexpr int TS_FAN = 8;    // blocks per subtile
 constexpr int TS_CG = 4;     // panel columns per unrolled group (code size: the group body must stay in the 32 KB L1.5 I-cache)
+constexpr int TS_KEEP = 12;   // published-column entries kept in registers between the dot and the update pass
 constexpr int TS_LDS = 36;   // shared-memory leading dimension (doubles): conflict-free m8n8k4 fragment loads
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -88,12 +89,15 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
             }
             if (w == 0) rowi[buf][lane] = a[k];
             __syncwarp();
-            // (2) g_c over this warp's 32 rows
+            // (2) g_c over this warp's 32 rows; the first TS_KEEP entries of the published column stay in registers for
+            // step (3) (the kernel is bound by shared-memory loads: every kept value saves one 16-byte broadcast load)
+            double vk[TS_KEEP];
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
             for (int r = 0; r < TS_B; r += 4) {
                 const double2 v01 = *reinterpret_cast<const double2*>(&vbuf[w][r]);
                 const double2 v23 = *reinterpret_cast<const double2*>(&vbuf[w][r + 2]);
+                if (r < TS_KEEP) { vk[r] = v01.x; vk[r + 1] = v01.y; vk[r + 2] = v23.x; vk[r + 3] = v23.y; }
                 d0 = fma(v01.x, a[r + 0], d0); d1 = fma(v01.y, a[r + 1], d1);
                 d2 = fma(v23.x, a[r + 2], d2); d3 = fma(v23.y, a[r + 3], d3);
             }
@@ -126,7 +130,9 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
             }
             const double cs = wc * scale;
 #pragma unroll
-            for (int r = 0; r < TS_B; r += 2) {
+            for (int r = 0; r < TS_KEEP; ++r) a[r] = fma(-cs, vk[r], a[r]);
+#pragma unroll
+            for (int r = TS_KEEP; r < TS_B; r += 2) {
                 const double2 v = *reinterpret_cast<const double2*>(&vbuf[w][r]);
                 a[r] = fma(-cs, v.x, a[r]);
                 a[r + 1] = fma(-cs, v.y, a[r + 1]);
