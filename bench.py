@@ -31,6 +31,15 @@ METRIC = "batched CNLS solves/s (n=6,m=128)"      # first half of BASELINE.json'
                                                   # m=4M, n=256) is the "large" object of the same JSON line
 UNIT = "solves/s"
 ALG_BYTES_PER_SOLVE = 128 * 8 + 48 + 8 + 48 + 8 + 12   # y, x0, S in; x, f, (exit, iters, t) out = 1148 B
+NCU_DRAM_BYTES_PER_SOLVE = (33.66e6 + 901.2e6) / 30000  # dram__bytes_read + dram__bytes_write of one ncu --set full capture
+ALG_FLOP_PER_SOLVE = 2.0e5 * 6.12                       # SURVEY.md 8d estimate per iteration x mean iterations of the stream
+
+
+def fp64_fma_peak():
+    p = os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["fp64_dfma_tflops"])
+    return 40.0
 
 
 def dist_env():
@@ -134,6 +143,7 @@ def cpu_port(B, nthreads, seed_start=0):
 # large-Jacobian regime (BASELINE.json config 4): GN iterations/s at m = 4M, n = 256, 64 equalities
 # =================================================================================================
 LARGE_METRIC = "GN iters/s (m=4M,n=256)"
+NCU_TRAIL_DRAM_BYTES_PER_ROW_COL = (2.248e9 + 1.897e9) / (1048576 * 232.0)   # profiles/r1_c4_trail_v2_ncu.txt
 LARGE_N, LARGE_NB = 256, 64
 
 
@@ -241,7 +251,12 @@ def large_arm(args, torch, dist, E, rank, world, local, dev):
                                    "linesearch_evals": dst["linesearch_evals"] / args.large_steps},
            "gpu_launches": int(dst["launches"]),
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "kernel": "tsqr_panel_kernel + tsqr_trail_kernel (one TSQR of [J | r])",
+                        "traffic": NCU_TRAIL_DRAM_BYTES_PER_ROW_COL * rows * 232.0, "peak_source": peak_src,
+                        "traffic_source": "largest launch of the factorisation (tsqr_trail_kernel, panel 0, level 0: 232 trailing "
+                                          "columns): ncu --set full at 1M rows (profiles/r1_c4_trail_v2_ncu.txt) 2.25 GB read + "
+                                          "1.90 GB written = 1.06x its algorithmic bytes (trailing block read once, written once, "
+                                          "V read once), scaled linearly to this run's rows",
+                        "kernel": "tsqr_panel_kernel + tsqr_trail_kernel (one TSQR of [J | r])",
                         "kernel_ms": tsqr_ms, "algorithmic_flops_per_launch": flops / world,
                         "note": "2 m (n+1)^2 flops per factorisation; trailing updates on mma.sync.m8n8k4.f64, panels on the FP64 FMA pipe"}}
     # ---- end to end: W and y start in pinned HOST memory every step, result read back ---------------
@@ -459,9 +474,19 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "enlsip_solve_batch_kernel<GaussPeaks>",
+                             "traffic": NCU_DRAM_BYTES_PER_SOLVE * B, "peak_source": peak_src,
+                             "kernel": "enlsip_solve_batch_kernel<GaussPeaks>",
                              "kernel_ms": kms, "algorithmic_bytes_per_solve": ALG_BYTES_PER_SOLVE,
-                             "note": "fused whole-solve kernel: FP64-latency bound, not HBM bound (see DESIGN.md)"},
+                             "traffic_source": "ncu --set full, 30000 solves (profiles/r1_c3_v4_ncu.txt): 1.12 KB read + 30.0 KB "
+                                               "written per solve; the writes are stack (local-memory) lines leaving L2, not data",
+                             "note": "fused whole-solve kernel: every intermediate stays on chip, so it is FP64/latency bound "
+                                     "and not HBM bound by construction (DESIGN.md 5.1); see roofline_fp64"},
+                "roofline_fp64": {"bound": "fp64 pipe", "achieved": value / world * ALG_FLOP_PER_SOLVE / 1e12,
+                                  "peak": fp64_fma_peak(), "unit": "TFLOP/s",
+                                  "frac": value / world * ALG_FLOP_PER_SOLVE / 1e12 / fp64_fma_peak(),
+                                  "algorithmic_flop_per_solve": ALG_FLOP_PER_SOLVE,
+                                  "note": "algorithmic flops (SURVEY.md 8d: ~2e5 per Gauss-Newton iteration x the mean iteration "
+                                          "count); ncu: FP64 pipe 12.7 % active, issue slots 34 % (profiles/r1_c3_v4_ncu.txt)"},
                 "quality": {"converged_fraction": conv, "mean_iterations": float(iters.mean()),
                             "kernel_info": kernel_info}}
         if not args.skip_cpu and world == 1:      # cpu_baseline: rank 0 at N = 1 only

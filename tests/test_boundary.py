@@ -44,6 +44,24 @@ def test_no_cpu_fallback(capi):
     x = np.zeros(4)
     rc = capi.lib().enlsipb200_det_exp(x.ctypes.data, x.ctypes.data, 4, 0)
     assert rc == -2
+    # the large-Jacobian regime fails the same way: no device, no solve
+    d = E.synth.gen_single_index(1200, 32, 8, seed=1)
+    with pytest.raises(capi.EngineError, match="(?i)no cuda device|cuda"):
+        E.LargeCnlsModel("single_index", d["x0"], d)
+
+
+def test_large_api_validation(capi):
+    """Argument checks of enlsipb200_large_create happen before any device is touched."""
+    import ctypes
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    rho = np.ones(8)
+    assert L.enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, 30, 1000, 1000, 4, 0, rho.ctypes.data, None, None, -1, ctypes.byref(h)) != 0
+    assert b"multiple of 32" in L.enlsipb200_large_last_error()
+    assert L.enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, 32, 100, 100, 4, 0, rho.ctypes.data, None, None, -1, ctypes.byref(h)) != 0
+    assert b"batched engine" in L.enlsipb200_large_last_error()          # n + m < 1000: Newton regime (EF:2658)
+    assert L.enlsipb200_large_create(99, 32, 1000, 1000, 4, 0, rho.ctypes.data, None, None, -1, ctypes.byref(h)) != 0
+    assert L.enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, 32, 2000, 1000, 4, 0, rho.ctypes.data, None, None, -1, ctypes.byref(h)) != 0
 
 
 def test_product_does_not_import_oracle():
