@@ -58,6 +58,7 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
     const bool valid = blk < nblk;
     double* base = A + (blk * TS_B) * (long long)ld + col0 + lane;
     double a[TS_B];
+    double myscale = 0.0;   // scale of this lane's own reflector (set when its column is the pivot)
 #pragma unroll
     for (int r = 0; r < TS_B; ++r) {
         double v = valid ? base[(long long)r * ld] : 0.0;
@@ -105,8 +106,7 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
             __syncthreads();
             const double g = ((dots[buf][0][lane] + dots[buf][1][lane]) + (dots[buf][2][lane] + dots[buf][3][lane])) +
                              ((dots[buf][4][lane] + dots[buf][5][lane]) + (dots[buf][6][lane] + dots[buf][7][lane]));
-            const double sigma = ((dots[buf][0][i] + dots[buf][1][i]) + (dots[buf][2][i] + dots[buf][3][i])) +
-                                 ((dots[buf][4][i] + dots[buf][5][i]) + (dots[buf][6][i] + dots[buf][7][i]));
+            const double sigma = __shfl_sync(0xffffffffu, g, i);   // lane i's own column: the same sum, bit for bit
             const double alpha = rowi[buf][i];
             double tau = 0.0, scale = 0.0, beta = alpha;
             if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta
@@ -121,10 +121,14 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
                 tau = dab * copysign(rs, alpha);
             }
             // (3) v_i . (column of this lane): columns > i get updated, columns < i feed the Gram matrix of V
+            // Finished columns (lanes < i) keep their reflector UNSCALED in registers (u_c = raw column below its pivot,
+            // v_c = e_c + myscale_c u_c): scaling happens once, when the panel is stored, instead of 32 single-lane
+            // multiplications per column.  rowi[c] then holds u_c[i], g_c = u_i . u_c over the rows below i.
+            if (lane == i) myscale = scale;
             const double gv = fma(scale, g, rowi[buf][lane]);
             const double wc = (lane > i) ? tau * gv : 0.0;
             if (w == 0) {
-                if (lane < i) Gs[lane][i] = gv;
+                if (lane < i) Gs[lane][i] = myscale * gv;     // v_c . v_i = myscale_c (u_c[i] + scale_i g_c)
                 if (lane == i) taus[i] = tau;
                 a[k] = (lane == i) ? beta : a[k] - wc;
             }
@@ -137,16 +141,12 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
                 a[r] = fma(-cs, v.x, a[r]);
                 a[r + 1] = fma(-cs, v.y, a[r + 1]);
             }
-            if (lane == i) {   // the column becomes the reflector (unit diagonal implied)
-#pragma unroll
-                for (int r = 0; r < TS_B; ++r)
-                    if (r > k || w > 0) a[r] *= scale;
-            }
         }
-        if (w == 0) {
+        if (w == 0) {   // finished rows of the top block: R on and above the diagonal, scaled reflector entries below it
 #pragma unroll
             for (int r = 0; r < TS_CG; ++r) {
-                base[(long long)(ib * TS_CG + r) * ld] = a[r];
+                const int row = ib * TS_CG + r;
+                base[(long long)row * ld] = (row > lane) ? a[r] * myscale : a[r];
                 a[r] = 0.0;
             }
         }
@@ -160,7 +160,7 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
     }
     if (valid && w > 0) {
 #pragma unroll
-        for (int r = 0; r < TS_B; ++r) base[(long long)r * ld] = a[r];
+        for (int r = 0; r < TS_B; ++r) base[(long long)r * ld] = a[r] * myscale;
     }
     __syncthreads();
     // compact-WY factor: T = U^-1 with U = striu(V'V) + diag(1/tau); column `lane` by back substitution.
