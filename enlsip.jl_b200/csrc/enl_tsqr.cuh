@@ -10,14 +10,17 @@
 //     level 0, 1, 2, ...: the rows are cut into blocks of 32; a "subtile" is 8 blocks (stride 8^level
 //       blocks apart, i.e. at level >= 1 the top blocks of the subtiles of the level below).
 //       tsqr_panel_kernel  : one CTA per subtile; Householder QR of its 256 x 32 panel held in
-//                            registers (lane = column, 8 warps x 32 rows), compact-WY T by
-//                            T = (striu(V'V) + diag(1/tau))^-1; V is stored in place, T in a side buffer
+//                            registers (lane = column, 8 warps x 32 rows), ONE block barrier per column
+//                            (a single pass of dot products with the raw pivot column gives the norm and every
+//                            v_i . a_c); compact-WY T = (striu(V'V) + diag(1/tau))^-1; V is stored in place, T
+//                            in a side buffer; the residual column of [J | r] is updated here as well
+//                            (b <- (I - V T' V') b with the reflectors still in registers)
 //       tsqr_trail_kernel  : one CTA per (subtile, 32-column block of the trailing matrix):
 //                            B <- (I - V T' V')B with three FP64 tensor-core products
 //                            (mma.sync.m8n8k4.f64 = DMMA.8x8x4): G = V'B, W = -T'G, B += V W
 //     the top 32 rows of the last level are the finished rows 32j..32j+31 of R: copied out, then
 //     zeroed in place so later panels see them as empty rows.
-//   the final column (the residual column of [J | r]) needs only its norm.
+//   after the last panel the residual column only needs its norm (R[n][n]).
 // Every subtile is independent inside a level, so each kernel is a plain grid over subtiles; the
 // price is 1/7 more flops than a flat tree (each level re-factors 1/8 of the rows).
 // Algorithmic flops: 2 m n^2 (n = number of columns).  See DESIGN.md for the roofline accounting.
@@ -43,7 +46,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2)
 tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int upper_only,
-                  double* __restrict__ Tbuf) {
+                  int rcol, double* __restrict__ Tbuf) {
     // One block-wide barrier per column: the raw column i is published (per warp), ONE pass of dot products
     // g_c = sum_{rows below the pivot} a_i[r] a_c[r] gives both the norm (g_i) and, because the reflector
     // v_i = e_i + scale * a_i[below] is linear in the raw column, every v_i . a_c = a_c[i] + scale * g_c.
@@ -59,6 +62,10 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
     double* base = A + (blk * TS_B) * (long long)ld + col0 + lane;
     double a[TS_B];
     double myscale = 0.0;   // scale of this lane's own reflector (set when its column is the pivot)
+    // the residual column of [J | r] (column rcol): lane = row here; updated at the end of this kernel with the
+    // block reflector of the panel, so the trailing-update kernel only sees full 32-column blocks
+    double* bptr = A + (blk * TS_B + lane) * (long long)ld + rcol;
+    double bval = (valid && rcol >= 0) ? *bptr : 0.0;
 #pragma unroll
     for (int r = 0; r < TS_B; ++r) {
         double v = valid ? base[(long long)r * ld] : 0.0;
@@ -180,6 +187,62 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
         double* Tg = Tbuf + sub * (TS_B * TS_B);
 #pragma unroll
         for (int r = 0; r < TS_B; ++r) Tg[r * TS_B + lane] = t[r];
+    }
+    if (rcol < 0) return;
+    // ---- residual column: b <- (I - V T' V') b for this subtile (the same update the trailing kernel applies to
+    //      the 32-column blocks, here with FMAs on the reflectors still held in registers) ----
+    double vs = myscale;
+    if (w == 0) {   // the top block's registers were cleared row by row: reload its unit lower trapezoid (own stores)
+#pragma unroll
+        for (int r = 0; r < TS_B; ++r) a[r] = (r > lane) ? base[(long long)r * ld] : ((r == lane) ? 1.0 : 0.0);
+        vs = 1.0;
+    }
+    __syncwarp();
+    vbuf[w][lane] = bval;
+    __syncwarp();
+    {
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < TS_B; r += 4) {
+            const double2 b01 = *reinterpret_cast<const double2*>(&vbuf[w][r]);
+            const double2 b23 = *reinterpret_cast<const double2*>(&vbuf[w][r + 2]);
+            g0 = fma(b01.x, a[r + 0], g0); g1 = fma(b01.y, a[r + 1], g1);
+            g2 = fma(b23.x, a[r + 2], g2); g3 = fma(b23.y, a[r + 3], g3);
+        }
+        dots[0][w][lane] = ((g0 + g1) + (g2 + g3)) * vs;       // (V_w' b_w)[lane]
+    }
+    __syncthreads();
+    if (w == 0) {
+        const double gc = ((dots[0][0][lane] + dots[0][1][lane]) + (dots[0][2][lane] + dots[0][3][lane])) +
+                          ((dots[0][4][lane] + dots[0][5][lane]) + (dots[0][6][lane] + dots[0][7][lane]));
+        rowi[0][lane] = gc;
+        __syncwarp();
+        const double* Tg = Tbuf + sub * (TS_B * TS_B);          // column `lane` of T: this lane's own stores
+        double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < TS_B; k += 2) {
+            w0 = fma(Tg[k * TS_B + lane], rowi[0][k], w0);
+            w1 = fma(Tg[(k + 1) * TS_B + lane], rowi[0][k + 1], w1);
+        }
+        rowi[1][lane] = -(w0 + w1);                              // W = -T' G
+    }
+    __syncthreads();
+    {
+        const double wc = rowi[1][lane] * vs;
+#pragma unroll
+        for (int r = 0; r < TS_B; ++r) a[r] *= wc;              // lane c: V[r][c] W[c] for the 32 rows of the warp
+        // butterfly reduce-scatter over the lanes: afterwards a[0] of lane r is sum_c V[r][c] W[c]
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int j = 0; j < sft; ++j) {
+                const double keep = up ? a[j + sft] : a[j];
+                const double send = up ? a[j] : a[j + sft];
+                a[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+        }
+        if (valid) *bptr = bval + a[0];
     }
 }
 
@@ -319,19 +382,16 @@ __device__ __forceinline__ void tsqr_trail_body(double* __restrict__ A, int ld, 
 
 constexpr int TS_TRAIL_SMEM = (TS_B * TS_LDS + 2 * TS_B * (TS_B + 4) + 4 * 32 * 32) * (int)sizeof(double);
 
-// 1-D grid of nsub * (ncb32 + 1) CTAs, column block fastest (CTAs sharing a reflector block V run together, so V
-// is read from HBM once): cb < ncb32 -> the 32-column block col0 + 32 (cb + 1); cb == ncb32 -> the 8-column block
-// at column `lastcol` holding the residual column of [J | r] (and 7 zero padding columns)
+// 1-D grid of nsub * ncb32 CTAs, column block fastest (CTAs sharing a reflector block V run together, so V is read
+// from HBM once): item cb is the 32-column block col0 + 32 (cb + 1).  The residual column of [J | r] is updated by the
+// panel kernel itself.
 __global__ void __launch_bounds__(256, 2)
-tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb32, int lastcol,
+tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb32,
                   const double* __restrict__ Tbuf) {
     extern __shared__ __align__(16) double smem[];
-    const long long sub = blockIdx.x / (unsigned)(ncb32 + 1);
-    const int cb = (int)(blockIdx.x % (unsigned)(ncb32 + 1));
-    if (cb < ncb32)
-        tsqr_trail_body<32>(A, ld, nblk, stride, col0, col0 + TS_B * (cb + 1), sub, Tbuf, smem);
-    else
-        tsqr_trail_body<8>(A, ld, nblk, stride, col0, lastcol, sub, Tbuf, smem);
+    const long long sub = blockIdx.x / (unsigned)ncb32;
+    const int cb = (int)(blockIdx.x % (unsigned)ncb32);
+    tsqr_trail_body<32>(A, ld, nblk, stride, col0, col0 + TS_B * (cb + 1), sub, Tbuf, smem);
 }
 
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
@@ -391,9 +451,12 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             long long nb_level = (nblk + stride - 1) / stride;
             if (level > 0 && nb_level <= 1) break;
             long long nsub = (nb_level + TS_FAN - 1) / TS_FAN;
-            tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, Tbuf);
-            tsqr_trail_kernel<<<(unsigned)(nsub * (ncb32 + 1)), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32, n, Tbuf);
-            launches += 2;
+            tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
+            ++launches;
+            if (ncb32 > 0) {
+                tsqr_trail_kernel<<<(unsigned)(nsub * ncb32), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32, Tbuf);
+                ++launches;
+            }
             stride *= TS_FAN;
         }
         tsqr_extract_kernel<<<1, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);

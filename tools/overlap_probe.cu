@@ -22,23 +22,23 @@ int main(int argc, char** argv) {
     cudaFuncSetAttribute(tsqr_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     cudaStream_t s1, s2; cudaStreamCreate(&s1); cudaStreamCreate(&s2);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, s1>>>(A1, ld, nblk, 1, 0, 0, T1);
-    tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, s2>>>(A2, ld, nblk, 1, 0, 0, T2);
+    tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, s1>>>(A1, ld, nblk, 1, 0, 0, -1, T1);
+    tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, s2>>>(A2, ld, nblk, 1, 0, 0, -1, T2);
     cudaDeviceSynchronize();
     const int ncb = 3, reps = 4;
     float tp, tt, tc;
     cudaEventRecord(e0, s1);
-    for (int r = 0; r < reps; ++r) tsqr_panel_kernel<<<(unsigned)nsub, 256, PAD, s1>>>(A1, ld, nblk, 1, 32, 0, T1);
+    for (int r = 0; r < reps; ++r) tsqr_panel_kernel<<<(unsigned)nsub, 256, PAD, s1>>>(A1, ld, nblk, 1, 32, 0, -1, T1);
     cudaEventRecord(e1, s1); cudaEventSynchronize(e1); cudaEventElapsedTime(&tp, e0, e1);
     cudaEventRecord(e0, s1);
-    for (int r = 0; r < reps; ++r) tsqr_trail_kernel<<<(unsigned)(nsub * (ncb + 1)), 256, TPAD, s1>>>(A2, ld, nblk, 1, 0, ncb, n, T2);
+    for (int r = 0; r < reps; ++r) tsqr_trail_kernel<<<(unsigned)(nsub * ncb), 256, TPAD, s1>>>(A2, ld, nblk, 1, 0, ncb, T2);
     cudaEventRecord(e1, s1); cudaEventSynchronize(e1); cudaEventElapsedTime(&tt, e0, e1);
     cudaDeviceSynchronize();
     cudaEventRecord(e0, s1);
     cudaStreamWaitEvent(s2, e0, 0);
     for (int r = 0; r < reps; ++r) {
-        tsqr_panel_kernel<<<(unsigned)nsub, 256, PAD, s1>>>(A1, ld, nblk, 1, 32, 0, T1);
-        tsqr_trail_kernel<<<(unsigned)(nsub * (ncb + 1)), 256, TPAD, s2>>>(A2, ld, nblk, 1, 0, ncb, n, T2);
+        tsqr_panel_kernel<<<(unsigned)nsub, 256, PAD, s1>>>(A1, ld, nblk, 1, 32, 0, -1, T1);
+        tsqr_trail_kernel<<<(unsigned)(nsub * ncb), 256, TPAD, s2>>>(A2, ld, nblk, 1, 0, ncb, T2);
     }
     cudaEvent_t e2; cudaEventCreate(&e2); cudaEventRecord(e2, s2); cudaStreamWaitEvent(s1, e2, 0);
     cudaEventRecord(e1, s1); cudaEventSynchronize(e1); cudaEventElapsedTime(&tc, e0, e1);
