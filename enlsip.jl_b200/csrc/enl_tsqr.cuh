@@ -33,6 +33,9 @@ constexpr int TS_B = 32;     // block rows = panel width
 constexpr int TS_FAN = 8;    // blocks per subtile
 constexpr int TS_CG = 4;     // panel columns per unrolled group (code size: the group body must stay in the 32 KB L1.5 I-cache)
 constexpr int TS_KEEP = 12;   // published-column entries kept in registers between the dot and the update pass
+#ifndef TS_TRAIL_CB
+#define TS_TRAIL_CB 32
+#endif
 constexpr int TS_LDS = 36;   // shared-memory leading dimension (doubles): conflict-free m8n8k4 fragment loads
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -385,13 +388,14 @@ constexpr int TS_TRAIL_SMEM = (TS_B * TS_LDS + 2 * TS_B * (TS_B + 4) + 4 * 32 * 
 // 1-D grid of nsub * ncb32 CTAs, column block fastest (CTAs sharing a reflector block V run together, so V is read
 // from HBM once): item cb is the 32-column block col0 + 32 (cb + 1).  The residual column of [J | r] is updated by the
 // panel kernel itself.
-__global__ void __launch_bounds__(256, 2)
-tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb32,
+template <int CB>
+__global__ void __launch_bounds__(256, (CB == 32 ? 2 : 3))
+tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb,
                   const double* __restrict__ Tbuf) {
     extern __shared__ __align__(16) double smem[];
-    const long long sub = blockIdx.x / (unsigned)ncb32;
-    const int cb = (int)(blockIdx.x % (unsigned)ncb32);
-    tsqr_trail_body<32>(A, ld, nblk, stride, col0, col0 + TS_B * (cb + 1), sub, Tbuf, smem);
+    const long long sub = blockIdx.x / (unsigned)ncb;
+    const int cb = (int)(blockIdx.x % (unsigned)ncb);
+    tsqr_trail_body<CB>(A, ld, nblk, stride, col0, col0 + TS_B + CB * cb, sub, Tbuf, smem);
 }
 
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
@@ -442,7 +446,7 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     const int npanels = n / TS_B;
     int launches = 0;
     // > 48 KB of dynamic shared memory needs the opt-in (per device, so it is simply set on every call)
-    cudaFuncSetAttribute(tsqr_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
+    cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
@@ -454,7 +458,9 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             ++launches;
             if (ncb32 > 0) {
-                tsqr_trail_kernel<<<(unsigned)(nsub * ncb32), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32, Tbuf);
+                constexpr int CBW = TS_TRAIL_CB;
+                const int ncb = ncb32 * (32 / CBW);
+                tsqr_trail_kernel<CBW><<<(unsigned)(nsub * ncb), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb, Tbuf);
                 ++launches;
             }
             stride *= TS_FAN;
