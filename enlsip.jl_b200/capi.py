@@ -53,7 +53,10 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs, relink = [], force or not os.path.exists(LIB_PATH)
     # the batched kernel is bound by instruction fetch: its translation unit is built for small code
-    for src, hdrs, extra in ((SRC, HEADERS, ["-DENL_COMPACT_CODE=1"]), (SRC_LARGE, HEADERS_LARGE, [])):
+    # the large regime's host driver (enl_large_host.h) runs its O(n^2 k) loops on the host: AVX2 for them (every B200
+    # host has it); no -mfma, so that the host arithmetic stays un-contracted like the CPU test backend's
+    for src, hdrs, extra in ((SRC, HEADERS, ["-DENL_COMPACT_CODE=1"]),
+                             (SRC_LARGE, HEADERS_LARGE, ["-Xcompiler", "-mavx2"])):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         newest = max(os.path.getmtime(p) for p in [src] + hdrs)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
