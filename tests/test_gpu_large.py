@@ -214,3 +214,16 @@ def test_large_options_vs_oracle(E, kw):
                    nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
         compare_with_oracle(out, r, 32)
     mod.close()
+
+
+def test_rank_deficient_jacobian_vs_oracle(E):
+    """pseudo_rank (EF:17-31) of the QRCP of J2 on the compressed problem: a Jacobian with two identical columns."""
+    from oracle import enlsip_oracle as O, problems as P
+    from tests.test_large_host import rank_deficient_problem, check_rank_deficient
+    d = rank_deficient_problem()
+    mod = E.LargeCnlsModel("single_index", d["x0"], d)
+    E.solve(mod, trace_cap=60)
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock=False)
+    out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, iters=mod.iterations, trace=mod.trace[0])
+    check_rank_deficient(out, r)
+    mod.close()

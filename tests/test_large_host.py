@@ -91,6 +91,38 @@ def test_large_host_driver_options_vs_oracle(kw):
         assert int(out["exit_code"][0]) == -2 and int(out["status"][0]) == -2
 
 
+def rank_deficient_problem():
+    """Two identical columns of W (outside the constrained blocks): J and J2 have rank n - 1 at every x."""
+    import enlsip_jl_b200 as E
+    d = E.synth.gen_single_index(1500, 32, 4, seed=13)
+    d["W"][:, 25] = d["W"][:, 21]
+    return d
+
+
+def check_rank_deficient(out, r):
+    """rankJ2 = n - t - 1 is found identically; the objective and every discrete output agree.  x itself is not
+    unique: QRCP may pivot on either of the two identical columns (an exact tie of column norms, broken by rounding),
+    which moves x along e_21 - e_25 only; everything identifiable (the other coordinates, x_21 + x_25) agrees."""
+    n = 32
+    assert int(out["exit_code"][0]) == r.exit_code and int(out["iters"][0]) == r.iterations
+    for k, t in enumerate(r.trace):
+        e = out["trace"][k]
+        assert (int(e[1]), int(e[2]), int(e[3]), int(e[4]), int(e[5]), int(e[6])) == (t.t, t.rankA, t.rankJ2, t.dimA, t.dimJ2, t.code)
+        assert t.rankJ2 == n - t.t - 1
+    assert abs(out["f"][0] - r.f) <= 1e-10 * r.f
+    dx = np.asarray(out["x"]).reshape(-1) - r.x
+    assert np.abs(np.delete(dx, [21, 25])).max() <= 1e-7
+    assert abs(dx[21] + dx[25]) <= 1e-7
+
+
+def test_rank_deficient_jacobian_vs_oracle():
+    from oracle import enlsip_oracle as O, problems as P
+    d = rank_deficient_problem()
+    out = run_large(d)
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock=False)
+    check_rank_deficient(out, r)
+
+
 def test_single_index_shards_are_position_independent():
     import enlsip_jl_b200 as E
     full = E.synth.gen_single_index(200000, 8, 2, seed=4)
