@@ -148,6 +148,8 @@ def solve(model: CnlsModel, silent=True, max_iter=100, scaling=False, time_limit
         return solve_large(model, silent=silent, max_iter=max_iter, scaling=scaling, time_limit=time_limit,
                            abs_tol=abs_tol, rel_tol=rel_tol, c_tol=c_tol, x_tol=x_tol, trace_cap=trace_cap)
     B, n = model.B, model.nb_parameters
+    if not silent and trace_cap == 0 and B == 1:
+        trace_cap = int(max_iter) + 1          # the iteration table of print_diagnosis needs the log
     o = capi.default_options()
     o.max_iter = int(max_iter)
     o.scaling = 1 if scaling else 0
@@ -238,7 +240,31 @@ def constraints_values(model: CnlsModel):
     return np.concatenate([sol - model.x_low[None, :], model.x_upp[None, :] - sol], axis=1)
 
 
+def iteration_table(model, b=0):
+    """The per-iteration table of the reference's `print_diagnosis` (EF:2551-2554, 2571-2580) for problem `b`, rebuilt
+    from the iteration log the engine returns (needs a solve with trace_cap > 0): iteration, objective,
+    ||active constraints||^2, ||p||, steplength, reduction of the objective."""
+    if model.trace is None:
+        return "(no iteration log: solve with trace_cap > 0 or silent=False)"
+    tr = _to_numpy(model.trace)[b]
+    k = min(int(_to_numpy(model.iterations)[b]), tr.shape[0])
+    lines = ["iter    objective   ||active_constraints||^2  ||p||       alpha     reduction"]
+    for i in range(k):
+        lines.append("%4d  %.7e       %.2e         %.2e  %.2e  %.3e" % (i + 1, tr[i, 0], tr[i, 11], tr[i, 8], tr[i, 7], tr[i, 12]))
+    return "\n".join(lines)
+
+
 def _diagnosis(model: CnlsModel):
+    if model.B == 1 and model.trace is not None:
+        cnt = _to_numpy(model.counters)[0] if model.counters is not None else (0, 0)
+        return "\n".join(["%s problem (n=%d, m=%d, constraints=%d)" % (model.family, model.nb_parameters, model.nb_residuals,
+                                                                       model.nb_constraints),
+                          iteration_table(model, 0),
+                          "Number of iterations...................: %4d" % int(_to_numpy(model.iterations)[0]),
+                          "Square sum of residuals................: %.7e" % float(_to_numpy(model.obj_value)[0]),
+                          "Number of function evaluations.........: %4d" % int(cnt[0]),
+                          "Number of Jacobian matrix evaluations..: %4d" % int(cnt[1]),
+                          "Termination status.....................: %s" % status(model)[0]])
     st = status(model)
     it = _to_numpy(model.iterations)
     f = _to_numpy(model.obj_value)

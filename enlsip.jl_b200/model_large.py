@@ -136,6 +136,8 @@ def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False,
                 rel_tol=None, c_tol=None, x_tol=None, trace_cap=0):
     """solve!(model; ...) (solver.jl:62-91) for the large regime; results land in the model (B = 1 arrays)."""
     n = model.nb_parameters
+    if not silent and trace_cap == 0:
+        trace_cap = int(max_iter) + 1          # the iteration table of print_diagnosis needs the log
     o = capi.default_options()
     o.max_iter = int(max_iter)
     o.scaling = 1 if scaling else 0
@@ -156,6 +158,10 @@ def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False,
     model.status_code, model.exit_code, model.sol, model.obj_value = st, ec, x, f
     model.iterations, model.nb_active, model.active, model.trace = it, na, act, tr
     if not silent:
-        print("single_index problem (n=%d, m=%d, constraints=%d): exit code %d after %d iterations, objective %.6e"
-              % (n, model.nb_residuals, model.nb_constraints, int(ec[0]), int(it[0]), float(f[0])))
+        from .model import iteration_table, status
+        print("single_index problem (n=%d, m=%d, constraints=%d)" % (n, model.nb_residuals, model.nb_constraints))
+        print(iteration_table(model, 0))
+        print("Number of iterations...................: %4d" % int(it[0]))
+        print("Square sum of residuals................: %.7e" % float(f[0]))
+        print("Termination status.....................: %s (exit code %d)" % (status(model)[0], int(ec[0])))
     return None

@@ -179,3 +179,19 @@ def test_reference_suite_on_gpu(E):
             assert np.any(out["trace"][:, :, 6] == 2)          # Newton steps taken
         assert set(E.status(m)) <= {"found_first_order_stationary_point", "failed", "maximum_iterations_exceeded"}
         print(name, "statuses", sorted(set(E.status(m))), "iters", list(np.asarray(m.iterations)), m.kernel_info())
+
+
+def test_silent_false_prints_iteration_table(E, capsys):
+    """solve!(model; silent=false) -> print_diagnosis (EF:2571-2580): one line per iteration with the reference's columns."""
+    from oracle import enlsip_oracle as O, problems as P
+    m = E.CnlsModel("hs65", E.synth.HS65_X0[None, :], x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(m, silent=False)
+    out = capsys.readouterr().out
+    r = O.solve(P.hs65(), wallclock=False)
+    rows = [ln for ln in out.splitlines() if ln[:4].strip().isdigit()]
+    assert len(rows) == r.iterations == int(m.iterations[0])
+    for ln, t in zip(rows, r.trace):
+        cols = ln.split()
+        assert abs(float(cols[1]) - t.f_new) <= 1e-6 * max(1.0, abs(t.f_new))
+        assert abs(float(cols[4]) - t.alpha) <= 1e-2 * max(1e-3, abs(t.alpha))
+    assert "found_first_order_stationary_point" in out
