@@ -362,6 +362,8 @@ struct LargeHandle : LargeOps, DenseAccel {
             if (p) cudaFree(p);
         if (dq_p) cudaFree(dq_p);
         dq_p = nullptr;
+        if (hpin) cudaFreeHost(hpin);
+        hpin = nullptr;
         dq_f = dq_m = dq_small = dJc = nullptr;
         dq_f_cap = dq_m_cap = dq_small_cap = dq_p_cap = 0;
         ownW = owny = dA = du = dr = ds = dv = dJp = dx = dp = dT = dpart = dout = dR = dStack = dR2 = nullptr;
@@ -392,6 +394,7 @@ struct LargeHandle : LargeOps, DenseAccel {
         LCU(cudaMalloc(&dT, sizeof(double) * (nsub > 64 ? nsub : 64) * TS_B * TS_B));
         LCU(cudaMalloc(&dpart, sizeof(double) * LI_PARTS * 4));
         LCU(cudaMalloc(&dout, sizeof(double) * 8));
+        LCU(cudaHostAlloc(&hpin, sizeof(double) * 8, cudaHostAllocDefault));
         LCU(cudaMalloc(&dR, sizeof(double) * rr_rows * ld));
         LCU(cudaMalloc(&dJc, sizeof(double) * (size_t)(n + 1) * (n + 1)));
         hR.resize((size_t)(n + 1) * (n + 1));
@@ -409,11 +412,14 @@ struct LargeHandle : LargeOps, DenseAccel {
             int rc = g_nccl.AllReduce(dout, dout, 4, NCCL_FLOAT64, NCCL_SUM, comm, st);
             if (rc != 0) return lfail(ENLSIPB200_ECUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
         }
-        LCU(cudaMemcpyAsync(out, dout, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+        // pinned landing buffer: a pageable destination costs a staging copy and an extra synchronisation per call
+        LCU(cudaMemcpyAsync(hpin, dout, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
         LCU(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; ++k) out[k] = hpin[k];
         return 0;
     }
     int cur_parts = LI_PARTS;
+    double* hpin = nullptr;
 
     // factor [J | r] at x into hR (row major (n+1) x ld), identical on every rank
     int factor_at(const double* x, bool want_host_R = true) {
@@ -468,34 +474,28 @@ struct LargeHandle : LargeOps, DenseAccel {
     }
     int set_direction(const double*, const double* p, double sums[3]) override {
         LCU(cudaSetDevice(device));
+        auto t0 = std::chrono::steady_clock::now();
         LCU(cudaMemcpyAsync(dp, p, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-        LCU(cudaEventRecord(e0, st));
         cur_parts = grid_rows();
         li_dir_kernel<<<cur_parts, 256, sizeof(double) * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart);
         ++launches;
         double o[4];
         int rc = finish4(o);
         if (rc != 0) return rc;
-        LCU(cudaEventRecord(e1, st));
-        LCU(cudaEventSynchronize(e1));
-        float ms; LCU(cudaEventElapsedTime(&ms, e0, e1));
-        ms_ls += ms;
+        ms_ls += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         sums[0] = o[0]; sums[1] = o[1]; sums[2] = o[2];
         return 0;
     }
     int ls_eval(double alpha, int with_coeffs, double o[4]) {
         LCU(cudaSetDevice(device));
-        LCU(cudaEventRecord(e0, st));
+        auto t0 = std::chrono::steady_clock::now();
         long long want = (m_local + 255) / 256;
         cur_parts = (int)(want < LI_PARTS ? (want > 0 ? want : 1) : LI_PARTS);
         li_ls_kernel<<<cur_parts, 256, 0, st>>>(du, dv, dy, dr, dJp, m_local, alpha, with_coeffs, dpart);
         ++launches;
         int rc = finish4(o);
         if (rc != 0) return rc;
-        LCU(cudaEventRecord(e1, st));
-        LCU(cudaEventSynchronize(e1));
-        float ms; LCU(cudaEventElapsedTime(&ms, e0, e1));
-        ms_ls += ms;
+        ms_ls += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ++n_ls;
         return 0;
     }

@@ -136,7 +136,7 @@ int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb20
  * device times of the two stages (CUDA events on the handle's stream) */
 int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
 /* cumulative counters: {factorisations, build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
- * evaluations, kernels launched, padded local rows, device QRCPs, device M*Q products, ms in those two
+ * evaluations (host clock around launch..result), kernels launched, padded local rows, device QRCPs, device M*Q products, ms in those two
  * (host clock, transfers included)} */
 int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
 
