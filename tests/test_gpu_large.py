@@ -227,3 +227,30 @@ def test_rank_deficient_jacobian_vs_oracle(E):
     out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, iters=mod.iterations, trace=mod.trace[0])
     check_rank_deficient(out, r)
     mod.close()
+
+
+def test_large_solve_seed_sweep_vs_oracle(E):
+    """Twelve more random instances (sizes, seeds, equality / inequality / bound mixes) against the live oracle: every
+    discrete output identical, objective 1e-10, iterate before the last step 1e-10."""
+    from oracle import enlsip_oracle as O, problems as P
+    from tests.test_large_host import compare_with_oracle
+    rng = np.random.default_rng(2024)
+    done = 0
+    for k in range(12):
+        n = int(rng.choice([32, 64, 96]))
+        m = int(rng.integers(1200, 5000))
+        nb = int(rng.integers(1, n // 4 + 1))
+        ineq = bool(k % 2)
+        bounds = (-2.0, 2.0) if (ineq and k % 4 == 1) else None
+        d = E.synth.gen_single_index(m, n, nb, seed=100 + k, ineq=ineq)
+        lo = None if bounds is None else np.full(n, bounds[0])
+        up = None if bounds is None else np.full(n, bounds[1])
+        mod = E.LargeCnlsModel("single_index", d["x0"], d, ineq=ineq, x_low=lo, x_upp=up)
+        E.solve(mod, trace_cap=100)
+        r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"], ineq=ineq, bounds=bounds), wallclock=False)
+        out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, status=mod.status_code, iters=mod.iterations,
+                   nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
+        compare_with_oracle(out, r, n)
+        mod.close()
+        done += 1
+    assert done == 12
