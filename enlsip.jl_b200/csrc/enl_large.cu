@@ -1,11 +1,13 @@
 // enl_large.cu -- large-Jacobian regime of the B200 ENLSIP engine (BASELINE.json config 4: one problem,
-// m = 4M residuals, n = 256, row-sharded over the GPUs of one box).
+// m = 4M residuals, n = 256, row-sharded over the GPUs of one box; config 5: n = 4096, m = 16384 on one GPU).
 //
 // Per Gauss-Newton iteration (reference: one pass of the `while exit_code == 0` loop, EF:2776-2878):
 //   li_build_kernel      r = tanh(Wx) - y, J = diag(1 - tanh^2) W         -> [J | r] in HBM   (new_point!, EF:34-52)
 //   tsqr_factor          [J | r] -> R (n+1 x n+1)   (enl_tsqr.cuh: Householder panels + DMMA trailing updates)
 //   NCCL all-gather      of the per-GPU R factors, stacked and re-factored identically on every GPU
-//   host small stage     the ENLSIP iteration on the compressed problem (enl_large_host.h), replicated per rank
+//   r_to_colmajor        R -> column-major [J~ | r~], which stays device resident for enl_dense.cuh
+//   host small stage     the ENLSIP iteration on the compressed problem (enl_large_host.h), replicated per rank;
+//                        its O(n^3) primitives (QRCP, J~ Q1) run on the device when n >= 384 (enl_dense.cuh)
 //   li_dir_kernel        v = W p, Jp = s .* v, {r.r, r.Jp, Jp.Jp}                              (EF:2222-2224)
 //   li_ls_kernel         per trial step: ||r(x + a p)||^2 and the linesearch model dots        (EF:1307-1340, 1665-1689)
 //   NCCL all-reduce      of those few doubles
@@ -421,7 +423,7 @@ struct LargeHandle : LargeOps, DenseAccel {
     int cur_parts = LI_PARTS;
     double* hpin = nullptr;
 
-    // factor [J | r] at x into hR (row major (n+1) x ld), identical on every rank
+    // factor [J | r] at x: dJc = column-major [J~ | r~] (identical on every rank), optionally copied to hR
     int factor_at(const double* x, bool want_host_R = true) {
         LCU(cudaSetDevice(device));
         LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
