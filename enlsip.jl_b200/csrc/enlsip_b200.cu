@@ -144,6 +144,14 @@ struct enlsipb200_handle_s {
     // staging for host-buffer calls
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    // family data passed as HOST pointers is uploaded lazily: per-problem slots travel chunk by chunk inside
+    // enlsipb200_solve_batch (host-buffer path), overlapped with the solves of the previous chunk
+    const double* host_src[3] = {nullptr, nullptr, nullptr};
+    long long host_count[3] = {0, 0, 0};
+    bool host_pending[3] = {false, false, false};
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_CHUNKS = 16;
+    cudaEvent_t ev_ready[MAX_CHUNKS] = {};
 };
 
 namespace {
@@ -176,20 +184,41 @@ int configure(enlsipb200_handle h) {
     return 0;
 }
 
+// first / last: this launch opens / closes the timed region of enlsipb200_last_kernel_ms (a chunked host-buffer solve
+// is one region from its first to its last kernel)
 template <class Fam, int G, int NT>
-int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st) {
+int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st, bool first = true, bool last = true) {
     using LY = Layout<Fam, G, NT>;
     long long groups_per_cta = NT / G;
     long long need = (a.B + groups_per_cta - 1) / groups_per_cta;
     int grid = (int)(need < (long long)h->grid ? need : (long long)h->grid);
     if (grid < 1) grid = 1;
     CU(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
-    CU(cudaEventRecord(h->ev0, st));
+    if (first) CU(cudaEventRecord(h->ev0, st));
     enlsip_solve_batch_kernel<Fam, G, NT><<<grid, NT, smem_total<Fam, G, NT>(), st>>>(a);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ev1, st));
+    if (last) CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
     h->launches += 1;
+    return 0;
+}
+
+// doubles per problem of a family-data slot (0 = the slot is shared by all problems of the batch)
+int slot_stride(int family, int slot) {
+    if (family == ENLSIPB200_FAMILY_GAUSS_PEAKS) return slot == 0 ? FamGaussPeaks::M : (slot == 1 ? 1 : 0);
+    return 0;
+}
+
+// upload pending host slots completely: all of them (B < 0: device-buffer solves), or those that cannot travel chunk by
+// chunk with a batch of B problems (slots shared by all problems, slots whose size does not match the batch)
+int flush_pending(enlsipb200_handle h, cudaStream_t st, long long B) {
+    for (int sl = 0; sl < 3; ++sl) {
+        if (!h->host_pending[sl]) continue;
+        const int sd = slot_stride(h->family, sl);
+        if (B >= 0 && sd > 0 && h->host_count[sl] == B * sd) continue;
+        CU(cudaMemcpyAsync(h->owned[sl], h->host_src[sl], (size_t)h->host_count[sl] * sizeof(double), cudaMemcpyHostToDevice, st));
+        h->host_pending[sl] = false;
+    }
     return 0;
 }
 
@@ -325,6 +354,11 @@ int enlsipb200_destroy(enlsipb200_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->copy_stream) {
+        for (int c = 0; c < enlsipb200_handle_s::MAX_CHUNKS; ++c)
+            if (h->ev_ready[c]) cudaEventDestroy(h->ev_ready[c]);
+        cudaStreamDestroy(h->copy_stream);
+    }
     delete h;
     return 0;
 }
@@ -342,14 +376,18 @@ int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_con
 int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream) {
     if (!h || slot < 0 || slot > 2) return fail(ENLSIPB200_EINVAL, "bad handle/slot");
     CU(cudaSetDevice(h->device));
-    if (on_device) { h->data[slot] = ptr; return 0; }
+    if (on_device) { h->data[slot] = ptr; h->host_pending[slot] = false; return 0; }
     if (h->owned_count[slot] < count) {
         if (h->owned[slot]) CU(cudaFree(h->owned[slot]));
         h->owned[slot] = nullptr;
         CU(cudaMalloc(&h->owned[slot], (size_t)count * sizeof(double)));
         h->owned_count[slot] = count;
     }
-    CU(cudaMemcpyAsync(h->owned[slot], ptr, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    // the copy itself is deferred to the next solve (see host_pending): the host buffer must stay valid until then
+    (void)stream;
+    h->host_src[slot] = ptr;
+    h->host_count[slot] = count;
+    h->host_pending[slot] = true;
     h->data[slot] = h->owned[slot];
     return 0;
 }
@@ -376,55 +414,100 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     a.bnd = h->bnd;
     a.out.trace_cap = trace ? trace_cap : 0;
     if (on_device) {
+        int rcf = flush_pending(h, st, -1);
+        if (rcf != 0) return rcf;
         a.x0 = x0;
         a.out.x = x; a.out.f = f; a.out.exit_code = exit_code; a.out.status = status; a.out.iters = iters;
         a.out.nact = nact; a.out.active = active; a.out.counters = counters; a.out.trace = trace;
-    } else {
-        // one staging allocation: [x0 | x | f | trace | ints...]
-        size_t nd = (size_t)B * n * 2 + (size_t)B + (trace ? (size_t)B * trace_cap * row_w : 0);
-        size_t ni = (size_t)B * (4 + lmax + 2);
-        size_t bytes = nd * 8 + ni * 4;
-        if (h->stage_bytes < bytes) {
-            if (h->stage) CU(cudaFree(h->stage));
-            h->stage = nullptr;
-            h->stage_bytes = 0;
-            if (cudaMalloc(&h->stage, bytes) != cudaSuccess) return fail(ENLSIPB200_ENOMEM, "cudaMalloc(staging)");
-            h->stage_bytes = bytes;
+        int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
+            return launch<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h, a, st);
+        });
+        if (rc != 0) return rc;
+        if (!stream) CU(cudaStreamSynchronize(st));
+        return 0;
+    }
+    // ---- host buffers: one staging allocation [x0 | x | f | trace | ints...], the batch cut into chunks whose
+    //      uploads (x0 and the pending per-problem family data) overlap the solves of the chunk before ----
+    size_t nd = (size_t)B * n * 2 + (size_t)B + (trace ? (size_t)B * trace_cap * row_w : 0);
+    size_t ni = (size_t)B * (4 + lmax + 2);
+    size_t bytes = nd * 8 + ni * 4;
+    if (h->stage_bytes < bytes) {
+        if (h->stage) CU(cudaFree(h->stage));
+        h->stage = nullptr;
+        h->stage_bytes = 0;
+        if (cudaMalloc(&h->stage, bytes) != cudaSuccess) return fail(ENLSIPB200_ENOMEM, "cudaMalloc(staging)");
+        h->stage_bytes = bytes;
+    }
+    double* dd = (double*)h->stage;
+    double* d_x0 = dd; dd += (size_t)B * n;
+    double* d_x = dd; dd += (size_t)B * n;
+    double* d_f = dd; dd += (size_t)B;
+    double* d_tr = nullptr;
+    if (trace) { d_tr = dd; dd += (size_t)B * trace_cap * row_w; }
+    int* di = (int*)dd;
+    int* d_ec = di; di += B;
+    int* d_st = di; di += B;
+    int* d_it = di; di += B;
+    int* d_na = di; di += B;
+    int* d_act = di; di += (size_t)B * lmax;
+    int* d_cnt = di;
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < enlsipb200_handle_s::MAX_CHUNKS; ++c) CU(cudaEventCreateWithFlags(&h->ev_ready[c], cudaEventDisableTiming));
+    }
+    int rcf = flush_pending(h, st, B);           // what cannot be chunked goes up whole, before the first kernel
+    if (rcf != 0) return rcf;
+    const long long min_chunk = 65536;
+    int nchunk = (int)((B + min_chunk - 1) / min_chunk);
+    if (nchunk > 8) nchunk = 8;
+    if (nchunk < 1) nchunk = 1;
+    const long long csize = (B + nchunk - 1) / nchunk;
+    cudaStream_t cs = h->copy_stream;
+    CU(cudaEventRecord(h->ev_ready[enlsipb200_handle_s::MAX_CHUNKS - 1], st));   // copies start after earlier work on st
+    CU(cudaStreamWaitEvent(cs, h->ev_ready[enlsipb200_handle_s::MAX_CHUNKS - 1], 0));
+    if (trace) CU(cudaMemsetAsync(d_tr, 0, (size_t)B * trace_cap * row_w * 8, st));
+    for (int c = 0; c < nchunk; ++c) {
+        const long long off = c * csize, cb = (off + csize <= B) ? csize : B - off;
+        if (cb <= 0) { nchunk = c; break; }
+        CU(cudaMemcpyAsync(d_x0 + off * n, x0 + off * n, (size_t)cb * n * 8, cudaMemcpyHostToDevice, cs));
+        for (int sl = 0; sl < 3; ++sl) {
+            const int sd = slot_stride(h->family, sl);
+            if (h->host_pending[sl] && sd > 0)
+                CU(cudaMemcpyAsync(h->owned[sl] + off * sd, h->host_src[sl] + off * sd, (size_t)cb * sd * 8, cudaMemcpyHostToDevice, cs));
         }
-        double* dd = (double*)h->stage;
-        double* d_x0 = dd; dd += (size_t)B * n;
-        a.out.x = dd; dd += (size_t)B * n;
-        a.out.f = dd; dd += (size_t)B;
-        if (trace) { a.out.trace = dd; dd += (size_t)B * trace_cap * row_w; }
-        int* di = (int*)dd;
-        a.out.exit_code = di; di += B;
-        a.out.status = di; di += B;
-        a.out.iters = di; di += B;
-        a.out.nact = di; di += B;
-        a.out.active = di; di += (size_t)B * lmax;
-        a.out.counters = di;
-        CU(cudaMemcpyAsync(d_x0, x0, (size_t)B * n * 8, cudaMemcpyHostToDevice, st));
-        if (trace) CU(cudaMemsetAsync(a.out.trace, 0, (size_t)B * trace_cap * row_w * 8, st));
-        a.x0 = d_x0;
+        CU(cudaEventRecord(h->ev_ready[c], cs));
     }
-    int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
-        return launch<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h, a, st);
-    });
-    if (rc != 0) return rc;
-    if (!on_device) {
-        CU(cudaMemcpyAsync(x, a.out.x, (size_t)B * n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(f, a.out.f, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(exit_code, a.out.exit_code, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(status, a.out.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(iters, a.out.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(nact, a.out.nact, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-        if (active) CU(cudaMemcpyAsync(active, a.out.active, (size_t)B * lmax * 4, cudaMemcpyDeviceToHost, st));
-        if (counters) CU(cudaMemcpyAsync(counters, a.out.counters, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost, st));
-        if (trace) CU(cudaMemcpyAsync(trace, a.out.trace, (size_t)B * trace_cap * row_w * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    } else if (!stream) {
-        CU(cudaStreamSynchronize(st));
+    for (int c = 0; c < nchunk; ++c) {
+        const long long off = c * csize, cb = (off + csize <= B) ? csize : B - off;
+        CU(cudaStreamWaitEvent(st, h->ev_ready[c], 0));
+        KernelArgs ac = a;
+        ac.B = cb;
+        ac.x0 = d_x0 + off * n;
+        const double* dp[3];
+        for (int sl = 0; sl < 3; ++sl) {
+            const int sd = slot_stride(h->family, sl);
+            dp[sl] = h->data[sl] ? h->data[sl] + off * sd : nullptr;
+        }
+        ac.fd = FamilyData{dp[0], dp[1], dp[2]};
+        ac.out.x = d_x + off * n; ac.out.f = d_f + off; ac.out.exit_code = d_ec + off; ac.out.status = d_st + off;
+        ac.out.iters = d_it + off; ac.out.nact = d_na + off; ac.out.active = d_act + off * lmax; ac.out.counters = d_cnt + off * 2;
+        ac.out.trace = trace ? d_tr + (size_t)off * trace_cap * row_w : nullptr;
+        int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
+            return launch<decltype(fam), decltype(g_)::value, decltype(nt_)::value>(h, ac, st, c == 0, c == nchunk - 1);
+        });
+        if (rc != 0) return rc;
+        CU(cudaMemcpyAsync(x + off * n, ac.out.x, (size_t)cb * n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(f + off, ac.out.f, (size_t)cb * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(exit_code + off, ac.out.exit_code, (size_t)cb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(status + off, ac.out.status, (size_t)cb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(iters + off, ac.out.iters, (size_t)cb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(nact + off, ac.out.nact, (size_t)cb * 4, cudaMemcpyDeviceToHost, st));
+        if (active) CU(cudaMemcpyAsync(active + off * lmax, ac.out.active, (size_t)cb * lmax * 4, cudaMemcpyDeviceToHost, st));
+        if (counters) CU(cudaMemcpyAsync(counters + off * 2, ac.out.counters, (size_t)cb * 2 * 4, cudaMemcpyDeviceToHost, st));
+        if (trace) CU(cudaMemcpyAsync(trace + (size_t)off * trace_cap * row_w, ac.out.trace, (size_t)cb * trace_cap * row_w * 8, cudaMemcpyDeviceToHost, st));
     }
+    for (int sl = 0; sl < 3; ++sl) h->host_pending[sl] = false;
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -70,7 +70,7 @@ class CnlsModel:
         self.nb_parameters, self.nb_residuals, self.nb_eqcons, self.nb_constraints, self.lmax = [d.value for d in dims]
         if n != self.nb_parameters:
             raise ValueError("family %s has n=%d, starting_point has %d columns" % (family, self.nb_parameters, n))
-        self._data_keep = []
+        self._data_keep = {}
         data = data or {}
         for slot, key in enumerate(_FAMILY_DATA[family]):
             if key not in data:
@@ -111,7 +111,7 @@ class CnlsModel:
         else:
             arr = np.ascontiguousarray(arr, dtype=np.float64)
             count = arr.size
-        self._data_keep.append(arr)
+        self._data_keep[slot] = arr        # host arrays are uploaded by the next solve: keep them alive
         capi.check(capi.lib().enlsipb200_set_data(self._h, slot, self._ptr(arr), count, 1 if dev else 0, self._stream()))
 
     def kernel_info(self):

@@ -70,9 +70,10 @@ int enlsipb200_destroy(enlsipb200_handle h);
 int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_constraints, int* lmax);
 
 /* family data arrays (GAUSS_PEAKS: slot 0 = y [B,128], slot 1 = S [B]; OSBORNE2: slot 0 = t [65], slot 1 = y [65],
- * shared by the whole batch).  `on_device` != 0: ptr is a
- * device pointer that must stay valid for the solve; otherwise the library copies host->device
- * (asynchronously on `stream` when the host memory is pinned). */
+ * shared by the whole batch).  `on_device` != 0: ptr is a device pointer that must stay valid for the solve.
+ * Otherwise ptr is a HOST buffer that must stay valid until the next enlsipb200_solve_batch returns: the upload
+ * happens inside that call -- with host-buffer solves chunk by chunk, overlapped with the solves of the previous
+ * chunk (pinned host memory makes the copies asynchronous). */
 int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream);
 
 /* solve B independent problems (replaces B calls of solve!).  All array arguments are host or

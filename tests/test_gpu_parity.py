@@ -195,3 +195,34 @@ def test_silent_false_prints_iteration_table(E, capsys):
         assert abs(float(cols[1]) - t.f_new) <= 1e-6 * max(1.0, abs(t.f_new))
         assert abs(float(cols[4]) - t.alpha) <= 1e-2 * max(1e-3, abs(t.alpha))
     assert "found_first_order_stationary_point" in out
+
+
+def test_host_buffer_pipeline_matches_device_path(E):
+    """Host-buffer solves cut the batch into chunks whose uploads overlap the previous chunk's solves (B = 150 000 ->
+    3 chunks, uneven tail): outputs must be bit-identical to one solve with device-resident inputs, and a second
+    solve on the same handle (nothing pending any more) must reproduce them."""
+    import torch
+    B = 150_000
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B)
+    mh = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(mh)
+    first = (np.asarray(mh.sol).copy(), np.asarray(mh.obj_value).copy(), np.asarray(mh.exit_code).copy(),
+             np.asarray(mh.iterations).copy(), np.asarray(mh.active).copy())
+    E.solve(mh)
+    md = E.CnlsModel("gauss_peaks", torch.from_numpy(x0).cuda(), data={"y": torch.from_numpy(y).cuda(), "S": torch.from_numpy(S).cuda()},
+                     x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(md)
+    dev = (md.sol.cpu().numpy(), md.obj_value.cpu().numpy(), md.exit_code.cpu().numpy(), md.iterations.cpu().numpy(),
+           md.active.cpu().numpy())
+    second = (np.asarray(mh.sol), np.asarray(mh.obj_value), np.asarray(mh.exit_code), np.asarray(mh.iterations), np.asarray(mh.active))
+    for a, b, c in zip(first, second, dev):
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a, c, equal_nan=True)
+    # new data through set_data travels with the next solve
+    y2 = y[::-1].copy()
+    mh.set_data(0, y2)
+    E.solve(mh)
+    md2 = E.CnlsModel("gauss_peaks", torch.from_numpy(x0).cuda(), data={"y": torch.from_numpy(y2).cuda(), "S": torch.from_numpy(S).cuda()},
+                      x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(md2)
+    assert np.array_equal(np.asarray(mh.obj_value), md2.obj_value.cpu().numpy(), equal_nan=True)
+    assert not np.array_equal(np.asarray(mh.obj_value), first[1], equal_nan=True)
