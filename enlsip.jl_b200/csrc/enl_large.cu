@@ -91,17 +91,27 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// one warp per row: u = w_i . x, r = det_tanh(u) - y, s = 1 - tanh^2; row i of [s W | r | 0..] into A
+// one warp per row: u = w_i . x, r = det_tanh(u) - y, s = 1 - tanh^2; row i of [s W | r | 0..] into A.
+// NC > 0: the warp also accumulates its share of J'r (lane owns columns 2 lane + 64 k, +1; NC = ceil(n / 64) register
+// pairs) and of r'r; the CTA folds its 8 warps in a fixed order into gpart[blockIdx][0..n] ([n] = r'r).  The gradient is
+// what the termination test of the new point reads (EF:2838, 2411), so that the factorisation can wait until the
+// iteration is known to continue.  NC == 0 (n > 64 * 8): no gradient here, li_grad_kernel does it.
+template <int NC>
 __global__ void __launch_bounds__(256) li_build_kernel(const double* __restrict__ W, const double* __restrict__ y,
                                                        const double* __restrict__ x, long long m, int n, int ld,
                                                        double* __restrict__ A, double* __restrict__ u,
-                                                       double* __restrict__ r, double* __restrict__ s) {
-    extern __shared__ double xs[];
+                                                       double* __restrict__ r, double* __restrict__ s,
+                                                       double* __restrict__ gpart) {
+    extern __shared__ double xs[];   // x [n]; then, NC > 0: 8 x (n + 1) partial gradients
     for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = x[j];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double ga[NC > 0 ? 2 * NC : 1];
+    double rsq = 0.0;
+#pragma unroll
+    for (int k = 0; k < (NC > 0 ? 2 * NC : 1); ++k) ga[k] = 0.0;
     for (long long i = warp0; i < m; i += nwarps) {
         const double* wr = W + i * n;
         double acc = 0.0;
@@ -115,13 +125,74 @@ __global__ void __launch_bounds__(256) li_build_kernel(const double* __restrict_
         const double rr = __dsub_rn(th, y[i]);
         const double ss = __dsub_rn(1.0, __dmul_rn(th, th));
         double* ar = A + i * ld;
-        for (int c = 2 * lane; c < n; c += 64) {
-            double2 wv = *reinterpret_cast<const double2*>(wr + c);
-            *reinterpret_cast<double2*>(ar + c) = make_double2(ss * wv.x, ss * wv.y);
+        if (NC > 0) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const int c = 2 * lane + 64 * k;
+                if (c < n) {
+                    double2 wv = *reinterpret_cast<const double2*>(wr + c);
+                    const double j0 = __dmul_rn(ss, wv.x), j1 = __dmul_rn(ss, wv.y);
+                    *reinterpret_cast<double2*>(ar + c) = make_double2(j0, j1);
+                    ga[2 * k] = fma(j0, rr, ga[2 * k]);
+                    ga[2 * k + 1] = fma(j1, rr, ga[2 * k + 1]);
+                }
+            }
+            rsq = fma(rr, rr, rsq);
+        } else {
+            for (int c = 2 * lane; c < n; c += 64) {
+                double2 wv = *reinterpret_cast<const double2*>(wr + c);
+                *reinterpret_cast<double2*>(ar + c) = make_double2(__dmul_rn(ss, wv.x), __dmul_rn(ss, wv.y));
+            }
         }
         if (lane < ld - n) ar[n + lane] = (lane == 0) ? rr : 0.0;
         if (lane == 0) { u[i] = uu; r[i] = rr; s[i] = ss; }
     }
+    if (NC > 0) {
+        double* gs = xs + n;
+        const int w = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const int c = 2 * lane + 64 * k;
+            if (c < n) { gs[w * (n + 1) + c] = ga[2 * k]; gs[w * (n + 1) + c + 1] = ga[2 * k + 1]; }
+        }
+        if (lane == 0) gs[w * (n + 1) + n] = rsq;
+        __syncthreads();
+        for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+            double t = 0.0;
+            for (int ww = 0; ww < 8; ++ww) t += gs[ww * (n + 1) + j];
+            gpart[(size_t)blockIdx.x * (n + 1) + j] = t;
+        }
+    }
+}
+
+// generic J'r for wide problems (n > 512): gpart[b][j] = sum over the rows of CTA b of A[i][j] * A[i][n]  (A = [J | r]),
+// [n] = r'r; thread = column
+__global__ void __launch_bounds__(256) li_grad_kernel(const double* __restrict__ A, int ld, long long m, int n,
+                                                      double* __restrict__ gpart) {
+    const long long per = (m + gridDim.x - 1) / gridDim.x;
+    const long long i0 = per * blockIdx.x, i1 = (i0 + per < m) ? i0 + per : m;
+    for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+        double t = 0.0;
+        for (long long i = i0; i < i1; ++i) t = fma(A[i * ld + j], A[i * ld + n], t);
+        gpart[(size_t)blockIdx.x * (n + 1) + j] = t;
+    }
+}
+
+// out[j] = sum_b gpart[b][j] in a fixed order (one thread per column, 4 independent chains)
+__global__ void __launch_bounds__(256) li_grad_finish_kernel(const double* __restrict__ gpart, int nparts, int n,
+                                                             double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nparts; b += 4) {
+        t0 += gpart[(size_t)b * (n + 1) + j];
+        t1 += gpart[(size_t)(b + 1) * (n + 1) + j];
+        t2 += gpart[(size_t)(b + 2) * (n + 1) + j];
+        t3 += gpart[(size_t)(b + 3) * (n + 1) + j];
+    }
+    for (; b < nparts; ++b) t0 += gpart[(size_t)b * (n + 1) + j];
+    out[j] = (t0 + t1) + (t2 + t3);
 }
 
 __device__ __forceinline__ void block_reduce4(double (&v)[4], double* part) {
@@ -366,6 +437,11 @@ struct LargeHandle : LargeOps, DenseAccel {
         dq_p = nullptr;
         if (hpin) cudaFreeHost(hpin);
         hpin = nullptr;
+        if (hgrad) cudaFreeHost(hgrad);
+        hgrad = nullptr;
+        if (dgpart) cudaFree(dgpart);
+        if (dgrad) cudaFree(dgrad);
+        dgpart = dgrad = nullptr;
         dq_f = dq_m = dq_small = dJc = nullptr;
         dq_f_cap = dq_m_cap = dq_small_cap = dq_p_cap = 0;
         ownW = owny = dA = du = dr = ds = dv = dJp = dx = dp = dT = dpart = dout = dR = dStack = dR2 = nullptr;
@@ -397,6 +473,9 @@ struct LargeHandle : LargeOps, DenseAccel {
         LCU(cudaMalloc(&dpart, sizeof(double) * LI_PARTS * 4));
         LCU(cudaMalloc(&dout, sizeof(double) * 8));
         LCU(cudaHostAlloc(&hpin, sizeof(double) * 8, cudaHostAllocDefault));
+        LCU(cudaMalloc(&dgpart, sizeof(double) * LI_PARTS * (size_t)(n + 1)));
+        LCU(cudaMalloc(&dgrad, sizeof(double) * (n + 1)));
+        LCU(cudaHostAlloc(&hgrad, sizeof(double) * (n + 1), cudaHostAllocDefault));
         LCU(cudaMalloc(&dR, sizeof(double) * rr_rows * ld));
         LCU(cudaMalloc(&dJc, sizeof(double) * (size_t)(n + 1) * (n + 1)));
         hR.resize((size_t)(n + 1) * (n + 1));
@@ -422,16 +501,53 @@ struct LargeHandle : LargeOps, DenseAccel {
     }
     int cur_parts = LI_PARTS;
     double* hpin = nullptr;
+    double *dgpart = nullptr, *dgrad = nullptr, *hgrad = nullptr;   // J'r partials [LI_PARTS][n+1], result [n+1], pinned copy
+    bool point_factored = true;
+    long long n_factor = 0;
 
-    // factor [J | r] at x: dJc = column-major [J~ | r~] (identical on every rank), optionally copied to hR
-    int factor_at(const double* x, bool want_host_R = true) {
+    // r, s, u and [J | r] at x (li_build_kernel), gradient J'r and r'r reduced over CTAs and ranks -> hgrad (pinned)
+    int eval_at(const double* x) {
         LCU(cudaSetDevice(device));
         LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         LCU(cudaEventRecord(e0, st));
+        int parts = grid_rows();
         if (m_local > 0) {
-            li_build_kernel<<<grid_rows(), 256, sizeof(double) * n, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds);
-            ++launches;
+            const int nc = (n + 63) / 64;
+            const size_t sh = sizeof(double) * (n + 8 * (size_t)(n + 1));
+            if (nc <= 1) li_build_kernel<1><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+            else if (nc <= 2) li_build_kernel<2><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+            else if (nc <= 4) li_build_kernel<4><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+            else if (nc <= 8) li_build_kernel<8><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+            else {
+                li_build_kernel<0><<<parts, 256, sizeof(double) * n, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                li_grad_kernel<<<parts, 256, 0, st>>>(dA, ld, m_local, n, dgpart);
+                ++launches;
+            }
+            li_grad_finish_kernel<<<(n + 256) / 256, 256, 0, st>>>(dgpart, parts, n, dgrad);
+            launches += 2;
+        } else {
+            LCU(cudaMemsetAsync(dgrad, 0, sizeof(double) * (n + 1), st));
         }
+        if (nranks > 1) {
+            int rc = g_nccl.AllReduce(dgrad, dgrad, (size_t)n + 1, NCCL_FLOAT64, NCCL_SUM, comm, st);
+            if (rc != 0) return lfail(ENLSIPB200_ECUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+        }
+        LCU(cudaEventRecord(e1, st));
+        LCU(cudaMemcpyAsync(hgrad, dgrad, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        LCU(cudaGetLastError());
+        LCU(cudaEventElapsedTime(&last_build_ms, e0, e1));
+        ms_build += last_build_ms;
+        ++n_newpoint;
+        point_factored = false;
+        return 0;
+    }
+
+    // factor the [J | r] of the last eval_at: dJc = column-major [J~ | r~] (identical on every rank), optionally
+    // copied to hR.  Destroys [J | r] (in-place Householder), so it runs at most once per point.
+    int factor_point(bool want_host_R = true) {
+        if (point_factored) return lfail(ENLSIPB200_EINVAL, "point already factored");
+        LCU(cudaSetDevice(device));
         LCU(cudaEventRecord(e1, st));
         LCU(cudaMemsetAsync(dR, 0, sizeof(double) * rr_rows * ld, st));
         launches += tsqr_factor(dA, ld, rows_pad, n, dR, ld, dT, dpart, st);
@@ -450,28 +566,38 @@ struct LargeHandle : LargeOps, DenseAccel {
             ++launches;
         }
         jq1_resident = false;
+        point_factored = true;
         LCU(cudaEventRecord(e2, st));
         if (want_host_R) LCU(cudaMemcpyAsync(hR.data(), dJc, sizeof(double) * (size_t)(n + 1) * (n + 1), cudaMemcpyDeviceToHost, st));
         LCU(cudaStreamSynchronize(st));
         LCU(cudaGetLastError());
-        LCU(cudaEventElapsedTime(&last_build_ms, e0, e1));
         LCU(cudaEventElapsedTime(&last_tsqr_ms, e1, e2));
-        ms_build += last_build_ms;
         ms_tsqr += last_tsqr_ms;
-        ++n_newpoint;
+        ++n_factor;
         return 0;
+    }
+    int factor_at(const double* x, bool want_host_R = true) {
+        int rc = eval_at(x);
+        return rc != 0 ? rc : factor_point(want_host_R);
     }
 
     // ---- LargeOps ----
-    int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
-        int rc = factor_at(x, false);
+    int eval_point(const double* x, double* gradf, double* rr, double* cx, double* A) override {
+        int rc = eval_at(x);
+        if (rc != 0) return rc;
+        for (int j = 0; j < n; ++j) gradf[j] = hgrad[j];
+        *rr = hgrad[n];
+        sc.cons(x, cx);
+        sc.jac(x, A);
+        return 0;
+    }
+    int compress(double* Jt, double* rt) override {
+        int rc = factor_point(false);
         if (rc != 0) return rc;
         const size_t mt = (size_t)n + 1;
         LCU(cudaMemcpyAsync(Jt, dJc, sizeof(double) * mt * n, cudaMemcpyDeviceToHost, st));
         LCU(cudaMemcpyAsync(rt, dJc + mt * n, sizeof(double) * mt, cudaMemcpyDeviceToHost, st));
         LCU(cudaStreamSynchronize(st));
-        sc.cons(x, cx);
-        sc.jac(x, A);
         return 0;
     }
     int set_direction(const double*, const double* p, double sums[3]) override {
@@ -670,9 +796,10 @@ int enlsipb200_large_factor(enlsipb200_large hh, const double* x, double* R, flo
 int enlsipb200_large_stats(enlsipb200_large hh, double* out, int count) {
     LargeHandle* h = LH(hh);
     if (!h || !out) return lfail(ENLSIPB200_EINVAL, "NULL argument");
-    double v[11] = {(double)h->n_newpoint, h->ms_build, h->ms_tsqr, h->ms_ls, h->ms_total, (double)h->n_ls,
-                    (double)h->launches, (double)h->rows_pad, (double)h->n_dev_qrcp, (double)h->n_dev_mulq, h->ms_dense};
-    for (int i = 0; i < count && i < 11; ++i) out[i] = v[i];
+    double v[12] = {(double)h->n_newpoint, h->ms_build, h->ms_tsqr, h->ms_ls, h->ms_total, (double)h->n_ls,
+                    (double)h->launches, (double)h->rows_pad, (double)h->n_dev_qrcp, (double)h->n_dev_mulq, h->ms_dense,
+                    (double)h->n_factor};
+    for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
     return 0;
 }
 

@@ -313,9 +313,13 @@ struct LargeOps {
     int n = 0, l = 0, q = 0;
     long long m = 0;         // true number of residuals (all shards)
     virtual ~LargeOps() {}
-    // evaluate r, J, c, A at x and compress: Jt ((n+1) x n, column major) = [R_J; 0],
-    // rt (n+1) = [z; rho];  cx (l), A (l x n, column major).  Returns 0 or an API error.
-    virtual int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) = 0;
+    // evaluate r, J, c, A at x (new_point!, EF:34-52): the m-sized part stays with the backend; returned are
+    // gradf = J'r (n), *rr = r'r, cx (l), A (l x n, column major).  Returns 0 or an API error.
+    // This is all the termination test of the point needs (EF:2838 reads ||J'r||, ||r||^2 and c), so the
+    // factorisation below is only paid for points from which the iteration goes on.
+    virtual int eval_point(const double* x, double* gradf, double* rr, double* cx, double* A) = 0;
+    // compress the point of the last eval_point: Jt ((n+1) x n, column major) = [R_J; 0], rt (n+1) = [z; rho]
+    virtual int compress(double* Jt, double* rt) = 0;
     // fix the direction of the linesearch at the current point: sums = {r.r, r.Jp, Jp.Jp}
     virtual int set_direction(const double* x, const double* p, double sums[3]) = 0;
     // ||r(x + alpha p)||^2
@@ -415,11 +419,25 @@ public:
     // ---- small helpers ------------------------------------------------------------------
     void check(int rc) { if (rc != 0) throw std::runtime_error("LargeOps failure"); }
 
-    void do_new_point(const Vec& x) { ProfScope prof_(0);   // EF:34-52
-        check(ops.new_point(x.data(), J.a.data(), rx.data(), cx.data(), A.a.data()));
+    // EF:34-52 in two halves.  do_eval_point: r, c, A at x and the two m-sized quantities of the termination test
+    // (gradf = J'r, returned ||r||^2).  do_factor: the compressed problem [J~ | r~] of that point -- called only when
+    // the iteration continues from it, after which gradf / ||r||^2 are re-derived from the compressed problem so that
+    // every quantity of an iteration comes from one and the same factorisation.
+    double do_eval_point(const Vec& x) { ProfScope prof_(0);
+        double rr = 0.0;
+        check(ops.eval_point(x.data(), gradf.data(), &rr, cx.data(), A.a.data()));
         ++n_new_point;
         jq1_valid = false;
+        cur_rr = rr;
+        return rr;
     }
+    double do_factor() { ProfScope prof_(0);
+        check(ops.compress(J.a.data(), rx.data()));
+        compute_gradf();
+        cur_rr = dotv(rx, rx);
+        return cur_rr;
+    }
+    double cur_rr = 0.0;   // ||r||^2 at the point of the last do_eval_point
     void compute_gradf() { ProfScope prof_(14);   // J' * rx
         for (int j = 0; j < n; ++j) gradf[j] = dot_n(J.col(j), rx.data(), mt);
     }
@@ -1606,8 +1624,8 @@ public:
             res.trace_x.insert(res.trace_x.end(), x.begin(), x.end());
         };
         try {
-            do_new_point(x);
-            f_opt = dotv(rx, rx);
+            do_eval_point(x);
+            f_opt = do_factor();
             IterL first;
             first.x = x; first.p.assign(n, 0.0); first.t = l; first.alpha = 1.0; first.lam.assign(l, 0.0);
             first.w.assign(l, 0.0); first.b_gn.assign(n, 0.0); first.d_gn.assign(n, 0.0);
@@ -1631,15 +1649,14 @@ public:
             first.alpha = alpha;
             first.w = w;
             for (int j = 0; j < n; ++j) x[j] = first.x[j] + alpha * first.p[j];
-            do_new_point(x);
-            compute_gradf();
-            rx_sum = dotv(rx, rx);
+            rx_sum = do_eval_point(x);
             first.restart = error_code < 0;
             double sigma_min, lam_abs_max;
             minmax_lagrangian_mult(first.lam, sigma_min, lam_abs_max);
             double delta_time = elapsed() - opt.time_limit;
             exit_code = check_termination_criteria(first, prev, x, rx_sum, nb_iteration, error_code, delta_time,
                                                    sigma_min, lam_abs_max, Psi_error);
+            if (exit_code == 0) rx_sum = do_factor();
             ++ndetail;
             record(0, first, rx_sum, active_cx_sum, exit_code);
             first.add = evaluate_violated_constraints(first.index_alpha_upp);
@@ -1668,14 +1685,13 @@ public:
                 it.alpha = alpha;
                 it.w = w;
                 for (int j = 0; j < n; ++j) x[j] = xk[j] + alpha * it.p[j];
-                do_new_point(x);
-                rx_sum = dotv(rx, rx);
-                compute_gradf();
+                rx_sum = do_eval_point(x);
                 it.restart = error_code < 0;
                 minmax_lagrangian_mult(it.lam, sigma_min, lam_abs_max);
                 delta_time = elapsed() - opt.time_limit;
                 exit_code = check_termination_criteria(it, prev, x, rx_sum, nb_iteration, error_code, delta_time,
                                                        sigma_min, lam_abs_max, Psi_error);
+                if (exit_code == 0) rx_sum = do_factor();
                 record(nb_iteration, it, rx_sum, active_cx_sum, exit_code);
                 if (exit_code == 0) {
                     f_opt = rx_sum;
@@ -1699,9 +1715,9 @@ public:
             res.x = x_opt;
             res.f = f_opt;
         } catch (const WouldThrow&) {
-            res.exit_code = -99; res.status = -1; res.x = x; res.f = dotv(rx, rx);
+            res.exit_code = -99; res.status = -1; res.x = x; res.f = cur_rr;
         } catch (const WouldHang&) {
-            res.exit_code = -98; res.status = -1; res.x = x; res.f = dotv(rx, rx);
+            res.exit_code = -98; res.status = -1; res.x = x; res.f = cur_rr;
         }
         res.iterations = ndetail;
         res.nact = W.t;

@@ -136,9 +136,9 @@ int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb20
 /* measurement / test hook: evaluate [J | r] at x and factor it; R [(n+1) x (n+1)] row major (may be NULL);
  * device times of the two stages (CUDA events on the handle's stream) */
 int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
-/* cumulative counters: {factorisations, build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
+/* cumulative counters: {points evaluated (new_point!), build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
  * evaluations (host clock around launch..result), kernels launched, padded local rows, device QRCPs, device M*Q products, ms in those two
- * (host clock, transfers included)} */
+ * (host clock, transfers included), factorisations of [J | r] (one per point from which the iteration continued)} */
 int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
 
 #ifdef __cplusplus

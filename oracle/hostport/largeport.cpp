@@ -64,18 +64,41 @@ struct CpuOps : LargeOps {
             }
         }
     }
-    int new_point(const double* x, double* Jt, double* rt, double* cx, double* A) override {
-        const int nc = n + 1;
-        long long m = rows;
+    int eval_point(const double* x, double* gradf, double* rr, double* cx, double* A) override {
+        const long long m = rows;
         u.resize(m); r.resize(m); s.resize(m);
         eval_u(x, u);
-        // augmented matrix [diag(s) W | r], column major for the Householder sweep
-        std::vector<double> M((size_t)m * nc);
-#pragma omp parallel for num_threads(nthreads) schedule(static)
+        double a = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : a)
         for (long long i = 0; i < m; ++i) {
             double th = enl::det_tanh(u[i]);
             r[i] = th - y[i];
             s[i] = 1.0 - th * th;
+            a += r[i] * r[i];
+        }
+        // J'r with J = diag(s) W
+        std::vector<double> g(n + 1, 0.0);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0;
+            for (long long i = 0; i < m; ++i) acc += (s[i] * W[(size_t)i * n + j]) * r[i];
+            g[j] = acc;
+        }
+        g[n] = a;
+        if (world > 1) ar(g.data(), n + 1);
+        for (int j = 0; j < n; ++j) gradf[j] = g[j];
+        *rr = g[n];
+        sc.cons(x, cx);
+        sc.jac(x, A);
+        return 0;
+    }
+    int compress(double* Jt, double* rt) override {
+        const int nc = n + 1;
+        long long m = rows;
+        // augmented matrix [diag(s) W | r], column major for the Householder sweep
+        std::vector<double> M((size_t)m * nc);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (long long i = 0; i < m; ++i) {
             for (int j = 0; j < n; ++j) M[(size_t)j * m + i] = s[i] * W[(size_t)i * n + j];
             M[(size_t)n * m + i] = r[i];
         }
@@ -97,8 +120,6 @@ struct CpuOps : LargeOps {
         for (int c = 0; c < n; ++c)
             for (int rr = 0; rr < mt; ++rr) Jt[(size_t)c * mt + rr] = (rr <= c && rr < m) ? M[(size_t)c * m + rr] : 0.0;
         for (int rr = 0; rr < mt; ++rr) rt[rr] = (rr < m) ? M[(size_t)n * m + rr] : 0.0;
-        sc.cons(x, cx);
-        sc.jac(x, A);
         return 0;
     }
     int set_direction(const double*, const double* p, double sums[3]) override {
@@ -200,9 +221,11 @@ extern "C" int largeport_new_point(int n, long long m, const double* W, const do
     CpuOps ops;
     ops.n = n; ops.m = m; ops.rows = m; ops.W = W; ops.y = y; ops.nthreads = nthreads < 1 ? 1 : nthreads;
     ops.sc.n = n; ops.sc.nb = 0;
-    std::vector<double> Jt((size_t)(n + 1) * n), rt(n + 1), cx(1), A(1);
+    std::vector<double> Jt((size_t)(n + 1) * n), rt(n + 1), cx(1), A(1), g(n);
+    double rr = 0;
     ops.l = 0; ops.q = 0;
-    ops.new_point(x, Jt.data(), rt.data(), cx.data(), A.data());
+    ops.eval_point(x, g.data(), &rr, cx.data(), A.data());
+    ops.compress(Jt.data(), rt.data());
     *rho_out = rt[n];
     return 0;
 }

@@ -23,7 +23,7 @@ def run(m, n, nb, seed, oracle=True, bounds=(-2.0, 2.0), max_iter=100):
     st = mod.stats()
     k = int(mod.iterations[0])
     print("engine m=%d n=%d nb=%d: ec=%d it=%d nact=%d f=%.12g  wall %.2fs (%.3f s / executed iteration)"
-          % (m, n, nb, mod.exit_code[0], k, mod.nb_active[0], mod.obj_value[0], t1 - t0, (t1 - t0) / max(st["factorisations"] - 1, 1)))
+          % (m, n, nb, mod.exit_code[0], k, mod.nb_active[0], mod.obj_value[0], t1 - t0, (t1 - t0) / max(st["points"] - 1, 1)))
     print("   stats", {a: round(b, 2) for a, b in st.items()})
     tr = mod.trace[0]
     print("   t / rankA / rankJ2 / code per iteration:", [(int(e[1]), int(e[2]), int(e[3]), int(e[6])) for e in tr[:min(k + 1, 12)]])
