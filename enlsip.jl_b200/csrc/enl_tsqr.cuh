@@ -26,6 +26,7 @@
 // Algorithmic flops: 2 m n^2 (n = number of columns).  See DESIGN.md for the roofline accounting.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace enl_large {
 
@@ -398,6 +399,184 @@ tsqr_trail_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
     tsqr_trail_body<CB>(A, ld, nblk, stride, col0, col0 + TS_B + CB * cb, sub, Tbuf, smem);
 }
 
+// ---------------------------------------------------------------------------------------------
+// trailing update, staged form: one CTA per (subtile, chunk of 32-column blocks)
+// ---------------------------------------------------------------------------------------------
+// The reflector block V (256 x 32) and T are brought into shared memory ONCE per CTA with cp.async and serve every
+// column block of the chunk; the 256 x 32 block of B is staged by cp.async as well, and the copy of the NEXT block is
+// in flight while the W stage and the second product of the current one run.  All DMMA operands then come from
+// shared memory (leading dimension 36 doubles: conflict-free m8n8k4 fragment loads for both products), so no warp
+// waits on a global load in front of the tensor pipe.
+//   pass 1  G = V'B : warps 0-3 take rows 0..127, warps 4-7 rows 128..255; inside a half each warp owns one 16 x 16
+//           quadrant of G (2 x 2 tiles, 4 independent accumulator chains); the two half sums land in G0 / G1 and are
+//           added, in that fixed order, where they are consumed -- no reduction tree, one barrier
+//   W stage W = -T'(G0 + G1), 2 tiles per warp
+//   pass 2  B_w += V_w W : warp w owns rows 32w..32w+31 (4 x 4 tiles), accumulators preloaded from the staged block
+// B is read from HBM once and written once; V once per chunk.
+constexpr int TR_LD = 36;
+constexpr int TR_ROWS = TS_B * TS_FAN;   // 256
+#ifndef TR_NW
+#define TR_NW 8                          // warps per CTA (8 or 16)
+#endif
+constexpr int TR_KS = TR_NW / 4;         // row splits of pass 1 (each split: 4 warps = the 4 quadrants of G)
+constexpr int TR_SMEM = (2 * TR_ROWS * TR_LD + (2 + TR_KS) * TS_B * TR_LD) * (int)sizeof(double);   // V, B | T, W, G[KS]
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
+tsqr_trail_staged_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb, int cbpc,
+                         const double* __restrict__ Tbuf) {
+    constexpr int NTH = 32 * NW;
+    constexpr int KS = NW / 4;            // row splits in pass 1
+    constexpr int KROWS = TR_ROWS / KS;   // rows per split
+    constexpr int RW = TR_ROWS / NW;      // rows per warp in pass 2
+    constexpr int RT = RW / 8;            // 8-row tiles per warp in pass 2
+    extern __shared__ __align__(16) double smem[];
+    double* Vs = smem;
+    double* Bs = Vs + TR_ROWS * TR_LD;
+    double* Ts = Bs + TR_ROWS * TR_LD;
+    double* Ws = Ts + TS_B * TR_LD;
+    double* Gs = Ws + TS_B * TR_LD;       // KS partial sums of G, one per row split
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int nchunks = (ncb + cbpc - 1) / cbpc;
+    const long long sub = blockIdx.x / (unsigned)nchunks;
+    const int chunk = (int)(blockIdx.x % (unsigned)nchunks);
+    const int cb_begin = chunk * cbpc;
+    const int cb_end = (cb_begin + cbpc < ncb) ? cb_begin + cbpc : ncb;
+    // 256 x 32 tile at column c0 of this subtile -> dst (16-byte chunks; 16 consecutive threads cover one row)
+    auto stage = [&](double* dst, int c0) {
+#pragma unroll
+        for (int q = 0; q < 4096 / NTH; ++q) {
+            const int id = tid + NTH * q;
+            const int row = id >> 4, c16 = id & 15;
+            const long long blk = (sub * TS_FAN + (row >> 5)) * stride;
+            const bool ok = blk < nblk;
+            const double* src = ok ? A + (blk * TS_B + (row & 31)) * (long long)ld + c0 + 2 * c16 : A;
+            cp_async16(dst + row * TR_LD + 2 * c16, src, ok);
+        }
+    };
+    stage(Vs, col0);
+    stage(Bs, col0 + TS_B * (cb_begin + 1));
+    cp_async_commit();
+    {
+        const double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+        for (int q = 0; q < 1024 / NTH; ++q) {
+            const int idx = tid + NTH * q;
+            Ts[(idx >> 5) * TR_LD + (idx & 31)] = Tg[idx];
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // the top block of V is a unit lower trapezoid (R of the panel sits on and above its diagonal)
+#pragma unroll
+    for (int q = 0; q < 1024 / NTH; ++q) {
+        const int idx = tid + NTH * q;
+        const int r = idx >> 5, c = idx & 31;
+        if (r <= c) Vs[r * TR_LD + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const long long myblk = (sub * TS_FAN + ((w * RW) >> 5)) * stride;   // block holding this warp's rows of pass 2
+    const bool valid = myblk < nblk;
+    const int kh = w >> 2, qd = w & 3;
+    const int ti0 = (qd >> 1) * 2, tj0 = (qd & 1) * 2;
+    double* Gk = Gs + kh * (TS_B * TR_LD);
+    for (int cb = cb_begin; cb < cb_end; ++cb) {
+        if (cb > cb_begin) {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        // ---- pass 1: this warp's quadrant of G over its share of the rows ----
+        double acc[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        {
+            const double* vp = Vs + (kh * KROWS + t) * TR_LD + ti0 * 8 + g;
+            const double* bp = Bs + (kh * KROWS + t) * TR_LD + tj0 * 8 + g;
+#pragma unroll 8
+            for (int kk = 0; kk < KROWS / 4; ++kk) {
+                const double a0 = vp[kk * 4 * TR_LD], a1 = vp[kk * 4 * TR_LD + 8];
+                const double b0 = bp[kk * 4 * TR_LD], b1 = bp[kk * 4 * TR_LD + 8];
+                dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+                dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+                dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+                dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(Gk + ((ti0 + i) * 8 + g) * TR_LD + (tj0 + j) * 8 + 2 * t) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+        // accumulators of pass 2: this warp's rows of the staged block
+        double b2[RT][4][2];
+#pragma unroll
+        for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < 4; ++cj) {
+                const double2 v = *reinterpret_cast<const double2*>(Bs + (w * RW + ri * 8 + g) * TR_LD + cj * 8 + 2 * t);
+                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
+            }
+        __syncthreads();
+        if (cb + 1 < cb_end) {   // Bs is free: the next block streams in during the W stage and pass 2
+            stage(Bs, col0 + TS_B * (cb + 2));
+            cp_async_commit();
+        }
+        // ---- W = -T' G, G = the row-split partial sums added in a fixed order: 16 tiles over the warps ----
+#pragma unroll
+        for (int id = w; id < 16; id += NW) {
+            const int ti = id >> 2, tj = id & 3;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int o = (kk * 4 + t) * TR_LD + tj * 8 + g;
+                double gv;
+                if (KS == 2) gv = Gs[o] + Gs[TS_B * TR_LD + o];
+                else gv = (Gs[o] + Gs[TS_B * TR_LD + o]) + (Gs[2 * TS_B * TR_LD + o] + Gs[3 * TS_B * TR_LD + o]);
+                dmma884(c0, c1, Ts[(kk * 4 + t) * TR_LD + ti * 8 + g], gv);
+            }
+            *reinterpret_cast<double2*>(Ws + (ti * 8 + g) * TR_LD + tj * 8 + 2 * t) = make_double2(-c0, -c1);
+        }
+        __syncthreads();
+        // ---- pass 2: B_w += V_w W ----
+        {
+            const double* vp = Vs + (w * RW + g) * TR_LD + t;
+            const double* wp = Ws + t * TR_LD + g;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                double av[RT], bw[4];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri) av[ri] = vp[ri * 8 * TR_LD + kk * 4];
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj) bw[cj] = wp[kk * 4 * TR_LD + cj * 8];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                    for (int cj = 0; cj < 4; ++cj) dmma884(b2[ri][cj][0], b2[ri][cj][1], av[ri], bw[cj]);
+            }
+        }
+        if (valid) {
+            double* Bb = A + (myblk * TS_B + ((w * RW) & 31)) * (long long)ld + col0 + TS_B * (cb + 1);
+#pragma unroll
+            for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj)
+                    *reinterpret_cast<double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t) =
+                        make_double2(b2[ri][cj][0], b2[ri][cj][1]);
+        }
+    }
+}
+
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
 __global__ void tsqr_extract_kernel(double* __restrict__ A, int ld, int col0, int ncols, double* __restrict__ Rout,
                                     int ldr) {
@@ -447,6 +626,9 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     int launches = 0;
     // > 48 KB of dynamic shared memory needs the opt-in (per device, so it is simply set on every call)
     cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
+    cudaFuncSetAttribute(tsqr_trail_staged_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
+    // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
+    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : 2; }();
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
@@ -457,7 +639,15 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             long long nsub = (nb_level + TS_FAN - 1) / TS_FAN;
             tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             ++launches;
-            if (ncb32 > 0) {
+            if (ncb32 > 0 && trail_mode == 2) {
+                // chunk = all column blocks of the subtile while there are enough subtiles to fill the machine
+                int cbpc = ncb32;
+                while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
+                const int nchunks = (ncb32 + cbpc - 1) / cbpc;
+                tsqr_trail_staged_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * TR_NW, TR_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32,
+                                                                                          cbpc, Tbuf);
+                ++launches;
+            } else if (ncb32 > 0) {
                 constexpr int CBW = TS_TRAIL_CB;
                 const int ncb = ncb32 * (32 / CBW);
                 tsqr_trail_kernel<CBW><<<(unsigned)(nsub * ncb), 256, TS_TRAIL_SMEM, st>>>(A, ld, nblk, stride, col0, ncb, Tbuf);
