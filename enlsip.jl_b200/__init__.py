@@ -7,9 +7,9 @@ library only: importing works without a GPU, but every solve raises if the exten
 device is missing -- there is no CPU fallback.
 """
 from . import capi, synth
-from .model import (CnlsModel, solve, solve_b, status, solution, sum_sq_residuals, constraints_values,
+from .model import (CnlsModel, UserFamily, solve, solve_b, status, solution, sum_sq_residuals, constraints_values,
                     total_nb_constraints, dict_status_codes)
 from .model_large import LargeCnlsModel, solve_large
 
-__all__ = ["capi", "synth", "CnlsModel", "solve", "solve_b", "status", "solution", "sum_sq_residuals",
+__all__ = ["capi", "synth", "CnlsModel", "UserFamily", "solve", "solve_b", "status", "solution", "sum_sq_residuals",
            "constraints_values", "total_nb_constraints", "dict_status_codes", "LargeCnlsModel", "solve_large"]

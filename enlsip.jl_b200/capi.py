@@ -8,7 +8,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libenlsip_b200.so")
 SRC = os.path.join(_HERE, "csrc", "enlsip_b200.cu")
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_linalg.h", "enl_families.h", "enl_solver.h")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_linalg.h", "enl_families.h", "enl_solver.h",
+                                                    "enl_user_family.h")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "enlsip_b200.h")]
 # second translation unit: the large-Jacobian regime (TSQR + host-driven iteration)
 SRC_LARGE = os.path.join(_HERE, "csrc", "enl_large.cu")
@@ -23,6 +24,7 @@ FAMILY_GAUSS_PEAKS = 1
 FAMILY_OSBORNE2 = 2
 FAMILY_CHAINED_ROSENBROCK10 = 3
 FAMILY_CHAINED_WOOD20 = 4
+FAMILY_USER = 64          # run-time compiled family: lives in the library written by compile_family()
 JAC_ANALYTIC = 0
 JAC_FORWARD_DIFF = 1
 TRACE_HDR = 16
@@ -31,6 +33,7 @@ EXIT_WOULD_THROW, EXIT_WOULD_HANG, EXIT_CAPACITY = -99, -98, -97
 EXPORTS = ["enlsipb200_version", "enlsipb200_last_error", "enlsipb200_default_options", "enlsipb200_create",
            "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data", "enlsipb200_solve_batch",
            "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count", "enlsipb200_det_exp",
+           "enlsipb200_compile_family",
            "enlsipb200_large_last_error", "enlsipb200_large_create", "enlsipb200_large_destroy",
            "enlsipb200_large_set_data", "enlsipb200_large_comm_id", "enlsipb200_large_comm_init",
            "enlsipb200_large_solve", "enlsipb200_large_factor", "enlsipb200_large_stats"]
@@ -73,31 +76,27 @@ def build(force=False, verbose=False):
 _lib = None
 
 
-def lib():
-    """Load the CUDA library.  Raises if it has not been built: no fallback of any kind."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError("libenlsip_b200.so is missing (%s): run __graft_entry__.build(); "
-                               "the engine has no CPU fallback" % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
-        vp, ip, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
-        L.enlsipb200_version.restype = ctypes.c_int
-        L.enlsipb200_last_error.restype = ctypes.c_char_p
-        L.enlsipb200_default_options.argtypes = [ctypes.POINTER(Options)]
-        L.enlsipb200_default_options.restype = None
-        L.enlsipb200_create.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.POINTER(vp)]
-        L.enlsipb200_destroy.argtypes = [vp]
-        L.enlsipb200_dims.argtypes = [vp, ip, ip, ip, ip, ip]
-        L.enlsipb200_set_data.argtypes = [vp, ctypes.c_int, vp, ctypes.c_longlong, ctypes.c_int, vp]
-        L.enlsipb200_solve_batch.argtypes = [vp, ctypes.c_longlong, vp, ctypes.POINTER(Options)] + [vp] * 9 + \
-                                            [ctypes.c_int, ctypes.c_int, vp]
-        L.enlsipb200_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
-        L.enlsipb200_kernel_info.argtypes = [vp, ip, ip, ip, ip, ip, ip]
-        L.enlsipb200_launch_count.argtypes = [vp]
-        L.enlsipb200_launch_count.restype = ctypes.c_longlong
-        L.enlsipb200_det_exp.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_int]
-        ll, ci = ctypes.c_longlong, ctypes.c_int
+def _bind(L, large=True):
+    """Attach the prototypes of include/enlsip_b200.h to a loaded library."""
+    vp, ip, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    ll, ci, cs = ctypes.c_longlong, ctypes.c_int, ctypes.c_char_p
+    L.enlsipb200_version.restype = ctypes.c_int
+    L.enlsipb200_last_error.restype = ctypes.c_char_p
+    L.enlsipb200_default_options.argtypes = [ctypes.POINTER(Options)]
+    L.enlsipb200_default_options.restype = None
+    L.enlsipb200_create.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, ctypes.POINTER(vp)]
+    L.enlsipb200_destroy.argtypes = [vp]
+    L.enlsipb200_dims.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.enlsipb200_set_data.argtypes = [vp, ctypes.c_int, vp, ctypes.c_longlong, ctypes.c_int, vp]
+    L.enlsipb200_solve_batch.argtypes = [vp, ctypes.c_longlong, vp, ctypes.POINTER(Options)] + [vp] * 9 + \
+                                        [ctypes.c_int, ctypes.c_int, vp]
+    L.enlsipb200_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.enlsipb200_kernel_info.argtypes = [vp, ip, ip, ip, ip, ip, ip]
+    L.enlsipb200_launch_count.argtypes = [vp]
+    L.enlsipb200_launch_count.restype = ctypes.c_longlong
+    L.enlsipb200_det_exp.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_int]
+    L.enlsipb200_compile_family.argtypes = [cs, ci, ci, ci, ci, ci, ci, ci, cs, cs]
+    if large:
         L.enlsipb200_large_last_error.restype = ctypes.c_char_p
         L.enlsipb200_large_create.argtypes = [ci, ci, ll, ll, ci, ci, vp, vp, vp, ci, ctypes.POINTER(vp)]
         L.enlsipb200_large_destroy.argtypes = [vp]
@@ -107,17 +106,55 @@ def lib():
         L.enlsipb200_large_solve.argtypes = [vp, vp, ctypes.POINTER(Options)] + [vp] * 8 + [ci]
         L.enlsipb200_large_factor.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         L.enlsipb200_large_stats.argtypes = [vp, vp, ci]
-        _lib = L
+    return L
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built: no fallback of any kind."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libenlsip_b200.so is missing (%s): run __graft_entry__.build(); "
+                               "the engine has no CPU fallback" % LIB_PATH)
+        _lib = _bind(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+USER_LIB_DIR = os.path.join(_HERE, "lib", "user")
+_user_libs = {}
+
+
+def compile_family(source, n, m, nb_eq=0, nb_ineq=0, stride0=0, stride1=0, has_jacobians=False, name=None):
+    """enlsipb200_compile_family: compile the solver around user CUDA source (the replacement of the reference's
+    closure arguments, cnls_model.jl:345-359).  Returns the loaded library, which exports the same C ABI with
+    family id FAMILY_USER.  Libraries are cached in lib/user/ by a hash of (source, sizes, solver headers)."""
+    import hashlib
+    hsh = hashlib.sha256()
+    hsh.update(repr((source, n, m, nb_eq, nb_ineq, stride0, stride1, bool(has_jacobians))).encode())
+    for p in [SRC] + HEADERS:
+        hsh.update(open(p, "rb").read())
+    tag = (name or "family") + "_" + hsh.hexdigest()[:16]
+    if tag in _user_libs:
+        return _user_libs[tag]
+    work = os.path.join(USER_LIB_DIR, tag)
+    out = os.path.join(USER_LIB_DIR, "libenlsip_b200_%s.so" % tag)
+    if not os.path.exists(out):
+        os.makedirs(work, exist_ok=True)
+        rc = lib().enlsipb200_compile_family(source.encode(), n, m, nb_eq, nb_ineq, stride0, stride1,
+                                             1 if has_jacobians else 0, out.encode(), work.encode())
+        check(rc)
+    L = _bind(ctypes.CDLL(out), large=False)
+    _user_libs[tag] = L
+    return L
 
 
 class EngineError(RuntimeError):
     pass
 
 
-def check(rc):
+def check(rc, L=None):
     if rc != 0:
-        raise EngineError("enlsip_b200 error %d: %s" % (rc, lib().enlsipb200_last_error().decode()))
+        raise EngineError("enlsip_b200 error %d: %s" % (rc, (L or lib()).enlsipb200_last_error().decode()))
 
 
 def check_large(rc):

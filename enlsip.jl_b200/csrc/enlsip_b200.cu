@@ -16,8 +16,16 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <unistd.h>
+
 #include "../../include/enlsip_b200.h"
 #include "enl_solver.h"
+// Run-time compiled family (enlsipb200_compile_family below): the generated prelude + the user's source are
+// force-included in front of this file (-include), then the family wrapper binds them to the solver.
+#if defined(ENL_USER_FAMILY)
+#include "enl_user_family.h"
+#endif
 
 using namespace enl;
 
@@ -206,6 +214,9 @@ int launch(enlsipb200_handle h, const KernelArgs& a, cudaStream_t st, bool first
 // doubles per problem of a family-data slot (0 = the slot is shared by all problems of the batch)
 int slot_stride(int family, int slot) {
     if (family == ENLSIPB200_FAMILY_GAUSS_PEAKS) return slot == 0 ? FamGaussPeaks::M : (slot == 1 ? 1 : 0);
+#if defined(ENL_USER_FAMILY)
+    if (family == ENLSIPB200_FAMILY_USER) return slot == 0 ? FamUser::STRIDE0 : (slot == 1 ? FamUser::STRIDE1 : 0);
+#endif
     return 0;
 }
 
@@ -228,6 +239,13 @@ using ic = std::integral_constant<int, V>;
 // family id (+ CTA size for the tuned family) -> template instantiation
 template <class F>
 int with_family(int family, int nt, F&& f) {
+#if defined(ENL_USER_FAMILY)
+    // a user library holds the user's family only (compile time: one kernel instead of ten); few rows: one thread per
+    // problem, otherwise one warp per problem
+    (void)nt;
+    if (family == ENLSIPB200_FAMILY_USER) return f(FamUser{}, ic<(FamUser::M <= 8 ? 1 : 32)>{}, ic<(FamUser::M <= 8 ? 64 : 32)>{});
+    return fail(ENLSIPB200_EINVAL, "this library was compiled for ENLSIPB200_FAMILY_USER only");
+#else
     switch (family) {
         case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<64>{});
         case ENLSIPB200_FAMILY_GAUSS_PEAKS:
@@ -243,7 +261,10 @@ int with_family(int family, int nt, F&& f) {
         case ENLSIPB200_FAMILY_CHAINED_ROSENBROCK10: return f(FamChainedRosenbrock<10>{}, ic<32>{}, ic<32>{});
         case ENLSIPB200_FAMILY_CHAINED_WOOD20: return f(FamChainedWood<20>{}, ic<32>{}, ic<32>{});
     }
+    if (family == ENLSIPB200_FAMILY_USER)
+        return fail(ENLSIPB200_EINVAL, "ENLSIPB200_FAMILY_USER lives in the library written by enlsipb200_compile_family");
     return fail(ENLSIPB200_EINVAL, "unknown family id");
+#endif
 }
 
 // lanes per problem / threads per CTA of each family
@@ -400,6 +421,10 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
         return fail(ENLSIPB200_EINVAL, "x0, x, f, exit_code, status, iters, nact are required");
     if ((h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS || h->family == ENLSIPB200_FAMILY_OSBORNE2) && (!h->data[0] || !h->data[1]))
         return fail(ENLSIPB200_EINVAL, "this family needs data slots 0 and 1 (GAUSS_PEAKS: y, S; OSBORNE2: t, y)");
+#if defined(ENL_USER_FAMILY)
+    if (!FamUser::HAS_ANALYTIC && (!opt || opt->jac_mode != ENLSIPB200_JAC_FORWARD_DIFF))
+        return fail(ENLSIPB200_EINVAL, "this user family was compiled without Jacobians: set jac_mode = ENLSIPB200_JAC_FORWARD_DIFF");
+#endif
     if (B == 0) return 0;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -508,6 +533,54 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     }
     for (int sl = 0; sl < 3; ++sl) h->host_pending[sl] = false;
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Replaces the reference's "any closure" plugin surface (cnls_model.jl:11-62, 345-378): the user's residual /
+// constraint functions arrive as CUDA C++ source and are compiled, together with the solver headers that sit next to
+// this library (../csrc relative to the .so, found through dladdr), into a library with this same C ABI.
+int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
+                              int has_jacobians, const char* out_lib_path, const char* work_dir) {
+    if (!source || !out_lib_path || !work_dir) return fail(ENLSIPB200_EINVAL, "NULL argument");
+    if (n < 1 || n > 16) return fail(ENLSIPB200_EINVAL, "user families support 1 <= n <= 16 parameters");
+    if (m < 1 || m > 4096) return fail(ENLSIPB200_EINVAL, "user families support 1 <= m <= 4096 residuals (larger problems: the large-Jacobian regime)");
+    if (nb_eq < 0 || nb_ineq < 0 || nb_eq + nb_ineq > 16) return fail(ENLSIPB200_EINVAL, "0 <= nb_eq + nb_ineq <= 16");
+    if (stride0 < 0 || stride1 < 0) return fail(ENLSIPB200_EINVAL, "negative data stride");
+    Dl_info info;
+    if (!dladdr((void*)&enlsipb200_version, &info) || !info.dli_fname) return fail(ENLSIPB200_EINVAL, "cannot locate the library on disk");
+    std::string lib = info.dli_fname;
+    const size_t slash = lib.rfind('/');
+    const std::string libdir = slash == std::string::npos ? "." : lib.substr(0, slash);
+    const std::string csrc = libdir + "/../csrc";
+    const std::string unit = csrc + "/enlsip_b200.cu";
+    if (access(unit.c_str(), R_OK) != 0) return fail(ENLSIPB200_EINVAL, "solver sources not found at " + csrc);
+    const std::string wd = work_dir;
+    const std::string pre = wd + "/enl_user_prelude.h";
+    FILE* fp = fopen(pre.c_str(), "w");
+    if (!fp) return fail(ENLSIPB200_EINVAL, "cannot write " + pre);
+    fprintf(fp, "// generated by enlsipb200_compile_family\n#pragma once\n#define ENL_USER_FAMILY 1\n#define ENL_USER_N %d\n"
+                "#define ENL_USER_M %d\n#define ENL_USER_Q %d\n#define ENL_USER_NI %d\n#define ENL_USER_STRIDE0 %d\n"
+                "#define ENL_USER_STRIDE1 %d\n#define ENL_USER_HAS_JAC %d\n#include \"%s/enl_base.h\"\nusing namespace enl;\n"
+                "#line 1 \"user_family_source\"\n%s\n",
+            n, m, nb_eq, nb_ineq, stride0, stride1, has_jacobians ? 1 : 0, csrc.c_str(), source);
+    fclose(fp);
+    const std::string log = wd + "/enl_user_build.log";
+    const char* nvcc = getenv("ENLSIP_NVCC");
+    std::string cmd = std::string(nvcc ? nvcc : "nvcc") +
+                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
+                      " -DENL_COMPACT_CODE=1 -include \"" + pre + "\" \"" + unit + "\" -o \"" + out_lib_path +
+                      "\" -ldl > \"" + log + "\" 2>&1";
+    const int rc = system(cmd.c_str());
+    if (rc != 0) {
+        std::string msg = "nvcc failed (" + cmd + "):\n";
+        if (FILE* lf = fopen(log.c_str(), "r")) {
+            char buf[512];
+            size_t got;
+            while (msg.size() < 6000 && (got = fread(buf, 1, sizeof(buf), lf)) > 0) msg.append(buf, got);
+            fclose(lf);
+        }
+        return fail(ENLSIPB200_EINVAL, msg);
+    }
     return 0;
 }
 

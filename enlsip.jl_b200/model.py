@@ -42,12 +42,40 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
+class UserFamily:
+    """A problem family given as CUDA C++ source: the device-side counterpart of the closures
+    ``residuals``, ``eq_constraints``, ``ineq_constraints`` (+ ``jacobian_*``) of the reference constructor
+    (cnls_model.jl:345-359).  See include/enlsip_b200.h (enlsipb200_compile_family) for the functions the source
+    defines.  ``data`` names up to three data slots: slots 0 / 1 hold ``stride0`` / ``stride1`` doubles per problem,
+    slot 2 is shared by the whole batch."""
+
+    def __init__(self, source, n, m, nb_eqcons=0, nb_ineqcons=0, data=(), stride0=0, stride1=0, has_jacobians=False,
+                 name="user"):
+        self.source, self.n, self.m, self.nb_eqcons, self.nb_ineqcons = source, int(n), int(m), int(nb_eqcons), int(nb_ineqcons)
+        self.data, self.stride0, self.stride1 = tuple(data), int(stride0), int(stride1)
+        self.has_jacobians, self.name = bool(has_jacobians), name
+        self._lib = None
+
+    def library(self):
+        if self._lib is None:
+            self._lib = capi.compile_family(self.source, self.n, self.m, self.nb_eqcons, self.nb_ineqcons, self.stride0,
+                                            self.stride1, self.has_jacobians, name=self.name)
+        return self._lib
+
+
 class CnlsModel:
     """A batch of B constrained nonlinear least squares problems of one device family."""
 
     def __init__(self, family, starting_point, data=None, x_low=None, x_upp=None, jacobian="analytic", device=-1):
-        if family not in _FAMILIES:
-            raise AssertionError("A device problem family must be provided: %s" % sorted(_FAMILIES))
+        if isinstance(family, UserFamily):
+            self._lib, fam_id, data_keys = family.library(), capi.FAMILY_USER, family.data
+            if jacobian == "analytic" and not family.has_jacobians:
+                jacobian = "forward_diff"      # no jacobian_* given: the reference differentiates for the user as well
+            family = family.name
+        elif family in _FAMILIES:
+            self._lib, fam_id, data_keys = capi.lib(), _FAMILIES[family], _FAMILY_DATA[family]
+        else:
+            raise AssertionError("A device problem family must be provided: %s or a UserFamily" % sorted(_FAMILIES))
         if jacobian not in _JAC:
             raise AssertionError("jacobian must be 'analytic' or 'forward_diff'")
         self.family = family
@@ -62,17 +90,17 @@ class CnlsModel:
         self.x_low = np.full(n, -np.inf) if x_low is None else np.ascontiguousarray(x_low, dtype=np.float64)
         self.x_upp = np.full(n, np.inf) if x_upp is None else np.ascontiguousarray(x_upp, dtype=np.float64)
         h = ctypes.c_void_p()
-        capi.check(capi.lib().enlsipb200_create(_FAMILIES[family], self.x_low.ctypes.data, self.x_upp.ctypes.data,
-                                                device, ctypes.byref(h)))
+        capi.check(self._lib.enlsipb200_create(fam_id, self.x_low.ctypes.data, self.x_upp.ctypes.data,
+                                               device, ctypes.byref(h)), self._lib)
         self._h = h
         dims = [ctypes.c_int() for _ in range(5)]
-        capi.check(capi.lib().enlsipb200_dims(h, *[ctypes.byref(d) for d in dims]))
+        capi.check(self._lib.enlsipb200_dims(h, *[ctypes.byref(d) for d in dims]), self._lib)
         self.nb_parameters, self.nb_residuals, self.nb_eqcons, self.nb_constraints, self.lmax = [d.value for d in dims]
         if n != self.nb_parameters:
             raise ValueError("family %s has n=%d, starting_point has %d columns" % (family, self.nb_parameters, n))
         self._data_keep = {}
         data = data or {}
-        for slot, key in enumerate(_FAMILY_DATA[family]):
+        for slot, key in enumerate(data_keys):
             if key not in data:
                 raise AssertionError("family %s needs data[%r]" % (family, key))
             self.set_data(slot, data[key])
@@ -112,20 +140,21 @@ class CnlsModel:
             arr = np.ascontiguousarray(arr, dtype=np.float64)
             count = arr.size
         self._data_keep[slot] = arr        # host arrays are uploaded by the next solve: keep them alive
-        capi.check(capi.lib().enlsipb200_set_data(self._h, slot, self._ptr(arr), count, 1 if dev else 0, self._stream()))
+        capi.check(self._lib.enlsipb200_set_data(self._h, slot, self._ptr(arr), count, 1 if dev else 0, self._stream()),
+                   self._lib)
 
     def kernel_info(self):
         v = [ctypes.c_int() for _ in range(6)]
-        capi.check(capi.lib().enlsipb200_kernel_info(self._h, *[ctypes.byref(d) for d in v]))
+        capi.check(self._lib.enlsipb200_kernel_info(self._h, *[ctypes.byref(d) for d in v]), self._lib)
         keys = ("regs_per_thread", "smem_bytes_per_cta", "threads_per_cta", "ctas_per_sm", "grid", "lanes_per_problem")
         return dict(zip(keys, [d.value for d in v]))
 
     def launch_count(self):
-        return int(capi.lib().enlsipb200_launch_count(self._h))
+        return int(self._lib.enlsipb200_launch_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
-            capi.lib().enlsipb200_destroy(self._h)
+            self._lib.enlsipb200_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -184,9 +213,9 @@ def solve(model: CnlsModel, silent=True, max_iter=100, scaling=False, time_limit
     cnt = out.get("counters") if out.get("counters") is not None else (mk_i(B, 2) if want_counters else None)
     tr = mk_z(B, trace_cap, row_w) if trace_cap > 0 else None
     p = model._ptr
-    capi.check(capi.lib().enlsipb200_solve_batch(model._h, B, p(x0), ctypes.byref(o), p(x), p(f), p(ec), p(st), p(it),
+    capi.check(model._lib.enlsipb200_solve_batch(model._h, B, p(x0), ctypes.byref(o), p(x), p(f), p(ec), p(st), p(it),
                                                  p(na), p(act), p(cnt), p(tr), int(trace_cap),
-                                                 1 if model.on_device else 0, model._stream()))
+                                                 1 if model.on_device else 0, model._stream()), model._lib)
     # solver.jl:84-87
     model.status_code = st
     model.exit_code = ec
@@ -207,7 +236,7 @@ solve_b = solve   # `solve!`
 
 def last_kernel_ms(model: CnlsModel) -> float:
     ms = ctypes.c_float()
-    capi.check(capi.lib().enlsipb200_last_kernel_ms(model._h, ctypes.byref(ms)))
+    capi.check(model._lib.enlsipb200_last_kernel_ms(model._h, ctypes.byref(ms)), model._lib)
     return float(ms.value)
 
 

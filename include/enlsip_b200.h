@@ -94,6 +94,25 @@ int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_
                            int* ctas_per_sm, int* grid, int* lanes_per_problem);
 long long enlsipb200_launch_count(enlsipb200_handle h);
 
+/* Run-time compiled problem family: the replacement of the reference's plugin surface -- `residuals`,
+ * `eq_constraints`, `ineq_constraints` and their optional `jacobian_*` closures handed to CnlsModel(...)
+ * (src/cnls_model.jl:345-359, wrapped at :11-62).  `source` is CUDA C++ defining, in namespace enl_user,
+ *     __device__ double residual(int i, const double* x, const double* d0, const double* d1, const double* d2);
+ *     __device__ void   constraints(const double* x, const double* d0, const double* d1, const double* d2, double* c);
+ *         c[0..nb_eq) equalities then c[nb_eq..nb_eq+nb_ineq) inequalities (>= 0)   (order of cnls_model.jl:402-403)
+ * and, if has_jacobians != 0,
+ *     __device__ void jac_residual(int i, const double* x, const double*, const double*, const double*, double* grad);                  -- grad[n]
+ *     __device__ void jac_constraints(const double* x, const double*, const double*, const double*, double* A);   -- A[(nb_eq+nb_ineq) x n], row major
+ * d0 / d1: this problem's rows of data slots 0 / 1 (stride0 / stride1 doubles per problem); d2: slot 2, shared by the batch.
+ * The helpers of csrc/enl_base.h (det_exp, det_tanh, add_rn, ...) are visible.  Without Jacobians the solve must use
+ * ENLSIPB200_JAC_FORWARD_DIFF (cnls_model.jl:65-82).  Bounds are given to enlsipb200_create as for any family.
+ * nvcc (PATH or $ENLSIP_NVCC) compiles the solver for this family into `out_lib_path`; the host then loads THAT library
+ * and uses this same API with family = ENLSIPB200_FAMILY_USER.  `work_dir`: writable directory for the generated
+ * prelude and the build log.  Limits: n <= 16, m <= 4096, nb_eq + nb_ineq <= 16. */
+#define ENLSIPB200_FAMILY_USER 64
+int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
+                              int has_jacobians, const char* out_lib_path, const char* work_dir);
+
 /* deterministic exp used by the synthetic families, exposed for bit-parity tests vs oracle/detmath.c */
 int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
 

@@ -1,0 +1,177 @@
+"""Run-time compiled problem families: the engine's replacement of the reference's closure plugin
+surface (`CnlsModel(residuals, n, m; eq_constraints, ineq_constraints, jacobian_*)`, src/cnls_model.jl:345-359).
+
+CPU part (no GPU): enlsipb200_compile_family cross-compiles the solver around user source for sm_100a, the library
+exports the C ABI, compute calls fail loudly without a device, compiler errors come back through last_error.
+GPU part: HS65 written as user source reproduces the built-in HS65 family bit for bit; a family with per-problem
+data, a shared table, one equality, one inequality and mixed finite / infinite bounds matches the oracle
+(analytic Jacobians: identical discrete outputs, objective to 1e-12; forward differences: to the FD noise floor).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+HS65_SRC = r'''
+namespace enl_user {   // test/problems/HS65.jl:7-17
+__device__ double residual(int i, const double* x, const double*, const double*, const double*) {
+    if (i == 0) return sub_rn(x[0], x[1]);
+    if (i == 1) return div_rn(sub_rn(add_rn(x[0], x[1]), 10.0), 3.0);
+    return sub_rn(x[2], 5.0);
+}
+__device__ void constraints(const double* x, const double*, const double*, const double*, double* c) {
+    c[0] = sub_rn(sub_rn(sub_rn(48.0, mul_rn(x[0], x[0])), mul_rn(x[1], x[1])), mul_rn(x[2], x[2]));
+}
+__device__ void jac_residual(int i, const double*, const double*, const double*, const double*, double* g) {
+    if (i == 0) { g[0] = 1.0; g[1] = -1.0; g[2] = 0.0; }
+    else if (i == 1) { g[0] = 1.0 / 3.0; g[1] = 1.0 / 3.0; g[2] = 0.0; }
+    else { g[0] = 0.0; g[1] = 0.0; g[2] = 1.0; }
+}
+__device__ void jac_constraints(const double* x, const double*, const double*, const double*, double* A) {
+    A[0] = mul_rn(-2.0, x[0]); A[1] = mul_rn(-2.0, x[1]); A[2] = mul_rn(-2.0, x[2]);
+}
+}
+'''
+
+# exponential decay fit: r_i = y_i - (x0 * exp(-x1 t_i) + x2), i < 24; equality x0 + x2 = S; inequality x0 - x2 >= 0
+# d0 = y (24 per problem), d1 = S (1 per problem), d2 = t (24, shared)
+DECAY_M = 24
+DECAY_SRC = r'''
+namespace enl_user {
+__device__ double residual(int i, const double* x, const double* y, const double*, const double* t) {
+    const double e = det_exp(mul_rn(-x[1], t[i]));
+    return sub_rn(y[i], add_rn(mul_rn(x[0], e), x[2]));
+}
+__device__ void constraints(const double* x, const double*, const double* S, const double*, double* c) {
+    c[0] = sub_rn(add_rn(x[0], x[2]), S[0]);
+    c[1] = sub_rn(x[0], x[2]);
+}
+__device__ void jac_residual(int i, const double* x, const double*, const double*, const double* t, double* g) {
+    const double e = det_exp(mul_rn(-x[1], t[i]));
+    g[0] = -e;
+    g[1] = mul_rn(mul_rn(x[0], t[i]), e);
+    g[2] = -1.0;
+}
+__device__ void jac_constraints(const double*, const double*, const double*, const double*, double* A) {
+    A[0] = 1.0; A[1] = 0.0; A[2] = 1.0;
+    A[3] = 1.0; A[4] = 0.0; A[5] = -1.0;
+}
+}
+'''
+DECAY_T = np.arange(DECAY_M, dtype=np.float64) / 4.0
+DECAY_LOW = np.array([-np.inf, 0.05, -np.inf])
+DECAY_UPP = np.array([np.inf, 5.0, 10.0])
+
+
+def decay_batch(B, seed=11):
+    from oracle import problems as P
+    rng = np.random.default_rng(seed)
+    truth = np.array([2.0, 0.7, 0.5]) * (1.0 + 0.1 * rng.uniform(-1, 1, (B, 3)))
+    y = np.stack([truth[b, 0] * P.det_exp((-truth[b, 1]) * DECAY_T) + truth[b, 2] for b in range(B)])
+    y = y + 0.01 * rng.standard_normal((B, DECAY_M))
+    S = truth[:, 0] + truth[:, 2]
+    x0 = truth * (1.0 + 0.1 * rng.uniform(-1, 1, (B, 3)))
+    return np.ascontiguousarray(y), np.ascontiguousarray(S), np.ascontiguousarray(x0)
+
+
+def decay_oracle_problem(y, S, x0, fd):
+    from oracle import enlsip_oracle as O, problems as P
+
+    def r(x):
+        return y - (x[0] * P.det_exp((-x[1]) * DECAY_T) + x[2])
+
+    def jr(x):
+        e = P.det_exp((-x[1]) * DECAY_T)
+        J = np.empty((DECAY_M, 3))
+        J[:, 0] = -e
+        J[:, 1] = (x[0] * DECAY_T) * e
+        J[:, 2] = -1.0
+        return J
+
+    return O.make_problem(3, DECAY_M, r, None if fd else jr,
+                          eq=lambda x: np.array([(x[0] + x[2]) - S]), jac_eq=None if fd else (lambda x: np.array([[1.0, 0.0, 1.0]])),
+                          nb_eq=1, ineq=lambda x: np.array([x[0] - x[2]]),
+                          jac_ineq=None if fd else (lambda x: np.array([[1.0, 0.0, -1.0]])), nb_ineq=1,
+                          x_low=DECAY_LOW, x_upp=DECAY_UPP, x0=x0, name="decay", fd=fd)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: the boundary
+# ------------------------------------------------------------------------------------------------
+def test_compile_family_exports_the_c_abi():
+    import enlsip_jl_b200 as E
+    fam = E.UserFamily(HS65_SRC, n=3, m=3, nb_ineqcons=1, has_jacobians=True, name="hs65_user")
+    L = fam.library()
+    for sym in ("enlsipb200_version", "enlsipb200_create", "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data",
+                "enlsipb200_solve_batch", "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count",
+                "enlsipb200_last_error"):
+        assert hasattr(L, sym), sym
+    import torch
+    if not torch.cuda.is_available():      # no CPU fallback: creating a handle fails loudly with ENOGPU
+        h = ctypes.c_void_p()
+        lo = np.full(3, -np.inf)
+        rc = L.enlsipb200_create(E.capi.FAMILY_USER, lo.ctypes.data, lo.ctypes.data, -1, ctypes.byref(h))
+        assert rc == -2, rc
+    # the stock library refuses the user id, and a user library refuses the built-in ids
+    h = ctypes.c_void_p()
+    lo = np.full(3, -np.inf)
+    assert E.capi.lib().enlsipb200_create(E.capi.FAMILY_USER, lo.ctypes.data, lo.ctypes.data, -1, ctypes.byref(h)) == -1
+    assert L.enlsipb200_create(E.capi.FAMILY_HS65, lo.ctypes.data, lo.ctypes.data, -1, ctypes.byref(h)) == -1
+
+
+def test_compile_family_reports_compiler_errors_and_bad_sizes():
+    import enlsip_jl_b200 as E
+    bad = E.UserFamily("namespace enl_user { __device__ double residual(int i) { return undefined_symbol; } }", n=2, m=4,
+                       nb_eqcons=1, name="broken")
+    with pytest.raises(E.capi.EngineError) as ei:
+        bad.library()
+    assert "undefined_symbol" in str(ei.value)
+    with pytest.raises(E.capi.EngineError):
+        E.UserFamily(HS65_SRC, n=40, m=3, nb_ineqcons=1, has_jacobians=True, name="too_wide").library()
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: parity
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_user_hs65_equals_builtin_bit_for_bit():
+    import enlsip_jl_b200 as E
+    x0 = np.vstack([E.synth.HS65_X0[None, :], E.synth.gen_hs65_batch(63)])
+    ref = E.CnlsModel("hs65", x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(ref)
+    fam = E.UserFamily(HS65_SRC, n=3, m=3, nb_ineqcons=1, has_jacobians=True, name="hs65_user")
+    usr = E.CnlsModel(fam, x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(usr)
+    assert np.array_equal(usr.exit_code, ref.exit_code)
+    assert np.array_equal(usr.iterations, ref.iterations)
+    assert np.array_equal(usr.active, ref.active)
+    assert np.array_equal(usr.sol, ref.sol)                 # same arithmetic, same bits
+    assert np.array_equal(usr.obj_value, ref.obj_value)
+    assert usr.launch_count() >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fd", [False, True])
+def test_user_family_with_data_vs_oracle(fd):
+    import enlsip_jl_b200 as E
+    from oracle import enlsip_oracle as O
+    B = 48
+    y, S, x0 = decay_batch(B)
+    fam = E.UserFamily(DECAY_SRC, n=3, m=DECAY_M, nb_eqcons=1, nb_ineqcons=1, data=("y", "S", "t"), stride0=DECAY_M,
+                       stride1=1, has_jacobians=True, name="decay")
+    mod = E.CnlsModel(fam, x0, data={"y": y, "S": S, "t": DECAY_T}, x_low=DECAY_LOW, x_upp=DECAY_UPP,
+                      jacobian="forward_diff" if fd else "analytic")
+    assert mod.nb_constraints == 2 + 1 + 2          # eq, ineq, one finite lower bound, two finite upper bounds
+    E.solve(mod)
+    same_status = same_iters = 0
+    for b in range(B):
+        o = O.solve(decay_oracle_problem(y[b], S[b], x0[b], fd), wallclock=False)
+        same_status += int(mod.status_code[b]) == o.status
+        same_iters += int(mod.iterations[b]) == o.iterations
+        if int(mod.status_code[b]) == o.status == 1:
+            tol = 1e-8 if fd else 1e-12
+            assert abs(mod.obj_value[b] - o.f) <= tol * max(1.0, abs(o.f)), (b, mod.obj_value[b], o.f)
+    if fd:      # FD noise floor (tests/test_oracle.py::test_fd_noise_floor): knife-edge decisions may flip
+        assert same_status >= 0.95 * B and same_iters >= 0.85 * B, (same_status, same_iters)
+    else:
+        assert same_status == B and same_iters >= B - 1, (same_status, same_iters)
