@@ -143,7 +143,7 @@ def cpu_port(B, nthreads, seed_start=0):
 # large-Jacobian regime (BASELINE.json config 4): GN iterations/s at m = 4M, n = 256, 64 equalities
 # =================================================================================================
 LARGE_METRIC = "GN iters/s (m=4M,n=256)"
-NCU_TRAIL_DRAM_BYTES_PER_ROW_COL = (2.248e9 + 1.897e9) / (1048576 * 232.0)   # profiles/r1_c4_trail_v2_ncu.txt
+NCU_TRAIL_DRAM_BYTES_PER_ROW_COL = (2.248e9 + 1.829e9) / (1048576 * 224.0)   # profiles/r1_c4_trail_staged_v0_ncu.txt
 LARGE_N, LARGE_NB = 256, 64
 
 
@@ -254,12 +254,12 @@ def large_arm(args, torch, dist, E, rank, world, local, dev):
                                    "linesearch_evals": dst["linesearch_evals"] / args.large_steps},
            "gpu_launches": int(dst["launches"]),
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                        "traffic": NCU_TRAIL_DRAM_BYTES_PER_ROW_COL * rows * 232.0, "peak_source": peak_src,
-                        "traffic_source": "largest launch of the factorisation (tsqr_trail_kernel, panel 0, level 0: 232 trailing "
-                                          "columns): ncu --set full at 1M rows (profiles/r1_c4_trail_v2_ncu.txt) 2.25 GB read + "
-                                          "1.90 GB written = 1.06x its algorithmic bytes (trailing block read once, written once, "
-                                          "V read once), scaled linearly to this run's rows",
-                        "kernel": "tsqr_panel_kernel + tsqr_trail_kernel (one TSQR of [J | r])",
+                        "traffic": NCU_TRAIL_DRAM_BYTES_PER_ROW_COL * rows * 224.0, "peak_source": peak_src,
+                        "traffic_source": "largest launch of the factorisation (tsqr_trail_staged_kernel, panel 0, level 0: 224 "
+                                          "trailing columns): ncu --set full at 1M rows (profiles/r1_c4_trail_staged_v0_ncu.txt) "
+                                          "2.25 GB read + 1.83 GB written = 1.04x its algorithmic bytes (trailing block read once, "
+                                          "written once, V read once), scaled linearly to this run's rows",
+                        "kernel": "tsqr_panel_kernel + tsqr_trail_staged_kernel (one TSQR of [J | r])",
                         "kernel_ms": tsqr_ms, "algorithmic_flops_per_launch": flops / world,
                         "note": "2 m (n+1)^2 flops per factorisation; trailing updates on mma.sync.m8n8k4.f64, panels on the FP64 FMA pipe"}}
     # ---- end to end: W and y start in pinned HOST memory every step, result read back ---------------

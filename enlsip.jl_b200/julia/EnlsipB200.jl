@@ -45,8 +45,34 @@ const dict_status_codes = Dict(          # cnls_model.jl:180-186
 last_error() = unsafe_string(ccall((:enlsipb200_last_error, libenlsip), Cstring, ()))
 check(rc::Cint) = rc == 0 || error("enlsip_b200 error $rc: $(last_error())")
 
+# ---- user problems: the reference's closure arguments as CUDA C++ source (include/enlsip_b200.h) ----
+using Libdl
+const FAMILY_USER = Cint(64)
+const stock_handle = Ref{Ptr{Cvoid}}(C_NULL)
+stocklib() = (stock_handle[] == C_NULL && (stock_handle[] = Libdl.dlopen(libenlsip)); stock_handle[])
+# entry point `name` of the stock library (lib == C_NULL) or of a library written by compile_family
+fsym(lib::Ptr{Cvoid}, name::Symbol) = Libdl.dlsym(lib == C_NULL ? stocklib() : lib, name)
+
+"""
+    compile_family(source; n, m, nb_eqcons=0, nb_ineqcons=0, stride0=0, stride1=0, has_jacobians=false)
+
+Device-side counterpart of the closures `residuals`, `eq_constraints`, `ineq_constraints`, `jacobian_*` of the
+reference constructor (cnls_model.jl:345-359): `source` defines `enl_user::residual`, `enl_user::constraints` (and
+optionally `jac_residual`, `jac_constraints`); the engine compiles its solver around them and returns the handle of a
+library with the same C ABI.  Pass it to `CnlsModel(lib, starting_point; ...)`.
+"""
+function compile_family(source::String; n::Integer, m::Integer, nb_eqcons::Integer=0, nb_ineqcons::Integer=0,
+                        stride0::Integer=0, stride1::Integer=0, has_jacobians::Bool=false,
+                        work_dir::String=mktempdir(), out::String=joinpath(work_dir, "libenlsip_b200_user.so"))
+    check(ccall((:enlsipb200_compile_family, libenlsip), Cint,
+                (Cstring, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cstring, Cstring),
+                source, n, m, nb_eqcons, nb_ineqcons, stride0, stride1, has_jacobians ? 1 : 0, out, work_dir))
+    return Libdl.dlopen(out)
+end
+
 mutable struct CnlsModel{T<:Float64}
     handle::Ptr{Cvoid}
+    lib::Ptr{Cvoid}                  # C_NULL: stock library; else the library of a user family (compile_family)
     family::Symbol
     nb_parameters::Int
     nb_residuals::Int
@@ -72,26 +98,34 @@ end
 `family` is `:hs65` or `:gauss_peaks`; `data` are the family's arrays in slot order
 (`:gauss_peaks`: `y` (128 x B) and `S` (B)).  Mirrors the assertions of cnls_model.jl:363-369.
 """
-function CnlsModel(family::Symbol, starting_point::Matrix{Float64}; data=(), x_low=fill(-Inf, size(starting_point, 1)),
-                   x_upp=fill(Inf, size(starting_point, 1)), jacobian::Symbol=:analytic, device::Integer=-1)
+function CnlsModel(family::Symbol, starting_point::Matrix{Float64}; kwargs...)
     fam = family === :hs65 ? FAMILY_HS65 : family === :gauss_peaks ? FAMILY_GAUSS_PEAKS :
           error("A device problem family must be provided")
+    return CnlsModel(C_NULL, fam, family, starting_point; kwargs...)
+end
+# user family: `lib` comes from compile_family; without jacobian_* the engine differentiates by forward differences
+CnlsModel(lib::Ptr{Cvoid}, starting_point::Matrix{Float64}; jacobian::Symbol=:forward_diff, kwargs...) =
+    CnlsModel(lib, FAMILY_USER, :user, starting_point; jacobian=jacobian, kwargs...)
+
+function CnlsModel(lib::Ptr{Cvoid}, fam::Cint, family::Symbol, starting_point::Matrix{Float64}; data=(),
+                   x_low=fill(-Inf, size(starting_point, 1)), x_upp=fill(Inf, size(starting_point, 1)),
+                   jacobian::Symbol=:analytic, device::Integer=-1)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:enlsipb200_create, libenlsip), Cint, (Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Ptr{Cvoid}}),
+    check(ccall(fsym(lib, :enlsipb200_create), Cint, (Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Ptr{Cvoid}}),
                 fam, x_low, x_upp, Cint(device), h))
     n, m, q, l, lmax = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
-    check(ccall((:enlsipb200_dims, libenlsip), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}),
+    check(ccall(fsym(lib, :enlsipb200_dims), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}),
                 h[], n, m, q, l, lmax))
     @assert size(starting_point, 1) == n[] "starting_point must be n x B"
     B = size(starting_point, 2)
     for (slot, arr) in enumerate(data)
-        check(ccall((:enlsipb200_set_data, libenlsip), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint, Ptr{Cvoid}),
+        check(ccall(fsym(lib, :enlsipb200_set_data), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint, Ptr{Cvoid}),
                     h[], Cint(slot - 1), arr, length(arr), Cint(0), C_NULL))
     end
-    model = CnlsModel{Float64}(h[], family, n[], m[], q[], l[], lmax[], starting_point, x_low, x_upp, jacobian,
+    model = CnlsModel{Float64}(h[], lib, family, n[], m[], q[], l[], lmax[], starting_point, x_low, x_upp, jacobian,
                                zeros(Cint, B), zeros(Cint, B), copy(starting_point), fill(NaN, B), zeros(Cint, B),
                                zeros(Cint, B), zeros(Cint, lmax[], B))
-    finalizer(m -> ccall((:enlsipb200_destroy, libenlsip), Cint, (Ptr{Cvoid},), m.handle), model)
+    finalizer(m -> ccall(fsym(m.lib, :enlsipb200_destroy), Cint, (Ptr{Cvoid},), m.handle), model)
     return model
 end
 
@@ -107,7 +141,7 @@ function solve!(model::CnlsModel; silent::Bool=true, max_iter::Int=100, scaling:
     B = size(model.starting_point, 2)
     opt = Ref(Options(max_iter, scaling, model.jacobian === :forward_diff ? JAC_FORWARD_DIFF : JAC_ANALYTIC, 0,
                       time_limit, abs_tol, rel_tol, c_tol, x_tol))
-    check(ccall((:enlsipb200_solve_batch, libenlsip), Cint,
+    check(ccall(fsym(model.lib, :enlsipb200_solve_batch), Cint,
                 (Ptr{Cvoid}, Clonglong, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
                  Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
                 model.handle, B, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,
