@@ -178,21 +178,15 @@ __global__ void __launch_bounds__(256) li_grad_kernel(const double* __restrict__
     }
 }
 
-// out[j] = sum_b gpart[b][j] in a fixed order (one thread per column, 4 independent chains)
+// out[j] = sum_b gpart[b][j] in a fixed order: one warp per column (lane l sums b = l, l + 32, ...; then a butterfly)
 __global__ void __launch_bounds__(256) li_grad_finish_kernel(const double* __restrict__ gpart, int nparts, int n,
                                                              double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j > n) return;
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    int b = 0;
-    for (; b + 3 < nparts; b += 4) {
-        t0 += gpart[(size_t)b * (n + 1) + j];
-        t1 += gpart[(size_t)(b + 1) * (n + 1) + j];
-        t2 += gpart[(size_t)(b + 2) * (n + 1) + j];
-        t3 += gpart[(size_t)(b + 3) * (n + 1) + j];
-    }
-    for (; b < nparts; ++b) t0 += gpart[(size_t)b * (n + 1) + j];
-    out[j] = (t0 + t1) + (t2 + t3);
+    double t = 0.0;
+    for (int b = lane; b < nparts; b += 32) t += gpart[(size_t)b * (n + 1) + j];
+    t = warp_sum(t);
+    if (lane == 0) out[j] = t;
 }
 
 __device__ __forceinline__ void block_reduce4(double (&v)[4], double* part) {
@@ -523,7 +517,7 @@ struct LargeHandle : LargeOps, DenseAccel {
                 li_grad_kernel<<<parts, 256, 0, st>>>(dA, ld, m_local, n, dgpart);
                 ++launches;
             }
-            li_grad_finish_kernel<<<(n + 256) / 256, 256, 0, st>>>(dgpart, parts, n, dgrad);
+            li_grad_finish_kernel<<<(n + 8) / 8, 256, 0, st>>>(dgpart, parts, n, dgrad);
             launches += 2;
         } else {
             LCU(cudaMemsetAsync(dgrad, 0, sizeof(double) * (n + 1), st));

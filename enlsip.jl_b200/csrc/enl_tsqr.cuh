@@ -251,6 +251,225 @@ tsqr_panel_kernel(double* __restrict__ A, int ld, long long nblk, long long stri
 }
 
 // ---------------------------------------------------------------------------------------------
+// panel factorisation, column-group form: warp w owns columns 4w..4w+3 of all 256 rows of the subtile
+// ---------------------------------------------------------------------------------------------
+// Same algorithm, same outputs (V in place, unscaled until stored; T; residual column) as tsqr_panel_kernel.  What
+// changes is the ownership: lane l of warp w holds columns 4w..4w+3 of the rows 32 r + l (r = 0..7: one row of every
+// 32-row block of the subtile).  Consequences:
+//   * a finished column group costs its warp only the 32 dot products that feed the T factor: no update, and none of
+//     the scalar chain;
+//   * the scalar chain of a column (norm, rsqrt, reciprocal -- dlarfg) runs in ONE warp, the owner of the column,
+//     which publishes the raw column together with tau and scale; the other 7 warps no longer replicate it;
+//   * every dot product is reduced inside a warp (shuffles), there is no cross-warp reduction; the pivot-row entry of
+//     a column is fetched from the owning lane by one shuffle.
+// One block barrier per column, as before.  Top block: rows <= i are masked out of the published column, so the
+// finished rows of R simply stay where they are (no progressive store, no register rotation).
+__device__ __forceinline__ double warp_allsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sums over the warp of 4 values per lane; every lane receives the 4 totals (fixed order: 10 shuffles instead of 20)
+__device__ __forceinline__ void warp_allsum4(const double (&d)[4], double (&g)[4], int lane) {
+    const bool hi = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    const double x = (hi ? d[2] : d[0]) + __shfl_xor_sync(0xffffffffu, hi ? d[0] : d[2], 16);
+    const double y = (hi ? d[3] : d[1]) + __shfl_xor_sync(0xffffffffu, hi ? d[1] : d[3], 16);
+    double z = (h8 ? y : x) + __shfl_xor_sync(0xffffffffu, h8 ? x : y, 8);   // column 2 hi + h8
+    z += __shfl_xor_sync(0xffffffffu, z, 4);
+    z += __shfl_xor_sync(0xffffffffu, z, 2);
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) g[c] = __shfl_sync(0xffffffffu, z, 16 * (c >> 1) + 8 * (c & 1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+tsqr_panel_cg_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int upper_only,
+                     int rcol, double* __restrict__ Tbuf) {
+    __shared__ double vbuf[2][TS_FAN][TS_B];   // published raw pivot column (rows <= i of the top block masked)
+    __shared__ double sc[2][2];                // tau, scale of the published column
+    __shared__ double Gs[TS_B][TS_B + 1];      // Gs[c][i] = v_c . v_i, c < i
+    __shared__ double taus[TS_B];
+    __shared__ double bsh[TS_FAN][TS_B];       // residual column of the subtile
+    __shared__ double gb[TS_B], wb[TS_B];
+    __shared__ double part[TS_FAN][TS_FAN][TS_B];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long sub = blockIdx.x;
+    double a[4][TS_FAN];
+    double ms[4] = {0.0, 0.0, 0.0, 0.0};
+    // residual column: thread (w, lane) <-> row lane of block w
+    const long long bblk = (sub * TS_FAN + w) * stride;
+    double* bptr = A + (bblk * TS_B + lane) * (long long)ld + rcol;
+    const bool bvalid = bblk < nblk;
+    const double bval = (bvalid && rcol >= 0) ? *bptr : 0.0;
+#pragma unroll
+    for (int r = 0; r < TS_FAN; ++r) {
+        const long long blk = (sub * TS_FAN + r) * stride;
+        double2 v01 = make_double2(0.0, 0.0), v23 = make_double2(0.0, 0.0);
+        if (blk < nblk) {
+            const double* src = A + (blk * TS_B + lane) * (long long)ld + col0 + 4 * w;
+            v01 = *reinterpret_cast<const double2*>(src);
+            v23 = *reinterpret_cast<const double2*>(src + 2);
+        }
+        a[0][r] = v01.x; a[1][r] = v01.y; a[2][r] = v23.x; a[3][r] = v23.y;
+        if (upper_only) {   // level >= 1: every block is the R block of a subtile below; under its diagonal lie stale reflectors
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane > 4 * w + j) a[j][r] = 0.0;
+        }
+    }
+#pragma unroll 1
+    for (int ib = 0; ib < TS_B / 4; ++ib) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = ib * 4 + k;
+            const int buf = k & 1;
+            if (w == ib) {
+                // ---- owner of column i: norm of the column below the pivot, dlarfg scalars, publication ----
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < TS_FAN; r += 2) {
+                    double x0 = a[k][r], x1 = a[k][r + 1];
+                    if (r == 0 && lane <= i) x0 = 0.0;      // top block: the pivot row and the rows above it
+                    vbuf[buf][r][lane] = x0;
+                    vbuf[buf][r + 1][lane] = x1;
+                    s0 = fma(x0, x0, s0);
+                    s1 = fma(x1, x1, s1);
+                }
+                const double sigma = warp_allsum(s0 + s1);
+                const double alpha = __shfl_sync(0xffffffffu, a[k][0], i);
+                double tau = 0.0, scale = 0.0, beta = alpha;
+                if (sigma != 0.0) {   // dlarfg: beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta (see tsqr_panel_kernel)
+                    const double s2 = fma(alpha, alpha, sigma);
+                    const double rs = rsqrt(s2);
+                    beta = -copysign(s2 * rs, alpha);
+                    const double dab = alpha - beta;
+                    scale = __drcp_rn(dab);
+                    tau = dab * copysign(rs, alpha);
+                }
+                if (lane == 0) { sc[buf][0] = tau; sc[buf][1] = scale; taus[i] = tau; }
+                if (lane == i) a[k][0] = beta;
+                ms[k] = scale;
+            }
+            __syncthreads();
+            {
+                // ---- every warp: u_i . (own columns); live columns (> i) are updated, finished ones feed T ----
+                double v[TS_FAN];
+#pragma unroll
+                for (int r = 0; r < TS_FAN; ++r) v[r] = vbuf[buf][r][lane];
+                const double tau = sc[buf][0], scale = sc[buf][1];
+                double d[4], g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double e0 = v[0] * a[j][0], e1 = v[1] * a[j][1];
+#pragma unroll
+                    for (int r = 2; r < TS_FAN; r += 2) { e0 = fma(v[r], a[j][r], e0); e1 = fma(v[r + 1], a[j][r + 1], e1); }
+                    d[j] = e0 + e1;
+                }
+                warp_allsum4(d, g, lane);
+                if (w >= ib) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool later = (w > ib) || (j > k);              // column 4w + j > i
+                        const double pr = __shfl_sync(0xffffffffu, a[j][0], i);   // its entry in the pivot row
+                        const double gv = fma(scale, g[j], pr);
+                        const double wc = later ? tau * gv : 0.0;
+                        if (w == ib && j < k && lane == 0) Gs[4 * w + j][i] = ms[j] * gv;   // v_c . v_i, c < i in the owner's group
+                        if (lane == i) a[j][0] -= wc;
+                        const double cs = wc * scale;
+#pragma unroll
+                        for (int r = 0; r < TS_FAN; ++r) a[j][r] = fma(-cs, v[r], a[j][r]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double pr = __shfl_sync(0xffffffffu, a[j][0], i);
+                        if (lane == 0) Gs[4 * w + j][i] = ms[j] * fma(scale, g[j], pr);
+                    }
+                }
+            }
+        }
+    }
+    // ---- store: R on and above the diagonal of the top block, scaled reflectors everywhere else ----
+#pragma unroll
+    for (int r = 0; r < TS_FAN; ++r) {
+        const long long blk = (sub * TS_FAN + r) * stride;
+        double o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool is_r = (r == 0) && (lane <= 4 * w + j);
+            o[j] = is_r ? a[j][r] : a[j][r] * ms[j];
+            // keep V (unit lower trapezoid, scaled) for the residual-column update below
+            a[j][r] = (r == 0 && lane < 4 * w + j) ? 0.0 : ((r == 0 && lane == 4 * w + j) ? 1.0 : o[j]);
+        }
+        if (blk < nblk) {
+            double* dst = A + (blk * TS_B + lane) * (long long)ld + col0 + 4 * w;
+            *reinterpret_cast<double2*>(dst) = make_double2(o[0], o[1]);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(o[2], o[3]);
+        }
+    }
+    bsh[w][lane] = bval;
+    __syncthreads();
+    // compact-WY factor (as in tsqr_panel_kernel): T = U^-1, U = striu(V'V) + diag(1/tau); lane = column
+    if (w == 0) {
+        double t[TS_B];
+#pragma unroll
+        for (int r = TS_B - 1; r >= 0; --r) {
+            double sa = (r == lane) ? 1.0 : 0.0, sb = 0.0;
+#pragma unroll
+            for (int kk = r + 1; kk < TS_B; kk += 2) {
+                sa = fma(-Gs[r][kk], t[kk], sa);
+                if (kk + 1 < TS_B) sb = fma(-Gs[r][kk + 1], t[kk + 1], sb);
+            }
+            t[r] = (r <= lane) ? (sa + sb) * taus[r] : 0.0;
+        }
+        double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+        for (int r = 0; r < TS_B; ++r) Tg[r * TS_B + lane] = t[r];
+    }
+    if (rcol < 0) return;
+    // ---- residual column: b <- (I - V T' V') b ----
+    {
+        double d[4] = {0.0, 0.0, 0.0, 0.0}, g[4];
+#pragma unroll
+        for (int r = 0; r < TS_FAN; ++r) {
+            const double br = bsh[r][lane];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = fma(br, a[j][r], d[j]);
+        }
+        warp_allsum4(d, g, lane);
+        if (lane < 4) gb[4 * w + lane] = (lane == 0) ? g[0] : ((lane == 1) ? g[1] : ((lane == 2) ? g[2] : g[3]));
+    }
+    __syncthreads();
+    if (w == 0) {
+        const double* Tg = Tbuf + sub * (TS_B * TS_B);          // column `lane` of T: this lane's own stores
+        double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < TS_B; kk += 2) {
+            w0 = fma(Tg[kk * TS_B + lane], gb[kk], w0);
+            w1 = fma(Tg[(kk + 1) * TS_B + lane], gb[kk + 1], w1);
+        }
+        wb[lane] = -(w0 + w1);                                   // W = -T' (V'b)
+    }
+    __syncthreads();
+    {
+        const double w4[4] = {wb[4 * w], wb[4 * w + 1], wb[4 * w + 2], wb[4 * w + 3]};
+#pragma unroll
+        for (int r = 0; r < TS_FAN; ++r) {
+            double e = a[0][r] * w4[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) e = fma(a[j][r], w4[j], e);
+            part[w][r][lane] = e;                                // this column group's share of (V W)[row 32 r + lane]
+        }
+    }
+    __syncthreads();
+    if (bvalid) {
+        const double t = ((part[0][w][lane] + part[1][w][lane]) + (part[2][w][lane] + part[3][w][lane])) +
+                         ((part[4][w][lane] + part[5][w][lane]) + (part[6][w][lane] + part[7][w][lane]));
+        *bptr = bval + t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // trailing update of one (subtile, column block)
 // ---------------------------------------------------------------------------------------------
 template <int CB>
@@ -628,6 +847,8 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     cudaFuncSetAttribute(tsqr_trail_staged_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
     // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
+    // development switch: ENLSIP_PANEL=1 selects the row-tile panel kernel (kept for A/B measurements)
+    static const int panel_mode = [] { const char* e = getenv("ENLSIP_PANEL"); return (e && e[0] == '1') ? 1 : 3; }();
     static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : 2; }();
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
@@ -637,7 +858,8 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             long long nb_level = (nblk + stride - 1) / stride;
             if (level > 0 && nb_level <= 1) break;
             long long nsub = (nb_level + TS_FAN - 1) / TS_FAN;
-            tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
+            if (panel_mode == 1) tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
+            else tsqr_panel_cg_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             ++launches;
             if (ncb32 > 0 && trail_mode == 2) {
                 // chunk = all column blocks of the subtile while there are enough subtiles to fill the machine
