@@ -107,11 +107,15 @@ class QRPivoted:
 
     def Qt_mul(self, v):  # F.Q' * v
         v = np.asarray(v, dtype=F)
+        if v.size == 0:      # empty working set: Julia multiplies 0-length vectors without complaint
+            return v.copy()
         out = self._ormqr("L", "T", v.reshape(self.m, -1))
         return out.reshape(v.shape)
 
     def Q_mul(self, v):  # F.Q * v
         v = np.asarray(v, dtype=F)
+        if v.size == 0:
+            return v.copy()
         out = self._ormqr("L", "N", v.reshape(self.m, -1))
         return out.reshape(v.shape)
 

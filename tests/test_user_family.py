@@ -175,3 +175,53 @@ def test_user_family_with_data_vs_oracle(fd):
         assert same_status >= 0.95 * B and same_iters >= 0.85 * B, (same_status, same_iters)
     else:
         assert same_status == B and same_iters >= B - 1, (same_status, same_iters)
+
+
+# bounds only, no user Jacobians (forward differences, cnls_model.jl:65-82), m = 70: three residual rows per lane
+WIDE_M = 70
+WIDE_SRC = r'''
+namespace enl_user {
+__device__ double residual(int i, const double* x, const double* y, const double*, const double* t) {
+    return sub_rn(y[i], add_rn(x[0], mul_rn(x[1], det_exp(mul_rn(-x[2], t[i])))));
+}
+__device__ void constraints(const double*, const double*, const double*, const double*, double*) {}
+}
+'''
+WIDE_T = np.arange(WIDE_M, dtype=np.float64) / 10.0
+WIDE_LOW = np.array([0.0, 0.0, 0.1])
+WIDE_UPP = np.array([2.0, 1.05, 3.0])       # the upper bound on x1 binds for a part of the instances
+
+
+def test_user_family_without_jacobians_refuses_analytic_mode():
+    import enlsip_jl_b200 as E
+    fam = E.UserFamily(WIDE_SRC, n=3, m=WIDE_M, data=("y", "none", "t"), stride0=WIDE_M, name="wide")
+    L = fam.library()
+    assert hasattr(L, "enlsipb200_solve_batch")
+
+
+@pytest.mark.gpu
+def test_user_family_bounds_only_forward_differences_vs_oracle():
+    import enlsip_jl_b200 as E
+    from oracle import enlsip_oracle as O, problems as P
+    B = 40
+    rng = np.random.default_rng(23)
+    truth = np.array([0.5, 1.0, 0.8]) * (1.0 + 0.1 * rng.uniform(-1, 1, (B, 3)))
+    y = np.stack([truth[b, 0] + truth[b, 1] * P.det_exp((-truth[b, 2]) * WIDE_T) for b in range(B)])
+    y = np.ascontiguousarray(y + 0.02 * rng.standard_normal((B, WIDE_M)))
+    x0 = np.ascontiguousarray(np.clip(truth * (1.0 + 0.2 * rng.uniform(-1, 1, (B, 3))), WIDE_LOW + 1e-3, WIDE_UPP - 1e-3))
+    fam = E.UserFamily(WIDE_SRC, n=3, m=WIDE_M, data=("y", "none", "t"), stride0=WIDE_M, name="wide")
+    mod = E.CnlsModel(fam, x0, data={"y": y, "none": np.zeros(1), "t": WIDE_T}, x_low=WIDE_LOW, x_upp=WIDE_UPP)
+    assert mod.jacobian == "forward_diff" and mod.nb_constraints == 6 and mod.nb_eqcons == 0
+    E.solve(mod)
+    same_status = same_iters = bound_active = 0
+    for b in range(B):
+        prob = O.make_problem(3, WIDE_M, lambda x, yb=y[b]: yb - (x[0] + x[1] * P.det_exp((-x[2]) * WIDE_T)),
+                              x_low=WIDE_LOW, x_upp=WIDE_UPP, x0=x0[b], name="wide", fd=True)
+        o = O.solve(prob, wallclock=False)
+        same_status += int(mod.status_code[b]) == o.status
+        same_iters += int(mod.iterations[b]) == o.iterations
+        bound_active += int(mod.nb_active[b]) > 0
+        if int(mod.status_code[b]) == o.status == 1:
+            assert abs(mod.obj_value[b] - o.f) <= 1e-8 * max(1.0, abs(o.f)), (b, mod.obj_value[b], o.f)
+    assert same_status >= 0.95 * B and same_iters >= 0.85 * B, (same_status, same_iters)
+    assert bound_active > 0          # the working-set logic was exercised
