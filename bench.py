@@ -259,7 +259,7 @@ def large_arm(args, torch, dist, E, rank, world, local, dev):
                                           "trailing columns): ncu --set full at 1M rows (profiles/r1_c4_trail_staged_v0_ncu.txt) "
                                           "2.25 GB read + 1.83 GB written = 1.04x its algorithmic bytes (trailing block read once, "
                                           "written once, V read once), scaled linearly to this run's rows",
-                        "kernel": "tsqr_panel_kernel + tsqr_trail_staged_kernel (one TSQR of [J | r])",
+                        "kernel": "tsqr_panel_cg_kernel + tsqr_trail_staged_kernel (one TSQR of [J | r])",
                         "kernel_ms": tsqr_ms, "algorithmic_flops_per_launch": flops / world,
                         "note": "2 m (n+1)^2 flops per factorisation; trailing updates on mma.sync.m8n8k4.f64, panels on the FP64 FMA pipe"}}
     # ---- end to end: W and y start in pinned HOST memory every step, result read back ---------------
