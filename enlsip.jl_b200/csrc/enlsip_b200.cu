@@ -267,9 +267,6 @@ int with_family(int family, int nt, F&& f) {
 #endif
 }
 
-// lanes per problem / threads per CTA of each family
-constexpr int HS_G = 1, HS_NT = 64;
-constexpr int GP_G = 32;
 static int gp_nt() { const char* e = getenv("ENLSIP_GP_NT"); int v = e ? atoi(e) : 512; return (v == 480 || v == 448 || v == 224 || v == 128 || v == 64) ? v : 512; }
 
 Options make_options(const enlsipb200_options* o, int n, int m) {
@@ -419,6 +416,7 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     if (!h) return fail(ENLSIPB200_EINVAL, "null handle");
     if (B < 0 || !x0 || !x || !f || !exit_code || !status || !iters || !nact)
         return fail(ENLSIPB200_EINVAL, "x0, x, f, exit_code, status, iters, nact are required");
+    if (B == 0) return 0;     // an empty batch is a no-op (and may come with empty data arrays)
     if ((h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS || h->family == ENLSIPB200_FAMILY_OSBORNE2) && (!h->data[0] || !h->data[1]))
         return fail(ENLSIPB200_EINVAL, "this family needs data slots 0 and 1 (GAUSS_PEAKS: y, S; OSBORNE2: t, y)");
 #if defined(ENL_USER_FAMILY)

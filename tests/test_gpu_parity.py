@@ -226,3 +226,25 @@ def test_host_buffer_pipeline_matches_device_path(E):
     E.solve(md2)
     assert np.array_equal(np.asarray(mh.obj_value), md2.obj_value.cpu().numpy(), equal_nan=True)
     assert not np.array_equal(np.asarray(mh.obj_value), first[1], equal_nan=True)
+
+
+def test_empty_and_ragged_batches(E):
+    """B = 0 is a no-op; batch sizes that do not fill a CTA (1, 5, 17, 33 problems at 16 problems per CTA) and sizes
+    one short / one over a multiple of the grid give, problem by problem, the bits of the full batch."""
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(2400)
+    full = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="forward_diff")
+    E.solve(full)
+    for B in (0, 1, 5, 17, 33, 148 * 16 - 1, 148 * 16 + 1):
+        m = E.CnlsModel("gauss_peaks", x0[:B], data={"y": y[:B], "S": S[:B]}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP,
+                        jacobian="forward_diff")
+        E.solve(m)
+        assert np.asarray(m.sol).shape == (B, 6)
+        assert np.array_equal(np.asarray(m.sol).view(np.uint64), np.asarray(full.sol)[:B].view(np.uint64)), B
+        assert np.array_equal(m.exit_code, full.exit_code[:B]) and np.array_equal(m.iterations, full.iterations[:B]), B
+    x0h = E.synth.gen_hs65_batch(130)
+    hf = E.CnlsModel("hs65", x0h, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(hf)
+    for B in (0, 1, 63, 65):
+        h = E.CnlsModel("hs65", x0h[:B], x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+        E.solve(h)
+        assert np.array_equal(np.asarray(h.sol).view(np.uint64), np.asarray(hf.sol)[:B].view(np.uint64)), B
