@@ -78,7 +78,7 @@ struct NcclApi {
     }
 };
 NcclApi g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
 // ---------------------------------------------------------------------------------------------
 // elementwise kernels of the single-index family
