@@ -15,7 +15,7 @@
 
 namespace enl_dense {
 
-constexpr double D_TOL3Z = 1.4901161193847656e-08;
+constexpr double D_TOL3Z = 1.0536712127723509e-08;   // dlaqp2: sqrt(dlamch('Epsilon')) = sqrt(2^-53)
 constexpr int APPLY_THREADS = 256;
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {

@@ -38,7 +38,7 @@ namespace enl_large {
 
 constexpr double EPS = 2.220446049250313e-16;
 constexpr double SQRT_EPS = 1.4901161193847656e-08;
-constexpr double TOL3Z = 1.4901161193847656e-08;   // sqrt(dlamch('Epsilon')) of dlaqp2
+constexpr double TOL3Z = 1.0536712127723509e-08;   // dlaqp2: sqrt(dlamch('Epsilon')) = sqrt(2^-53) (same constant as enl_base.h)
 
 struct WouldThrow { const char* what; };
 struct WouldHang { const char* what; };
@@ -306,6 +306,33 @@ inline int pseudo_rank(const QRP& F, double eps_rank) {
     return r - ((r == len && fabs(F.diag(r - 1)) > tol) ? 0 : 1);
 }
 
+// What the iteration logic reads of a pivoted QR factorisation: sizes, diag(R), the permutation.  The factors
+// themselves (reflectors, R) stay with the SmallBackend that produced them (host memory or HBM).
+struct FactorInfo {
+    int rows = 0, cols = 0, k = 0;
+    Vec diagv;               // diag(R), k entries
+    std::vector<int> p;      // jpvt, 0-based
+    double diag(int i) const { return diagv[i]; }
+    std::vector<int> invperm() const {
+        std::vector<int> ip(cols);
+        for (int j = 0; j < cols; ++j) ip[p[j]] = j;
+        return ip;
+    }
+    void take(const QRP& F) {
+        rows = F.rows; cols = F.cols; k = F.k; p = F.p;
+        diagv.resize(k);
+        for (int i = 0; i < k; ++i) diagv[i] = F.f(i, i);
+    }
+};
+inline int pseudo_rank(const FactorInfo& F, double eps_rank) {   // EF:17-31
+    int len = F.k;
+    if (len <= 0 || fabs(F.diag(0)) < eps_rank) return 0;
+    double tol = fabs(F.diag(0)) * sqrt((double)len) * eps_rank;
+    int r = 1;
+    while (r < len && fabs(F.diag(r - 1)) > tol) ++r;
+    return r - ((r == len && fabs(F.diag(r - 1)) > tol) ? 0 : 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // what the driver needs from the m-sized world (device resident in the product)
 // ------------------------------------------------------------------------------------------
@@ -328,6 +355,11 @@ struct LargeOps {
     virtual int ls_coeffs(double alpha, double out[4]) = 0;
     // constraints only (host or device, tiny)
     virtual int cons(const double* x, double* cx) = 0;
+    // Wall-clock seconds since the start of the solve as every rank must see them: the time-limit test (EF:2509) is the
+    // only termination input that is not bit-replicated across the ranks of a row-sharded solve, and ranks that disagree
+    // on it leave each other alone in the next collective.  Sharded backends return the mean over the ranks (one sum
+    // all-reduce of elapsed / nranks).
+    virtual double agreed_elapsed(double local_elapsed) { return local_elapsed; }
 };
 
 struct LargeOptions {
@@ -384,106 +416,138 @@ struct WorkingSetL {   // structures.jl:209-267, 1-based ids, 0 = empty
     }
 };
 
-struct ConstraintL {   // structures.jl:145-150 ; A is t x n (row i = gradient of active constraint i)
+struct ConstraintL {   // structures.jl:145-150 ; the t x n matrix A (row i = gradient of active constraint i) lives in the SmallBackend
     Vec cx;
-    Mat A;
     bool scaling = false;
     Vec diag_scale;
 };
 
-class LargeSolver {
-public:
-    LargeOps& ops;
-    LargeOptions opt;
-    int n, l, q, mt;
-    long long m;
+// ------------------------------------------------------------------------------------------
+// The matrix-sized half of the small stage: everything of the iteration that touches A (l x n), the active
+// block C.A (t x n), the compressed Jacobian J~ ((n+1) x n), J~*Q1 and the three pivoted QR factorisations
+// (EF:700 F_A, EF:769 F_L11, EF:223 F_J2).  The driver below keeps the scalar logic, the working set and the
+// O(n) vectors; it hands vectors in and gets vectors / diagonals / permutations back.
+//   HostSmall    (this header): host memory, the CPU test backend;
+//   DeviceSmall  (enl_small.cuh, product): everything resident in HBM, CUDA kernels only.
+// Size-dependent error situations of the reference (BoundsError, DimensionMismatch, SingularException) are
+// decided by the driver from FactorInfo BEFORE a backend call, so a backend never has to throw.
+// ------------------------------------------------------------------------------------------
+struct SmallBackend {
+    virtual ~SmallBackend() {}
+    // new_point! (EF:34-52), first half: r, c, A at x; returns J'r (n), ||r||^2 and c (l).  A stays with the backend.
+    virtual int eval_point(const double* x, double* gradf, double* rr, double* cx) = 0;
+    // second half: compress [J | r] of that point; returns r~ (n+1) and J~' r~ (n)
+    virtual int compress(double* rt, double* gradf) = 0;
+    // C.A = A[active, :]
+    virtual void gather_active(const int* active, int t) = 0;
+    // structures.jl:160-178: rown[i] = ||C.A[i, :]||; scaling: C.A[i, :] /= (|rown[i]| < eps ? 1 : rown[i])
+    virtual void evaluate_scaling(int t, bool scaling, double* rown) = 0;
+    // surviving side effect of the reverted first-order deletion with scaling (EF:742-745):
+    // C.A[i, :] = A[active[i], :] * diag_scale[i]
+    virtual void rebuild_scaled_rows(const int* active, int t, const double* diag_scale) = 0;
+    virtual void remove_active_row(int s0) = 0;                  // 0-based row of C.A
+    virtual void factor_A(int t, FactorInfo& F) = 0;             // qr(C.A', ColumnNorm())          EF:700
+    virtual void factor_L11(FactorInfo& F) = 0;                  // qr(F_A.R', ColumnNorm())        EF:769
+    virtual void factor_J2(int rankA, FactorInfo& F) = 0;        // J*Q1 (once per F_A); qr(J2, ColumnNorm())   EF:219-223
+    // EF:461-508: v = R^-1 (Q1' gradf)[1:r] (zero padded to t), grad_res = ||(Q1' gradf)[r+1:n]||,
+    //             u = R^-1 R^-T (-c[P])[1:r] (zero padded to t)
+    virtual void first_lagrange(int prankA, int t, const Vec& gradf, const Vec& Ccx, Vec& v, Vec& u, double& grad_res) = 0;
+    // EF:514-537: v = R^-1 (J1' (r + J p_gn))[1:r] (zero padded to t)
+    virtual void second_lagrange(int prankA, int t, const Vec& p_gn, Vec& v) = 0;
+    // EF:116-153 (sizes already validated by the driver)
+    virtual void sub_search_direction(int t, int rankA, int dimA, int dimJ2, int code, const Vec& Ccx, Vec& p, Vec& b,
+                                      Vec& d) = 0;
+    // EF:1249-1251: b = F_L11.Q' (-c[P])
+    virtual void subspace_rhs(int t, const Vec& Ccx, Vec& b) = 0;
+    // EF:1131-1147: d = F_J2.Q' (-(r + J1 p1)), p1 = P_L11[1:rankA,1:rankA] [R11[1:dimA,1:dimA] \ b[1:dimA]; 0]  (rankA > 0)
+    //               d = F_J2.Q' (-r)                                                                     (rankA <= 0)
+    virtual void subspace_d(int rankA, int dimA, int rankJ2, const Vec& b, Vec& d) = 0;
+    // EF:2222-2224: Jp = J~ p (n+1), Ap = A p (l), active_Ap = C.A p (t)
+    virtual void products(const Vec& p, int t, Vec& Jp, Vec& Ap, Vec& active_Ap) = 0;
+    // EF:2497: ||C.A' C.cx||
+    virtual double At_c_norm(int t, const Vec& Ccx) = 0;
+};
 
-    // live buffers (compressed residual world + constraints)
+// Host-memory backend: the CPU test path (oracle/hostport/largeport.cpp).  The product never instantiates it.
+struct HostSmall : SmallBackend {
+    LargeOps& ops;
+    int n, l, mt;
     Mat J;      // mt x n
     Vec rx;     // mt
-    Vec cx;     // l
     Mat A;      // l x n
-    Vec gradf;
-    Vec K[4];
-    WorkingSetL W;
-    ConstraintL C;
+    Mat CA;     // t x n
     QRP F_A, F_L11, F_J2;
     Mat JQ1;          // J * F_A.Q, formed once per F_A (EF:219, 526, 1249 recompute it)
     bool jq1_valid = false;
-    int n_new_point = 0, n_res_eval = 0;
+    bool jq1_on_device = false;   // legacy DenseAccel route: JQ1 lives on the device, the host copy holds its leading columns
 
-    LargeSolver(LargeOps& o, const LargeOptions& op) : ops(o), opt(op) {
-        n = o.n; l = o.l; q = o.q; m = o.m; mt = n + 1;
+    explicit HostSmall(LargeOps& o) : ops(o), n(o.n), l(o.l), mt(o.n + 1) {
+        J = Mat(mt, n);
+        rx.assign(mt, 0.0);
+        A = Mat(l, n);
     }
-
-    // ---- small helpers ------------------------------------------------------------------
-    void check(int rc) { if (rc != 0) throw std::runtime_error("LargeOps failure"); }
-
-    // EF:34-52 in two halves.  do_eval_point: r, c, A at x and the two m-sized quantities of the termination test
-    // (gradf = J'r, returned ||r||^2).  do_factor: the compressed problem [J~ | r~] of that point -- called only when
-    // the iteration continues from it, after which gradf / ||r||^2 are re-derived from the compressed problem so that
-    // every quantity of an iteration comes from one and the same factorisation.
-    double do_eval_point(const Vec& x) { ProfScope prof_(0);
-        double rr = 0.0;
-        check(ops.eval_point(x.data(), gradf.data(), &rr, cx.data(), A.a.data()));
-        ++n_new_point;
+    int eval_point(const double* x, double* gradf, double* rr, double* cx) override {
         jq1_valid = false;
-        cur_rr = rr;
-        return rr;
+        return ops.eval_point(x, gradf, rr, cx, A.a.data());
     }
-    double do_factor() { ProfScope prof_(0);
-        check(ops.compress(J.a.data(), rx.data()));
-        compute_gradf();
-        cur_rr = dotv(rx, rx);
-        return cur_rr;
-    }
-    double cur_rr = 0.0;   // ||r||^2 at the point of the last do_eval_point
-    void compute_gradf() { ProfScope prof_(14);   // J' * rx
+    int compress(double* rt, double* gradf) override {
+        int rc = ops.compress(J.a.data(), rx.data());
+        if (rc != 0) return rc;
+        for (int r = 0; r < mt; ++r) rt[r] = rx[r];
         for (int j = 0; j < n; ++j) gradf[j] = dot_n(J.col(j), rx.data(), mt);
+        return 0;
     }
-    void gather_active() { ProfScope prof_(1);   // C.cx = cx[active], C.A = A[active, :]
-        int t = W.t;
-        C.cx.resize(t);
-        C.A = Mat(t, n);
-        for (int i = 0; i < t; ++i) C.cx[i] = cx[W.active[i] - 1];
+    void gather_active(const int* active, int t) override { ProfScope prof_(1);
+        CA = Mat(t, n);
         for (int j = 0; j < n; ++j) {
             const double* aj = A.col(j);
-            double* cj = C.A.col(j);
-            for (int i = 0; i < t; ++i) cj[i] = aj[W.active[i] - 1];
+            double* cj = CA.col(j);
+            for (int i = 0; i < t; ++i) cj[i] = aj[active[i] - 1];
         }
     }
-    void evaluate_scaling() {   // structures.jl:160-178
-        int t = C.A.rows;
-        C.diag_scale.assign(t, 0.0);
+    void evaluate_scaling(int t, bool scaling, double* rown) override {
         Vec row(n);
         for (int i = 0; i < t; ++i) {
-            for (int j = 0; j < n; ++j) row[j] = C.A(i, j);
+            for (int j = 0; j < n; ++j) row[j] = CA(i, j);
             double row_i = normv(row);
-            C.diag_scale[i] = row_i;
-            if (C.scaling) {
+            rown[i] = row_i;
+            if (scaling) {
                 if (fabs(row_i) < EPS) row_i = 1.0;
-                for (int j = 0; j < n; ++j) C.A(i, j) = C.A(i, j) / row_i;
-                C.cx[i] = C.cx[i] / row_i;
-                C.diag_scale[i] = 1.0 / row_i;
+                for (int j = 0; j < n; ++j) CA(i, j) = CA(i, j) / row_i;
             }
         }
     }
-    void factor_A() { ProfScope prof_(2);   // F_A = qr(C.A', ColumnNorm())
-        int t = C.A.rows;
+    void rebuild_scaled_rows(const int* active, int t, const double* diag_scale) override {
+        for (int i = 0; i < t; ++i) {
+            int k = active[i] - 1;
+            for (int j = 0; j < n; ++j) CA(i, j) = A(k, j) * diag_scale[i];
+        }
+    }
+    void remove_active_row(int s0) override {
+        Mat A2(CA.rows - 1, n);
+        for (int i = 0, o = 0; i < CA.rows; ++i) {
+            if (i == s0) continue;
+            for (int j = 0; j < n; ++j) A2(o, j) = CA(i, j);
+            ++o;
+        }
+        CA = A2;
+    }
+    void factor_A(int t, FactorInfo& F) override { ProfScope prof_(2);
         Mat At(n, t);
         for (int i = 0; i < t; ++i)
-            for (int j = 0; j < n; ++j) At(j, i) = C.A(i, j);
+            for (int j = 0; j < n; ++j) At(j, i) = CA(i, j);
         F_A.factor(At);
         jq1_valid = false;
+        F.take(F_A);
     }
-    void factor_L11() { ProfScope prof_(3);   // F_L11 = qr(F_A.R', ColumnNorm()); F_A.R is min(n,t) x t
+    void factor_L11(FactorInfo& F) override { ProfScope prof_(3);   // F_A.R is min(n,t) x t
         int kr = F_A.k, t = F_A.cols;
         Mat Rt(t, kr);
         for (int r = 0; r < kr; ++r)
             for (int c = 0; c < t; ++c) Rt(c, r) = F_A.R(r, c);
         F_L11.factor(Rt);
+        F.take(F_L11);
     }
-    bool jq1_on_device = false;   // JQ1 lives on the device; the host copy holds only its leading min(t, n) columns
     void ensure_JQ1() { ProfScope prof_(4);
         if (!jq1_valid) {
             const int lead = std::min(F_A.cols, n);
@@ -502,41 +566,67 @@ public:
             jq1_valid = true;
         }
     }
-
-    // EF:116-153.  J1 = JQ1[:, 0:rankA]
-    void sub_search_direction(int t, int rankA, int dimA, int dimJ2, int code, Vec& p, Vec& b, Vec& d) {
+    void factor_J2(int rankA, FactorInfo& F) override {
+        ensure_JQ1();
+        if (!(jq1_on_device && F_J2.factor_device_tail(rankA, mt, n - rankA))) {
+            if (jq1_on_device) throw std::runtime_error("device-resident J*Q1 lost");
+            Mat J2(mt, n - rankA);
+            for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
+            F_J2.factor(J2);
+        }
+        F.take(F_J2);
+    }
+    void first_lagrange(int prankA, int t, const Vec& gradf, const Vec& Ccx, Vec& v, Vec& u, double& grad_res) override {
+        Vec b = gradf;
+        F_A.Qt_mul(b.data());
+        v.assign(t, 0.0);
+        for (int i = 0; i < prankA; ++i) v[i] = b[i];
+        solve_upper(F_A, prankA, v.data());
+        grad_res = (n > prankA) ? norm_n(b.data() + prankA, n - prankA) : 0.0;
+        Vec y(t, 0.0);
+        u.assign(t, 0.0);
+        for (int i = 0; i < prankA; ++i) y[i] = -Ccx[F_A.p[i]];
+        solve_upperT(F_A, prankA, y.data());
+        for (int i = 0; i < prankA; ++i) u[i] = y[i];
+        solve_upper(F_A, prankA, u.data());
+    }
+    void second_lagrange(int prankA, int t, const Vec& p_gn, Vec& v) override {
+        ensure_JQ1();
+        // b = J1' (rx + J p_gn), J1 = JQ1[:, 0:t]
+        Vec s(rx);
+        for (int c = 0; c < n; ++c) {
+            const double* jc = J.col(c);
+            double pc = p_gn[c];
+            for (int r = 0; r < mt; ++r) s[r] += jc[r] * pc;
+        }
+        v.assign(t, 0.0);
+        for (int i = 0; i < prankA; ++i) v[i] = dot_n(JQ1.col(i), s.data(), mt);
+        solve_upper(F_A, prankA, v.data());
+    }
+    void sub_search_direction(int t, int rankA, int dimA, int dimJ2, int code, const Vec& Ccx, Vec& p, Vec& b,
+                              Vec& d) override {
         Vec p1;
         if (code == 1) {
             b.resize(t);
-            for (int i = 0; i < t; ++i) b[i] = -C.cx[F_A.p[i]];
+            for (int i = 0; i < t; ++i) b[i] = -Ccx[F_A.p[i]];
             p1 = b;
-            // LowerTriangular(F_A.R') \ b : R' is t x min(n,t); the reference solve needs it square
-            if (F_A.k < t) throw WouldThrow{"DimensionMismatch in L11 solve"};
             solve_upperT(F_A, t, p1.data());
-        } else if (code == -1) {
+        } else {
             b.resize(t);
-            for (int i = 0; i < t; ++i) b[i] = -C.cx[F_A.p[i]];
+            for (int i = 0; i < t; ++i) b[i] = -Ccx[F_A.p[i]];
             F_L11.Qt_mul(b.data());
-            if (dimA > t || dimA > F_L11.k) throw WouldThrow{"BoundsError R11[1:dimA,1:dimA]"};
-            if (dimA > (int)b.size()) throw WouldThrow{"BoundsError b[1:dimA]"};
             Vec dp1(std::max(dimA, 0));
             for (int i = 0; i < dimA; ++i) dp1[i] = b[i];
             solve_upper(F_L11, std::max(dimA, 0), dp1.data());
             // [dp1; zeros(t-dimA)][invperm(F_L11.p)][1:rankA]
-            if (t - dimA < 0) throw WouldThrow{"negative zeros() length"};
             Vec full(t, 0.0);
             for (int i = 0; i < dimA; ++i) full[i] = dp1[i];
             std::vector<int> ip = F_L11.invperm();
-            if ((int)ip.size() != t) throw WouldThrow{"BoundsError in invperm indexing"};
-            if (rankA > t) throw WouldThrow{"BoundsError [1:rankA]"};
             p1.resize(rankA);
             for (int i = 0; i < rankA; ++i) p1[i] = full[ip[i]];
-        } else {
-            throw WouldThrow{"sub_search_direction: code"};
         }
         int np1 = (int)p1.size();
         // d_temp = -J1*p1 - rx   (J1 has rankA columns; code 1: p1 has t == rankA entries)
-        if (np1 != rankA) throw WouldThrow{"DimensionMismatch J1*p1"};
         d.assign(mt, 0.0);
         for (int c = 0; c < rankA; ++c) {
             const double* jc = JQ1.col(c);
@@ -545,38 +635,195 @@ public:
         }
         for (int r = 0; r < mt; ++r) d[r] = -d[r] - rx[r];
         F_J2.Qt_mul(d.data());
-        if (dimJ2 > F_J2.k) throw WouldThrow{"BoundsError R22[1:dimJ2,1:dimJ2]"};
-        if (dimJ2 > mt) throw WouldThrow{"BoundsError d[1:dimJ2]"};
         int dj = std::max(dimJ2, 0);
         Vec dp2(dj);
         for (int i = 0; i < dj; ++i) dp2[i] = d[i];
         solve_upper(F_J2, dj, dp2.data());
-        int tail = (code == 1) ? (n - t - dimJ2) : (n - rankA - dimJ2);
-        if (tail < 0) throw WouldThrow{"negative zeros() length"};
-        int k2 = dj + tail;   // length of [dp2; zeros]
         std::vector<int> ip2 = F_J2.invperm();
-        if ((int)ip2.size() != k2) {
-            // indexing a k2-vector with a permutation of another length: BoundsError unless shorter and in range
-            for (int v : ip2) if (v >= k2) throw WouldThrow{"BoundsError p2 permutation"};
-        }
         Vec y(np1 + (int)ip2.size());
         for (int i = 0; i < np1; ++i) y[i] = p1[i];
         for (size_t i = 0; i < ip2.size(); ++i) y[np1 + i] = (ip2[i] < dj) ? dp2[ip2[i]] : 0.0;
-        if ((int)y.size() != n) throw WouldThrow{"DimensionMismatch in Q1*[p1;p2]"};
         F_A.Q_mul(y.data());
         p = y;
+    }
+    void subspace_rhs(int t, const Vec& Ccx, Vec& b) override {
+        ensure_JQ1();
+        b.resize(t);
+        for (int i = 0; i < t; ++i) b[i] = -Ccx[F_A.p[i]];
+        F_L11.Qt_mul(b.data());
+    }
+    void subspace_d(int rankA, int dimA, int rankJ2, const Vec& b, Vec& d) override {
+        d.assign(mt, 0.0);
+        if (rankA <= 0) {
+            for (int r = 0; r < mt; ++r) d[r] = -rx[r];
+        } else {
+            Vec dp1(std::max(dimA, 0));
+            for (int i = 0; i < dimA; ++i) dp1[i] = b[i];
+            solve_upper(F_L11, std::max(dimA, 0), dp1.data());
+            // p1 = P[1:rankA,1:rankA] * [dp1; zeros] : P[p[j], j] = 1
+            Vec p1(rankA, 0.0);
+            for (int j = 0; j < rankA; ++j) {
+                int r = F_L11.p[j];
+                if (r < rankA) p1[r] += (j < dimA) ? dp1[j] : 0.0;
+            }
+            for (int c = 0; c < rankA; ++c) {
+                const double* jc = JQ1.col(c);
+                double pc = p1[c];
+                for (int r = 0; r < mt; ++r) d[r] += jc[r] * pc;
+            }
+            for (int r = 0; r < mt; ++r) d[r] = -(rx[r] + d[r]);
+        }
+        if (rankJ2 > 0) F_J2.Qt_mul(d.data());
+    }
+    void products(const Vec& p, int t, Vec& Jp, Vec& Ap, Vec& active_Ap) override {
+        Jp.assign(mt, 0.0);
+        for (int c = 0; c < n; ++c) {
+            const double* jc = J.col(c);
+            double pc = p[c];
+            if (pc == 0.0) continue;
+            for (int r = 0; r < mt; ++r) Jp[r] += jc[r] * pc;
+        }
+        // A * p for every row, columns outermost (A is column major): per row the same summation order
+        // c = 0..n-1 as the row-wise dot product of the reference
+        Ap.assign(l, 0.0);
+        for (int c = 0; c < n; ++c) {
+            double pc = p[c];
+            for (int r = 0; r < l; ++r) Ap[r] += A(r, c) * pc;
+        }
+        active_Ap.assign(t, 0.0);
+        for (int c = 0; c < n; ++c) {
+            double pc = p[c];
+            for (int r = 0; r < t; ++r) active_Ap[r] += CA(r, c) * pc;
+        }
+    }
+    double At_c_norm(int t, const Vec& Ccx) override {
+        if (!CA.rows) return 0.0;
+        Vec v(n, 0.0);
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < CA.rows; ++i) v[j] += CA(i, j) * Ccx[i];
+        (void)t;
+        return normv(v);
+    }
+};
+
+class LargeSolver {
+public:
+    LargeOps& ops;
+    LargeOptions opt;
+    int n, l, q, mt;
+    long long m;
+
+    // the matrix-sized state lives in the backend; here: vectors and scalars
+    HostSmall* own_small = nullptr;
+    SmallBackend* sb = nullptr;
+    Vec rx;     // r~ (mt)
+    Vec cx;     // l
+    Vec gradf;
+    Vec K[4];
+    WorkingSetL W;
+    ConstraintL C;
+    FactorInfo F_A, F_L11, F_J2;
+    int n_new_point = 0, n_res_eval = 0;
+
+    // backend == nullptr: host memory (CPU tests); the product passes its device backend
+    LargeSolver(LargeOps& o, const LargeOptions& op, SmallBackend* backend = nullptr) : ops(o), opt(op) {
+        n = o.n; l = o.l; q = o.q; m = o.m; mt = n + 1;
+        if (backend) sb = backend;
+        else { own_small = new HostSmall(o); sb = own_small; }
+    }
+    ~LargeSolver() { delete own_small; }
+    LargeSolver(const LargeSolver&) = delete;
+    LargeSolver& operator=(const LargeSolver&) = delete;
+
+    // ---- small helpers ------------------------------------------------------------------
+    void check(int rc) { if (rc != 0) throw std::runtime_error("LargeOps failure"); }
+
+    // EF:34-52 in two halves.  do_eval_point: r, c, A at x and the two m-sized quantities of the termination test
+    // (gradf = J'r, returned ||r||^2).  do_factor: the compressed problem [J~ | r~] of that point -- called only when
+    // the iteration continues from it, after which gradf / ||r||^2 are re-derived from the compressed problem so that
+    // every quantity of an iteration comes from one and the same factorisation.
+    double do_eval_point(const Vec& x) { ProfScope prof_(0);
+        double rr = 0.0;
+        check(sb->eval_point(x.data(), gradf.data(), &rr, cx.data()));
+        ++n_new_point;
+        cur_rr = rr;
+        return rr;
+    }
+    double do_factor() { ProfScope prof_(0);
+        check(sb->compress(rx.data(), gradf.data()));
+        cur_rr = dotv(rx, rx);
+        return cur_rr;
+    }
+    double cur_rr = 0.0;   // ||r||^2 at the point of the last do_eval_point
+    void gather_active() {   // C.cx = cx[active], C.A = A[active, :]
+        int t = W.t;
+        C.cx.resize(t);
+        for (int i = 0; i < t; ++i) C.cx[i] = cx[W.active[i] - 1];
+        sb->gather_active(W.active.data(), t);
+    }
+    void evaluate_scaling() {   // structures.jl:160-178
+        int t = W.t;
+        C.diag_scale.assign(t, 0.0);
+        Vec rown(t, 0.0);
+        sb->evaluate_scaling(t, C.scaling, rown.data());
+        for (int i = 0; i < t; ++i) {
+            double row_i = rown[i];
+            C.diag_scale[i] = row_i;
+            if (C.scaling) {
+                if (fabs(row_i) < EPS) row_i = 1.0;
+                C.cx[i] = C.cx[i] / row_i;
+                C.diag_scale[i] = 1.0 / row_i;
+            }
+        }
+    }
+    void factor_A() { sb->factor_A(W.t, F_A); }          // F_A = qr(C.A', ColumnNorm())
+    void factor_L11() { sb->factor_L11(F_L11); }          // F_L11 = qr(F_A.R', ColumnNorm())
+
+    static void need_nonzero_diag(const FactorInfo& F, int k, const char* what) {   // LAPACK trtrs: SingularException
+        for (int i = 0; i < k; ++i)
+            if (F.diag(i) == 0.0) throw WouldThrow{what};
+    }
+
+    // EF:116-153.  The reference's BoundsError / DimensionMismatch / SingularException situations depend on sizes and
+    // on diag(R) only: decided here, the backend then runs the arithmetic.
+    void sub_search_direction(int t, int rankA, int dimA, int dimJ2, int code, Vec& p, Vec& b, Vec& d) {
+        int np1;
+        if (code == 1) {
+            // LowerTriangular(F_A.R') \ b : R' is t x min(n,t); the reference solve needs it square
+            if (F_A.k < t) throw WouldThrow{"DimensionMismatch in L11 solve"};
+            need_nonzero_diag(F_A, t, "SingularException (lower)");
+            np1 = t;
+        } else if (code == -1) {
+            if (dimA > t || dimA > F_L11.k) throw WouldThrow{"BoundsError R11[1:dimA,1:dimA]"};
+            need_nonzero_diag(F_L11, std::max(dimA, 0), "SingularException (upper)");
+            if (t - dimA < 0) throw WouldThrow{"negative zeros() length"};
+            if (F_L11.cols != t) throw WouldThrow{"BoundsError in invperm indexing"};
+            if (rankA > t) throw WouldThrow{"BoundsError [1:rankA]"};
+            np1 = rankA;
+        } else {
+            throw WouldThrow{"sub_search_direction: code"};
+        }
+        // d_temp = -J1*p1 - rx   (J1 has rankA columns; code 1: p1 has t == rankA entries)
+        if (np1 != rankA) throw WouldThrow{"DimensionMismatch J1*p1"};
+        if (dimJ2 > F_J2.k) throw WouldThrow{"BoundsError R22[1:dimJ2,1:dimJ2]"};
+        if (dimJ2 > mt) throw WouldThrow{"BoundsError d[1:dimJ2]"};
+        int dj = std::max(dimJ2, 0);
+        need_nonzero_diag(F_J2, dj, "SingularException (upper)");
+        int tail = (code == 1) ? (n - t - dimJ2) : (n - rankA - dimJ2);
+        if (tail < 0) throw WouldThrow{"negative zeros() length"};
+        int k2 = dj + tail;   // length of [dp2; zeros]
+        if (F_J2.cols != k2) {
+            // indexing a k2-vector with a permutation of another length: BoundsError unless shorter and in range
+            for (int j = 0; j < F_J2.cols; ++j) if (j >= k2) throw WouldThrow{"BoundsError p2 permutation"};
+        }
+        if (np1 + F_J2.cols != n) throw WouldThrow{"DimensionMismatch in Q1*[p1;p2]"};
+        sb->sub_search_direction(t, rankA, dimA, dimJ2, code, C.cx, p, b, d);
     }
 
     // EF:206-234
     void gn_search_direction(int rankA, int t, IterL& it, Vec& p_gn) { ProfScope prof_(5);
         int code = (rankA == t) ? 1 : -1;
-        ensure_JQ1();
-        if (!(jq1_on_device && F_J2.factor_device_tail(rankA, mt, n - rankA))) {
-            if (jq1_on_device) throw std::runtime_error("device-resident J*Q1 lost");
-            Mat J2(mt, n - rankA);
-            for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
-            F_J2.factor(J2);
-        }
+        sb->factor_J2(rankA, F_J2);
         int rankJ2 = pseudo_rank(F_J2, opt.eps_rank);
         Vec b, d;
         sub_search_direction(t, rankA, rankA, rankJ2, code, p_gn, b, d);
@@ -590,24 +837,14 @@ public:
 
     // EF:461-508
     void first_lagrange_mult_estimate(Vec& lam, IterL& it) { ProfScope prof_(6);
-        int t = C.A.rows;
+        int t = W.t;
         std::vector<int> inv_p = F_A.invperm();
         int prankA = pseudo_rank(F_A, opt.eps_rank);
-        Vec b = gradf;
-        F_A.Qt_mul(b.data());
-        Vec v(t, 0.0);
-        for (int i = 0; i < prankA; ++i) v[i] = b[i];
-        solve_upper(F_A, prankA, v.data());
-        Vec lam_ls(t);
-        for (int i = 0; i < t; ++i) lam_ls[i] = v[inv_p[i]];
-        it.grad_res = (n > prankA) ? norm_n(b.data() + prankA, n - prankA) : 0.0;
-        Vec y(t, 0.0), u(t, 0.0);
-        for (int i = 0; i < prankA; ++i) y[i] = -C.cx[F_A.p[i]];
-        solve_upperT(F_A, prankA, y.data());
-        for (int i = 0; i < prankA; ++i) u[i] = y[i];
-        solve_upper(F_A, prankA, u.data());
+        need_nonzero_diag(F_A, prankA, "SingularException (upper)");
+        Vec v, u;
+        sb->first_lagrange(prankA, t, gradf, C.cx, v, u, it.grad_res);
         lam.resize(t);
-        for (int i = 0; i < t; ++i) lam[i] = lam_ls[i] + u[inv_p[i]];
+        for (int i = 0; i < t; ++i) lam[i] = v[inv_p[i]] + u[inv_p[i]];
         if (C.scaling)
             for (int i = 0; i < t; ++i) lam[i] = lam[i] * C.diag_scale[i];
     }
@@ -615,18 +852,10 @@ public:
     // EF:514-537
     void second_lagrange_mult_estimate(Vec& lam, const Vec& p_gn, int t) { ProfScope prof_(7);
         int prankA = pseudo_rank(F_A, SQRT_EPS);
-        ensure_JQ1();
-        // b = J1' (rx + J p_gn), J1 = JQ1[:, 0:t]
-        Vec s(rx);
-        for (int c = 0; c < n; ++c) {
-            const double* jc = J.col(c);
-            double pc = p_gn[c];
-            for (int r = 0; r < mt; ++r) s[r] += jc[r] * pc;
-        }
-        Vec v(t, 0.0);
         if (prankA > t) throw WouldThrow{"BoundsError b[1:prankA]"};
-        for (int i = 0; i < prankA; ++i) v[i] = dot_n(JQ1.col(i), s.data(), mt);
-        solve_upper(F_A, prankA, v.data());
+        need_nonzero_diag(F_A, prankA, "SingularException (upper)");
+        Vec v;
+        sb->second_lagrange(prankA, t, p_gn, v);
         std::vector<int> ip = F_A.invperm();
         lam.resize(t);
         for (int i = 0; i < t; ++i) lam[i] = v[ip[i]];
@@ -650,7 +879,7 @@ public:
 
     // EF:574-603 : returns a 1-based position (0 = none)
     int check_constraint_deletion(const Vec& lam, double grad_res) {
-        int t = C.A.rows;
+        int t = W.t;
         double lam_max = 1.0;
         if (!lam.empty()) {
             lam_max = 0.0;
@@ -717,10 +946,7 @@ public:
             it.index_del = 0;
             it.dele = false;
             if (C.scaling) {
-                for (int i = 0; i < W.t; ++i) {
-                    int k = W.active[i] - 1;
-                    for (int j = 0; j < n; ++j) C.A(i, j) = A(k, j) * C.diag_scale[i];
-                }
+                sb->rebuild_scaled_rows(W.active.data(), W.t, C.diag_scale.data());
                 factor_A();
             }
         }
@@ -740,13 +966,7 @@ public:
                 W.remove_constraint(s2);
                 it.dele = true;
                 it.index_del = index_s2;
-                Mat A2(C.A.rows - 1, n);
-                for (int i = 0, o = 0; i < C.A.rows; ++i) {
-                    if (i == s2 - 1) continue;
-                    for (int j = 0; j < n; ++j) A2(o, j) = C.A(i, j);
-                    ++o;
-                }
-                C.A = A2;
+                sb->remove_active_row(s2 - 1);
                 factor_A();
                 rankA = pseudo_rank(F_A, opt.eps_rank);
                 factor_L11();
@@ -821,7 +1041,7 @@ public:
     }
     // EF:1041-1113 ; R = factor whose diagonal is used, y = right-hand side
     int determine_solving_dim(int previous_dimR, int rankR, double predicted_linear_progress, double obj_progress,
-                              double prelin_previous_dim, const QRP& Rf, const Vec& y, double previous_alpha,
+                              double prelin_previous_dim, const FactorInfo& Rf, const Vec& y, double previous_alpha,
                               bool restart) {
         const double c1 = 0.1;
         int newdim = rankR, mindim = 1;
@@ -864,11 +1084,10 @@ public:
         const double alpha_low = 0.2;
         double previous_alpha = prev.alpha;
         int previous_dimA;
-        Vec d(mt);
+        Vec d;
         if (rankA <= 0) {
             dimA = 0;
             previous_dimA = 0;
-            for (int r = 0; r < mt; ++r) d[r] = -rx[r];
         } else {
             previous_dimA = abs(prev.dimA) + t - prev.t;
             double nrm_b_asprev = norm_range(b, previous_dimA);
@@ -877,26 +1096,11 @@ public:
             dimA = determine_solving_dim(previous_dimA, rankA, nrm_b, constraint_progress, nrm_b_asprev, F_L11, b,
                                          previous_alpha, restart);
             if (dimA > F_L11.k || dimA > (int)b.size()) throw WouldThrow{"BoundsError R11[1:dimA]"};
-            Vec dp1(std::max(dimA, 0));
-            for (int i = 0; i < dimA; ++i) dp1[i] = b[i];
-            solve_upper(F_L11, std::max(dimA, 0), dp1.data());
+            need_nonzero_diag(F_L11, std::max(dimA, 0), "SingularException (upper)");
             if (rankA - dimA < 0) throw WouldThrow{"negative zeros() length"};
             if (rankA > F_L11.cols) throw WouldThrow{"BoundsError in F_L11.P[1:rankA,1:rankA]"};
-            // p1 = P[1:rankA,1:rankA] * [dp1; zeros] : P[p[j], j] = 1
-            Vec p1(rankA, 0.0);
-            for (int j = 0; j < rankA; ++j) {
-                int r = F_L11.p[j];
-                if (r < rankA) p1[r] += (j < dimA) ? dp1[j] : 0.0;
-            }
-            std::fill(d.begin(), d.end(), 0.0);
-            for (int c = 0; c < rankA; ++c) {
-                const double* jc = JQ1.col(c);
-                double pc = p1[c];
-                for (int r = 0; r < mt; ++r) d[r] += jc[r] * pc;
-            }
-            for (int r = 0; r < mt; ++r) d[r] = -(rx[r] + d[r]);
         }
-        if (rankJ2 > 0) F_J2.Qt_mul(d.data());
+        sb->subspace_d(rankA, dimA, rankJ2, b, d);
         int previous_dimJ2 = abs(prev.dimJ2) + prev.t - t;
         double nrm_d_asprev = norm_range(d, previous_dimJ2);
         double nrm_d = normv(d);
@@ -976,10 +1180,7 @@ public:
             dimA = rankA; dimJ2 = rankJ2;
             p = p_gn; b = cur.b_gn; d = cur.d_gn;
         } else if (method_code == -1) {
-            ensure_JQ1();
-            b.resize(W.t);
-            for (int i = 0; i < W.t; ++i) b[i] = -C.cx[F_A.p[i]];
-            F_L11.Qt_mul(b.data());
+            sb->subspace_rhs(W.t, C.cx, b);
             choose_subspace_dimensions(rx_sum, active_cx_sum, W.t, rankJ2, rankA, b, prev, restart, dimA, dimJ2);
             sub_search_direction(W.t, rankA, dimA, dimJ2, method_code, p, b, d);
             if (dimA == rankA && dimJ2 == rankJ2) method_code = 1;
@@ -1413,24 +1614,18 @@ public:
     }
 
     // EF:2149-2178
-    double upper_bound_steplength(const Vec& p, int index_del, int& index_alpha_upp) { ProfScope prof_(11);
+    double upper_bound_steplength(const Vec& Ap, int index_del, int& index_alpha_upp) { ProfScope prof_(11);
         double alpha_upper = INFINITY;
         index_alpha_upp = 0;
         int mx = 0;
         for (int v : W.inactive) mx = std::max(mx, abs(v));
         if (!W.inactive.empty() && mx > 0) {
-            // A * p for every row, columns outermost (A is column major): per row the same summation order
-            // c = 0..n-1 as the row-wise dot product of the reference, so the values are bit-identical
-            Vec g_all(l, 0.0);
-            for (int c = 0; c < n; ++c) {
-                const double pc = p[c];
-                const double* ac = A.col(c);
-                for (int r = 0; r < l; ++r) g_all[r] += ac[r] * pc;
-            }
+            // g = A * p for every row: the Ap of compute_steplength (same summation order c = 0..n-1 as the row-wise
+            // dot product of the reference)
             for (int i = 0; i < W.l - W.t; ++i) {
                 int j = W.inactive[i];
                 if (j != index_del) {
-                    const double g = g_all[j - 1];
+                    const double g = Ap[j - 1];
                     double a_j = -cx[j - 1] / g;
                     if (cx[j - 1] > 0 && g < 0 && a_j < alpha_upper) { alpha_upper = a_j; index_alpha_upp = j; }
                 }
@@ -1444,23 +1639,8 @@ public:
         const Vec& p = it.p;
         int dimA = it.dimA;
         // Jp (compressed), Ap, active_Ap
-        Vec Jp(mt, 0.0);
-        for (int c = 0; c < n; ++c) {
-            const double* jc = J.col(c);
-            double pc = p[c];
-            if (pc == 0.0) continue;
-            for (int r = 0; r < mt; ++r) Jp[r] += jc[r] * pc;
-        }
-        Vec Ap(l, 0.0);
-        for (int c = 0; c < n; ++c) {
-            double pc = p[c];
-            for (int r = 0; r < l; ++r) Ap[r] += A(r, c) * pc;
-        }
-        Vec active_Ap(W.t, 0.0);
-        for (int c = 0; c < n; ++c) {
-            double pc = p[c];
-            for (int r = 0; r < W.t; ++r) active_Ap[r] += C.A(r, c) * pc;
-        }
+        Vec Jp, Ap, active_Ap;
+        sb->products(p, W.t, Jp, Ap, active_Ap);
         if (C.scaling)
             for (int r = 0; r < W.t; ++r) active_Ap[r] = active_Ap[r] / C.diag_scale[r];
         Psi_error = 0;
@@ -1481,7 +1661,7 @@ public:
                 it.index_alpha_upp = 0;
             } else {
                 int index_alpha_upp;
-                double alpha_upp = upper_bound_steplength(p, it.index_del, index_alpha_upp);
+                double alpha_upp = upper_bound_steplength(Ap, it.index_del, index_alpha_upp);
                 double alpha_low = alpha_upp / 3000.0;
                 double magfy = (it.rankJ2 < prev.rankJ2) ? 6.0 : 3.0;
                 double alpha0 = fmin(fmin(1.0, magfy * prev.alpha), alpha_upp);
@@ -1567,13 +1747,7 @@ public:
             double xd = 0.0;
             for (int j = 0; j < n; ++j) xd += (prev.x[j] - x[j]) * (prev.x[j] - x[j]);
             double x_diff = sqrt(xd);
-            double Atcx_nrm = 0.0;
-            if (C.A.rows) {
-                Vec v(n, 0.0);
-                for (int j = 0; j < n; ++j)
-                    for (int i = 0; i < C.A.rows; ++i) v[j] += C.A(i, j) * C.cx[i];
-                Atcx_nrm = normv(v);
-            }
+            double Atcx_nrm = sb->At_c_norm(W.t, C.cx);
             double aps = 0.0;
             for (int i = 0; i < W.t; ++i) { double wv = it.w[W.active[i] - 1]; aps += wv * wv; }
             if (nb_iter >= opt.max_iter) exit_code = -2;
@@ -1603,10 +1777,8 @@ public:
     // EF:2638-2880
     LargeResult solve(const double* x0, bool want_trace) {
         LargeResult res;
-        J = Mat(mt, n);
         rx.assign(mt, 0.0);
         cx.assign(l, 0.0);
-        A = Mat(l, n);
         gradf.assign(n, 0.0);
         C.scaling = opt.scaling != 0;
         Vec x(x0, x0 + n), x_opt = x;
@@ -1633,7 +1805,6 @@ public:
             init_working_set(first);
             first.t = W.t;
             gather_active();
-            compute_gradf();
             Vec p_gn(n, 0.0);
             evaluate_scaling();
             update_working_set(first, p_gn);
@@ -1653,7 +1824,7 @@ public:
             first.restart = error_code < 0;
             double sigma_min, lam_abs_max;
             minmax_lagrangian_mult(first.lam, sigma_min, lam_abs_max);
-            double delta_time = elapsed() - opt.time_limit;
+            double delta_time = ops.agreed_elapsed(elapsed()) - opt.time_limit;
             exit_code = check_termination_criteria(first, prev, x, rx_sum, nb_iteration, error_code, delta_time,
                                                    sigma_min, lam_abs_max, Psi_error);
             if (exit_code == 0) rx_sum = do_factor();
@@ -1688,7 +1859,7 @@ public:
                 rx_sum = do_eval_point(x);
                 it.restart = error_code < 0;
                 minmax_lagrangian_mult(it.lam, sigma_min, lam_abs_max);
-                delta_time = elapsed() - opt.time_limit;
+                delta_time = ops.agreed_elapsed(elapsed()) - opt.time_limit;
                 exit_code = check_termination_criteria(it, prev, x, rx_sum, nb_iteration, error_code, delta_time,
                                                        sigma_min, lam_abs_max, Psi_error);
                 if (exit_code == 0) rx_sum = do_factor();

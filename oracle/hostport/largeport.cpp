@@ -162,6 +162,12 @@ struct CpuOps : LargeOps {
         return 0;
     }
     int cons(const double* x, double* cx) override { sc.cons(x, cx); return 0; }
+    double agreed_elapsed(double local_elapsed) override {   // the mean over the ranks: one value for all
+        if (world <= 1) return local_elapsed;
+        double v = local_elapsed / world;
+        ar(&v, 1);
+        return v;
+    }
 };
 
 }  // namespace
