@@ -13,7 +13,7 @@ HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_linalg.h"
           [os.path.join(os.path.dirname(_HERE), "include", "enlsip_b200.h")]
 # second translation unit: the large-Jacobian regime (TSQR + host-driven iteration)
 SRC_LARGE = os.path.join(_HERE, "csrc", "enl_large.cu")
-HEADERS_LARGE = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_tsqr.cuh", "enl_dense.cuh", "enl_large_host.h",
+HEADERS_LARGE = [os.path.join(_HERE, "csrc", f) for f in ("enl_base.h", "enl_tsqr.cuh", "enl_small.cuh", "enl_large_host.h",
                                                           "enl_large_family.h")] + \
                 [os.path.join(os.path.dirname(_HERE), "include", "enlsip_b200.h")]
 OBJ_DIR = os.path.join(_HERE, "lib", "obj")
@@ -36,7 +36,8 @@ EXPORTS = ["enlsipb200_version", "enlsipb200_last_error", "enlsipb200_default_op
            "enlsipb200_compile_family",
            "enlsipb200_large_last_error", "enlsipb200_large_create", "enlsipb200_large_destroy",
            "enlsipb200_large_set_data", "enlsipb200_large_comm_id", "enlsipb200_large_comm_init",
-           "enlsipb200_large_solve", "enlsipb200_large_factor", "enlsipb200_large_stats"]
+           "enlsipb200_large_solve", "enlsipb200_large_factor", "enlsipb200_large_stats",
+           "enlsipb200_dense_qrcp", "enlsipb200_dense_mulq"]
 
 
 class Options(ctypes.Structure):
@@ -106,6 +107,8 @@ def _bind(L, large=True):
         L.enlsipb200_large_solve.argtypes = [vp, vp, ctypes.POINTER(Options)] + [vp] * 8 + [ci]
         L.enlsipb200_large_factor.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         L.enlsipb200_large_stats.argtypes = [vp, vp, ci]
+        L.enlsipb200_dense_qrcp.argtypes = [ci, ci, vp, vp, vp, ci]
+        L.enlsipb200_dense_mulq.argtypes = [ci, ci, ci, vp, vp, vp, ci]
     return L
 
 

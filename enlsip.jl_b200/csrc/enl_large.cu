@@ -5,9 +5,11 @@
 //   li_build_kernel      r = tanh(Wx) - y, J = diag(1 - tanh^2) W         -> [J | r] in HBM   (new_point!, EF:34-52)
 //   tsqr_factor          [J | r] -> R (n+1 x n+1)   (enl_tsqr.cuh: Householder panels + DMMA trailing updates)
 //   NCCL all-gather      of the per-GPU R factors, stacked and re-factored identically on every GPU
-//   r_to_colmajor        R -> column-major [J~ | r~], which stays device resident for enl_dense.cuh
-//   host small stage     the ENLSIP iteration on the compressed problem (enl_large_host.h), replicated per rank;
-//                        its O(n^3) primitives (QRCP, J~ Q1) run on the device when n >= 384 (enl_dense.cuh)
+//   r_to_colmajor        R -> column-major [J~ | r~], device resident
+//   small stage          the ENLSIP iteration on the compressed problem: every matrix (A, C.A, J~, J~ Q1, the three
+//                        pivoted QR factorisations, triangular solves, multiplier and direction products) lives in HBM
+//                        and is worked on by the kernels of enl_small.cuh; the host (enl_large_host.h, replicated per
+//                        rank) keeps the scalar decision logic, the working set and O(n) vectors
 //   li_dir_kernel        v = W p, Jp = s .* v, {r.r, r.Jp, Jp.Jp}                              (EF:2222-2224)
 //   li_ls_kernel         per trial step: ||r(x + a p)||^2 and the linesearch model dots        (EF:1307-1340, 1665-1689)
 //   NCCL all-reduce      of those few doubles
@@ -27,7 +29,7 @@
 #include "enl_large_family.h"
 #include "enl_large_host.h"
 #include "enl_tsqr.cuh"
-#include "enl_dense.cuh"
+#include "enl_small.cuh"
 
 using namespace enl_large;
 
@@ -281,124 +283,45 @@ __global__ void r_to_colmajor_kernel(const double* __restrict__ R, int ld, int n
 // ---------------------------------------------------------------------------------------------
 // device implementation of LargeOps
 // ---------------------------------------------------------------------------------------------
-// Work below this many matrix entries stays on the host (launch latency of 2 kernels per column dominates)
-constexpr long long DENSE_ACCEL_MIN = 384LL * 384LL;
+// structural non-zeros of the single-index constraint Jacobian (row-major l x n, zero elsewhere): block rows
+__global__ void si_jac_blocks_kernel(const double* __restrict__ x, int nb, int ineq, int n, double* __restrict__ Arow) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * nb) return;
+    const int k = e >> 2;
+    const double v = 2.0 * x[e];
+    Arow[(size_t)k * n + e] = ineq ? -v : v;
+}
+// ... and the constant bound rows [+e_j ; -e_j] (cnls_model.jl:402-403), written once
+__global__ void si_jac_bounds_kernel(const int* __restrict__ idx, int nlo, int nup, int row0, int n, double* __restrict__ Arow) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nlo + nup) return;
+    Arow[(size_t)(row0 + e) * n + idx[e]] = (e < nlo) ? 1.0 : -1.0;
+}
 
-struct LargeHandle : LargeOps, DenseAccel {
+struct LargeHandle : LargeOps, SmallBackend {
     int device = 0;
-    // ---- DenseAccel: device QRCP / M*Q of the compressed problem when it is large (config 5) ----
-    double *dq_f = nullptr, *dq_m = nullptr, *dq_small = nullptr;
-    int* dq_p = nullptr;
-    size_t dq_f_cap = 0, dq_m_cap = 0, dq_small_cap = 0, dq_p_cap = 0;
+    // ---- SmallBackend state: the small stage's matrices, all column major in HBM ----
+    int tcap = 0, lv = 0;             // capacity of the working set min(l, n); length of the scratch vectors
+    double* dArow = nullptr;          // A, row major l x n  (= column-major n x l)
+    double *dCA = nullptr, *dCA2 = nullptr;   // C.A, row major t x n (= C.A' column major n x t); spare for row removal
+    double *dFA = nullptr, *dtauA = nullptr;  // factors of qr(C.A')   n x t
+    double *dFL = nullptr, *dtauL = nullptr;  // factors of qr(R_A')   t x min(n, t)
+    double *dJQ1 = nullptr;                    // J~ Q1                 (n+1) x n
+    double *dF2 = nullptr, *dtau2 = nullptr;   // factors of qr(J2)     (n+1) x (n - rankA)
+    int *dpA = nullptr, *dipA = nullptr, *dpL = nullptr, *dipL = nullptr, *dp2 = nullptr, *dip2 = nullptr, *dact = nullptr, *dbidx = nullptr;
+    double* dvec[8] = {nullptr};      // scratch vectors
+    double* dscal = nullptr;
+    double* hst = nullptr;            // pinned staging, 4 * lv doubles
+    int* hsti = nullptr;              // pinned staging for permutations
+    enl_small::QrWork qw;
+    enl_small::WyWork ww;
+    int fa_rows = 0, fa_cols = 0, fa_k = 0, fl_rows = 0, fl_cols = 0, fl_k = 0, f2_rows = 0, f2_cols = 0, f2_k = 0;
+    bool jq1_valid = false;
+    int ca_rows = 0;
     long long n_dev_qrcp = 0, n_dev_mulq = 0;
-    double ms_dense = 0;
-    bool grow(double** p, size_t* cap, size_t want) {
-        if (*cap >= want) return true;
-        if (*p) cudaFree(*p);
-        *p = nullptr; *cap = 0;
-        if (cudaMalloc(p, sizeof(double) * want) != cudaSuccess) return false;
-        *cap = want;
-        return true;
-    }
-    bool qrcp(double* f, int rows, int cols, double* tau, int* jpvt) override {
-        if ((long long)rows * cols < DENSE_ACCEL_MIN) return false;
-        auto t0 = std::chrono::steady_clock::now();
-        const int k = rows < cols ? rows : cols;
-        if (cudaSetDevice(device) != cudaSuccess) return false;
-        if (!grow(&dq_f, &dq_f_cap, (size_t)rows * cols)) return false;
-        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * cols + enl_dense::MULQ_CHUNKS * (size_t)(rows + 1))) return false;
-        if (dq_p_cap < (size_t)cols) {
-            if (dq_p) cudaFree(dq_p);
-            dq_p = nullptr; dq_p_cap = 0;
-            if (cudaMalloc(&dq_p, sizeof(int) * cols) != cudaSuccess) return false;
-            dq_p_cap = cols;
-        }
-        double* dtau = dq_small;            // [cols]
-        double* dvn = dq_small + cols;      // [2 cols]
-        bool ok = cudaMemcpyAsync(dq_f, f, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        launches += enl_dense::qrcp_device(dq_f, rows, cols, dtau, dq_p, dvn, st);
-        ok = ok && cudaMemcpyAsync(f, dq_f, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(jpvt, dq_p, sizeof(int) * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-        if (!ok) throw std::runtime_error("device QRCP failed");
-        ++n_dev_qrcp;
-        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return true;
-    }
-    bool jq1(const double* fA, int nq, int k, const double* tauA, double* JQ1_host, int mr, int ncols_host) override {
-        if ((long long)mr * nq < DENSE_ACCEL_MIN || nq != n || mr != n + 1) return false;
-        auto t0 = std::chrono::steady_clock::now();
-        if (cudaSetDevice(device) != cudaSuccess) return false;
-        if (!grow(&dq_m, &dq_m_cap, (size_t)mr * nq)) return false;
-        if (k > 0 && !grow(&dq_f, &dq_f_cap, (size_t)nq * k)) return false;
-        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * (k + 1) + enl_dense::MULQ_CHUNKS * (size_t)(mr + 1))) return false;
-        double* dtau = dq_small;
-        double* dw = dq_small + 3 * (size_t)(k + 1);
-        bool ok = cudaMemcpyAsync(dq_m, dJc, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
-        if (k > 0) {
-            ok = ok && cudaMemcpyAsync(dq_f, fA, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
-            ok = ok && cudaMemcpyAsync(dtau, tauA, sizeof(double) * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
-            launches += enl_dense::mulq_device(dq_m, mr, nq, dq_f, nq, k, dtau, dw, st);
-        }
-        if (ncols_host > 0)
-            ok = ok && cudaMemcpyAsync(JQ1_host, dq_m, sizeof(double) * (size_t)mr * ncols_host, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-        if (!ok) throw std::runtime_error("device J*Q1 failed");
-        jq1_resident = true;
-        ++n_dev_mulq;
-        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return true;
-    }
-    bool qrcp_tail(int c0, int rows, int cols, double* f_host, double* tau, int* jpvt) override {
-        if (!jq1_resident || rows != n + 1 || c0 + cols != n) return false;
-        auto t0 = std::chrono::steady_clock::now();
-        const int k = rows < cols ? rows : cols;
-        if (cudaSetDevice(device) != cudaSuccess) return false;
-        if (!grow(&dq_f, &dq_f_cap, (size_t)rows * cols)) return false;
-        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * cols + enl_dense::MULQ_CHUNKS * (size_t)(rows + 1))) return false;
-        if (dq_p_cap < (size_t)cols) {
-            if (dq_p) cudaFree(dq_p);
-            dq_p = nullptr; dq_p_cap = 0;
-            if (cudaMalloc(&dq_p, sizeof(int) * cols) != cudaSuccess) return false;
-            dq_p_cap = cols;
-        }
-        double* dtau = dq_small;
-        double* dvn = dq_small + cols;
-        bool ok = cudaMemcpyAsync(dq_f, dq_m + (size_t)c0 * rows, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
-        launches += enl_dense::qrcp_device(dq_f, rows, cols, dtau, dq_p, dvn, st);
-        ok = ok && cudaMemcpyAsync(f_host, dq_f, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(jpvt, dq_p, sizeof(int) * cols, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-        if (!ok) throw std::runtime_error("device QRCP (tail) failed");
-        ++n_dev_qrcp;
-        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return true;
-    }
-    bool mul_Q(const double* f, int nq, int k, const double* tau, double* M, int mr) override {
-        if ((long long)mr * nq < DENSE_ACCEL_MIN || k < 16) return false;
-        auto t0 = std::chrono::steady_clock::now();
-        if (cudaSetDevice(device) != cudaSuccess) return false;
-        if (!grow(&dq_f, &dq_f_cap, (size_t)nq * k)) return false;
-        if (!grow(&dq_m, &dq_m_cap, (size_t)mr * nq)) return false;
-        if (!grow(&dq_small, &dq_small_cap, (size_t)3 * k + enl_dense::MULQ_CHUNKS * (size_t)(mr + 1))) return false;
-        jq1_resident = false;                     // dq_m is overwritten
-        double* dtau = dq_small;                  // [k]
-        double* dw = dq_small + 3 * (size_t)k;    // [16 mr]
-        bool ok = cudaMemcpyAsync(dq_f, f, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(dtau, tau, sizeof(double) * k, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(dq_m, M, sizeof(double) * (size_t)mr * nq, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        launches += enl_dense::mulq_device(dq_m, mr, nq, dq_f, nq, k, dtau, dw, st);
-        ok = ok && cudaMemcpyAsync(M, dq_m, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-        if (!ok) throw std::runtime_error("device M*Q failed");
-        ++n_dev_mulq;
-        ms_dense += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return true;
-    }
+    double ms_small = 0;              // host wall clock inside the small-stage calls (kernels + waits)
 
-    long long m_local = 0, rows_pad = 0;
+    long long m_local = 0, rows_pad = 0, dT_subtiles = 0;
     int ld = 0, rr_rows = 0;
     SingleIndexConstraints sc;
     cudaStream_t st = nullptr;
@@ -411,7 +334,6 @@ struct LargeHandle : LargeOps, DenseAccel {
     double *dx = nullptr, *dp = nullptr, *dT = nullptr, *dpart = nullptr, *dout = nullptr;
     double *dR = nullptr, *dStack = nullptr, *dR2 = nullptr;
     double* dJc = nullptr;          // [J~ | r~] column major (n+1) x (n+1): stays resident for enl_dense.cuh
-    bool jq1_resident = false;      // dq_m holds J~ * Q1 of the current working set
     std::vector<double> hR;         // host copy of dJc
     // comm
     NcclApi::Comm comm = nullptr;
@@ -425,10 +347,21 @@ struct LargeHandle : LargeOps, DenseAccel {
     ~LargeHandle() override { release(); }
     void release() {
         cudaSetDevice(device);
-        for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2, dq_f, dq_m, dq_small, dJc})
+        for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2, dJc, dArow, dCA, dCA2, dFA,
+                          dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, ww.Vb, ww.T, ww.W, ww.W2})
             if (p) cudaFree(p);
-        if (dq_p) cudaFree(dq_p);
-        dq_p = nullptr;
+        for (double*& p : dvec) { if (p) cudaFree(p); p = nullptr; }
+        for (int* p : {dpA, dipA, dpL, dipL, dp2, dip2, dact, dbidx, qw.flags})
+            if (p) cudaFree(p);
+        if (qw.state) cudaFree(qw.state);
+        if (qw.ticket) cudaFree(qw.ticket);
+        qw = enl_small::QrWork();
+        ww = enl_small::WyWork();
+        dArow = dCA = dCA2 = dFA = dtauA = dFL = dtauL = dJQ1 = dF2 = dtau2 = dscal = nullptr;
+        dpA = dipA = dpL = dipL = dp2 = dip2 = dact = dbidx = nullptr;
+        if (hst) cudaFreeHost(hst);
+        if (hsti) cudaFreeHost(hsti);
+        hst = nullptr; hsti = nullptr;
         if (hpin) cudaFreeHost(hpin);
         hpin = nullptr;
         if (hgrad) cudaFreeHost(hgrad);
@@ -436,8 +369,7 @@ struct LargeHandle : LargeOps, DenseAccel {
         if (dgpart) cudaFree(dgpart);
         if (dgrad) cudaFree(dgrad);
         dgpart = dgrad = nullptr;
-        dq_f = dq_m = dq_small = dJc = nullptr;
-        dq_f_cap = dq_m_cap = dq_small_cap = dq_p_cap = 0;
+        dJc = nullptr;
         ownW = owny = dA = du = dr = ds = dv = dJp = dx = dp = dT = dpart = dout = dR = dStack = dR2 = nullptr;
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -463,7 +395,8 @@ struct LargeHandle : LargeOps, DenseAccel {
         LCU(cudaMalloc(&dp, sizeof(double) * n));
         long long nblk = rows_pad / TS_B;
         long long nsub = (nblk + TS_FAN - 1) / TS_FAN;
-        LCU(cudaMalloc(&dT, sizeof(double) * (nsub > 64 ? nsub : 64) * TS_B * TS_B));
+        dT_subtiles = nsub > 64 ? nsub : 64;
+        LCU(cudaMalloc(&dT, sizeof(double) * dT_subtiles * TS_B * TS_B));
         LCU(cudaMalloc(&dpart, sizeof(double) * LI_PARTS * 4));
         LCU(cudaMalloc(&dout, sizeof(double) * 8));
         LCU(cudaHostAlloc(&hpin, sizeof(double) * 8, cudaHostAllocDefault));
@@ -473,6 +406,54 @@ struct LargeHandle : LargeOps, DenseAccel {
         LCU(cudaMalloc(&dR, sizeof(double) * rr_rows * ld));
         LCU(cudaMalloc(&dJc, sizeof(double) * (size_t)(n + 1) * (n + 1)));
         hR.resize((size_t)(n + 1) * (n + 1));
+        return alloc_small();
+    }
+    // the small stage's matrices and scratch (sizes from n, l)
+    int alloc_small() {
+        const size_t mt = (size_t)n + 1;
+        tcap = l < n ? l : n;
+        lv = (int)(mt > (size_t)l ? mt : (size_t)l) + 32;
+        LCU(cudaMalloc(&dArow, sizeof(double) * (size_t)l * n));
+        LCU(cudaMemsetAsync(dArow, 0, sizeof(double) * (size_t)l * n, st));
+        LCU(cudaMalloc(&dCA, sizeof(double) * (size_t)(tcap + 1) * n));
+        LCU(cudaMalloc(&dFA, sizeof(double) * (size_t)n * (tcap + 1)));
+        LCU(cudaMalloc(&dtauA, sizeof(double) * (tcap + 1)));
+        LCU(cudaMalloc(&dFL, sizeof(double) * (size_t)(tcap + 1) * (tcap + 1)));
+        LCU(cudaMalloc(&dtauL, sizeof(double) * (tcap + 1)));
+        LCU(cudaMalloc(&dJQ1, sizeof(double) * mt * n));
+        LCU(cudaMalloc(&dF2, sizeof(double) * mt * n));
+        LCU(cudaMalloc(&dtau2, sizeof(double) * mt));
+        for (int** p : {&dpA, &dipA, &dpL, &dipL}) LCU(cudaMalloc(p, sizeof(int) * (tcap + 1)));
+        for (int** p : {&dp2, &dip2}) LCU(cudaMalloc(p, sizeof(int) * (n + 1)));
+        LCU(cudaMalloc(&dact, sizeof(int) * (l + 1)));
+        for (double*& p : dvec) LCU(cudaMalloc(&p, sizeof(double) * lv));
+        LCU(cudaMalloc(&dscal, sizeof(double) * 8));
+        LCU(cudaHostAlloc(&hst, sizeof(double) * 4 * (size_t)lv, cudaHostAllocDefault));
+        LCU(cudaHostAlloc(&hsti, sizeof(int) * 2 * (size_t)lv, cudaHostAllocDefault));
+        const int maxc = (int)mt;    // no factorisation of the solve has more columns than n (< n + 1)
+        qw.cap_cols = maxc;
+        LCU(cudaMalloc(&qw.vn1, sizeof(double) * maxc));
+        LCU(cudaMalloc(&qw.vn2, sizeof(double) * maxc));
+        LCU(cudaMalloc(&qw.F, sizeof(double) * (size_t)maxc * enl_small::QR_NB));
+        LCU(cudaMalloc(&qw.auxv, sizeof(double) * enl_small::QR_NB));
+        LCU(cudaMalloc(&qw.flags, sizeof(int) * maxc));
+        LCU(cudaMalloc(&qw.state, sizeof(enl_small::QrState)));
+        LCU(cudaMalloc(&qw.ticket, sizeof(unsigned int)));
+        LCU(cudaMalloc(&ww.Vb, sizeof(double) * mt * 32));
+        LCU(cudaMalloc(&ww.T, sizeof(double) * 32 * 32));
+        LCU(cudaMalloc(&ww.W, sizeof(double) * mt * 32));
+        LCU(cudaMalloc(&ww.W2, sizeof(double) * mt * 32));
+        // constant bound rows of A
+        const int nlo = (int)sc.lo_idx.size(), nup = (int)sc.up_idx.size();
+        if (nlo + nup > 0) {
+            std::vector<int> idx(sc.lo_idx);
+            idx.insert(idx.end(), sc.up_idx.begin(), sc.up_idx.end());
+            LCU(cudaMalloc(&dbidx, sizeof(int) * idx.size()));
+            LCU(cudaMemcpyAsync(dbidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
+            si_jac_bounds_kernel<<<(nlo + nup + 255) / 256, 256, 0, st>>>(dbidx, nlo, nup, sc.nb, n, dArow);
+            LCU(cudaStreamSynchronize(st));
+        }
+        LCU(cudaGetLastError());
         return 0;
     }
     int grid_rows() const {   // CTAs for the warp-per-row kernels
@@ -503,6 +484,11 @@ struct LargeHandle : LargeOps, DenseAccel {
     int eval_at(const double* x) {
         LCU(cudaSetDevice(device));
         LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        if (sc.nb > 0) {   // constraint Jacobian A(x): only the block rows depend on x
+            si_jac_blocks_kernel<<<(4 * sc.nb + 255) / 256, 256, 0, st>>>(dx, sc.nb, sc.ineq ? 1 : 0, n, dArow);
+            ++launches;
+        }
+        jq1_valid = false;
         LCU(cudaEventRecord(e0, st));
         int parts = grid_rows();
         if (m_local > 0) {
@@ -559,7 +545,7 @@ struct LargeHandle : LargeOps, DenseAccel {
             r_to_colmajor_kernel<<<grid, block, 0, st>>>(dfinal, ld, nc, dJc);
             ++launches;
         }
-        jq1_resident = false;
+        jq1_valid = false;
         point_factored = true;
         LCU(cudaEventRecord(e2, st));
         if (want_host_R) LCU(cudaMemcpyAsync(hR.data(), dJc, sizeof(double) * (size_t)(n + 1) * (n + 1), cudaMemcpyDeviceToHost, st));
@@ -575,24 +561,331 @@ struct LargeHandle : LargeOps, DenseAccel {
         return rc != 0 ? rc : factor_point(want_host_R);
     }
 
-    // ---- LargeOps ----
-    int eval_point(const double* x, double* gradf, double* rr, double* cx, double* A) override {
+    // =========================================================================================
+    // SmallBackend on the device (kernels: enl_small.cuh).  Vectors travel host <-> device per call (a few KB);
+    // matrices never leave HBM.
+    // =========================================================================================
+    std::vector<int> hpA, hpL, hp2;     // host copies of the three permutations
+    struct SmallScope {
+        LargeHandle* h; std::chrono::steady_clock::time_point t0;
+        explicit SmallScope(LargeHandle* hh) : h(hh), t0(std::chrono::steady_clock::now()) { cudaSetDevice(hh->device); }
+        ~SmallScope() { h->ms_small += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    };
+    void sm_check(cudaError_t e, const char* what) {
+        if (e != cudaSuccess) throw std::runtime_error(std::string("device small stage: ") + what + ": " + cudaGetErrorString(e));
+    }
+    void up(double* d, const double* src, int cnt) {   // pageable source: staged by the runtime before the call returns
+        if (cnt > 0) sm_check(cudaMemcpyAsync(d, src, sizeof(double) * cnt, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    void up_i(int* d, const int* src, int cnt) {
+        if (cnt > 0) sm_check(cudaMemcpyAsync(d, src, sizeof(int) * cnt, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    void down(int slot_off, const double* d, int cnt) {  // into the pinned staging area at hst + slot_off
+        if (cnt > 0) sm_check(cudaMemcpyAsync(hst + slot_off, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st), "D2H");
+    }
+    void sm_sync() {
+        sm_check(cudaStreamSynchronize(st), "synchronize");
+        sm_check(cudaGetLastError(), "kernel");
+    }
+    void k_reflect(const double* f, int frows, int k, const double* tau, double* v, int transpose) {
+        if (frows <= 0) return;
+        enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
+        ++launches;
+    }
+    void k_trsv_upper(const double* f, int ldf, int k, double* x) {
+        if (k <= 0) return;
+        enl_small::trsv_upper_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        ++launches;
+    }
+    void k_trsv_upperT(const double* f, int ldf, int k, double* x) {
+        if (k <= 0) return;
+        enl_small::trsv_upperT_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        ++launches;
+    }
+    void k_copy_pad(double* dst, const double* src, int k, int len) {
+        if (len <= 0) return;
+        enl_small::copy_pad_kernel<<<(len + 255) / 256, 256, 0, st>>>(dst, src, k, len);
+        ++launches;
+    }
+    // diag(R), inverse permutation and the permutation itself of a finished factorisation -> FactorInfo
+    void finish_factor(const double* f, int rows, int cols, const int* dperm, int* diperm, FactorInfo& F, std::vector<int>& hperm) {
+        const int k = rows < cols ? rows : cols;
+        F.rows = rows; F.cols = cols; F.k = k;
+        F.diagv.assign(k, 0.0);
+        F.p.assign(cols, 0);
+        if (cols > 0) {
+            enl_small::qr_finish_kernel<<<(cols + 255) / 256, 256, 0, st>>>(f, rows, cols, dperm, dvec[7], diperm);
+            ++launches;
+            down(0, dvec[7], k);
+            sm_check(cudaMemcpyAsync(hsti, dperm, sizeof(int) * cols, cudaMemcpyDeviceToHost, st), "D2H");
+            sm_sync();
+            for (int i = 0; i < k; ++i) F.diagv[i] = hst[i];
+            for (int i = 0; i < cols; ++i) F.p[i] = hsti[i];
+        }
+        hperm = F.p;
+    }
+
+    int new_point_eval(const double* x, double* gradf, double* rr, double* cx) override {
         int rc = eval_at(x);
         if (rc != 0) return rc;
         for (int j = 0; j < n; ++j) gradf[j] = hgrad[j];
         *rr = hgrad[n];
         sc.cons(x, cx);
-        sc.jac(x, A);
         return 0;
     }
-    int compress(double* Jt, double* rt) override {
+    int new_point_compress(double* rt, double* gradf) override {
         int rc = factor_point(false);
         if (rc != 0) return rc;
-        const size_t mt = (size_t)n + 1;
-        LCU(cudaMemcpyAsync(Jt, dJc, sizeof(double) * mt * n, cudaMemcpyDeviceToHost, st));
-        LCU(cudaMemcpyAsync(rt, dJc + mt * n, sizeof(double) * mt, cudaMemcpyDeviceToHost, st));
+        SmallScope sc_(this);
+        const int mt = n + 1;
+        const double* rtd = dJc + (size_t)mt * n;
+        launches += enl_small::gemv_t(dJc, mt, mt, n, rtd, dvec[0], st);     // J~' r~
+        down(0, rtd, mt);
+        down(lv, dvec[0], n);
         LCU(cudaStreamSynchronize(st));
+        LCU(cudaGetLastError());
+        for (int r = 0; r < mt; ++r) rt[r] = hst[r];
+        for (int j = 0; j < n; ++j) gradf[j] = hst[lv + j];
         return 0;
+    }
+    void gather_active(const int* active, int t) override {
+        SmallScope sc_(this);
+        ca_rows = t;
+        if (t <= 0) return;
+        up_i(dact, active, t);
+        enl_small::gather_rows_kernel<<<t, 256, 0, st>>>(dArow, n, dact, dCA);
+        ++launches;
+    }
+    void evaluate_scaling(int t, bool scaling, double* rown) override {
+        SmallScope sc_(this);
+        if (t <= 0) return;
+        enl_small::row_norm_scale_kernel<<<t, 256, 0, st>>>(dCA, n, scaling ? 1 : 0, dvec[0]);
+        ++launches;
+        down(0, dvec[0], t);
+        sm_sync();
+        for (int i = 0; i < t; ++i) rown[i] = hst[i];
+    }
+    void rebuild_scaled_rows(const int* active, int t, const double* diag_scale) override {
+        SmallScope sc_(this);
+        if (t <= 0) return;
+        up_i(dact, active, t);
+        up(dvec[0], diag_scale, t);
+        enl_small::rebuild_scaled_rows_kernel<<<t, 256, 0, st>>>(dArow, n, dact, dvec[0], dCA);
+        ++launches;
+    }
+    void remove_active_row(int s0) override {
+        SmallScope sc_(this);
+        const int below = ca_rows - 1 - s0;
+        if (below > 0) {
+            if (!dCA2) sm_check(cudaMalloc(&dCA2, sizeof(double) * (size_t)(tcap + 1) * n), "cudaMalloc");
+            const size_t bytes = sizeof(double) * (size_t)below * n;
+            sm_check(cudaMemcpyAsync(dCA2, dCA + (size_t)(s0 + 1) * n, bytes, cudaMemcpyDeviceToDevice, st), "D2D");
+            sm_check(cudaMemcpyAsync(dCA + (size_t)s0 * n, dCA2, bytes, cudaMemcpyDeviceToDevice, st), "D2D");
+        }
+        ca_rows -= 1;
+    }
+    void factor_A(int t, FactorInfo& F) override {
+        SmallScope sc_(this);
+        fa_rows = n; fa_cols = t; fa_k = n < t ? n : t;
+        jq1_valid = false;
+        if (t > 0) {
+            sm_check(cudaMemcpyAsync(dFA, dCA, sizeof(double) * (size_t)n * t, cudaMemcpyDeviceToDevice, st), "D2D");
+            launches += enl_small::qrcp_device(dFA, n, t, dtauA, dpA, qw, st);
+            ++n_dev_qrcp;
+        }
+        finish_factor(dFA, n, t, dpA, dipA, F, hpA);
+    }
+    void factor_L11(FactorInfo& F) override {    // qr(F_A.R', ColumnNorm()); F_A.R is min(n, t) x t
+        SmallScope sc_(this);
+        const int kr = fa_k, t = fa_cols;
+        fl_rows = t; fl_cols = kr; fl_k = t < kr ? t : kr;
+        if (t > 0 && kr > 0) {
+            const long long ne = (long long)t * kr;
+            enl_small::build_rt_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dFA, n, t, kr, dFL);
+            ++launches;
+            launches += enl_small::qrcp_device(dFL, t, kr, dtauL, dpL, qw, st);
+            ++n_dev_qrcp;
+        }
+        finish_factor(dFL, t, kr, dpL, dipL, F, hpL);
+    }
+    void ensure_jq1() {
+        if (jq1_valid) return;
+        const int mt = n + 1;
+        sm_check(cudaMemcpyAsync(dJQ1, dJc, sizeof(double) * (size_t)mt * n, cudaMemcpyDeviceToDevice, st), "D2D");
+        if (fa_k > 0) {
+            launches += enl_small::mulq_device(dJQ1, mt, n, dFA, n, fa_k, dtauA, ww, st);
+            ++n_dev_mulq;
+        }
+        jq1_valid = true;
+    }
+    void factor_J2(int rankA, FactorInfo& F) override {
+        SmallScope sc_(this);
+        ensure_jq1();
+        const int mt = n + 1, cols2 = n - rankA;
+        f2_rows = mt; f2_cols = cols2; f2_k = mt < cols2 ? mt : cols2;
+        if (cols2 > 0) {
+            sm_check(cudaMemcpyAsync(dF2, dJQ1 + (size_t)rankA * mt, sizeof(double) * (size_t)mt * cols2, cudaMemcpyDeviceToDevice, st), "D2D");
+            launches += enl_small::qrcp_device(dF2, mt, cols2, dtau2, dp2, qw, st);
+            ++n_dev_qrcp;
+        }
+        finish_factor(dF2, mt, cols2, dp2, dip2, F, hp2);
+    }
+    void first_lagrange(int prankA, int t, const Vec& gradf, const Vec& Ccx, Vec& v, Vec& u, double& grad_res) override {
+        SmallScope sc_(this);
+        Vec y0(t > 0 ? t : 1, 0.0);
+        for (int i = 0; i < prankA; ++i) y0[i] = -Ccx[hpA[i]];
+        up(dvec[0], gradf.data(), n);
+        up(dvec[1], y0.data(), t);
+        k_reflect(dFA, n, fa_k, dtauA, dvec[0], 1);                      // b = Q1' gradf
+        k_copy_pad(dvec[2], dvec[0], prankA, t);
+        k_trsv_upper(dFA, n, prankA, dvec[2]);                           // v = R^-1 b[1:r]
+        enl_small::norm_range_kernel<<<1, 1024, 0, st>>>(dvec[0], prankA, n, dscal);
+        ++launches;
+        k_trsv_upperT(dFA, n, prankA, dvec[1]);                          // u = R^-1 R^-T (-c[P])[1:r]
+        k_trsv_upper(dFA, n, prankA, dvec[1]);
+        down(0, dvec[2], t);
+        down(lv, dvec[1], t);
+        down(2 * lv, dscal, 1);
+        sm_sync();
+        v.assign(hst, hst + t);
+        u.assign(hst + lv, hst + lv + t);
+        grad_res = (n > prankA) ? hst[2 * lv] : 0.0;
+    }
+    void second_lagrange(int prankA, int t, const Vec& p_gn, Vec& v) override {
+        SmallScope sc_(this);
+        ensure_jq1();
+        const int mt = n + 1;
+        const double* rtd = dJc + (size_t)mt * n;
+        up(dvec[0], p_gn.data(), n);
+        launches += enl_small::gemv_n(dJc, mt, mt, n, dvec[0], 1.0, rtd, 1.0, dvec[1], st);    // s = r + J p_gn
+        if (t > 0) sm_check(cudaMemsetAsync(dvec[2], 0, sizeof(double) * t, st), "memset");
+        launches += enl_small::gemv_t(dJQ1, mt, mt, prankA, dvec[1], dvec[2], st);             // J1' s
+        k_trsv_upper(dFA, n, prankA, dvec[2]);
+        down(0, dvec[2], t);
+        sm_sync();
+        v.assign(hst, hst + t);
+    }
+    void sub_search_direction(int t, int rankA, int dimA, int dimJ2, int code, const Vec& Ccx, Vec& p, Vec& b, Vec& d) override {
+        SmallScope sc_(this);
+        ensure_jq1();
+        const int mt = n + 1;
+        const double* rtd = dJc + (size_t)mt * n;
+        Vec b0(t > 0 ? t : 1, 0.0);
+        for (int i = 0; i < t; ++i) b0[i] = -Ccx[hpA[i]];
+        up(dvec[0], b0.data(), t);
+        const double* p1;
+        if (code == 1) {
+            k_trsv_upperT(dFA, n, t, dvec[0]);                          // L11 p1 = -P'c
+            p1 = dvec[0];
+        } else {
+            k_reflect(dFL, fl_rows, fl_k, dtauL, dvec[0], 1);           // b = Q2'(-P'c)
+            k_copy_pad(dvec[1], dvec[0], dimA, t);
+            k_trsv_upper(dFL, fl_rows, dimA, dvec[1]);                  // [R11[1:dimA] \ b[1:dimA]; 0]
+            if (rankA > 0) {
+                enl_small::gather_pad_kernel<<<(rankA + 255) / 256, 256, 0, st>>>(dvec[2], dvec[1], dipL, t, rankA);
+                ++launches;
+            }
+            p1 = dvec[2];
+        }
+        launches += enl_small::gemv_n(dJQ1, mt, mt, rankA, p1, -1.0, rtd, -1.0, dvec[3], st);   // -J1 p1 - r
+        k_reflect(dF2, mt, f2_k, dtau2, dvec[3], 1);                    // d = Q3'(...)
+        const int dj = dimJ2 > 0 ? dimJ2 : 0;
+        k_copy_pad(dvec[4], dvec[3], dj, dj);
+        k_trsv_upper(dF2, mt, dj, dvec[4]);
+        if (rankA > 0) sm_check(cudaMemcpyAsync(dvec[5], p1, sizeof(double) * rankA, cudaMemcpyDeviceToDevice, st), "D2D");
+        if (f2_cols > 0) {
+            enl_small::gather_pad_kernel<<<(f2_cols + 255) / 256, 256, 0, st>>>(dvec[5] + rankA, dvec[4], dip2, dj, f2_cols);
+            ++launches;
+        }
+        k_reflect(dFA, n, fa_k, dtauA, dvec[5], 0);                     // p = Q1 [p1; p2]
+        down(0, dvec[5], n);
+        down(lv, dvec[3], mt);
+        if (code != 1) down(2 * lv, dvec[0], t);
+        sm_sync();
+        p.assign(hst, hst + n);
+        d.assign(hst + lv, hst + lv + mt);
+        if (code == 1) b.assign(b0.begin(), b0.begin() + t);
+        else b.assign(hst + 2 * lv, hst + 2 * lv + t);
+    }
+    void subspace_rhs(int t, const Vec& Ccx, Vec& b) override {
+        SmallScope sc_(this);
+        ensure_jq1();
+        Vec b0(t > 0 ? t : 1, 0.0);
+        for (int i = 0; i < t; ++i) b0[i] = -Ccx[hpA[i]];
+        up(dvec[0], b0.data(), t);
+        k_reflect(dFL, fl_rows, fl_k, dtauL, dvec[0], 1);
+        down(0, dvec[0], t);
+        sm_sync();
+        b.assign(hst, hst + t);
+    }
+    void subspace_d(int rankA, int dimA, int rankJ2, const Vec& b, Vec& d) override {
+        SmallScope sc_(this);
+        const int mt = n + 1;
+        const double* rtd = dJc + (size_t)mt * n;
+        int ra = rankA > 0 ? rankA : 0;
+        if (ra > 0) {
+            const int da = dimA > 0 ? dimA : 0;
+            up(dvec[0], b.data(), (int)b.size());
+            k_copy_pad(dvec[1], dvec[0], da, da);
+            k_trsv_upper(dFL, fl_rows, da, dvec[1]);
+            sm_check(cudaMemsetAsync(dvec[2], 0, sizeof(double) * ra, st), "memset");
+            if (da > 0) {
+                enl_small::scatter_perm_kernel<<<(da + 255) / 256, 256, 0, st>>>(dvec[2], dvec[1], dpL, da, ra);
+                ++launches;
+            }
+        }
+        launches += enl_small::gemv_n(dJQ1, mt, mt, ra, dvec[2], -1.0, rtd, -1.0, dvec[3], st);   // -(r + J1 p1)
+        if (rankJ2 > 0) k_reflect(dF2, mt, f2_k, dtau2, dvec[3], 1);
+        down(0, dvec[3], mt);
+        sm_sync();
+        d.assign(hst, hst + mt);
+    }
+    void products(const Vec& p, int t, Vec& Jp, Vec& Ap, Vec& active_Ap) override {
+        SmallScope sc_(this);
+        const int mt = n + 1;
+        up(dvec[0], p.data(), n);
+        launches += enl_small::gemv_n(dJc, mt, mt, n, dvec[0], 1.0, nullptr, 0.0, dvec[1], st);
+        launches += enl_small::gemv_t(dArow, n, n, l, dvec[0], dvec[2], st);
+        launches += enl_small::gemv_t(dCA, n, n, t, dvec[0], dvec[3], st);
+        down(0, dvec[1], mt);
+        down(lv, dvec[2], l);
+        down(2 * lv, dvec[3], t);
+        sm_sync();
+        Jp.assign(hst, hst + mt);
+        Ap.assign(hst + lv, hst + lv + l);
+        active_Ap.assign(hst + 2 * lv, hst + 2 * lv + t);
+    }
+    double At_c_norm(int t, const Vec& Ccx) override {
+        SmallScope sc_(this);
+        if (ca_rows <= 0 || t <= 0) return 0.0;
+        up(dvec[0], Ccx.data(), t);
+        launches += enl_small::gemv_n(dCA, n, n, t, dvec[0], 1.0, nullptr, 0.0, dvec[1], st);
+        enl_small::norm_range_kernel<<<1, 1024, 0, st>>>(dvec[1], 0, n, dscal);
+        ++launches;
+        down(0, dscal, 1);
+        sm_sync();
+        return hst[0];
+    }
+
+    // ---- LargeOps ----
+    // the host-matrix forms of new_point! belong to the CPU test backend; the product keeps A and J~ in HBM
+    // (new_point_eval / new_point_compress above) and has no host path to fall back to
+    int eval_point(const double*, double*, double*, double*, double*) override {
+        return lfail(ENLSIPB200_EINVAL, "host-matrix eval_point is not part of the product path");
+    }
+    int compress(double*, double*) override {
+        return lfail(ENLSIPB200_EINVAL, "host-matrix compress is not part of the product path");
+    }
+    double agreed_elapsed(double local_elapsed) override {
+        if (nranks <= 1) return local_elapsed;
+        cudaSetDevice(device);
+        hst[0] = local_elapsed / nranks;
+        if (cudaMemcpyAsync(dscal, hst, sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            g_nccl.AllReduce(dscal, dscal, 1, NCCL_FLOAT64, NCCL_SUM, comm, st) != 0 ||
+            cudaMemcpyAsync(hst, dscal, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            throw std::runtime_error("agreed_elapsed: all-reduce of the wall clock failed");
+        return hst[0];
     }
     int set_direction(const double*, const double* p, double sums[3]) override {
         LCU(cudaSetDevice(device));
@@ -634,6 +927,23 @@ struct LargeHandle : LargeOps, DenseAccel {
 LargeHandle* LH(enlsipb200_large h) { return reinterpret_cast<LargeHandle*>(h); }
 
 }  // namespace
+
+// scratch of the known-answer hooks (enlsipb200_dense_*)
+namespace {
+struct DenseScratch {
+    enl_small::QrWork qw;
+    enl_small::WyWork ww;
+    std::vector<void*> owned;
+    template <class T>
+    bool get(T** p, size_t count) {
+        if (cudaMalloc(p, sizeof(T) * (count > 0 ? count : 1)) != cudaSuccess) return false;
+        owned.push_back(*p);
+        return true;
+    }
+    ~DenseScratch() { for (void* p : owned) cudaFree(p); }
+};
+}  // namespace
+
 
 // =============================================================================================
 // C ABI (include/enlsip_b200.h, large-Jacobian section)
@@ -717,6 +1027,15 @@ int enlsipb200_large_comm_init(enlsipb200_large hh, const void* id128, int rank,
     h->rank = rank; h->nranks = nranks;
     LCU(cudaMalloc(&h->dStack, sizeof(double) * (size_t)nranks * h->rr_rows * h->ld));
     LCU(cudaMalloc(&h->dR2, sizeof(double) * (size_t)h->rr_rows * h->ld));
+    {   // the T-factor buffer also serves the second-stage TSQR of the nranks stacked R factors: one 32 x 32 per subtile
+        const long long nsub2 = ((long long)nranks * h->rr_rows / TS_B + TS_FAN - 1) / TS_FAN;
+        if (nsub2 > h->dT_subtiles) {
+            LCU(cudaFree(h->dT));
+            h->dT = nullptr;
+            LCU(cudaMalloc(&h->dT, sizeof(double) * nsub2 * TS_B * TS_B));
+            h->dT_subtiles = nsub2;
+        }
+    }
     return 0;
 }
 
@@ -737,16 +1056,13 @@ int enlsipb200_large_solve(enlsipb200_large hh, const double* x0, const enlsipb2
     opt.eps_x = (o->x_tol == o->x_tol) ? o->x_tol : rel_tol;
     auto t0 = std::chrono::steady_clock::now();
     LargeResult R;
-    dense_accel() = h;        // large compressed problems (n >= 384) factor on the device (enl_dense.cuh)
     try {
-        LargeSolver S(*h, opt);
+        LargeSolver S(*h, opt, h);      // h is the SmallBackend: the small stage runs on the device
         R = S.solve(x0, trace != nullptr && trace_cap > 0);
     } catch (const std::exception& e) {
-        dense_accel() = nullptr;
-        if (g_lerr.empty()) g_lerr = e.what();
+        g_lerr = e.what();
         return ENLSIPB200_ECUDA;
     }
-    dense_accel() = nullptr;
     double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     h->ms_total += total;
     memcpy(x, R.x.data(), sizeof(double) * h->n);
@@ -791,9 +1107,58 @@ int enlsipb200_large_stats(enlsipb200_large hh, double* out, int count) {
     LargeHandle* h = LH(hh);
     if (!h || !out) return lfail(ENLSIPB200_EINVAL, "NULL argument");
     double v[12] = {(double)h->n_newpoint, h->ms_build, h->ms_tsqr, h->ms_ls, h->ms_total, (double)h->n_ls,
-                    (double)h->launches, (double)h->rows_pad, (double)h->n_dev_qrcp, (double)h->n_dev_mulq, h->ms_dense,
+                    (double)h->launches, (double)h->rows_pad, (double)h->n_dev_qrcp, (double)h->n_dev_mulq, h->ms_small,
                     (double)h->n_factor};
     for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
+    return 0;
+}
+
+// ---- known-answer hooks of enl_small.cuh (tests/test_gpu_kat.py) ----
+int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device) {
+    if (rows < 1 || cols < 1 || !f || !tau || !jpvt) return lfail(ENLSIPB200_EINVAL, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return lfail(ENLSIPB200_ENOGPU, "no CUDA device");
+    if (device < 0) LCU(cudaGetDevice(&device));
+    LCU(cudaSetDevice(device));
+    DenseScratch S;
+    double *df = nullptr, *dtau = nullptr;
+    int* dp = nullptr;
+    const int k = rows < cols ? rows : cols;
+    bool ok = S.get(&df, (size_t)rows * cols) && S.get(&dtau, k) && S.get(&dp, cols) && S.get(&S.qw.vn1, cols) &&
+              S.get(&S.qw.vn2, cols) && S.get(&S.qw.F, (size_t)cols * enl_small::QR_NB) && S.get(&S.qw.auxv, enl_small::QR_NB) &&
+              S.get(&S.qw.flags, cols) && S.get(&S.qw.state, 1) && S.get(&S.qw.ticket, 1);
+    if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
+    S.qw.cap_cols = cols;
+    LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice));
+    LCU(cudaMemset(dtau, 0, sizeof(double) * k));
+    enl_small::qrcp_device(df, rows, cols, dtau, dp, S.qw, nullptr);
+    LCU(cudaDeviceSynchronize());
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(f, df, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(jpvt, dp, sizeof(int) * cols, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device) {
+    if (mr < 1 || nq < 1 || k < 0 || k > nq || !f || !tau || !M) return lfail(ENLSIPB200_EINVAL, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return lfail(ENLSIPB200_ENOGPU, "no CUDA device");
+    if (device < 0) LCU(cudaGetDevice(&device));
+    LCU(cudaSetDevice(device));
+    DenseScratch S;
+    double *df = nullptr, *dtau = nullptr, *dM = nullptr;
+    bool ok = S.get(&df, (size_t)nq * (k > 0 ? k : 1)) && S.get(&dtau, k) && S.get(&dM, (size_t)mr * nq) &&
+              S.get(&S.ww.Vb, (size_t)nq * 32) && S.get(&S.ww.T, 32 * 32) && S.get(&S.ww.W, (size_t)mr * 32) &&
+              S.get(&S.ww.W2, (size_t)mr * 32);
+    if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
+    LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(dtau, tau, sizeof(double) * k, cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(dM, M, sizeof(double) * (size_t)mr * nq, cudaMemcpyHostToDevice));
+    enl_small::mulq_device(dM, mr, nq, df, nq, k, dtau, S.ww, nullptr);
+    LCU(cudaDeviceSynchronize());
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(M, dM, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -83,10 +83,6 @@ inline double norm_range(const Vec& v, int k) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Optional device acceleration of the two O(n^3) primitives below (enl_dense.cuh).  When the compressed problem
-// is itself large (config 5: n = 4096) the product installs an accelerator; the CPU test backend never does.
-// Both calls return false when they decline (small matrix), and the host code path runs.
-// ------------------------------------------------------------------------------------------
 // Wall-clock profile of the host driver (development aid, printed when ENLSIP_PROF is set)
 struct HostProf {
     static constexpr int N = 16;
@@ -111,23 +107,6 @@ struct ProfScope {
     }
 };
 
-struct DenseAccel {
-    virtual ~DenseAccel() {}
-    // f: rows x cols column major, factored in place; tau [min(rows, cols)]; jpvt [cols], 0-based
-    virtual bool qrcp(double* f, int rows, int cols, double* tau, int* jpvt) = 0;
-    // M (mr x nq, column major) <- M * Q, Q = H(0) ... H(k-1) stored in f (nq x k, column major) / tau
-    virtual bool mul_Q(const double* f, int nq, int k, const double* tau, double* M, int mr) = 0;
-    // Device-resident variants: the compressed Jacobian J~ ((n+1) x n) of the last new_point never left the device.
-    //   jq1:       JQ1 = J~ * Q (kept on the device); its leading `ncols_host` columns are copied to JQ1_host
-    //   qrcp_tail: QRCP of the columns c0.. of that device-resident JQ1 ((n+1) x (n - c0)), factors to f_host
-    virtual bool jq1(const double* fA, int nq, int k, const double* tauA, double* JQ1_host, int mr, int ncols_host) = 0;
-    virtual bool qrcp_tail(int c0, int rows, int cols, double* f_host, double* tau, int* jpvt) = 0;
-};
-inline DenseAccel*& dense_accel() {
-    static thread_local DenseAccel* a = nullptr;
-    return a;
-}
-
 // ------------------------------------------------------------------------------------------
 // qr(M, ColumnNorm()) = LAPACK dgeqp3 (restated as the unblocked dlaqp2: first-max pivot, dlarfg
 // with beta = -sign(alpha)*dlapy2, partial-norm downdate with the tol3z recompute rule)
@@ -143,7 +122,6 @@ struct QRP {
         rows = M.rows; cols = M.cols; k = std::min(rows, cols);
         tau.assign(k, 0.0);
         p.resize(cols);
-        if (dense_accel() && k > 0 && dense_accel()->qrcp(f.a.data(), rows, cols, tau.data(), p.data())) return;
         Vec vn1(cols), vn2(cols);
         for (int j = 0; j < cols; ++j) {
             p[j] = j;
@@ -205,15 +183,6 @@ struct QRP {
             }
         }
     }
-    // QRCP of the columns c0.. of the device-resident J*Q1 (DenseAccel::qrcp_tail); false -> caller uses factor()
-    bool factor_device_tail(int c0, int rows_, int cols_) {
-        if (!dense_accel() || cols_ <= 0) return false;
-        f = Mat(rows_, cols_);
-        rows = rows_; cols = cols_; k = std::min(rows, cols);
-        tau.assign(k, 0.0);
-        p.resize(cols);
-        return dense_accel()->qrcp_tail(c0, rows, cols, f.a.data(), tau.data(), p.data());
-    }
     double R(int r, int c) const { return (r <= c) ? f(r, c) : 0.0; }
     double diag(int i) const { return f(i, i); }
     std::vector<int> invperm() const {
@@ -247,7 +216,6 @@ struct QRP {
     // reflector is a rank-one update of the columns i.. of M
     void mul_Q(Mat& M) const {
         const int mr = M.rows;
-        if (dense_accel() && k > 0 && dense_accel()->mul_Q(f.a.data(), rows, k, tau.data(), M.a.data(), mr)) return;
         Vec w(mr);
         for (int i = 0; i < k; ++i) {
             double ti = tau[i];
@@ -435,9 +403,9 @@ struct ConstraintL {   // structures.jl:145-150 ; the t x n matrix A (row i = gr
 struct SmallBackend {
     virtual ~SmallBackend() {}
     // new_point! (EF:34-52), first half: r, c, A at x; returns J'r (n), ||r||^2 and c (l).  A stays with the backend.
-    virtual int eval_point(const double* x, double* gradf, double* rr, double* cx) = 0;
+    virtual int new_point_eval(const double* x, double* gradf, double* rr, double* cx) = 0;
     // second half: compress [J | r] of that point; returns r~ (n+1) and J~' r~ (n)
-    virtual int compress(double* rt, double* gradf) = 0;
+    virtual int new_point_compress(double* rt, double* gradf) = 0;
     // C.A = A[active, :]
     virtual void gather_active(const int* active, int t) = 0;
     // structures.jl:160-178: rown[i] = ||C.A[i, :]||; scaling: C.A[i, :] /= (|rown[i]| < eps ? 1 : rown[i])
@@ -479,18 +447,17 @@ struct HostSmall : SmallBackend {
     QRP F_A, F_L11, F_J2;
     Mat JQ1;          // J * F_A.Q, formed once per F_A (EF:219, 526, 1249 recompute it)
     bool jq1_valid = false;
-    bool jq1_on_device = false;   // legacy DenseAccel route: JQ1 lives on the device, the host copy holds its leading columns
 
     explicit HostSmall(LargeOps& o) : ops(o), n(o.n), l(o.l), mt(o.n + 1) {
         J = Mat(mt, n);
         rx.assign(mt, 0.0);
         A = Mat(l, n);
     }
-    int eval_point(const double* x, double* gradf, double* rr, double* cx) override {
+    int new_point_eval(const double* x, double* gradf, double* rr, double* cx) override {
         jq1_valid = false;
         return ops.eval_point(x, gradf, rr, cx, A.a.data());
     }
-    int compress(double* rt, double* gradf) override {
+    int new_point_compress(double* rt, double* gradf) override {
         int rc = ops.compress(J.a.data(), rx.data());
         if (rc != 0) return rc;
         for (int r = 0; r < mt; ++r) rt[r] = rx[r];
@@ -550,30 +517,16 @@ struct HostSmall : SmallBackend {
     }
     void ensure_JQ1() { ProfScope prof_(4);
         if (!jq1_valid) {
-            const int lead = std::min(F_A.cols, n);
-            jq1_on_device = false;
-            if (dense_accel()) {
-                Mat lead_cols(mt, lead);
-                if (dense_accel()->jq1(F_A.f.a.data(), F_A.rows, F_A.k, F_A.tau.data(), lead_cols.a.data(), mt, lead)) {
-                    JQ1 = std::move(lead_cols);
-                    jq1_on_device = true;
-                }
-            }
-            if (!jq1_on_device) {
-                JQ1 = J;
-                F_A.mul_Q(JQ1);
-            }
+            JQ1 = J;
+            F_A.mul_Q(JQ1);
             jq1_valid = true;
         }
     }
     void factor_J2(int rankA, FactorInfo& F) override {
         ensure_JQ1();
-        if (!(jq1_on_device && F_J2.factor_device_tail(rankA, mt, n - rankA))) {
-            if (jq1_on_device) throw std::runtime_error("device-resident J*Q1 lost");
-            Mat J2(mt, n - rankA);
-            for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
-            F_J2.factor(J2);
-        }
+        Mat J2(mt, n - rankA);
+        for (int c = rankA; c < n; ++c) std::copy(JQ1.col(c), JQ1.col(c) + mt, J2.col(c - rankA));
+        F_J2.factor(J2);
         F.take(F_J2);
     }
     void first_lagrange(int prankA, int t, const Vec& gradf, const Vec& Ccx, Vec& v, Vec& u, double& grad_res) override {
@@ -744,13 +697,13 @@ public:
     // every quantity of an iteration comes from one and the same factorisation.
     double do_eval_point(const Vec& x) { ProfScope prof_(0);
         double rr = 0.0;
-        check(sb->eval_point(x.data(), gradf.data(), &rr, cx.data()));
+        check(sb->new_point_eval(x.data(), gradf.data(), &rr, cx.data()));
         ++n_new_point;
         cur_rr = rr;
         return rr;
     }
     double do_factor() { ProfScope prof_(0);
-        check(sb->compress(rx.data(), gradf.data()));
+        check(sb->new_point_compress(rx.data(), gradf.data()));
         cur_rr = dotv(rx, rx);
         return cur_rr;
     }

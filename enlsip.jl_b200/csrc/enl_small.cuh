@@ -1,0 +1,837 @@
+// enl_small.cuh -- the matrix-sized half of the large regime's small stage as CUDA kernels (sm_100a).
+//
+// The ENLSIP iteration on the compressed problem [J~ | r~] ((n+1) x (n+1), enl_large.cu) needs, per iteration
+// (reference: src/enlsip_functions.jl = EF):
+//   * qr(C.A', ColumnNorm())  (EF:700), qr(F_A.R', ColumnNorm()) (EF:769), qr(J2, ColumnNorm()) (EF:223)
+//         -> qrcp_device(): LAPACK dgeqp3 restated for the GPU -- blocked dlaqps panels (nb = 32, the trailing
+//            rank-nb update on FP64 tensor cores, mma.sync.m8n8k4.f64) for the leading min(m,n) - 128 columns,
+//            unblocked dlaqp2 steps for the rest (dgeqp3's crossover nx = 128), first-max pivot, dlarfg with
+//            beta = -sign(alpha) dlapy2, partial-norm downdate with the tol3z recompute rule (deferred to the end of a
+//            panel in the blocked part exactly like dlaqps' lsticc list);
+//   * J * F_A.Q                (EF:219)  -> mulq_device(): compact-WY panels (dlarft T factors), three DMMA GEMMs each;
+//   * F.Q' v, F.Q v            (EF:137, 143, 152, 484)  -> reflect_vec_kernel;
+//   * R \ v, R' \ v            (EF:133-147, 486-500)    -> trsv_upper_kernel, trsv_upperT_kernel (blocked by 32);
+//   * J p, A p, J1 p1, J1' s, C.A' c (EF:2222-2224, 526, 2497) -> gemv_n_kernel / gemv_t_kernel.
+// Column-major storage everywhere (a row-major l x n matrix is the column-major n x l matrix of its transpose).
+// Everything is enqueued on one stream; indices that depend on the data (where a dlaqps panel stops) live in a device
+// state block, so the host never synchronises inside a factorisation.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace enl_small {
+
+constexpr double S_TOL3Z = 1.0536712127723509e-08;   // sqrt(dlamch('Epsilon')) = sqrt(2^-53)
+constexpr int QR_NB = 32;                             // dgeqp3 block size (ilaenv(1, 'DGEQRF') = 32)
+constexpr int QR_NX = 128;                            // dgeqp3 crossover (ilaenv(3, 'DGEQRF') = 128)
+
+__device__ __forceinline__ double s_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the CTA, identical in every thread (fixed order); sh: 32 doubles
+__device__ __forceinline__ double s_block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = s_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += sh[i];
+    return t;
+}
+__device__ __forceinline__ double s_lapy2(double x, double y) {
+    const double xa = fabs(x), ya = fabs(y), w = fmax(xa, ya), z = fmin(xa, ya);
+    if (z == 0.0) return w;
+    const double q = z / w;
+    return w * sqrt(1.0 + q * q);
+}
+__device__ __forceinline__ void s_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// =============================================================================================
+// GEMM on FP64 tensor cores:  C (M x N, ldc) = alpha * A (M x K, lda) * op(B) + beta * C
+//   op(B) = B (K x N, ldb)            TRANSB = false
+//   op(B) = B' with B (N x K, ldb)    TRANSB = true
+// CTA tile 64 x 64, K in slabs of 32 staged through shared memory, 8 warps, each warp owns a 16 x 32 sub-tile
+// (2 x 4 m8n8 accumulators).  Grid-stride over the tiles: sizes may come from a device state block (dims != nullptr:
+// {M, N, K, rowoff, coloff, kcol0} are read on the device, see qrcp_device).
+// =============================================================================================
+struct GemmDims { int M, N, K; };
+
+template <bool TRANSB>
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                          double* __restrict__ C, int ldc, int M, int N, int K, double alpha, double beta,
+                                          int tm, int tn, double (*As)[65], double (*Bs)[65]) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = (w & 3) * 16, wn = (w >> 2) * 32;      // warp sub-tile origin inside the 64 x 64 tile
+    const int gr = lane >> 2, gc = lane & 3;               // fragment coordinates
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int m0 = tm * 64, n0 = tn * 64;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        __syncthreads();
+        // As[k][m] = A(m0 + m, k0 + k): threads walk m fastest (coalesced, column major)
+        for (int e = tid; e < 32 * 64; e += 256) {
+            const int mm = e & 63, kk = e >> 6;
+            const int gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gk * lda + gm] : 0.0;
+        }
+        if (TRANSB) {   // Bs[k][n] = B(n0 + n, k0 + k)
+            for (int e = tid; e < 32 * 64; e += 256) {
+                const int nn = e & 63, kk = e >> 6;
+                const int gn = n0 + nn, gk = k0 + kk;
+                Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gk * ldb + gn] : 0.0;
+            }
+        } else {        // Bs[k][n] = B(k0 + k, n0 + n)
+            for (int e = tid; e < 32 * 64; e += 256) {
+                const int kk = e & 31, nn = e >> 5;
+                const int gn = n0 + nn, gk = k0 + kk;
+                Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gn * ldb + gk] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 32; ks += 4) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = As[ks + gc][wm + 8 * i + gr];      // A fragment: row = lane/4, k = lane%4
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + gc][wn + 8 * j + gr];      // B fragment: k = lane%4, col = lane/4
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    // D fragment: row = lane/4, cols = 2 (lane%4), 2 (lane%4) + 1
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gm = m0 + wm + 8 * i + gr, gn = n0 + wn + 8 * j + 2 * gc + h;
+                if (gm < M && gn < N) {
+                    double* cp = C + (size_t)gn * ldc + gm;
+                    const double v = alpha * acc[i][j][h];
+                    *cp = (beta == 0.0) ? v : fma(beta, *cp, v);
+                }
+            }
+}
+
+template <bool TRANSB>
+__global__ void __launch_bounds__(256) gemm_dmma_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B,
+                                                        int ldb, double* __restrict__ C, int ldc, int M, int N, int K,
+                                                        double alpha, double beta) {
+    __shared__ double As[32][65];
+    __shared__ double Bs[32][65];
+    const int tmn = (M + 63) / 64, tnn = (N + 63) / 64;
+    for (int t = blockIdx.x; t < tmn * tnn; t += gridDim.x)
+        gemm_tile<TRANSB>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, t % tmn, t / tmn, As, Bs);
+}
+
+inline int gemm_grid(int M, int N) {
+    long long t = (long long)((M + 63) / 64) * ((N + 63) / 64);
+    return (int)(t < 1 ? 1 : (t > 148 * 8 ? 148 * 8 : t));
+}
+// C = alpha A op(B) + beta C on the stream; returns the number of launches
+template <bool TRANSB>
+inline int gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K, double alpha,
+                double beta, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    gemm_dmma_kernel<TRANSB><<<gemm_grid(M, N), 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+    return 1;
+}
+
+// =============================================================================================
+// QRCP (LAPACK dgeqp3 semantics)
+// =============================================================================================
+// Device state of one factorisation.
+struct QrState {
+    int j0;        // first column of the current dlaqps panel (= number of finished columns)
+    int k;         // columns of the current panel already factored
+    int stop;      // a norm has to be recomputed: the panel ends after k columns (dlaqps: lsticc != 0)
+    int jb;        // columns this panel may take (min(nb, topbmn - j0))
+    int active;    // the blocked phase still has work
+    double tau_k;  // tau of the panel column handed from the pivot kernel to the gemv kernel
+};
+
+__global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols, double* vn1, double* vn2, int* jpvt,
+                               QrState* stt, int topbmn) {
+    __shared__ double sh[32];
+    const int c = blockIdx.x;
+    const double* cc = f + (size_t)c * rows;
+    double s = 0.0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) s = fma(cc[r], cc[r], s);
+    s = s_block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        vn1[c] = vn2[c] = sqrt(s);
+        jpvt[c] = c;
+        if (c == 0) {
+            stt->j0 = 0; stt->k = 0; stt->stop = 0;
+            stt->jb = topbmn < QR_NB ? topbmn : QR_NB;
+            stt->active = topbmn > 0 ? 1 : 0;
+            stt->tau_k = 0.0;
+        }
+    }
+}
+
+// One CTA, 1024 threads.  Panel column k (global column jc = j0 + k, pivot row rk = jc):
+//   1. finish column k-1 (dlaqps lines after the F column): F(:, k-1) += F(:, 0:k-1) auxv; row rk-1 of A updated;
+//      partial-norm downdate of the trailing columns; a flagged column ends the panel (stop = 1);
+//   2. pivot search over vn1[jc..cols), swap of the columns of A, the rows of F, jpvt, vn1 / vn2;
+//   3. A(rk:, jc) -= A(rk:, j0:jc) F(k, 0:k)';   4. dlarfg.
+// F: cols x QR_NB (row = global column), auxv: QR_NB, flags: cols ints (1 = recompute this column's norm).
+__global__ void __launch_bounds__(1024) qr_panel_col_kernel(double* __restrict__ f, int rows, int cols, double* vn1,
+                                                             double* vn2, int* jpvt, double* tau, double* __restrict__ F,
+                                                             double* auxv, int* flags, QrState* stt, int kk) {
+    __shared__ double sh[32];
+    __shared__ double s_best[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_pvt, s_any;
+    __shared__ double frow[QR_NB], aux[QR_NB];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    // kk: the host's column counter inside the panel (0 .. QR_NB; the call with kk == jb only finishes column jb - 1).
+    // stt->k = number of finished columns of the panel, valid when the panel ends (early stop or kk == jb).
+    if (!stt->active || stt->stop) return;
+    const int j0 = stt->j0, k = kk, jb = stt->jb;
+    if (k > jb) return;
+    // ---- 1. finish column k-1 ----
+    if (k > 0) {
+        const int kp = k - 1, jcp = j0 + kp, rkp = jcp;
+        if (tid < QR_NB) aux[tid] = (tid < kp) ? auxv[tid] : 0.0;
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+        // F(j, kp) += sum_{i < kp} F(j, i) aux[i]   (all rows j of F: j0 .. cols-1; rows j0..jcp are 0 + update like LAPACK)
+        for (int j = j0 + tid; j < cols; j += blockDim.x) {
+            double s = 0.0;
+            for (int i = 0; i < kp; ++i) s = fma(F[(size_t)i * cols + j], aux[i], s);
+            if (kp > 0) F[(size_t)kp * cols + j] += s;
+        }
+        __syncthreads();
+        // row rkp of A, trailing columns: A(rkp, j) -= sum_{i <= kp} A(rkp, j0 + i) F(j, i)   (A(rkp, jcp) counts as 1)
+        if (tid < QR_NB) frow[tid] = (tid < kp) ? f[(size_t)(j0 + tid) * rows + rkp] : (tid == kp ? 1.0 : 0.0);
+        __syncthreads();
+        int any = 0;
+        for (int j = jcp + 1 + tid; j < cols; j += blockDim.x) {
+            double s = 0.0;
+            for (int i = 0; i <= kp; ++i) s = fma(frow[i], F[(size_t)i * cols + j], s);
+            double* ap = f + (size_t)j * rows + rkp;
+            const double a = *ap - s;
+            *ap = a;
+            const double v1 = vn1[j];
+            if (v1 != 0.0) {
+                double temp = fabs(a) / v1;
+                temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+                const double rq = v1 / vn2[j];
+                const double temp2 = temp * (rq * rq);
+                if (temp2 <= S_TOL3Z) { flags[j] = 1; any = 1; }
+                else vn1[j] = v1 * sqrt(temp);
+            }
+        }
+        if (any) s_any = 1;
+        __syncthreads();
+        if (s_any) {
+            if (tid == 0) { stt->stop = 1; stt->k = k; }      // panel ends with k columns
+            return;
+        }
+    }
+    if (tid == 0) stt->k = k;
+    if (k >= jb) return;
+    // ---- 2. pivot ----
+    const int jc = j0 + k, rk = jc;
+    double best = -1.0; int idx = cols;
+    for (int j = jc + tid; j < cols; j += blockDim.x) {
+        const double v = vn1[j];
+        if (v > best) { best = v; idx = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (lane == 0) { s_best[w] = best; s_idx[w] = idx; }
+    __syncthreads();
+    if (tid == 0) {
+        double b = s_best[0]; int bi = s_idx[0];
+        for (int q = 1; q < nw; ++q)
+            if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
+        if (bi >= cols) bi = jc;
+        s_pvt = bi;
+        if (bi != jc) {
+            const int tp = jpvt[bi]; jpvt[bi] = jpvt[jc]; jpvt[jc] = tp;
+            vn1[bi] = vn1[jc]; vn2[bi] = vn2[jc];
+        }
+    }
+    __syncthreads();
+    const int pvt = s_pvt;
+    double* cj = f + (size_t)jc * rows;
+    if (pvt != jc) {
+        double* cp = f + (size_t)pvt * rows;
+        for (int r = tid; r < rows; r += blockDim.x) { const double a = cj[r]; cj[r] = cp[r]; cp[r] = a; }
+        for (int i = tid; i < k; i += blockDim.x) {
+            const double a = F[(size_t)i * cols + pvt]; F[(size_t)i * cols + pvt] = F[(size_t)i * cols + jc]; F[(size_t)i * cols + jc] = a;
+        }
+    }
+    __syncthreads();
+    // ---- 3. column update with the panel's earlier reflectors ----
+    if (k > 0) {
+        if (tid < QR_NB) frow[tid] = (tid < k) ? F[(size_t)tid * cols + jc] : 0.0;
+        __syncthreads();
+        for (int r = rk + tid; r < rows; r += blockDim.x) {
+            double s = 0.0;
+            for (int i = 0; i < k; ++i) s = fma(f[(size_t)(j0 + i) * rows + r], frow[i], s);
+            cj[r] -= s;
+        }
+        __syncthreads();
+    }
+    // ---- 4. dlarfg ----
+    double tau_k = 0.0;
+    if (rk < rows - 1) {
+        double s = 0.0;
+        for (int r = rk + 1 + tid; r < rows; r += blockDim.x) s = fma(cj[r], cj[r], s);
+        s = s_block_sum(s, sh);
+        const double xn = sqrt(s);
+        if (xn != 0.0) {
+            const double alpha = cj[rk];
+            const double beta = -copysign(s_lapy2(alpha, xn), alpha);
+            tau_k = (beta - alpha) / beta;
+            const double sc = 1.0 / (alpha - beta);
+            __syncthreads();
+            for (int r = rk + 1 + tid; r < rows; r += blockDim.x) cj[r] *= sc;
+            if (tid == 0) cj[rk] = beta;
+        }
+    }
+    if (tid == 0) { tau[jc] = tau_k; stt->tau_k = tau_k; }
+}
+
+// Grid kernel of panel column k: F(j, k) = tau * A(rk:, j)' v for the trailing columns j > jc (v = [1; A(rk+1:, jc)]),
+// F(j0..jc, k) = 0, and auxv(i) = -tau * A(rk:, j0 + i)' v for i < k.  One warp per column, v staged in shared memory.
+__global__ void __launch_bounds__(256) qr_panel_gemv_kernel(const double* __restrict__ f, int rows, int cols,
+                                                            double* __restrict__ F, double* auxv, QrState* stt, int kk) {
+    extern __shared__ double vs[];
+    if (!stt->active || stt->stop) return;
+    const int j0 = stt->j0, k = kk;
+    if (k >= stt->jb) return;
+    const int jc = j0 + k, rk = jc;
+    const double tau_k = stt->tau_k;
+    const int len = rows - rk;
+    const double* cj = f + (size_t)jc * rows + rk;
+    for (int r = threadIdx.x; r < len; r += blockDim.x) vs[r] = (r == 0) ? 1.0 : cj[r];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    // items: trailing columns jc+1 .. cols-1, then the k panel columns (auxv), then the zero entries j0..jc
+    const int ntrail = cols - jc - 1;
+    for (int it = gw; it < ntrail + k; it += nwarps) {
+        const int col = (it < ntrail) ? (jc + 1 + it) : (j0 + (it - ntrail));
+        const double* cc = f + (size_t)col * rows + rk;
+        double s = 0.0;
+        for (int r = lane; r < len; r += 32) s = fma(cc[r], vs[r], s);
+        s = s_warp_sum(s);
+        if (lane == 0) {
+            if (it < ntrail) F[(size_t)k * cols + col] = tau_k * s;
+            else auxv[it - ntrail] = -tau_k * s;
+        }
+    }
+    if (blockIdx.x == 0)
+        for (int j = j0 + threadIdx.x; j <= jc; j += blockDim.x) F[(size_t)k * cols + j] = 0.0;
+}
+
+// Trailing update of a finished panel (kb = stt->k columns): A(j0+kb:, j0+kb:) -= A(j0+kb:, j0:j0+kb) F(j0+kb:, 0:kb)'
+__global__ void __launch_bounds__(256) qr_panel_trail_kernel(double* __restrict__ f, int rows, int cols,
+                                                             const double* __restrict__ F, const QrState* stt) {
+    __shared__ double As[32][65];
+    __shared__ double Bs[32][65];
+    if (!stt->active) return;
+    const int j0 = stt->j0, kb = stt->k;
+    if (kb <= 0) return;
+    const int r0 = j0 + kb, c0 = j0 + kb;
+    const int M = rows - r0, N = cols - c0;
+    if (M <= 0 || N <= 0) return;
+    const double* A = f + (size_t)j0 * rows + r0;          // M x kb, lda = rows
+    const double* B = F + c0;                               // N x kb, ldb = cols
+    double* C = f + (size_t)c0 * rows + r0;
+    const int tmn = (M + 63) / 64, tnn = (N + 63) / 64;
+    for (int t = blockIdx.x; t < tmn * tnn; t += gridDim.x)
+        gemm_tile<true>(A, rows, B, cols, C, rows, M, N, kb, -1.0, 1.0, t % tmn, t / tmn, As, Bs);
+}
+
+// After the trailing update: recompute the flagged norms (dlaqps: the lsticc list), one CTA per candidate column;
+// the last CTA to finish (atomic ticket) opens the next panel.
+__global__ void __launch_bounds__(256) qr_panel_close_kernel(const double* __restrict__ f, int rows, int cols, double* vn1,
+                                                             double* vn2, int* flags, QrState* stt, int topbmn,
+                                                             unsigned int* ticket) {
+    __shared__ double sh[32];
+    __shared__ int s_last;
+    if (!stt->active) return;
+    const int j0 = stt->j0, kb = stt->k;
+    const int rnext = j0 + kb;          // first row of the trailing matrix
+    for (int j = rnext + blockIdx.x; j < cols; j += gridDim.x) {
+        if (!flags[j]) continue;          // uniform per CTA
+        const double* cc = f + (size_t)j * rows;
+        double s = 0.0;
+        for (int r = rnext + threadIdx.x; r < rows; r += blockDim.x) s = fma(cc[r], cc[r], s);
+        s = s_block_sum(s, sh);
+        __syncthreads();
+        if (threadIdx.x == 0) { vn1[j] = vn2[j] = sqrt(s); flags[j] = 0; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        *ticket = 0;
+        const int nj = j0 + kb;
+        stt->j0 = nj; stt->k = 0; stt->stop = 0;
+        const int left = topbmn - nj;
+        stt->jb = left < QR_NB ? left : QR_NB;
+        stt->active = left > 0 ? 1 : 0;
+    }
+}
+
+// ---- unblocked dlaqp2 steps (the last min(m,n) - topbmn columns; host-driven column index i) ----
+__global__ void __launch_bounds__(1024) qr_p2_pivot_house_kernel(double* __restrict__ f, int rows, int cols, int i,
+                                                                  double* vn1, double* vn2, int* jpvt, double* tau) {
+    __shared__ double sh[32];
+    __shared__ double s_best[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_pvt;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    double best = -1.0; int idx = cols;
+    for (int j = i + tid; j < cols; j += blockDim.x) {
+        const double v = vn1[j];
+        if (v > best) { best = v; idx = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (lane == 0) { s_best[w] = best; s_idx[w] = idx; }
+    __syncthreads();
+    if (tid == 0) {
+        double b = s_best[0]; int bi = s_idx[0];
+        for (int q = 1; q < nw; ++q)
+            if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
+        if (bi >= cols) bi = i;
+        s_pvt = bi;
+        if (bi != i) {
+            const int tp = jpvt[bi]; jpvt[bi] = jpvt[i]; jpvt[i] = tp;
+            vn1[bi] = vn1[i]; vn2[bi] = vn2[i];
+        }
+    }
+    __syncthreads();
+    const int pvt = s_pvt;
+    double* ci = f + (size_t)i * rows;
+    if (pvt != i) {
+        double* cp = f + (size_t)pvt * rows;
+        for (int r = tid; r < rows; r += blockDim.x) { const double a = ci[r]; ci[r] = cp[r]; cp[r] = a; }
+    }
+    __syncthreads();
+    double tau_i = 0.0;
+    if (i < rows - 1) {
+        double s = 0.0;
+        for (int r = i + 1 + tid; r < rows; r += blockDim.x) s = fma(ci[r], ci[r], s);
+        s = s_block_sum(s, sh);
+        const double xn = sqrt(s);
+        if (xn != 0.0) {
+            const double alpha = ci[i];
+            const double beta = -copysign(s_lapy2(alpha, xn), alpha);
+            tau_i = (beta - alpha) / beta;
+            const double sc = 1.0 / (alpha - beta);
+            __syncthreads();
+            for (int r = i + 1 + tid; r < rows; r += blockDim.x) ci[r] *= sc;
+            if (tid == 0) ci[i] = beta;
+        }
+    }
+    if (tid == 0) tau[i] = tau_i;
+}
+
+// apply H_i to the trailing columns (one warp per column) + dlaqp2 partial-norm downdate of that column
+__global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f, int rows, int cols, int i, double* vn1,
+                                                          double* vn2, const double* __restrict__ tau) {
+    extern __shared__ double vs[];
+    const int len = rows - i - 1;
+    const double* v = f + (size_t)i * rows + i + 1;
+    for (int r = threadIdx.x; r < len; r += blockDim.x) vs[r] = v[r];
+    __syncthreads();
+    const double tau_i = tau[i];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = i + 1 + gw; c < cols; c += nwarps) {
+        double* cc = f + (size_t)c * rows + i;
+        double ci = cc[0];
+        if (tau_i != 0.0) {
+            double s = 0.0;
+            for (int r = lane; r < len; r += 32) s = fma(vs[r], cc[1 + r], s);
+            s = s_warp_sum(s);
+            const double wv = (ci + s) * tau_i;
+            for (int r = lane; r < len; r += 32) cc[1 + r] = fma(-wv, vs[r], cc[1 + r]);
+            ci -= wv;
+            if (lane == 0) cc[0] = ci;
+        }
+        __syncwarp();
+        const double v1 = vn1[c];
+        if (v1 != 0.0) {
+            const double tq = fabs(ci) / v1;
+            const double temp = fmax(1.0 - tq * tq, 0.0);
+            const double rq = v1 / vn2[c];
+            const double temp2 = temp * (rq * rq);
+            if (temp2 <= S_TOL3Z) {
+                double s = 0.0;
+                if (i < rows - 1) {
+                    for (int r = lane; r < len; r += 32) s = fma(cc[1 + r], cc[1 + r], s);
+                    s = s_warp_sum(s);
+                }
+                if (lane == 0) vn1[c] = vn2[c] = sqrt(s);
+            } else if (lane == 0) {
+                vn1[c] = v1 * sqrt(temp);
+            }
+        }
+    }
+}
+
+// diag(R) and the inverse permutation of a finished factorisation
+__global__ void qr_finish_kernel(const double* __restrict__ f, int rows, int cols, const int* __restrict__ jpvt,
+                                 double* diag, int* ipvt) {
+    const int k = rows < cols ? rows : cols;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) diag[i] = f[(size_t)i * rows + i];
+    if (i < cols) ipvt[jpvt[i]] = i;
+}
+
+struct QrWork {          // scratch of one factorisation (sized for the largest matrix of the solve)
+    double *vn1 = nullptr, *vn2 = nullptr, *F = nullptr, *auxv = nullptr;
+    int* flags = nullptr;
+    QrState* state = nullptr;
+    unsigned int* ticket = nullptr;
+    int cap_cols = 0;
+};
+
+// f: rows x cols column major on the device, factored in place (dgeqp3 layout); tau [min(rows, cols)]; jpvt [cols]
+// (0-based).  Returns the number of kernels launched.  No host synchronisation.
+inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st) {
+    const int minmn = rows < cols ? rows : cols;
+    if (minmn <= 0) return 0;
+    // dgeqp3: blocked (dlaqps) while j <= topbmn = minmn - nx, if nb < minmn and nx < minmn
+    int topbmn = (QR_NB < minmn && QR_NX < minmn) ? (minmn - QR_NX) : 0;
+    int launches = 0;
+    cudaMemsetAsync(wk.flags, 0, sizeof(int) * cols, st);
+    cudaMemsetAsync(wk.ticket, 0, sizeof(unsigned int), st);
+    qr_init_kernel<<<cols, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.state, topbmn);
+    ++launches;
+    if (topbmn > 0) {
+        const size_t shv = sizeof(double) * (size_t)rows;
+        const int ggrid = 148 * 2;
+        // A panel that stops early (a norm to recompute) re-opens at its next column, so more than ceil(topbmn / nb)
+        // panels may be needed; each stopped panel still retires at least one column.  Enqueue the regular count plus a
+        // margin, then (rarely) top up after looking at the state.
+        int panels = (topbmn + QR_NB - 1) / QR_NB;
+        int budget = panels + 2;
+        for (;;) {
+            for (int pnl = 0; pnl < budget; ++pnl) {
+                for (int k = 0; k < QR_NB; ++k) {
+                    qr_panel_col_kernel<<<1, 1024, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, tau, wk.F, wk.auxv, wk.flags, wk.state, k);
+                    qr_panel_gemv_kernel<<<ggrid, 256, shv, st>>>(f, rows, cols, wk.F, wk.auxv, wk.state, k);
+                    launches += 2;
+                }
+                qr_panel_col_kernel<<<1, 1024, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, tau, wk.F, wk.auxv, wk.flags, wk.state, QR_NB);
+                qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+                qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
+                launches += 3;
+            }
+            QrState h;
+            cudaMemcpyAsync(&h, wk.state, sizeof(QrState), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            if (!h.active) break;
+            budget = (topbmn - h.j0 + QR_NB - 1) / QR_NB + 2;
+        }
+    }
+    for (int i = topbmn; i < minmn; ++i) {
+        qr_p2_pivot_house_kernel<<<1, 1024, 0, st>>>(f, rows, cols, i, wk.vn1, wk.vn2, jpvt, tau);
+        ++launches;
+        if (i < cols - 1) {
+            const int len = rows - i - 1;
+            int ncol = cols - i - 1;
+            int grid = (ncol + 7) / 8;
+            if (grid > 148 * 4) grid = 148 * 4;
+            qr_p2_apply_kernel<<<grid, 256, sizeof(double) * (size_t)(len > 0 ? len : 1), st>>>(f, rows, cols, i, wk.vn1, wk.vn2, tau);
+            ++launches;
+        }
+    }
+    return launches;
+}
+
+// =============================================================================================
+// M <- M * Q,  Q = H(0) ... H(k-1) stored in f (frows x k, dgeqp3 layout) / tau : compact-WY panels of 32
+// =============================================================================================
+// explicit V of a panel: Vb (len x pw, ld = len) = rows j0.. of the columns j0..j0+pw of f with unit diagonal, zeros above
+__global__ void wy_build_v_kernel(const double* __restrict__ f, int frows, int j0, int pw, double* __restrict__ Vb) {
+    const int len = frows - j0;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)len * pw) return;
+    const int r = (int)(e % len), c = (int)(e / len);
+    Vb[e] = (r < c) ? 0.0 : (r == c ? 1.0 : f[(size_t)(j0 + c) * frows + j0 + r]);
+}
+// dlarft (forward, columnwise): T (pw x pw upper, ld = 32) from Vb and tau; one CTA
+__global__ void __launch_bounds__(1024) wy_build_t_kernel(const double* __restrict__ Vb, int len, int pw,
+                                                          const double* __restrict__ tau, double* __restrict__ T) {
+    __shared__ double G[32][33];
+    __shared__ double Ts[32][33];
+    __shared__ double tmp[32];
+    const int a = threadIdx.x & 31, b = threadIdx.x >> 5;     // G(a, b) = V(:, a)' V(:, b), a < b
+    double s = 0.0;
+    if (a < b && b < pw)
+        for (int r = b; r < len; ++r) s = fma(Vb[(size_t)a * len + r], Vb[(size_t)b * len + r], s);
+    G[a][b] = s;
+    Ts[a][b] = 0.0;
+    __syncthreads();
+    for (int i = 0; i < pw; ++i) {
+        const double ti = tau[i];
+        // T(0:i, i) = -tau_i * T(0:i, 0:i) * G(0:i, i)
+        if (threadIdx.x < 32) {
+            double acc = 0.0;
+            if ((int)threadIdx.x < i)
+                for (int c = threadIdx.x; c < i; ++c) acc = fma(Ts[threadIdx.x][c], G[c][i], acc);
+            tmp[threadIdx.x] = -ti * acc;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < i) Ts[threadIdx.x][i] = tmp[threadIdx.x];
+        if (threadIdx.x == 0) Ts[i][i] = ti;
+        __syncthreads();
+    }
+    T[b * 32 + a] = (a < pw && b < pw) ? Ts[a][b] : 0.0;    // column major, ld = 32
+}
+
+struct WyWork { double *Vb = nullptr, *T = nullptr, *W = nullptr, *W2 = nullptr; };   // Vb: frows x 32, T: 32 x 32, W/W2: mr x 32
+
+// M: mr x nq column major (ld = mr); f: frows (= nq) x k
+inline int mulq_device(double* M, int mr, int nq, const double* f, int frows, int k, const double* tau, WyWork& wk,
+                       cudaStream_t st) {
+    int launches = 0;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+        const int pw = (k - j0) < 32 ? (k - j0) : 32;
+        const int len = frows - j0;
+        if (len <= 0) break;
+        const long long ne = (long long)len * pw;
+        wy_build_v_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(f, frows, j0, pw, wk.Vb);
+        wy_build_t_kernel<<<1, 1024, 0, st>>>(wk.Vb, len, pw, tau + j0, wk.T);
+        launches += 2;
+        // W = M(:, j0:) Vb ; W2 = W T ; M(:, j0:) -= W2 Vb'
+        launches += gemm<false>(M + (size_t)j0 * mr, mr, wk.Vb, len, wk.W, mr, mr, pw, len, 1.0, 0.0, st);
+        launches += gemm<false>(wk.W, mr, wk.T, 32, wk.W2, mr, mr, pw, pw, 1.0, 0.0, st);
+        launches += gemm<true>(wk.W2, mr, wk.Vb, len, M + (size_t)j0 * mr, mr, mr, len, pw, -1.0, 1.0, st);
+    }
+    return launches;
+}
+
+// =============================================================================================
+// vectors: F.Q' v / F.Q v (reflector sweep), triangular solves, gemv, small glue
+// =============================================================================================
+// v (frows entries) <- Q' v (forward sweep, transpose = 1) or Q v (backward sweep); one CTA, v kept in shared memory
+__global__ void __launch_bounds__(1024) reflect_vec_kernel(const double* __restrict__ f, int frows, int k,
+                                                           const double* __restrict__ tau, double* __restrict__ v,
+                                                           int transpose) {
+    extern __shared__ double vsm[];
+    __shared__ double sh[32];
+    for (int r = threadIdx.x; r < frows; r += blockDim.x) vsm[r] = v[r];
+    __syncthreads();
+    for (int s = 0; s < k; ++s) {
+        const int i = transpose ? s : (k - 1 - s);
+        const double ti = tau[i];
+        if (ti == 0.0) continue;
+        const double* ci = f + (size_t)i * frows;
+        double acc = 0.0;
+        for (int r = i + 1 + threadIdx.x; r < frows; r += blockDim.x) acc = fma(ci[r], vsm[r], acc);
+        acc = s_block_sum(acc, sh);
+        const double w = (vsm[i] + acc) * ti;
+        __syncthreads();
+        for (int r = i + 1 + threadIdx.x; r < frows; r += blockDim.x) vsm[r] = fma(-w, ci[r], vsm[r]);
+        if (threadIdx.x == 0) vsm[i] -= w;
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < frows; r += blockDim.x) v[r] = vsm[r];
+}
+
+// x (k entries) <- UpperTriangular(f[0:k, 0:k]) \ x ; one CTA of 1024 threads, blocks of 32 from the bottom
+__global__ void __launch_bounds__(1024) trsv_upper_kernel(const double* __restrict__ f, int ldf, int k, double* __restrict__ x) {
+    extern __shared__ double xs[];
+    for (int r = threadIdx.x; r < k; r += blockDim.x) xs[r] = x[r];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b1 = k; b1 > 0; b1 -= 32) {
+        const int b0 = b1 - 32 > 0 ? b1 - 32 : 0;
+        if (w == 0) {                                  // back substitution inside the diagonal block (one warp)
+            for (int i = b1 - 1; i >= b0; --i) {
+                const double xi = xs[i] / f[(size_t)i * ldf + i];
+                __syncwarp();
+                if (lane == 0) xs[i] = xi;
+                const int r = b0 + lane;
+                if (r < i) xs[r] = fma(-f[(size_t)i * ldf + r], xi, xs[r]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // rows above the block: x_r -= sum_{c in block} R(r, c) x_c
+        for (int r = threadIdx.x; r < b0; r += blockDim.x) {
+            double s = 0.0;
+            for (int c = b0; c < b1; ++c) s = fma(f[(size_t)c * ldf + r], xs[c], s);
+            xs[r] -= s;
+        }
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < k; r += blockDim.x) x[r] = xs[r];
+}
+
+// x (k entries) <- LowerTriangular(f[0:k, 0:k]') \ x ; forward, blocks of 32: one warp per column of the block for the
+// part of the dot product that lies above the block, one warp for the in-block recurrence
+__global__ void __launch_bounds__(1024) trsv_upperT_kernel(const double* __restrict__ f, int ldf, int k, double* __restrict__ x) {
+    extern __shared__ double xs[];
+    for (int r = threadIdx.x; r < k; r += blockDim.x) xs[r] = x[r];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < k; b0 += 32) {
+        const int b1 = b0 + 32 < k ? b0 + 32 : k;
+        const int i = b0 + w;
+        if (i < b1) {
+            const double* ci = f + (size_t)i * ldf;
+            double s = 0.0;
+            for (int r = lane; r < b0; r += 32) s = fma(ci[r], xs[r], s);
+            s = s_warp_sum(s);
+            if (lane == 0) xs[i] -= s;
+        }
+        __syncthreads();
+        if (w == 0) {
+            for (int ii = b0; ii < b1; ++ii) {
+                const double xi = xs[ii] / f[(size_t)ii * ldf + ii];
+                __syncwarp();
+                if (lane == 0) xs[ii] = xi;
+                const int c = ii + 1 + lane;           // later columns of the block: x_c -= R(ii, c) x_ii
+                if (c < b1) xs[c] = fma(-f[(size_t)c * ldf + ii], xi, xs[c]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < k; r += blockDim.x) x[r] = xs[r];
+}
+
+// y (rows) = alpha * A (rows x cols, lda) x + beta * y0   (y0 may be nullptr = 0); thread per row, columns streamed
+__global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, int lda, int rows, int cols,
+                                                     const double* __restrict__ x, double alpha, const double* __restrict__ y0,
+                                                     double beta, double* __restrict__ y) {
+    extern __shared__ double xs[];
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) xs[c] = x[c];
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= cols; c += 4) {
+        s0 = fma(A[(size_t)c * lda + r], xs[c], s0);
+        s1 = fma(A[(size_t)(c + 1) * lda + r], xs[c + 1], s1);
+        s2 = fma(A[(size_t)(c + 2) * lda + r], xs[c + 2], s2);
+        s3 = fma(A[(size_t)(c + 3) * lda + r], xs[c + 3], s3);
+    }
+    for (; c < cols; ++c) s0 = fma(A[(size_t)c * lda + r], xs[c], s0);
+    const double s = (s0 + s1) + (s2 + s3);
+    y[r] = alpha * s + (y0 ? beta * y0[r] : 0.0);
+}
+// y (cols) = A' x : one warp per column
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ A, int lda, int rows, int cols,
+                                                     const double* __restrict__ x, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = gw; c < cols; c += nwarps) {
+        const double* cc = A + (size_t)c * lda;
+        double s = 0.0;
+        for (int r = lane; r < rows; r += 32) s = fma(cc[r], x[r], s);
+        s = s_warp_sum(s);
+        if (lane == 0) y[c] = s;
+    }
+}
+inline int gemv_n(const double* A, int lda, int rows, int cols, const double* x, double alpha, const double* y0, double beta,
+                  double* y, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    gemv_n_kernel<<<(rows + 255) / 256, 256, sizeof(double) * (size_t)(cols > 0 ? cols : 1), st>>>(A, lda, rows, cols, x, alpha, y0, beta, y);
+    return 1;
+}
+inline int gemv_t(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st) {
+    if (cols <= 0) return 0;
+    int grid = (cols + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    gemv_t_kernel<<<grid, 256, 0, st>>>(A, lda, rows, cols, x, y);
+    return 1;
+}
+
+// out[0] = ||v[lo:hi)||  (one CTA)
+__global__ void __launch_bounds__(1024) norm_range_kernel(const double* __restrict__ v, int lo, int hi, double* out) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) s = fma(v[r], v[r], s);
+    s = s_block_sum(s, sh);
+    if (threadIdx.x == 0) out[0] = sqrt(s);
+}
+// dst[i] = i < k ? src[i] : 0,  i < len
+__global__ void copy_pad_kernel(double* dst, const double* src, int k, int len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst[i] = (i < k) ? src[i] : 0.0;
+}
+// dst[i] = (idx[i] < k) ? src[idx[i]] : 0,  i < len      (x[invperm][..] of a zero-padded vector)
+__global__ void gather_pad_kernel(double* dst, const double* src, const int* idx, int k, int len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) { const int j = idx[i]; dst[i] = (j < k) ? src[j] : 0.0; }
+}
+// p1 = P[0:ra, 0:ra] * [dp1 (k entries); 0] : p1[perm[j]] = dp1[j] for j < k, perm[j] < ra   (dst pre-zeroed)
+__global__ void scatter_perm_kernel(double* dst, const double* src, const int* perm, int k, int ra) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k && j < ra) { const int r = perm[j]; if (r < ra) dst[r] = src[j]; }
+}
+// ---- rows of A (row-major l x n = column-major n x l) ----
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ Arow, int n, const int* __restrict__ active,
+                                                          double* __restrict__ CA) {
+    const double* src = Arow + (size_t)(active[blockIdx.x] - 1) * n;
+    double* dst = CA + (size_t)blockIdx.x * n;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = src[c];
+}
+__global__ void __launch_bounds__(256) row_norm_scale_kernel(double* __restrict__ CA, int n, int scaling, double* __restrict__ rown) {
+    __shared__ double sh[32];
+    double* row = CA + (size_t)blockIdx.x * n;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) s = fma(row[c], row[c], s);
+    s = s_block_sum(s, sh);
+    double nr = sqrt(s);
+    if (threadIdx.x == 0) rown[blockIdx.x] = nr;
+    if (scaling) {
+        if (fabs(nr) < 2.220446049250313e-16) nr = 1.0;
+        for (int c = threadIdx.x; c < n; c += blockDim.x) row[c] = row[c] / nr;
+    }
+}
+__global__ void __launch_bounds__(256) rebuild_scaled_rows_kernel(const double* __restrict__ Arow, int n,
+                                                                  const int* __restrict__ active, const double* __restrict__ ds,
+                                                                  double* __restrict__ CA) {
+    const double* src = Arow + (size_t)(active[blockIdx.x] - 1) * n;
+    double* dst = CA + (size_t)blockIdx.x * n;
+    const double d = ds[blockIdx.x];
+    for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = src[c] * d;
+}
+// Rt (t x kr, ld = t): Rt(c, r) = R_A(r, c), R_A = upper triangle of FA (ld = n)
+__global__ void build_rt_kernel(const double* __restrict__ FA, int n, int t, int kr, double* __restrict__ Rt) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)t * kr) return;
+    const int c = (int)(e % t), r = (int)(e / t);
+    Rt[e] = (r <= c) ? FA[(size_t)c * n + r] : 0.0;
+}
+
+}  // namespace enl_small

@@ -114,7 +114,7 @@ class LargeCnlsModel:
         v = np.zeros(12)
         capi.check_large(capi.lib().enlsipb200_large_stats(self._h, v.ctypes.data, 12))
         keys = ("points", "build_ms", "tsqr_ms", "linesearch_ms", "solve_wall_ms", "linesearch_evals",
-                "launches", "rows_pad", "device_qrcp", "device_mulq", "dense_ms", "factorisations")
+                "launches", "rows_pad", "device_qrcp", "device_mulq", "small_stage_ms", "factorisations")
         return dict(zip(keys, [float(a) for a in v]))
 
     def launch_count(self):

@@ -156,9 +156,19 @@ int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb20
  * device times of the two stages (CUDA events on the handle's stream) */
 int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
 /* cumulative counters: {points evaluated (new_point!), build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
- * evaluations (host clock around launch..result), kernels launched, padded local rows, device QRCPs, device M*Q products, ms in those two
- * (host clock, transfers included), factorisations of [J | r] (one per point from which the iteration continued)} */
+ * evaluations (host clock around launch..result), kernels launched, padded local rows, device QRCPs, device M*Q products,
+ * ms inside the small-stage calls (host clock: kernels + the waits for their results), factorisations of [J | r] (one per
+ * point from which the iteration continued)} */
 int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
+
+/* Known-answer hooks of the small stage's dense kernels (csrc/enl_small.cuh), host buffers, column major:
+ *   enlsipb200_dense_qrcp : `qr(M, ColumnNorm())` of src/enlsip_functions.jl:223 / :700 / :769 = LAPACK dgeqp3
+ *       f [rows x cols] in/out (dgeqp3 layout: R above, reflectors below the diagonal), tau [min(rows, cols)],
+ *       jpvt [cols] 0-based;
+ *   enlsipb200_dense_mulq : `J * F_A.Q` of src/enlsip_functions.jl:219: M [mr x nq] <- M * H(0) ... H(k-1), the
+ *       reflectors in f [nq x k] / tau [k] (dgeqp3 layout). */
+int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device);
+int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device);
 
 #ifdef __cplusplus
 }

@@ -74,3 +74,10 @@ extern "C" int hostport_solve(int family, long long B, const double* x0, const d
 extern "C" void hostport_det_exp(const double* x, double* y, long long n) {
     for (long long i = 0; i < n; ++i) y[i] = enl::det_exp(x[i]);
 }
+
+// Known-answer hook: the batched engine's `qr(., ColumnNorm())` restatement (enl_linalg.h qrcp_small, the routine every
+// lane runs on the group's shared state) on a host matrix: f [rows x cols] column major in/out, tau, jpvt (0-based).
+extern "C" void hostport_qrcp(int rows, int cols, double* f, double* tau, int* jpvt) {
+    std::vector<double> vn1(cols), vn2(cols);
+    qrcp_small(SV<1>{f}, rows, rows, cols, SV<1>{tau}, SI<1>{jpvt}, SV<1>{vn1.data()}, SV<1>{vn2.data()});
+}

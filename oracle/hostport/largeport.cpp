@@ -235,3 +235,15 @@ extern "C" int largeport_new_point(int n, long long m, const double* W, const do
     *rho_out = rt[n];
     return 0;
 }
+
+// Known-answer hook: the large regime's host `qr(., ColumnNorm())` restatement (enl_large_host.h QRP::factor):
+// f [rows x cols] column major in/out, tau [min(rows, cols)], jpvt [cols] 0-based.
+extern "C" void largeport_qrcp(int rows, int cols, double* f, double* tau, int* jpvt) {
+    Mat M(rows, cols);
+    std::memcpy(M.a.data(), f, sizeof(double) * (size_t)rows * cols);
+    QRP F;
+    F.factor(M);
+    std::memcpy(f, F.f.a.data(), sizeof(double) * (size_t)rows * cols);
+    for (int i = 0; i < F.k; ++i) tau[i] = F.tau[i];
+    for (int j = 0; j < cols; ++j) jpvt[j] = F.p[j];
+}

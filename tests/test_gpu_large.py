@@ -123,7 +123,8 @@ def test_large_full_size_properties(E):
 @pytest.mark.parametrize("m,n,nb,seed", [(4096, 512, 128, 31), (3000, 384, 64, 32)])
 def test_wide_problem_device_small_stage_vs_oracle(E, m, n, nb, seed):
     """BASELINE config 5 shape at reduced size (inequalities + bounds on every parameter, l = nb + 2n): the compressed
-    problem is large enough for the device QRCP / M*Q of enl_dense.cuh (src/enlsip_functions.jl:219-223, 700)."""
+    small stage (blocked QRCP, compact-WY J*Q1, triangular solves: csrc/enl_small.cuh; src/enlsip_functions.jl:219-223,
+    700) works on matrices beyond dgeqp3's blocking crossover."""
     from oracle import enlsip_oracle as O, problems as P
     from tests.test_large_host import compare_with_oracle
     d = E.synth.gen_single_index(m, n, nb, seed=seed, ineq=True)
@@ -131,7 +132,7 @@ def test_wide_problem_device_small_stage_vs_oracle(E, m, n, nb, seed):
     mod = E.LargeCnlsModel("single_index", d["x0"], d, ineq=True, x_low=lo, x_upp=up)
     E.solve(mod, trace_cap=60)
     st = mod.stats()
-    assert st["device_mulq"] > 0 and (n < 512 or st["device_qrcp"] > 0)      # the device path really ran
+    assert st["device_mulq"] > 0 and st["device_qrcp"] > 0                   # the device small stage really ran
     r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"], ineq=True, bounds=(-2.0, 2.0)), wallclock=False)
     out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, status=mod.status_code, iters=mod.iterations,
                nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
@@ -191,6 +192,32 @@ def test_c4_1M_rows_vs_golden(E, golden_dir):
         assert np.linalg.norm(mod.trace[0][i, 16:16 + n] - xi) <= 1e-10 * np.linalg.norm(xi), i
     assert np.linalg.norm(mod.sol[0] - gold["x"]) <= 1e-8 * np.linalg.norm(gold["x"])
     assert np.array_equal(np.sort(mod.active[0][: int(mod.nb_active[0])]), gold["active"])
+    mod.close()
+
+
+def test_c4_named_size_vs_golden(E, golden_dir):
+    """BASELINE config 4 at the NAMED size and on the data bench.py times (m = 2^22, n = 256, 64 equalities,
+    synth.gen_single_index seed 4) against the committed oracle solve on the full 4M x 256 Jacobian
+    (tests/golden/c4_2p22_oracle.npz, make_c4_fixture.py 22: 444 s on 8 cores): identical exit code / iteration count /
+    per-iteration trace / working set, objective 1e-10, iterates 1e-10 before the last step (flat merit function)."""
+    import os
+    gold = np.load(os.path.join(golden_dir, "c4_2p22_oracle.npz"))
+    m, n, nb = int(gold["m"]), 256, 64
+    assert m == 1 << 22
+    d = E.synth.gen_single_index(m, n, nb, seed=4)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d)
+    E.solve(mod, trace_cap=40)
+    assert int(mod.exit_code[0]) == int(gold["exit_code"]) and int(mod.iterations[0]) == int(gold["iterations"])
+    k = gold["trace"].shape[0]
+    assert np.array_equal(mod.trace[0][:k, 1:7].astype(np.int32), gold["trace"])
+    assert abs(float(mod.obj_value[0]) - float(gold["f"])) <= 1e-10 * float(gold["f"])
+    for i in range(k - 1):
+        xi = gold["x_iter"][i]
+        assert np.linalg.norm(mod.trace[0][i, 16:16 + n] - xi) <= 1e-10 * np.linalg.norm(xi), i
+    assert np.linalg.norm(mod.sol[0] - gold["x"]) <= 1e-8 * np.linalg.norm(gold["x"])
+    assert np.array_equal(np.sort(mod.active[0][: int(mod.nb_active[0])]), gold["active"])
+    st = mod.stats()
+    assert st["device_qrcp"] > 0 and st["device_mulq"] > 0
     mod.close()
 
 

@@ -109,6 +109,39 @@ def test_options_time_limit_max_iter_scaling(E):
     assert np.mean(np.asarray(m.status_code) == 1) > 0.85
 
 
+def test_batched_row_scaling_vs_live_oracle(E):
+    """solve!(model; scaling = true) (structures.jl:160-178, EF:504-506, 532-534, 739) in the batched engine against
+    the oracle's trace: HS65 (bounds + 1 inequality) and Gaussian peaks (1 equality + 12 bounds), analytic Jacobians."""
+    from oracle import enlsip_oracle as O, problems as P
+    x0 = E.synth.gen_hs65_batch(48, start=5000)
+    m = E.CnlsModel("hs65", x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    E.solve(m, trace_cap=60, scaling=True)
+    y, S, x0g, _ = E.synth.gen_gauss_peaks_batch(24, start=2_000_000)
+    g = E.CnlsModel("gauss_peaks", x0g, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="analytic")
+    E.solve(g, trace_cap=60, scaling=True)
+    cases = [(m, lambda b: P.hs65(x0[b]), 3, 48), (g, lambda b: P.gauss_peaks(y[b], S[b], x0g[b], fd=False), 6, 24)]
+    for mod, prob, n, B in cases:
+        same = 0
+        for b in range(B):
+            o = O.solve(prob(b), wallclock=False, scaling=True)
+            assert int(mod.status_code[b]) == o.status, (n, b, mod.exit_code[b], o.exit_code)
+            tr_ok = int(mod.iterations[b]) == o.iterations and int(mod.exit_code[b]) == o.exit_code and \
+                [int(v) for v in mod.active[b] if v > 0] == o.active
+            if tr_ok:
+                for k, tr in enumerate(o.trace[:60]):
+                    row = mod.trace[b, k]
+                    tr_ok = tr_ok and (tr.t, tr.rankA, tr.rankJ2, tr.dimA, tr.dimJ2, tr.code) == tuple(int(v) for v in row[1:7])
+            if tr_ok:
+                same += 1
+                if o.exit_code > -90:
+                    assert abs(mod.obj_value[b] - o.f) <= 1e-10 * max(abs(o.f), 1e-300), (n, b)
+                    if 2 <= len(o.trace) <= 60:
+                        xp = mod.trace[b, len(o.trace) - 2, 16:16 + n]
+                        assert np.linalg.norm(xp - o.trace[-2].x_new) <= 1e-10 * np.linalg.norm(xp), (n, b)
+        print("scaling=True parity: n=%d identical traces %d / %d" % (n, same, B))
+        assert same >= 0.95 * B, (n, same, B)
+
+
 def test_device_buffers_and_determinism(E):
     """torch CUDA tensors (zero copy) give bit-identical results to host buffers; re-solving is idempotent; results do
     not depend on the position of a problem in the batch (the work queue hands problems to arbitrary warps)."""
