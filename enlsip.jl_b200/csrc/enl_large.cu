@@ -348,11 +348,12 @@ struct LargeHandle : LargeOps, SmallBackend {
     void release() {
         cudaSetDevice(device);
         for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2, dJc, dArow, dCA, dCA2, dFA,
-                          dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, ww.Vb, ww.T, ww.W, ww.W2})
+                          dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, qw.pbest, qw.psum, ww.Vb, ww.T, ww.W, ww.W2, ww.part})
             if (p) cudaFree(p);
         for (double*& p : dvec) { if (p) cudaFree(p); p = nullptr; }
-        for (int* p : {dpA, dipA, dpL, dipL, dp2, dip2, dact, dbidx, qw.flags})
+        for (int* p : {dpA, dipA, dpL, dipL, dp2, dip2, dact, dbidx, qw.flags, qw.pidx})
             if (p) cudaFree(p);
+        qw.drop_graphs();
         if (qw.state) cudaFree(qw.state);
         if (qw.ticket) cudaFree(qw.ticket);
         qw = enl_small::QrWork();
@@ -436,6 +437,9 @@ struct LargeHandle : LargeOps, SmallBackend {
         LCU(cudaMalloc(&qw.vn2, sizeof(double) * maxc));
         LCU(cudaMalloc(&qw.F, sizeof(double) * (size_t)maxc * enl_small::QR_NB));
         LCU(cudaMalloc(&qw.auxv, sizeof(double) * enl_small::QR_NB));
+        LCU(cudaMalloc(&qw.pbest, sizeof(double) * enl_small::QR_MAXPART));
+        LCU(cudaMalloc(&qw.psum, sizeof(double) * enl_small::QR_MAXPART));
+        LCU(cudaMalloc(&qw.pidx, sizeof(int) * enl_small::QR_MAXPART));
         LCU(cudaMalloc(&qw.flags, sizeof(int) * maxc));
         LCU(cudaMalloc(&qw.state, sizeof(enl_small::QrState)));
         LCU(cudaMalloc(&qw.ticket, sizeof(unsigned int)));
@@ -443,6 +447,7 @@ struct LargeHandle : LargeOps, SmallBackend {
         LCU(cudaMalloc(&ww.T, sizeof(double) * 32 * 32));
         LCU(cudaMalloc(&ww.W, sizeof(double) * mt * 32));
         LCU(cudaMalloc(&ww.W2, sizeof(double) * mt * 32));
+        LCU(cudaMalloc(&ww.part, sizeof(double) * mt * 32 * enl_small::GEMM_MAX_SPLITS));
         // constant bound rows of A
         const int nlo = (int)sc.lo_idx.size(), nup = (int)sc.up_idx.size();
         if (nlo + nup > 0) {
@@ -589,17 +594,20 @@ struct LargeHandle : LargeOps, SmallBackend {
     }
     void k_reflect(const double* f, int frows, int k, const double* tau, double* v, int transpose) {
         if (frows <= 0) return;
-        enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
+        if (frows <= enl_small::VEC_WARP_MAX) enl_small::reflect_vec_warp_kernel<<<1, 32, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
+        else enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
         ++launches;
     }
     void k_trsv_upper(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
-        enl_small::trsv_upper_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upper_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        else enl_small::trsv_upper_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;
     }
     void k_trsv_upperT(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
-        enl_small::trsv_upperT_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upperT_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
+        else enl_small::trsv_upperT_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;
     }
     void k_copy_pad(double* dst, const double* src, int k, int len) {
@@ -930,6 +938,7 @@ LargeHandle* LH(enlsipb200_large h) { return reinterpret_cast<LargeHandle*>(h); 
 
 // scratch of the known-answer hooks (enlsipb200_dense_*)
 namespace {
+float g_dense_ms = 0.0f;     // device time (CUDA events) of the last hook call
 struct DenseScratch {
     enl_small::QrWork qw;
     enl_small::WyWork ww;
@@ -1126,19 +1135,33 @@ int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt,
     const int k = rows < cols ? rows : cols;
     bool ok = S.get(&df, (size_t)rows * cols) && S.get(&dtau, k) && S.get(&dp, cols) && S.get(&S.qw.vn1, cols) &&
               S.get(&S.qw.vn2, cols) && S.get(&S.qw.F, (size_t)cols * enl_small::QR_NB) && S.get(&S.qw.auxv, enl_small::QR_NB) &&
-              S.get(&S.qw.flags, cols) && S.get(&S.qw.state, 1) && S.get(&S.qw.ticket, 1);
+              S.get(&S.qw.flags, cols) && S.get(&S.qw.state, 1) && S.get(&S.qw.ticket, 1) &&
+              S.get(&S.qw.pbest, enl_small::QR_MAXPART) && S.get(&S.qw.psum, enl_small::QR_MAXPART) &&
+              S.get(&S.qw.pidx, enl_small::QR_MAXPART);
     if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
     S.qw.cap_cols = cols;
     LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice));
     LCU(cudaMemset(dtau, 0, sizeof(double) * k));
-    enl_small::qrcp_device(df, rows, cols, dtau, dp, S.qw, nullptr);
-    LCU(cudaDeviceSynchronize());
-    LCU(cudaGetLastError());
+    cudaStream_t hs = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    LCU(cudaStreamCreate(&hs));
+    LCU(cudaEventCreate(&ev0)); LCU(cudaEventCreate(&ev1));
+    LCU(cudaEventRecord(ev0, hs));
+    enl_small::qrcp_device(df, rows, cols, dtau, dp, S.qw, hs);
+    LCU(cudaEventRecord(ev1, hs));
+    cudaError_t es = cudaStreamSynchronize(hs);
+    if (es == cudaSuccess) es = cudaGetLastError();
+    cudaEventElapsedTime(&g_dense_ms, ev0, ev1);
+    S.qw.drop_graphs();
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(hs);
+    LCU(es);
     LCU(cudaMemcpy(f, df, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost));
     LCU(cudaMemcpy(tau, dtau, sizeof(double) * k, cudaMemcpyDeviceToHost));
     LCU(cudaMemcpy(jpvt, dp, sizeof(int) * cols, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+float enlsipb200_dense_last_ms(void) { return g_dense_ms; }
 
 int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device) {
     if (mr < 1 || nq < 1 || k < 0 || k > nq || !f || !tau || !M) return lfail(ENLSIPB200_EINVAL, "bad arguments");
@@ -1150,14 +1173,21 @@ int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* 
     double *df = nullptr, *dtau = nullptr, *dM = nullptr;
     bool ok = S.get(&df, (size_t)nq * (k > 0 ? k : 1)) && S.get(&dtau, k) && S.get(&dM, (size_t)mr * nq) &&
               S.get(&S.ww.Vb, (size_t)nq * 32) && S.get(&S.ww.T, 32 * 32) && S.get(&S.ww.W, (size_t)mr * 32) &&
-              S.get(&S.ww.W2, (size_t)mr * 32);
+              S.get(&S.ww.W2, (size_t)mr * 32) && S.get(&S.ww.part, (size_t)mr * 32 * enl_small::GEMM_MAX_SPLITS);
     if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
     LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)nq * k, cudaMemcpyHostToDevice));
     LCU(cudaMemcpy(dtau, tau, sizeof(double) * k, cudaMemcpyHostToDevice));
     LCU(cudaMemcpy(dM, M, sizeof(double) * (size_t)mr * nq, cudaMemcpyHostToDevice));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    LCU(cudaEventCreate(&ev0)); LCU(cudaEventCreate(&ev1));
+    LCU(cudaEventRecord(ev0, nullptr));
     enl_small::mulq_device(dM, mr, nq, df, nq, k, dtau, S.ww, nullptr);
-    LCU(cudaDeviceSynchronize());
-    LCU(cudaGetLastError());
+    LCU(cudaEventRecord(ev1, nullptr));
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es == cudaSuccess) es = cudaGetLastError();
+    cudaEventElapsedTime(&g_dense_ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    LCU(es);
     LCU(cudaMemcpy(M, dM, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -58,10 +58,9 @@ __device__ __forceinline__ void s_dmma884(double& d0, double& d1, double a, doub
 //   op(B) = B (K x N, ldb)            TRANSB = false
 //   op(B) = B' with B (N x K, ldb)    TRANSB = true
 // CTA tile 64 x 64, K in slabs of 32 staged through shared memory, 8 warps, each warp owns a 16 x 32 sub-tile
-// (2 x 4 m8n8 accumulators).  Grid-stride over the tiles: sizes may come from a device state block (dims != nullptr:
-// {M, N, K, rowoff, coloff, kcol0} are read on the device, see qrcp_device).
+// (2 x 4 m8n8 accumulators).  Grid-stride over the tiles.
 // =============================================================================================
-struct GemmDims { int M, N, K; };
+inline int imin_host(int a, int b) { return a < b ? a : b; }
 
 template <bool TRANSB>
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
@@ -151,18 +150,51 @@ inline int gemm(const double* A, int lda, const double* B, int ldb, double* C, i
     return 1;
 }
 
+// Skinny products (N <= 64, long K: W = M V of the compact-WY update): the K range is cut into `splits` slabs, one CTA per
+// (tile, slab) writes its partial product, a second kernel adds the partials in slab order (deterministic).
+template <bool TRANSB>
+__global__ void __launch_bounds__(256) gemm_dmma_splitk_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B,
+                                                               int ldb, double* __restrict__ part, int M, int N, int K, int kc) {
+    __shared__ double As[32][65];
+    __shared__ double Bs[32][65];
+    const int tmn = (M + 63) / 64, tnn = (N + 63) / 64;
+    const int ks = blockIdx.y, k0 = ks * kc;
+    const int kl = (K - k0) < kc ? (K - k0) : kc;
+    if (kl <= 0) return;
+    const double* Ak = A + (size_t)k0 * lda;
+    const double* Bk = TRANSB ? (B + (size_t)k0 * ldb) : (B + k0);
+    double* Cp = part + (size_t)ks * M * N;
+    for (int t = blockIdx.x; t < tmn * tnn; t += gridDim.x)
+        gemm_tile<TRANSB>(Ak, lda, Bk, ldb, Cp, M, M, N, kl, 1.0, 0.0, t % tmn, t / tmn, As, Bs);
+}
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int splits, long long mn, double alpha, double beta,
+                                     double* __restrict__ C, int M, int ldc) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= mn) return;
+    double t = 0.0;
+    for (int q = 0; q < splits; ++q) t += part[(size_t)q * mn + e];
+    double* cp = C + (size_t)(e / M) * ldc + (e % M);
+    *cp = (beta == 0.0) ? alpha * t : fma(beta, *cp, alpha * t);
+}
+constexpr int GEMM_MAX_SPLITS = 16;
+
 // =============================================================================================
 // QRCP (LAPACK dgeqp3 semantics)
 // =============================================================================================
 // Device state of one factorisation.
 struct QrState {
     int j0;        // first column of the current dlaqps panel (= number of finished columns)
-    int k;         // columns of the current panel already factored
+    int k;         // columns of the current panel already factored (valid when the panel ends)
     int stop;      // a norm has to be recomputed: the panel ends after k columns (dlaqps: lsticc != 0)
     int jb;        // columns this panel may take (min(nb, topbmn - j0))
     int active;    // the blocked phase still has work
-    double tau_k;  // tau of the panel column handed from the pivot kernel to the gemv kernel
+    int pvt;       // pivot column chosen for the panel column in flight
+    int anyflag;   // some column was flagged by the norm downdate of the column just finished
+    unsigned int ticket1, ticket2;
+    double tau_k, sc_k, beta_k;   // dlarfg scalars of the panel column in flight (the column itself is stored unscaled
+                                  // until the next finish kernel scales it in place)
 };
+constexpr int QR_MAXPART = 1024;   // partial results of the multi-CTA reductions
 
 __global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols, double* vn1, double* vn2, int* jpvt,
                                QrState* stt, int topbmn) {
@@ -179,77 +211,69 @@ __global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols,
             stt->j0 = 0; stt->k = 0; stt->stop = 0;
             stt->jb = topbmn < QR_NB ? topbmn : QR_NB;
             stt->active = topbmn > 0 ? 1 : 0;
-            stt->tau_k = 0.0;
+            stt->pvt = 0; stt->anyflag = 0; stt->ticket1 = 0; stt->ticket2 = 0;
+            stt->tau_k = 0.0; stt->sc_k = 1.0; stt->beta_k = 0.0;
         }
     }
 }
 
-// One CTA, 1024 threads.  Panel column k (global column jc = j0 + k, pivot row rk = jc):
-//   1. finish column k-1 (dlaqps lines after the F column): F(:, k-1) += F(:, 0:k-1) auxv; row rk-1 of A updated;
-//      partial-norm downdate of the trailing columns; a flagged column ends the panel (stop = 1);
-//   2. pivot search over vn1[jc..cols), swap of the columns of A, the rows of F, jpvt, vn1 / vn2;
-//   3. A(rk:, jc) -= A(rk:, j0:jc) F(k, 0:k)';   4. dlarfg.
-// F: cols x QR_NB (row = global column), auxv: QR_NB, flags: cols ints (1 = recompute this column's norm).
-__global__ void __launch_bounds__(1024) qr_panel_col_kernel(double* __restrict__ f, int rows, int cols, double* vn1,
-                                                             double* vn2, int* jpvt, double* tau, double* __restrict__ F,
-                                                             double* auxv, int* flags, QrState* stt, int kk) {
-    __shared__ double sh[32];
-    __shared__ double s_best[32];
-    __shared__ int s_idx[32];
-    __shared__ int s_pvt, s_any;
+// Panel column kk, kernel 1 of 3 (grid over the trailing columns, one THREAD per column; kk = 0 .. jb):
+//   finish column kk-1 (dlaqps, after the F column): F(j, kk-1) += F(j, 0:kk-1) auxv; pivot row of A updated;
+//   partial-norm downdate, a column under the tol3z rule is flagged and ends the panel;
+//   CTA 0 also scales the finished column in place (it was kept unscaled for the gemv) and stores beta;
+//   then the pivot search for column kk: first maximum of vn1 over the trailing columns, per-CTA candidates combined
+//   in index order by the last CTA (atomic ticket), which also swaps jpvt / vn1 / vn2 / the rows of F.
+__global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __restrict__ f, int rows, int cols, double* vn1,
+                                                                    double* vn2, int* jpvt, double* __restrict__ F,
+                                                                    const double* __restrict__ auxv, int* flags,
+                                                                    QrState* stt, double* pbest, int* pidx, int kk) {
     __shared__ double frow[QR_NB], aux[QR_NB];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
-    // kk: the host's column counter inside the panel (0 .. QR_NB; the call with kk == jb only finishes column jb - 1).
-    // stt->k = number of finished columns of the panel, valid when the panel ends (early stop or kk == jb).
+    __shared__ double s_best[8];
+    __shared__ int s_idx[8];
+    __shared__ int s_last;
     if (!stt->active || stt->stop) return;
     const int j0 = stt->j0, k = kk, jb = stt->jb;
     if (k > jb) return;
-    // ---- 1. finish column k-1 ----
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int jc = j0 + k;                       // the column about to be factored; trailing set = [jc, cols)
     if (k > 0) {
         const int kp = k - 1, jcp = j0 + kp, rkp = jcp;
-        if (tid < QR_NB) aux[tid] = (tid < kp) ? auxv[tid] : 0.0;
-        if (tid == 0) s_any = 0;
-        __syncthreads();
-        // F(j, kp) += sum_{i < kp} F(j, i) aux[i]   (all rows j of F: j0 .. cols-1; rows j0..jcp are 0 + update like LAPACK)
-        for (int j = j0 + tid; j < cols; j += blockDim.x) {
-            double s = 0.0;
-            for (int i = 0; i < kp; ++i) s = fma(F[(size_t)i * cols + j], aux[i], s);
-            if (kp > 0) F[(size_t)kp * cols + j] += s;
+        if (tid < QR_NB) {
+            aux[tid] = (tid < kp) ? auxv[tid] : 0.0;
+            frow[tid] = (tid < kp) ? f[(size_t)(j0 + tid) * rows + rkp] : (tid == kp ? 1.0 : 0.0);
+        }
+        if (blockIdx.x == 0) {                   // column jcp: v = [1; x * sc], R(rkp, jcp) = beta
+            const double sc = stt->sc_k;
+            double* cj = f + (size_t)jcp * rows;
+            if (sc != 1.0)
+                for (int r = rkp + 1 + tid; r < rows; r += blockDim.x) cj[r] *= sc;
+            if (tid == 0) cj[rkp] = stt->beta_k;
         }
         __syncthreads();
-        // row rkp of A, trailing columns: A(rkp, j) -= sum_{i <= kp} A(rkp, j0 + i) F(j, i)   (A(rkp, jcp) counts as 1)
-        if (tid < QR_NB) frow[tid] = (tid < kp) ? f[(size_t)(j0 + tid) * rows + rkp] : (tid == kp ? 1.0 : 0.0);
-        __syncthreads();
-        int any = 0;
-        for (int j = jcp + 1 + tid; j < cols; j += blockDim.x) {
+    }
+    double best = -1.0; int idx = cols;
+    int any = 0;
+    for (int j = jc + blockIdx.x * blockDim.x + tid; j < cols; j += gridDim.x * blockDim.x) {
+        if (k > 0) {
+            const int kp = k - 1, rkp = j0 + kp;
             double s = 0.0;
-            for (int i = 0; i <= kp; ++i) s = fma(frow[i], F[(size_t)i * cols + j], s);
+            for (int i = 0; i < kp; ++i) s = fma(F[(size_t)i * cols + j], aux[i], s);
+            const double fjk = F[(size_t)kp * cols + j] + s;
+            if (kp > 0) F[(size_t)kp * cols + j] = fjk;
+            double ru = frow[kp] * fjk;
+            for (int i = 0; i < kp; ++i) ru = fma(frow[i], F[(size_t)i * cols + j], ru);
             double* ap = f + (size_t)j * rows + rkp;
-            const double a = *ap - s;
+            const double a = *ap - ru;
             *ap = a;
             const double v1 = vn1[j];
             if (v1 != 0.0) {
                 double temp = fabs(a) / v1;
                 temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
                 const double rq = v1 / vn2[j];
-                const double temp2 = temp * (rq * rq);
-                if (temp2 <= S_TOL3Z) { flags[j] = 1; any = 1; }
+                if (temp * (rq * rq) <= S_TOL3Z) { flags[j] = 1; any = 1; }
                 else vn1[j] = v1 * sqrt(temp);
             }
         }
-        if (any) s_any = 1;
-        __syncthreads();
-        if (s_any) {
-            if (tid == 0) { stt->stop = 1; stt->k = k; }      // panel ends with k columns
-            return;
-        }
-    }
-    if (tid == 0) stt->k = k;
-    if (k >= jb) return;
-    // ---- 2. pivot ----
-    const int jc = j0 + k, rk = jc;
-    double best = -1.0; int idx = cols;
-    for (int j = jc + tid; j < cols; j += blockDim.x) {
         const double v = vn1[j];
         if (v > best) { best = v; idx = j; }
     }
@@ -259,92 +283,158 @@ __global__ void __launch_bounds__(1024) qr_panel_col_kernel(double* __restrict__
         const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
         if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
     }
+    __threadfence();                     // this thread's F / A / vn1 / flags writes before the ticket below
+    any = __syncthreads_or(any);
     if (lane == 0) { s_best[w] = best; s_idx[w] = idx; }
     __syncthreads();
     if (tid == 0) {
         double b = s_best[0]; int bi = s_idx[0];
-        for (int q = 1; q < nw; ++q)
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
             if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
-        if (bi >= cols) bi = jc;
-        s_pvt = bi;
-        if (bi != jc) {
-            const int tp = jpvt[bi]; jpvt[bi] = jpvt[jc]; jpvt[jc] = tp;
-            vn1[bi] = vn1[jc]; vn2[bi] = vn2[jc];
-        }
+        pbest[blockIdx.x] = b; pidx[blockIdx.x] = bi;
+        if (any) atomicOr(&stt->anyflag, 1);
+        __threadfence();
+        s_last = (atomicAdd(&stt->ticket1, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    const int pvt = s_pvt;
-    double* cj = f + (size_t)jc * rows;
-    if (pvt != jc) {
-        double* cp = f + (size_t)pvt * rows;
-        for (int r = tid; r < rows; r += blockDim.x) { const double a = cj[r]; cj[r] = cp[r]; cp[r] = a; }
-        for (int i = tid; i < k; i += blockDim.x) {
-            const double a = F[(size_t)i * cols + pvt]; F[(size_t)i * cols + pvt] = F[(size_t)i * cols + jc]; F[(size_t)i * cols + jc] = a;
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        stt->ticket1 = 0;
+        const int flagged = stt->anyflag;
+        stt->anyflag = 0;
+        if (flagged) { stt->stop = 1; stt->k = k; }
+        else {
+            stt->k = k;
+            if (k < jb) {
+                double b = -1.0; int bi = cols;
+                for (int q = 0; q < (int)gridDim.x; ++q) {
+                    const double pb = ((volatile double*)pbest)[q]; const int pi = ((volatile int*)pidx)[q];
+                    if (pb > b || (pb == b && pi < bi)) { b = pb; bi = pi; }
+                }
+                if (bi >= cols) bi = jc;
+                stt->pvt = bi;
+                if (bi != jc) {              // other CTAs wrote these: read past L1
+                    const int tp = __ldcg(jpvt + bi); jpvt[bi] = __ldcg(jpvt + jc); jpvt[jc] = tp;
+                    vn1[bi] = __ldcg(vn1 + jc); vn2[bi] = __ldcg(vn2 + jc);
+                    for (int i = 0; i < k; ++i) {
+                        const double t = __ldcg(F + (size_t)i * cols + bi);
+                        F[(size_t)i * cols + bi] = __ldcg(F + (size_t)i * cols + jc);
+                        F[(size_t)i * cols + jc] = t;
+                    }
+                }
+            }
         }
     }
-    __syncthreads();
-    // ---- 3. column update with the panel's earlier reflectors ----
-    if (k > 0) {
-        if (tid < QR_NB) frow[tid] = (tid < k) ? F[(size_t)tid * cols + jc] : 0.0;
-        __syncthreads();
-        for (int r = rk + tid; r < rows; r += blockDim.x) {
-            double s = 0.0;
-            for (int i = 0; i < k; ++i) s = fma(f[(size_t)(j0 + i) * rows + r], frow[i], s);
-            cj[r] -= s;
-        }
-        __syncthreads();
-    }
-    // ---- 4. dlarfg ----
-    double tau_k = 0.0;
-    if (rk < rows - 1) {
-        double s = 0.0;
-        for (int r = rk + 1 + tid; r < rows; r += blockDim.x) s = fma(cj[r], cj[r], s);
-        s = s_block_sum(s, sh);
-        const double xn = sqrt(s);
-        if (xn != 0.0) {
-            const double alpha = cj[rk];
-            const double beta = -copysign(s_lapy2(alpha, xn), alpha);
-            tau_k = (beta - alpha) / beta;
-            const double sc = 1.0 / (alpha - beta);
-            __syncthreads();
-            for (int r = rk + 1 + tid; r < rows; r += blockDim.x) cj[r] *= sc;
-            if (tid == 0) cj[rk] = beta;
-        }
-    }
-    if (tid == 0) { tau[jc] = tau_k; stt->tau_k = tau_k; }
 }
 
-// Grid kernel of panel column k: F(j, k) = tau * A(rk:, j)' v for the trailing columns j > jc (v = [1; A(rk+1:, jc)]),
-// F(j0..jc, k) = 0, and auxv(i) = -tau * A(rk:, j0 + i)' v for i < k.  One warp per column, v staged in shared memory.
+// kernel 2 of 3 (grid over row slices of 256): swap the pivot column in, A(rk:, jc) -= A(rk:, j0:jc) F(jc, 0:k)',
+// partial sums of squares below the diagonal; the last CTA (ticket) computes the dlarfg scalars.
+__global__ void __launch_bounds__(256) qr_panel_column_kernel(double* __restrict__ f, int rows, int cols, double* tau,
+                                                              const double* __restrict__ F, QrState* stt, double* psum, int kk) {
+    __shared__ double frow[QR_NB];
+    __shared__ double sh[32];
+    __shared__ int s_last;
+    if (!stt->active || stt->stop) return;
+    const int j0 = stt->j0, k = kk;
+    if (k >= stt->jb) return;
+    const int jc = j0 + k, rk = jc, pvt = stt->pvt;
+    const int tid = threadIdx.x;
+    if (tid < QR_NB) frow[tid] = (tid < k) ? F[(size_t)tid * cols + jc] : 0.0;
+    __syncthreads();
+    double* cj = f + (size_t)jc * rows;
+    double* cp = f + (size_t)pvt * rows;
+    double part = 0.0;
+    for (int r = blockIdx.x * blockDim.x + tid; r < rows; r += gridDim.x * blockDim.x) {
+        double a = cp[r];
+        if (pvt != jc) cp[r] = cj[r];
+        if (r >= rk) {
+            double s = 0.0;
+            for (int i = 0; i < k; ++i) s = fma(f[(size_t)(j0 + i) * rows + r], frow[i], s);
+            a -= s;
+            if (r > rk) part = fma(a, a, part);
+        }
+        cj[r] = a;
+    }
+    __threadfence();
+    part = s_block_sum(part, sh);
+    if (tid == 0) {
+        psum[blockIdx.x] = part;
+        __threadfence();
+        s_last = (atomicAdd(&stt->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last || tid != 0) return;
+    __threadfence();
+    stt->ticket2 = 0;
+    double tot = 0.0;
+    for (int q = 0; q < (int)gridDim.x; ++q) tot += ((volatile double*)psum)[q];
+    double tau_k = 0.0, sc = 1.0;
+    const double alpha = ((volatile double*)cj)[rk];
+    double beta = alpha;
+    if (rk < rows - 1) {
+        const double xn = sqrt(tot);
+        if (xn != 0.0) {
+            beta = -copysign(s_lapy2(alpha, xn), alpha);
+            tau_k = (beta - alpha) / beta;
+            sc = 1.0 / (alpha - beta);
+        }
+    }
+    tau[jc] = tau_k;
+    stt->tau_k = tau_k; stt->sc_k = sc; stt->beta_k = beta;
+}
+
+// kernel 3 of 3 (grid, 8 columns per CTA, threads walk the rows): with v = [1; sc * x] (x = the unscaled column jc below
+// the diagonal)  F(j, k) = tau * A(rk:, j)' v for the trailing columns j > jc,  F(j0..jc, k) = 0,
+// auxv(i) = -tau * A(rk:, j0 + i)' v for the panel columns i < k.
+constexpr int QR_GCOLS = 8;
 __global__ void __launch_bounds__(256) qr_panel_gemv_kernel(const double* __restrict__ f, int rows, int cols,
-                                                            double* __restrict__ F, double* auxv, QrState* stt, int kk) {
-    extern __shared__ double vs[];
+                                                            double* __restrict__ F, double* auxv, const QrState* stt, int kk) {
+    __shared__ double red[8][QR_GCOLS];
     if (!stt->active || stt->stop) return;
     const int j0 = stt->j0, k = kk;
     if (k >= stt->jb) return;
     const int jc = j0 + k, rk = jc;
-    const double tau_k = stt->tau_k;
-    const int len = rows - rk;
-    const double* cj = f + (size_t)jc * rows + rk;
-    for (int r = threadIdx.x; r < len; r += blockDim.x) vs[r] = (r == 0) ? 1.0 : cj[r];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    // items: trailing columns jc+1 .. cols-1, then the k panel columns (auxv), then the zero entries j0..jc
-    const int ntrail = cols - jc - 1;
-    for (int it = gw; it < ntrail + k; it += nwarps) {
-        const int col = (it < ntrail) ? (jc + 1 + it) : (j0 + (it - ntrail));
-        const double* cc = f + (size_t)col * rows + rk;
-        double s = 0.0;
-        for (int r = lane; r < len; r += 32) s = fma(cc[r], vs[r], s);
-        s = s_warp_sum(s);
-        if (lane == 0) {
-            if (it < ntrail) F[(size_t)k * cols + col] = tau_k * s;
-            else auxv[it - ntrail] = -tau_k * s;
+    const double tau_k = stt->tau_k, sc = stt->sc_k;
+    const int ntrail = cols - jc - 1, nitems = ntrail + k;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double* x = f + (size_t)jc * rows;
+    for (int it0 = blockIdx.x * QR_GCOLS; it0 < nitems; it0 += gridDim.x * QR_GCOLS) {
+        const double* cptr[QR_GCOLS];
+#pragma unroll
+        for (int c = 0; c < QR_GCOLS; ++c) {
+            int it = it0 + c;
+            if (it >= nitems) it = nitems - 1;
+            const int col = (it < ntrail) ? (jc + 1 + it) : (j0 + (it - ntrail));
+            cptr[c] = f + (size_t)col * rows;
+        }
+        double acc[QR_GCOLS];
+#pragma unroll
+        for (int c = 0; c < QR_GCOLS; ++c) acc[c] = 0.0;
+        for (int r = rk + 1 + tid; r < rows; r += 256) {
+            const double xv = x[r];
+#pragma unroll
+            for (int c = 0; c < QR_GCOLS; ++c) acc[c] = fma(cptr[c][r], xv, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < QR_GCOLS; ++c) acc[c] = s_warp_sum(acc[c]);
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int c = 0; c < QR_GCOLS; ++c) red[w][c] = acc[c];
+        __syncthreads();
+        if (tid < QR_GCOLS && it0 + tid < nitems) {
+            double t = 0.0;
+            for (int q = 0; q < 8; ++q) t += red[q][tid];
+            const int it = it0 + tid;
+            const int col = (it < ntrail) ? (jc + 1 + it) : (j0 + (it - ntrail));
+            const double dotv = f[(size_t)col * rows + rk] + sc * t;          // head of v is 1
+            if (it < ntrail) F[(size_t)k * cols + col] = tau_k * dotv;
+            else auxv[it - ntrail] = -tau_k * dotv;
         }
     }
     if (blockIdx.x == 0)
-        for (int j = j0 + threadIdx.x; j <= jc; j += blockDim.x) F[(size_t)k * cols + j] = 0.0;
+        for (int j = j0 + tid; j <= jc; j += blockDim.x) F[(size_t)k * cols + j] = 0.0;
 }
 
 // Trailing update of a finished panel (kb = stt->k columns): A(j0+kb:, j0+kb:) -= A(j0+kb:, j0:j0+kb) F(j0+kb:, 0:kb)'
@@ -502,6 +592,119 @@ __global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f
     }
 }
 
+// ---- the whole factorisation in ONE CTA (dlaqp2 semantics): matrices of up to QR_ONE_CTA_MAX entries, i.e. the small
+// stage of an n ~ 256 problem (config 4: 256 x 64, 64 x 64, 257 x 192), where a kernel launch per column step costs more
+// than the step.  32 warps: pivot search and dlarfg by the whole CTA, one warp per trailing column for H_i and the
+// partial-norm downdate (recompute rule applied on the spot, the trailing matrix is always up to date).
+constexpr long long QR_ONE_CTA_MAX = 160 * 1024;   // entries (1.25 MB): beyond this the L2 round trips of a single SM lose
+__global__ void __launch_bounds__(1024) qr_one_cta_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau,
+                                                          int* __restrict__ jpvt) {
+    extern __shared__ double sm[];          // vn1[cols] | vn2[cols] | v[rows]
+    __shared__ double sh[32];
+    __shared__ double s_best[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_pvt;
+    double* vn1 = sm;
+    double* vn2 = sm + cols;
+    double* v = sm + 2 * cols;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int k = rows < cols ? rows : cols;
+    for (int c = w; c < cols; c += 32) {
+        const double* cc = f + (size_t)c * rows;
+        double s = 0.0;
+        for (int r = lane; r < rows; r += 32) s = fma(cc[r], cc[r], s);
+        s = s_warp_sum(s);
+        if (lane == 0) { vn1[c] = vn2[c] = sqrt(s); jpvt[c] = c; }
+    }
+    __syncthreads();
+    for (int i = 0; i < k; ++i) {
+        double best = -1.0; int idx = cols;
+        for (int j = i + tid; j < cols; j += 1024) {
+            const double x = vn1[j];
+            if (x > best) { best = x; idx = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+        if (lane == 0) { s_best[w] = best; s_idx[w] = idx; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = s_best[0]; int bi = s_idx[0];
+            for (int q = 1; q < 32; ++q)
+                if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
+            if (bi >= cols) bi = i;
+            s_pvt = bi;
+            if (bi != i) {
+                const int tp = jpvt[bi]; jpvt[bi] = jpvt[i]; jpvt[i] = tp;
+                vn1[bi] = vn1[i]; vn2[bi] = vn2[i];
+            }
+        }
+        __syncthreads();
+        const int pvt = s_pvt;
+        double* ci = f + (size_t)i * rows;
+        double* cp = f + (size_t)pvt * rows;
+        // swap (rows above i too: they are finished rows of R) and stage the new column i (rows i..) in shared memory
+        double part = 0.0;
+        for (int r = tid; r < rows; r += 1024) {
+            const double a = cp[r];
+            if (pvt != i) { cp[r] = ci[r]; ci[r] = a; }
+            if (r >= i) v[r] = a;
+            if (r > i) part = fma(a, a, part);
+        }
+        double tau_i = 0.0;
+        if (i < rows - 1) {
+            const double xn = sqrt(s_block_sum(part, sh));     // syncs inside: v[] is visible afterwards
+            if (xn != 0.0) {
+                const double alpha = v[i];
+                const double beta = -copysign(s_lapy2(alpha, xn), alpha);
+                tau_i = (beta - alpha) / beta;
+                const double sc = 1.0 / (alpha - beta);
+                __syncthreads();
+                for (int r = i + 1 + tid; r < rows; r += 1024) { const double x = v[r] * sc; v[r] = x; ci[r] = x; }
+                if (tid == 0) ci[i] = beta;
+            }
+        }
+        if (tid == 0) tau[i] = tau_i;
+        __syncthreads();
+        // H_i on the trailing columns + dlaqp2 norm downdate, one warp per column
+        const int len = rows - i - 1;
+        for (int c = i + 1 + w; c < cols; c += 32) {
+            double* cc = f + (size_t)c * rows + i;
+            double c0 = cc[0];
+            if (tau_i != 0.0) {
+                double s = 0.0;
+                for (int r = lane; r < len; r += 32) s = fma(v[i + 1 + r], cc[1 + r], s);
+                s = s_warp_sum(s);
+                const double wv = (c0 + s) * tau_i;
+                for (int r = lane; r < len; r += 32) cc[1 + r] = fma(-wv, v[i + 1 + r], cc[1 + r]);
+                c0 -= wv;
+                if (lane == 0) cc[0] = c0;
+                __syncwarp();
+            }
+            const double v1 = vn1[c];
+            if (v1 != 0.0) {
+                const double tq = fabs(c0) / v1;
+                const double temp = fmax(1.0 - tq * tq, 0.0);
+                const double rq = v1 / vn2[c];
+                if (temp * (rq * rq) <= S_TOL3Z) {
+                    double s = 0.0;
+                    if (i < rows - 1) {
+                        for (int r = lane; r < len; r += 32) s = fma(cc[1 + r], cc[1 + r], s);
+                        s = s_warp_sum(s);
+                    }
+                    if (lane == 0) vn1[c] = vn2[c] = sqrt(s);
+                } else if (lane == 0) {
+                    vn1[c] = v1 * sqrt(temp);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // diag(R) and the inverse permutation of a finished factorisation
 __global__ void qr_finish_kernel(const double* __restrict__ f, int rows, int cols, const int* __restrict__ jpvt,
                                  double* diag, int* ipvt) {
@@ -511,19 +714,52 @@ __global__ void qr_finish_kernel(const double* __restrict__ f, int rows, int col
     if (i < cols) ipvt[jpvt[i]] = i;
 }
 
+struct QrGraph {          // one dlaqps panel (3 x 32 + 3 kernels) captured as a CUDA graph; indices come from the device state
+    cudaGraphExec_t exec = nullptr;
+    const void* f = nullptr; int rows = 0, cols = 0; const void* tau = nullptr; const void* jpvt = nullptr; int topbmn = 0;
+};
 struct QrWork {          // scratch of one factorisation (sized for the largest matrix of the solve)
-    double *vn1 = nullptr, *vn2 = nullptr, *F = nullptr, *auxv = nullptr;
-    int* flags = nullptr;
+    double *vn1 = nullptr, *vn2 = nullptr, *F = nullptr, *auxv = nullptr, *pbest = nullptr, *psum = nullptr;
+    int *flags = nullptr, *pidx = nullptr;
     QrState* state = nullptr;
     unsigned int* ticket = nullptr;
     int cap_cols = 0;
+    QrGraph graphs[6];
+    int next_graph = 0;
+    bool use_graphs = true;
+    void drop_graphs() {
+        for (QrGraph& g : graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = QrGraph(); }
+    }
 };
 
+inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, int topbmn, cudaStream_t st) {
+    const int g_fin = imin_host((cols + 255) / 256, QR_MAXPART), g_col = imin_host((rows + 255) / 256, QR_MAXPART);
+    const int g_gemv = imin_host((cols + QR_GCOLS - 1) / QR_GCOLS + 4, 148 * 8);
+    int launches = 0;
+    for (int k = 0; k < QR_NB; ++k) {
+        qr_panel_finish_pivot_kernel<<<g_fin, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.F, wk.auxv, wk.flags, wk.state, wk.pbest, wk.pidx, k);
+        qr_panel_column_kernel<<<g_col, 256, 0, st>>>(f, rows, cols, tau, wk.F, wk.state, wk.psum, k);
+        qr_panel_gemv_kernel<<<g_gemv, 256, 0, st>>>(f, rows, cols, wk.F, wk.auxv, wk.state, k);
+        launches += 3;
+    }
+    qr_panel_finish_pivot_kernel<<<g_fin, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.F, wk.auxv, wk.flags, wk.state, wk.pbest, wk.pidx, QR_NB);
+    qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+    qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
+    return launches + 3;
+}
+
 // f: rows x cols column major on the device, factored in place (dgeqp3 layout); tau [min(rows, cols)]; jpvt [cols]
-// (0-based).  Returns the number of kernels launched.  No host synchronisation.
+// (0-based).  Returns the number of kernels launched.  At most one host synchronisation (blocked phase only).
 inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
+    if ((long long)rows * cols <= QR_ONE_CTA_MAX && (size_t)(2 * cols + rows) * sizeof(double) <= 200 * 1024) {
+        const size_t shb = sizeof(double) * (size_t)(2 * cols + rows);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(qr_one_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        qr_one_cta_kernel<<<1, 1024, shb, st>>>(f, rows, cols, tau, jpvt);
+        return 1;
+    }
     // dgeqp3: blocked (dlaqps) while j <= topbmn = minmn - nx, if nb < minmn and nx < minmn
     int topbmn = (QR_NB < minmn && QR_NX < minmn) ? (minmn - QR_NX) : 0;
     int launches = 0;
@@ -532,24 +768,37 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
     qr_init_kernel<<<cols, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.state, topbmn);
     ++launches;
     if (topbmn > 0) {
-        const size_t shv = sizeof(double) * (size_t)rows;
-        const int ggrid = 148 * 2;
         // A panel that stops early (a norm to recompute) re-opens at its next column, so more than ceil(topbmn / nb)
         // panels may be needed; each stopped panel still retires at least one column.  Enqueue the regular count plus a
         // margin, then (rarely) top up after looking at the state.
-        int panels = (topbmn + QR_NB - 1) / QR_NB;
-        int budget = panels + 2;
+        const int per_panel = 3 * QR_NB + 3;
+        cudaGraphExec_t exec = nullptr;
+        if (wk.use_graphs && st != nullptr) {
+            for (QrGraph& g : wk.graphs)
+                if (g.exec && g.f == f && g.rows == rows && g.cols == cols && g.tau == tau && g.jpvt == jpvt && g.topbmn == topbmn) exec = g.exec;
+            if (!exec) {
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    qr_enqueue_panel(f, rows, cols, tau, jpvt, wk, topbmn, st);
+                    if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph &&
+                        cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                        QrGraph& slot = wk.graphs[wk.next_graph];
+                        wk.next_graph = (wk.next_graph + 1) % 6;
+                        if (slot.exec) cudaGraphExecDestroy(slot.exec);
+                        slot.exec = exec; slot.f = f; slot.rows = rows; slot.cols = cols; slot.tau = tau; slot.jpvt = jpvt; slot.topbmn = topbmn;
+                    } else {
+                        exec = nullptr;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                if (!exec) { cudaGetLastError(); wk.use_graphs = false; }
+            }
+        }
+        int budget = (topbmn + QR_NB - 1) / QR_NB + 2;
         for (;;) {
             for (int pnl = 0; pnl < budget; ++pnl) {
-                for (int k = 0; k < QR_NB; ++k) {
-                    qr_panel_col_kernel<<<1, 1024, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, tau, wk.F, wk.auxv, wk.flags, wk.state, k);
-                    qr_panel_gemv_kernel<<<ggrid, 256, shv, st>>>(f, rows, cols, wk.F, wk.auxv, wk.state, k);
-                    launches += 2;
-                }
-                qr_panel_col_kernel<<<1, 1024, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, tau, wk.F, wk.auxv, wk.flags, wk.state, QR_NB);
-                qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
-                qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
-                launches += 3;
+                if (exec) { cudaGraphLaunch(exec, st); launches += per_panel; }
+                else launches += qr_enqueue_panel(f, rows, cols, tau, jpvt, wk, topbmn, st);
             }
             QrState h;
             cudaMemcpyAsync(&h, wk.state, sizeof(QrState), cudaMemcpyDeviceToHost, st);
@@ -584,16 +833,27 @@ __global__ void wy_build_v_kernel(const double* __restrict__ f, int frows, int j
     const int r = (int)(e % len), c = (int)(e / len);
     Vb[e] = (r < c) ? 0.0 : (r == c ? 1.0 : f[(size_t)(j0 + c) * frows + j0 + r]);
 }
-// dlarft (forward, columnwise): T (pw x pw upper, ld = 32) from Vb and tau; one CTA
+// dlarft (forward, columnwise): T (pw x pw upper, ld = 32) from Vb and tau; one CTA.  The Gram matrix V'V is accumulated
+// from 64-row slabs of Vb staged in shared memory (coalesced loads), thread (a, b) owns G(a, b).
 __global__ void __launch_bounds__(1024) wy_build_t_kernel(const double* __restrict__ Vb, int len, int pw,
                                                           const double* __restrict__ tau, double* __restrict__ T) {
+    __shared__ double Vs[64][33];
     __shared__ double G[32][33];
     __shared__ double Ts[32][33];
     __shared__ double tmp[32];
     const int a = threadIdx.x & 31, b = threadIdx.x >> 5;     // G(a, b) = V(:, a)' V(:, b), a < b
     double s = 0.0;
-    if (a < b && b < pw)
-        for (int r = b; r < len; ++r) s = fma(Vb[(size_t)a * len + r], Vb[(size_t)b * len + r], s);
+    for (int r0 = 0; r0 < len; r0 += 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * 32; e += 1024) {
+            const int rr = e & 63, c = e >> 6;
+            Vs[rr][c] = (r0 + rr < len && c < pw) ? Vb[(size_t)c * len + r0 + rr] : 0.0;
+        }
+        __syncthreads();
+        if (a < b)
+#pragma unroll 8
+            for (int rr = 0; rr < 64; ++rr) s = fma(Vs[rr][a], Vs[rr][b], s);
+    }
     G[a][b] = s;
     Ts[a][b] = 0.0;
     __syncthreads();
@@ -614,7 +874,7 @@ __global__ void __launch_bounds__(1024) wy_build_t_kernel(const double* __restri
     T[b * 32 + a] = (a < pw && b < pw) ? Ts[a][b] : 0.0;    // column major, ld = 32
 }
 
-struct WyWork { double *Vb = nullptr, *T = nullptr, *W = nullptr, *W2 = nullptr; };   // Vb: frows x 32, T: 32 x 32, W/W2: mr x 32
+struct WyWork { double *Vb = nullptr, *T = nullptr, *W = nullptr, *W2 = nullptr, *part = nullptr; };   // Vb: frows x 32, T: 32 x 32, W/W2: mr x 32, part: GEMM_MAX_SPLITS x mr x 32
 
 // M: mr x nq column major (ld = mr); f: frows (= nq) x k
 inline int mulq_device(double* M, int mr, int nq, const double* f, int frows, int k, const double* tau, WyWork& wk,
@@ -629,7 +889,19 @@ inline int mulq_device(double* M, int mr, int nq, const double* f, int frows, in
         wy_build_t_kernel<<<1, 1024, 0, st>>>(wk.Vb, len, pw, tau + j0, wk.T);
         launches += 2;
         // W = M(:, j0:) Vb ; W2 = W T ; M(:, j0:) -= W2 Vb'
-        launches += gemm<false>(M + (size_t)j0 * mr, mr, wk.Vb, len, wk.W, mr, mr, pw, len, 1.0, 0.0, st);
+        int splits = len / 256;                                   // W = M V: N = 32, K = len
+        if (splits > GEMM_MAX_SPLITS) splits = GEMM_MAX_SPLITS;
+        if (splits >= 2 && wk.part) {
+            const int kc = ((len + splits - 1) / splits + 31) / 32 * 32;
+            splits = (len + kc - 1) / kc;
+            dim3 grid((mr + 63) / 64, splits);
+            gemm_dmma_splitk_kernel<false><<<grid, 256, 0, st>>>(M + (size_t)j0 * mr, mr, wk.Vb, len, wk.part, mr, pw, len, kc);
+            const long long mn = (long long)mr * pw;
+            splitk_reduce_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(wk.part, splits, mn, 1.0, 0.0, wk.W, mr, mr);
+            launches += 2;
+        } else {
+            launches += gemm<false>(M + (size_t)j0 * mr, mr, wk.Vb, len, wk.W, mr, mr, pw, len, 1.0, 0.0, st);
+        }
         launches += gemm<false>(wk.W, mr, wk.T, 32, wk.W2, mr, mr, pw, pw, 1.0, 0.0, st);
         launches += gemm<true>(wk.W2, mr, wk.Vb, len, M + (size_t)j0 * mr, mr, mr, len, pw, -1.0, 1.0, st);
     }
@@ -663,6 +935,64 @@ __global__ void __launch_bounds__(1024) reflect_vec_kernel(const double* __restr
     }
     for (int r = threadIdx.x; r < frows; r += blockDim.x) v[r] = vsm[r];
 }
+
+// the same sweep by ONE warp (no block barrier): vectors of a few hundred entries, where 32 warps only wait for each other
+__global__ void __launch_bounds__(32) reflect_vec_warp_kernel(const double* __restrict__ f, int frows, int k,
+                                                              const double* __restrict__ tau, double* __restrict__ v,
+                                                              int transpose) {
+    extern __shared__ double vsm[];
+    const int lane = threadIdx.x;
+    for (int r = lane; r < frows; r += 32) vsm[r] = v[r];
+    __syncwarp();
+    for (int s = 0; s < k; ++s) {
+        const int i = transpose ? s : (k - 1 - s);
+        const double ti = tau[i];
+        if (ti == 0.0) continue;
+        const double* ci = f + (size_t)i * frows;
+        double acc = 0.0;
+        for (int r = i + 1 + lane; r < frows; r += 32) acc = fma(ci[r], vsm[r], acc);
+        acc = s_warp_sum(acc);
+        const double w = (vsm[i] + acc) * ti;
+        __syncwarp();
+        for (int r = i + 1 + lane; r < frows; r += 32) vsm[r] = fma(-w, ci[r], vsm[r]);
+        if (lane == 0) vsm[i] -= w;
+        __syncwarp();
+    }
+    for (int r = lane; r < frows; r += 32) v[r] = vsm[r];
+}
+// triangular solves by one warp, column oriented (k of a few hundred): x_i = x_i / R_ii, then the remaining entries
+__global__ void __launch_bounds__(32) trsv_upper_warp_kernel(const double* __restrict__ f, int ldf, int k, double* __restrict__ x) {
+    extern __shared__ double xs[];
+    const int lane = threadIdx.x;
+    for (int r = lane; r < k; r += 32) xs[r] = x[r];
+    __syncwarp();
+    for (int i = k - 1; i >= 0; --i) {
+        const double* ci = f + (size_t)i * ldf;
+        const double xi = xs[i] / ci[i];
+        __syncwarp();
+        for (int r = lane; r < i; r += 32) xs[r] = fma(-ci[r], xi, xs[r]);
+        if (lane == 0) xs[i] = xi;
+        __syncwarp();
+    }
+    for (int r = lane; r < k; r += 32) x[r] = xs[r];
+}
+__global__ void __launch_bounds__(32) trsv_upperT_warp_kernel(const double* __restrict__ f, int ldf, int k, double* __restrict__ x) {
+    extern __shared__ double xs[];
+    const int lane = threadIdx.x;
+    for (int r = lane; r < k; r += 32) xs[r] = x[r];
+    __syncwarp();
+    for (int i = 0; i < k; ++i) {
+        const double* ci = f + (size_t)i * ldf;
+        double s = 0.0;
+        for (int r = lane; r < i; r += 32) s = fma(ci[r], xs[r], s);
+        s = s_warp_sum(s);
+        __syncwarp();
+        if (lane == 0) xs[i] = (xs[i] - s) / ci[i];
+        __syncwarp();
+    }
+    for (int r = lane; r < k; r += 32) x[r] = xs[r];
+}
+constexpr int VEC_WARP_MAX = 640;     // up to this many entries the one-warp kernels are used
 
 // x (k entries) <- UpperTriangular(f[0:k, 0:k]) \ x ; one CTA of 1024 threads, blocks of 32 from the bottom
 __global__ void __launch_bounds__(1024) trsv_upper_kernel(const double* __restrict__ f, int ldf, int k, double* __restrict__ x) {

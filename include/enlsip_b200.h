@@ -169,6 +169,8 @@ int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
  *       reflectors in f [nq x k] / tau [k] (dgeqp3 layout). */
 int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device);
 int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device);
+/* device time (CUDA events around the kernels, transfers excluded) of the last enlsipb200_dense_* call, in ms */
+float enlsipb200_dense_last_ms(void);
 
 #ifdef __cplusplus
 }
