@@ -16,8 +16,10 @@
 // Everything is enqueued on one stream; indices that depend on the data (where a dlaqps panel stops) live in a device
 // state block, so the host never synchronises inside a factorisation.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace enl_small {
 
@@ -217,7 +219,8 @@ __global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols,
     }
 }
 
-// Panel column kk, kernel 1 of 3 (grid over the trailing columns, one THREAD per column; kk = 0 .. jb):
+// F is stored row-major here: F(j, i) at F[j * QR_NB + i] (one 256-byte line per column j of the matrix).
+// Panel column kk, kernel 1 of 3 (grid over the trailing columns, one WARP per column, lane = panel index; kk = 0 .. jb):
 //   finish column kk-1 (dlaqps, after the F column): F(j, kk-1) += F(j, 0:kk-1) auxv; pivot row of A updated;
 //   partial-norm downdate, a column under the tol3z rule is flagged and ends the panel;
 //   CTA 0 also scales the finished column in place (it was kept unscaled for the gemv) and stores beta;
@@ -227,61 +230,53 @@ __global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __re
                                                                     double* vn2, int* jpvt, double* __restrict__ F,
                                                                     const double* __restrict__ auxv, int* flags,
                                                                     QrState* stt, double* pbest, int* pidx, int kk) {
-    __shared__ double frow[QR_NB], aux[QR_NB];
-    __shared__ double s_best[8];
-    __shared__ int s_idx[8];
+    __shared__ double s_best[32];
+    __shared__ int s_idx[32];
     __shared__ int s_last;
     if (!stt->active || stt->stop) return;
     const int j0 = stt->j0, k = kk, jb = stt->jb;
     if (k > jb) return;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
     const int jc = j0 + k;                       // the column about to be factored; trailing set = [jc, cols)
+    const int kp = k - 1, rkp = j0 + kp;
+    double aux_l = 0.0, frow_l = 0.0;            // lane i: auxv(i) for i < kp; A(rkp, j0 + i) for i < kp, 1 for i == kp
     if (k > 0) {
-        const int kp = k - 1, jcp = j0 + kp, rkp = jcp;
-        if (tid < QR_NB) {
-            aux[tid] = (tid < kp) ? auxv[tid] : 0.0;
-            frow[tid] = (tid < kp) ? f[(size_t)(j0 + tid) * rows + rkp] : (tid == kp ? 1.0 : 0.0);
-        }
+        aux_l = (lane < kp) ? auxv[lane] : 0.0;
+        frow_l = (lane < kp) ? f[(size_t)(j0 + lane) * rows + rkp] : (lane == kp ? 1.0 : 0.0);
         if (blockIdx.x == 0) {                   // column jcp: v = [1; x * sc], R(rkp, jcp) = beta
             const double sc = stt->sc_k;
-            double* cj = f + (size_t)jcp * rows;
+            double* cj = f + (size_t)rkp * rows;
             if (sc != 1.0)
                 for (int r = rkp + 1 + tid; r < rows; r += blockDim.x) cj[r] *= sc;
             if (tid == 0) cj[rkp] = stt->beta_k;
         }
-        __syncthreads();
     }
-    double best = -1.0; int idx = cols;
+    double best = -1.0; int idx = cols;          // per warp (identical in its lanes)
     int any = 0;
-    for (int j = jc + blockIdx.x * blockDim.x + tid; j < cols; j += gridDim.x * blockDim.x) {
+    for (int j = jc + blockIdx.x * nw + w; j < cols; j += gridDim.x * nw) {
+        double v = 0.0;
         if (k > 0) {
-            const int kp = k - 1, rkp = j0 + kp;
-            double s = 0.0;
-            for (int i = 0; i < kp; ++i) s = fma(F[(size_t)i * cols + j], aux[i], s);
-            const double fjk = F[(size_t)kp * cols + j] + s;
-            if (kp > 0) F[(size_t)kp * cols + j] = fjk;
-            double ru = frow[kp] * fjk;
-            for (int i = 0; i < kp; ++i) ru = fma(frow[i], F[(size_t)i * cols + j], ru);
+            double fl = (lane <= kp) ? F[(size_t)j * QR_NB + lane] : 0.0;   // F(j, lane); beyond kp: stale, never read
+            const double s = s_warp_sum(fl * aux_l);                 // lanes >= kp contribute 0
+            const double fjk = __shfl_sync(0xffffffffu, fl, kp) + s;
+            if (lane == kp) { fl = fjk; if (kp > 0) F[(size_t)j * QR_NB + kp] = fjk; }
+            const double ru = s_warp_sum(frow_l * fl);               // sum_{i <= kp} A(rkp, j0 + i) F(j, i)
             double* ap = f + (size_t)j * rows + rkp;
-            const double a = *ap - ru;
-            *ap = a;
-            const double v1 = vn1[j];
+            const double a = __shfl_sync(0xffffffffu, (lane == 0) ? *ap : 0.0, 0) - ru;
+            double v1 = vn1[j];
             if (v1 != 0.0) {
                 double temp = fabs(a) / v1;
                 temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
                 const double rq = v1 / vn2[j];
-                if (temp * (rq * rq) <= S_TOL3Z) { flags[j] = 1; any = 1; }
-                else vn1[j] = v1 * sqrt(temp);
+                if (temp * (rq * rq) <= S_TOL3Z) { any = 1; if (lane == 0) flags[j] = 1; }
+                else { v1 = v1 * sqrt(temp); if (lane == 0) vn1[j] = v1; }
             }
+            if (lane == 0) *ap = a;
+            v = v1;
+        } else {
+            v = vn1[j];
         }
-        const double v = vn1[j];
         if (v > best) { best = v; idx = j; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
     }
     __threadfence();                     // this thread's F / A / vn1 / flags writes before the ticket below
     any = __syncthreads_or(any);
@@ -289,7 +284,7 @@ __global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __re
     __syncthreads();
     if (tid == 0) {
         double b = s_best[0]; int bi = s_idx[0];
-        for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+        for (int q = 1; q < nw; ++q)
             if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
         pbest[blockIdx.x] = b; pidx[blockIdx.x] = bi;
         if (any) atomicOr(&stt->anyflag, 1);
@@ -299,29 +294,48 @@ __global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid == 0) {
-        stt->ticket1 = 0;
-        const int flagged = stt->anyflag;
-        stt->anyflag = 0;
-        if (flagged) { stt->stop = 1; stt->k = k; }
-        else {
+    // last CTA: combine the per-CTA candidates (parallel loads past L1, first maximum), bookkeeping by thread 0
+    double b = -1.0; int bi = cols;
+    for (int q = tid; q < (int)gridDim.x; q += blockDim.x) {
+        const double pb = __ldcg(pbest + q); const int pi = __ldcg(pidx + q);
+        if (pb > b || (pb == b && pi < bi)) { b = pb; bi = pi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_best[w] = b; s_idx[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        // warp 0 finishes: lanes hold the per-warp results
+        b = (lane < nw) ? s_best[lane] : -1.0; bi = (lane < nw) ? s_idx[lane] : cols;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+        }
+        const int flagged = __ldcg(&stt->anyflag);
+        if (bi >= cols) bi = jc;
+        const bool pivoting = !flagged && k < jb;
+        if (pivoting && bi != jc && lane < k) {          // swap the rows of F (k <= 32 entries)
+            const double t = __ldcg(F + (size_t)bi * QR_NB + lane);
+            F[(size_t)bi * QR_NB + lane] = __ldcg(F + (size_t)jc * QR_NB + lane);
+            F[(size_t)jc * QR_NB + lane] = t;
+        }
+        if (lane == 0) {
+            stt->ticket1 = 0;
+            stt->anyflag = 0;
             stt->k = k;
-            if (k < jb) {
-                double b = -1.0; int bi = cols;
-                for (int q = 0; q < (int)gridDim.x; ++q) {
-                    const double pb = ((volatile double*)pbest)[q]; const int pi = ((volatile int*)pidx)[q];
-                    if (pb > b || (pb == b && pi < bi)) { b = pb; bi = pi; }
-                }
-                if (bi >= cols) bi = jc;
+            if (flagged) stt->stop = 1;
+            else if (k < jb) {
                 stt->pvt = bi;
                 if (bi != jc) {              // other CTAs wrote these: read past L1
                     const int tp = __ldcg(jpvt + bi); jpvt[bi] = __ldcg(jpvt + jc); jpvt[jc] = tp;
                     vn1[bi] = __ldcg(vn1 + jc); vn2[bi] = __ldcg(vn2 + jc);
-                    for (int i = 0; i < k; ++i) {
-                        const double t = __ldcg(F + (size_t)i * cols + bi);
-                        F[(size_t)i * cols + bi] = __ldcg(F + (size_t)i * cols + jc);
-                        F[(size_t)i * cols + jc] = t;
-                    }
                 }
             }
         }
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(256) qr_panel_column_kernel(double* __restrict
     if (k >= stt->jb) return;
     const int jc = j0 + k, rk = jc, pvt = stt->pvt;
     const int tid = threadIdx.x;
-    if (tid < QR_NB) frow[tid] = (tid < k) ? F[(size_t)tid * cols + jc] : 0.0;
+    if (tid < QR_NB) frow[tid] = (tid < k) ? F[(size_t)jc * QR_NB + tid] : 0.0;
     __syncthreads();
     double* cj = f + (size_t)jc * rows;
     double* cp = f + (size_t)pvt * rows;
@@ -364,11 +378,16 @@ __global__ void __launch_bounds__(256) qr_panel_column_kernel(double* __restrict
         s_last = (atomicAdd(&stt->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (!s_last || tid != 0) return;
+    if (!s_last) return;
     __threadfence();
+    // last CTA: the partial sums in CTA order (loads in parallel, fixed-order adds by thread 0 through shared memory)
+    __shared__ double ps[QR_MAXPART];
+    for (int q = tid; q < (int)gridDim.x; q += blockDim.x) ps[q] = __ldcg(psum + q);
+    __syncthreads();
+    if (tid != 0) return;
     stt->ticket2 = 0;
     double tot = 0.0;
-    for (int q = 0; q < (int)gridDim.x; ++q) tot += ((volatile double*)psum)[q];
+    for (int q = 0; q < (int)gridDim.x; ++q) tot += ps[q];
     double tau_k = 0.0, sc = 1.0;
     const double alpha = ((volatile double*)cj)[rk];
     double beta = alpha;
@@ -429,12 +448,12 @@ __global__ void __launch_bounds__(256) qr_panel_gemv_kernel(const double* __rest
             const int it = it0 + tid;
             const int col = (it < ntrail) ? (jc + 1 + it) : (j0 + (it - ntrail));
             const double dotv = f[(size_t)col * rows + rk] + sc * t;          // head of v is 1
-            if (it < ntrail) F[(size_t)k * cols + col] = tau_k * dotv;
+            if (it < ntrail) F[(size_t)col * QR_NB + k] = tau_k * dotv;
             else auxv[it - ntrail] = -tau_k * dotv;
         }
     }
     if (blockIdx.x == 0)
-        for (int j = j0 + tid; j <= jc; j += blockDim.x) F[(size_t)k * cols + j] = 0.0;
+        for (int j = j0 + tid; j <= jc; j += blockDim.x) F[(size_t)j * QR_NB + k] = 0.0;
 }
 
 // Trailing update of a finished panel (kb = stt->k columns): A(j0+kb:, j0+kb:) -= A(j0+kb:, j0:j0+kb) F(j0+kb:, 0:kb)'
@@ -449,11 +468,11 @@ __global__ void __launch_bounds__(256) qr_panel_trail_kernel(double* __restrict_
     const int M = rows - r0, N = cols - c0;
     if (M <= 0 || N <= 0) return;
     const double* A = f + (size_t)j0 * rows + r0;          // M x kb, lda = rows
-    const double* B = F + c0;                               // N x kb, ldb = cols
+    const double* B = F + (size_t)c0 * QR_NB;               // F(c0:, 0:kb)' = kb x N column major, ldb = QR_NB
     double* C = f + (size_t)c0 * rows + r0;
     const int tmn = (M + 63) / 64, tnn = (N + 63) / 64;
     for (int t = blockIdx.x; t < tmn * tnn; t += gridDim.x)
-        gemm_tile<true>(A, rows, B, cols, C, rows, M, N, kb, -1.0, 1.0, t % tmn, t / tmn, As, Bs);
+        gemm_tile<false>(A, rows, B, QR_NB, C, rows, M, N, kb, -1.0, 1.0, t % tmn, t / tmn, As, Bs);
 }
 
 // After the trailing update: recompute the flagged norms (dlaqps: the lsticc list), one CTA per candidate column;
@@ -705,6 +724,174 @@ __global__ void __launch_bounds__(1024) qr_one_cta_kernel(double* __restrict__ f
     }
 }
 
+// ---- the whole factorisation in ONE THREAD-BLOCK CLUSTER (dlaqp2 semantics), the matrix resident in shared memory ----
+// Column c of the matrix lives in the shared memory of CTA c % 8 (slot c / 8).  Per column step: every CTA proposes its
+// best remaining column (first maximum of the partial norms by current position), the proposals are exchanged through
+// distributed shared memory, the owner of the winner runs dlarfg and stores the reflector into every CTA's shared
+// memory, then each CTA applies it to its own columns (one warp per column) and downdates their norms.  Two cluster
+// barriers per step and no L2 round trip: a 257 x 192 factorisation (config 4's J2) is ~2 us per column.
+// Columns are never moved: `pos` tracks the position dlaqp2's swaps would have given them.
+constexpr int QC_CTAS = 8, QC_THREADS = 512;
+constexpr size_t QC_MAX_SMEM = 200 * 1024;
+inline size_t qc_smem_bytes(int rows, int cols) {
+    const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
+    return sizeof(double) * ((size_t)ncl * rows + rows + 2 + 2 * (size_t)ncl + QC_CTAS) + sizeof(int) * ((size_t)ncl + cols + 2 * QC_CTAS + 2);
+}
+__global__ void __cluster_dims__(QC_CTAS, 1, 1) __launch_bounds__(QC_THREADS)
+qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau, int* __restrict__ jpvt) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ double sm[];
+    __shared__ double sh[32];
+    __shared__ double s_rb[16];
+    __shared__ int s_rp[16], s_rs[16];
+    __shared__ int s_wphys;
+    const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
+    double* Al = sm;                                // [ncl][rows]
+    double* vbuf = Al + (size_t)ncl * rows;         // [rows] reflector (entries i+1..), [rows] = tau
+    double* vn1 = vbuf + rows + 2;                  // [ncl]
+    double* vn2 = vn1 + ncl;                        // [ncl]
+    double* cval = vn2 + ncl;                       // [QC_CTAS] proposals: value
+    int* pos = reinterpret_cast<int*>(cval + QC_CTAS);   // [ncl] current position of the local column
+    int* l2p = pos + ncl;                           // [cols] position -> column (replicated in every CTA)
+    int* cpos = l2p + cols;                         // [QC_CTAS] proposals: position
+    int* cphys = cpos + QC_CTAS;                    // [QC_CTAS] proposals: column
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = QC_THREADS / 32;
+    const int nloc = (cols > rank) ? (cols - rank + QC_CTAS - 1) / QC_CTAS : 0;     // my columns: rank, rank + 8, ...
+    const int k = rows < cols ? rows : cols;
+    for (int s = w; s < nloc; s += nw) {
+        const double* src = f + (size_t)(rank + s * QC_CTAS) * rows;
+        double* dst = Al + (size_t)s * rows;
+        double acc = 0.0;
+        for (int r = lane; r < rows; r += 32) { const double x = src[r]; dst[r] = x; acc = fma(x, x, acc); }
+        acc = s_warp_sum(acc);
+        if (lane == 0) { vn1[s] = vn2[s] = sqrt(acc); pos[s] = rank + s * QC_CTAS; }
+    }
+    for (int c = tid; c < cols; c += QC_THREADS) l2p[c] = c;
+    cluster.sync();        // every CTA has read its input: the output may overwrite f at the end
+    for (int i = 0; i < k; ++i) {
+        // ---- 1. local proposal: largest vn1 among my columns still to the right of i, ties -> smallest position
+        double best = -1.0; int bpos = 0x7fffffff, bslot = -1;
+        for (int s = tid; s < nloc; s += QC_THREADS) {
+            const int p = pos[s];
+            if (p >= i) {
+                const double x = vn1[s];
+                if (x > best || (x == best && p < bpos)) { best = x; bpos = p; bslot = s; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+            if (ob > best || (ob == best && op < bpos)) { best = ob; bpos = op; bslot = os; }
+        }
+        if (lane == 0) { s_rb[w] = best; s_rp[w] = bpos; s_rs[w] = bslot; }
+        __syncthreads();
+        if (tid < QC_CTAS) {
+            double b = s_rb[0]; int bp = s_rp[0], bs = s_rs[0];
+            for (int q = 1; q < nw; ++q)
+                if (s_rb[q] > b || (s_rb[q] == b && s_rp[q] < bp)) { b = s_rb[q]; bp = s_rp[q]; bs = s_rs[q]; }
+            // thread t delivers this CTA's proposal to CTA t
+            double* rv = cluster.map_shared_rank(cval, tid);
+            int* rp = cluster.map_shared_rank(cpos, tid);
+            int* rph = cluster.map_shared_rank(cphys, tid);
+            rv[rank] = b; rp[rank] = bp; rph[rank] = (bs >= 0) ? (rank + bs * QC_CTAS) : -1;
+        }
+        cluster.sync();
+        // ---- 2. the winner, identically in every CTA; position bookkeeping of dlaqp2's column swap
+        if (tid == 0) {
+            double b = -1.0; int bp = 0x7fffffff, bph = -1;
+            for (int q = 0; q < QC_CTAS; ++q)
+                if (cphys[q] >= 0 && (cval[q] > b || (cval[q] == b && cpos[q] < bp))) { b = cval[q]; bp = cpos[q]; bph = cphys[q]; }
+            if (bph < 0) { bp = i; bph = l2p[i]; }          // nothing comparable (NaN norms): keep the column in place
+            const int q = l2p[i];                           // the column sitting at position i moves to the winner's place
+            l2p[bp] = q; l2p[i] = bph;
+            if (q % QC_CTAS == rank) pos[q / QC_CTAS] = bp;
+            if (bph % QC_CTAS == rank) pos[bph / QC_CTAS] = i;
+            s_wphys = bph;
+        }
+        __syncthreads();
+        const int wphys = s_wphys;
+        // ---- 3. owner: dlarfg, reflector into every CTA
+        if (wphys % QC_CTAS == rank) {
+            double* col = Al + (size_t)(wphys / QC_CTAS) * rows;
+            double tau_i = 0.0;
+            if (i < rows - 1) {
+                double part = 0.0;
+                for (int r = i + 1 + tid; r < rows; r += QC_THREADS) part = fma(col[r], col[r], part);
+                const double xn = sqrt(s_block_sum(part, sh));
+                if (xn != 0.0) {
+                    const double alpha = col[i];
+                    const double beta = -copysign(s_lapy2(alpha, xn), alpha);
+                    tau_i = (beta - alpha) / beta;
+                    const double sc = 1.0 / (alpha - beta);
+                    __syncthreads();
+                    for (int r = i + 1 + tid; r < rows; r += QC_THREADS) col[r] *= sc;
+                    if (tid == 0) col[i] = beta;
+                    __syncthreads();
+                }
+            }
+            const int len = rows - i - 1;
+            for (int e = tid; e < (len + 1) * QC_CTAS; e += QC_THREADS) {
+                const int dstr = e % QC_CTAS, r = e / QC_CTAS;       // r == len: the tau slot
+                double* rv = cluster.map_shared_rank(vbuf, dstr);
+                if (r < len) rv[i + 1 + r] = col[i + 1 + r];
+                else rv[rows] = tau_i;
+            }
+            if (tid == 0) tau[i] = tau_i;
+        }
+        cluster.sync();
+        // ---- 4. H_i on my remaining columns + dlaqp2 norm downdate, one warp per column
+        const double tau_i = vbuf[rows];
+        const int len = rows - i - 1;
+        for (int s = w; s < nloc; s += nw) {
+            if (pos[s] <= i) continue;
+            double* cc = Al + (size_t)s * rows + i;
+            double c0 = cc[0];
+            if (tau_i != 0.0) {
+                double acc = 0.0;
+                for (int r = lane; r < len; r += 32) acc = fma(vbuf[i + 1 + r], cc[1 + r], acc);
+                acc = s_warp_sum(acc);
+                const double wv = (c0 + acc) * tau_i;
+                for (int r = lane; r < len; r += 32) cc[1 + r] = fma(-wv, vbuf[i + 1 + r], cc[1 + r]);
+                c0 -= wv;
+                __syncwarp();
+                if (lane == 0) cc[0] = c0;
+            }
+            const double v1 = vn1[s];
+            if (v1 != 0.0) {
+                const double tq = fabs(c0) / v1;
+                const double temp = fmax(1.0 - tq * tq, 0.0);
+                const double rq = v1 / vn2[s];
+                if (temp * (rq * rq) <= S_TOL3Z) {
+                    double acc = 0.0;
+                    if (i < rows - 1) {
+                        for (int r = lane; r < len; r += 32) acc = fma(cc[1 + r], cc[1 + r], acc);
+                        acc = s_warp_sum(acc);
+                    }
+                    __syncwarp();
+                    if (lane == 0) vn1[s] = vn2[s] = sqrt(acc);
+                } else {
+                    __syncwarp();
+                    if (lane == 0) vn1[s] = v1 * sqrt(temp);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    // output in dgeqp3 layout: the column now at position p goes to column p of f
+    for (int s = w; s < nloc; s += nw) {
+        const int p = pos[s];
+        const double* src = Al + (size_t)s * rows;
+        double* dst = f + (size_t)p * rows;
+        for (int r = lane; r < rows; r += 32) dst[r] = src[r];
+        if (lane == 0) jpvt[p] = rank + s * QC_CTAS;
+    }
+}
+
 // diag(R) and the inverse permutation of a finished factorisation
 __global__ void qr_finish_kernel(const double* __restrict__ f, int rows, int cols, const int* __restrict__ jpvt,
                                  double* diag, int* ipvt) {
@@ -733,7 +920,7 @@ struct QrWork {          // scratch of one factorisation (sized for the largest 
 };
 
 inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, int topbmn, cudaStream_t st) {
-    const int g_fin = imin_host((cols + 255) / 256, QR_MAXPART), g_col = imin_host((rows + 255) / 256, QR_MAXPART);
+    const int g_fin = imin_host((cols + 7) / 8, QR_MAXPART), g_col = imin_host((rows + 255) / 256, QR_MAXPART);
     const int g_gemv = imin_host((cols + QR_GCOLS - 1) / QR_GCOLS + 4, 148 * 8);
     int launches = 0;
     for (int k = 0; k < QR_NB; ++k) {
@@ -753,6 +940,12 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
 inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
+    if (qc_smem_bytes(rows, cols) <= QC_MAX_SMEM && !getenv("ENLSIP_QR_NO_CLUSTER")) {
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM); attr_set = true; }
+        qr_cluster_kernel<<<QC_CTAS, QC_THREADS, qc_smem_bytes(rows, cols), st>>>(f, rows, cols, tau, jpvt);
+        return 1;
+    }
     if ((long long)rows * cols <= QR_ONE_CTA_MAX && (size_t)(2 * cols + rows) * sizeof(double) <= 200 * 1024) {
         const size_t shb = sizeof(double) * (size_t)(2 * cols + rows);
         static bool attr_set = false;

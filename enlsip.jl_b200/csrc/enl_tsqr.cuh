@@ -797,10 +797,11 @@ tsqr_trail_staged_kernel(double* __restrict__ A, int ld, long long nblk, long lo
 }
 
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
+// (one CTA per row: at n = 4096 a single CTA needed 140 us per panel)
 __global__ void tsqr_extract_kernel(double* __restrict__ A, int ld, int col0, int ncols, double* __restrict__ Rout,
                                     int ldr) {
-    for (int idx = threadIdx.x; idx < TS_B * (ld - col0); idx += blockDim.x) {
-        int r = idx / (ld - col0), c = col0 + idx % (ld - col0);
+    const int r = blockIdx.x;
+    for (int c = col0 + threadIdx.x; c < ld; c += blockDim.x) {
         double v = A[(long long)r * ld + c];
         if (c < col0 + TS_B && c - col0 < r) v = 0.0;
         if (c < ncols) Rout[(long long)(col0 + r) * ldr + c] = v;
@@ -877,7 +878,7 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             }
             stride *= TS_FAN;
         }
-        tsqr_extract_kernel<<<1, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);
+        tsqr_extract_kernel<<<TS_B, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);
         ++launches;
     }
     const int nparts = 296;
