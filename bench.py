@@ -109,6 +109,11 @@ def cpu_port(B, nthreads, seed_start=0):
     import __graft_entry__ as ge
     import enlsip_jl_b200 as E
     lib = ctypes.CDLL(ge.build_hostport())
+    # every `qr(., ColumnNorm())` of the solve runs in OpenBLAS' dgeqp3 (the routine Julia calls), not in the engine's
+    # restatement of it (oracle/hostport/hostport.cpp: hostport_use_lapack)
+    lib.hostport_use_lapack.argtypes = [ctypes.c_char_p]
+    blas = ge.openblas_path()
+    cpu_port.lapack = bool(blas) and lib.hostport_use_lapack(blas.encode()) == 0
 
     class Opt(ctypes.Structure):
         _fields_ = [("max_iter", ctypes.c_int), ("scaling", ctypes.c_int), ("jac_mode", ctypes.c_int),
@@ -156,42 +161,166 @@ def fp64_tensor_peak():
     return 40.0, "fallback: B200 FP64 tensor datasheet figure"
 
 
-def gen_large_shard(torch, dev, m_global, row0, rows, n=LARGE_N, nb=LARGE_NB, chunk=1 << 18):
-    """Device-side synthetic single-index problem; rows [row0, row0 + rows) of the global matrix.
-    Chunks of 2^18 rows own their generator seed, so every world size sees the same global W and y."""
-    g0 = torch.Generator(device=dev).manual_seed(4)
-    truth = torch.rand(n, dtype=torch.float64, device=dev, generator=g0) * 2 - 1
-    x0 = truth * (1 + 0.05 * (torch.rand(n, dtype=torch.float64, device=dev, generator=g0) * 2 - 1))
-    W = torch.empty(rows, n, dtype=torch.float64, device=dev)
-    y = torch.empty(rows, dtype=torch.float64, device=dev)
-    for c in range(row0 // chunk, (row0 + rows - 1) // chunk + 1):
-        g = torch.Generator(device=dev).manual_seed(4000 + c)
-        Wc = torch.randn(chunk, n, dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
-        yc = torch.tanh(Wc @ truth) + 0.01 * torch.randn(chunk, dtype=torch.float64, device=dev, generator=g)
-        lo, hi = max(row0, c * chunk), min(row0 + rows, (c + 1) * chunk)
-        W[lo - row0:hi - row0] = Wc[lo - c * chunk:hi - c * chunk]
-        y[lo - row0:hi - row0] = yc[lo - c * chunk:hi - c * chunk]
-        del Wc, yc
-    tr = truth.cpu().numpy()
-    rho = (tr[:4 * nb] ** 2).reshape(nb, 4).sum(axis=1)
-    return W, y, x0.cpu().numpy(), rho
-
-
-def large_cpu_baseline(sample_rows, m_global):
-    """The reference's dense path for one C4-shaped problem on the host cores: the oracle restatement (numpy + the
-    same LAPACK dgeqp3/dormqr/dtrtrs Julia calls, OpenBLAS threads = all cores) on a row sample; the cost of an
-    iteration is linear in m, so iterations/s at m_global = (sample iterations/s) * sample_rows / m_global."""
+def gen_large_shard(torch, dev, m_global, row0, rows, n=LARGE_N, nb=LARGE_NB):
+    """Rows [row0, row0 + rows) of the C4 problem of SURVEY.md 8d: synth.gen_single_index(m, 256, 64, seed=4), the very
+    data of tests/golden/c4_2p22_oracle.npz (row chunks own their generator seed, so every world size sees the same
+    global W and y).  Generated on the host, then moved to the device."""
     import enlsip_jl_b200 as E
-    from oracle import enlsip_oracle as O, problems as P
-    d = E.synth.gen_single_index(sample_rows, LARGE_N, LARGE_NB, seed=4)
+    d = E.synth.gen_single_index(m_global, n, nb, seed=4, start=row0, rows=rows)
+    W = torch.from_numpy(d["W"]).to(dev)
+    y = torch.from_numpy(d["y"]).to(dev)
+    return W, y, d["x0"], d["rho"]
+
+
+def c5_flops(n, m, t):
+    """Dense FP64 flops of one Gauss-Newton iteration of the reference's own math:
+    qr(A_act') 2nt^2 - 2/3 t^3, J*Q1 4mnt, qr(J2) 2mk^2 - 2/3 k^3 with k = n - t."""
+    k = n - t
+    return 2.0 * n * t * t - 2.0 / 3.0 * t ** 3 + 4.0 * m * n * t + 2.0 * m * k * k - 2.0 / 3.0 * k ** 3
+
+
+def large_cpu_reference(n, m_rows, nb, seed, ineq, bounds, cores):
+    """One Gauss-Newton iteration of the reference's dense algorithm on the host cores (oracle/hostport/largeport.cpp
+    largeport_ref_iteration): new_point!, dgeqp3 of A_act', dormqr J*Q1 on the full m x n Jacobian, dgeqp3 of J2,
+    triangular solves -- the LAPACK routines Julia calls, from the SciPy wheel's OpenBLAS, all threads.
+    Returns (seconds, t, phase seconds) or None when the library cannot be bound."""
+    import ctypes
+    import __graft_entry__ as ge
+    import enlsip_jl_b200 as E
+    blas = ge.openblas_path()
+    if not blas:
+        return None
+    lib = ctypes.CDLL(ge.build_largeport())
+    vp = ctypes.c_void_p
+    lib.largeport_ref_iteration.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                            vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]
+    d = E.synth.gen_single_index(m_rows, n, nb, seed=seed, ineq=ineq)
+    lo = None if bounds is None else np.full(n, float(bounds[0]))
+    up = None if bounds is None else np.full(n, float(bounds[1]))
+    secs = np.zeros(5); pdir = np.zeros(n); t = ctypes.c_int(0)
+    pp = lambda a: None if a is None else a.ctypes.data_as(vp)
+    rc = lib.largeport_ref_iteration(blas.encode(), n, m_rows, nb, 1 if ineq else 0, pp(lo), pp(up), pp(d["W"]), pp(d["y"]),
+                                     pp(d["rho"]), pp(d["x0"]), cores, pp(secs), pp(pdir), ctypes.byref(t))
+    if rc != 0:
+        return None
+    return float(secs[0]), int(t.value), [float(v) for v in secs]
+
+
+def large_cpu_baseline(sample_rows, m_global, passes_per_iteration=4.0 / 3.0):
+    """C4 on the host cores: the reference's algorithm with OpenBLAS LAPACK on `sample_rows` of the m_global rows (the
+    whole problem when sample_rows == m_global).  Every dense step of an iteration is linear in m, so
+    seconds(m_global) = seconds(sample) * m_global / sample_rows.  `passes_per_iteration`: a solve that reports k
+    iterations executes k + 1 passes of the loop (EF:2776-2878; the last one terminates) -- 4 passes for the 3 reported
+    iterations of this problem, the same accounting as the GPU arm."""
+    cores = os.cpu_count() or 1
+    got = large_cpu_reference(LARGE_N, sample_rows, LARGE_NB, 4, False, None, cores)
+    if got is None:
+        return {"value": None, "unit": "iters/s", "cores": cores, "kind": "reference-algorithm", "sample": "OpenBLAS could not be bound"}
+    secs, t, ph = got
+    per_pass = secs * m_global / sample_rows
+    v = 1.0 / (per_pass * passes_per_iteration)
+    return {"value": v, "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": "%d of the %d rows (n=256, 64 equalities): one pass of the reference's dense iteration "
+                      "(new_point! %.2f s, dgeqp3(A') + dormqr J*Q1 %.2f s, dgeqp3(J2) %.2f s, solves %.2f s) with OpenBLAS "
+                      "LAPACK on all cores, scaled linearly to %d rows, %.3g passes per reported iteration; C++ restatement "
+                      "(oracle/hostport/largeport.cpp) -- Julia itself is absent from this image"
+                      % (sample_rows, m_global, ph[1], ph[2], ph[3], ph[4], m_global, passes_per_iteration)}
+
+
+C5_N, C5_M, C5_NB = 4096, 16384, 1024
+C5_METRIC = "GN iters/s (n=4096,m=16384)"
+
+
+def c5_cpu_baseline(scale=2, passes_per_iteration=8.0 / 7.0, t_full=511):
+    """C5 on the host cores: the same reference-algorithm pass on the problem shrunk by `scale` in every dimension
+    (one problem cannot be row-sampled without changing its shape), scaled by the algorithmic flop ratio."""
+    cores = os.cpu_count() or 1
+    n, m, nb = C5_N // scale, C5_M // scale, C5_NB // scale
+    got = large_cpu_reference(n, m, nb, 5, True, (-2.0, 2.0), cores)
+    if got is None:
+        return {"value": None, "unit": "iters/s", "cores": cores, "kind": "reference-algorithm", "sample": "OpenBLAS could not be bound"}
+    secs, t, ph = got
+    ratio = c5_flops(C5_N, C5_M, t_full) / c5_flops(n, m, t)
+    per_pass = secs * ratio
+    return {"value": 1.0 / (per_pass * passes_per_iteration), "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": "the C5 family at n=%d, m=%d, %d inequalities + bounds (t = %d active): one pass of the reference's dense "
+                      "iteration with OpenBLAS LAPACK on all cores in %.2f s (new_point! %.2f, dgeqp3(A') + dormqr J*Q1 %.2f, "
+                      "dgeqp3(J2) %.2f, solves %.2f), scaled by the flop ratio %.1f to the named size (t = %d), %.3g passes "
+                      "per reported iteration" % (n, m, nb, t, secs, ph[1], ph[2], ph[3], ph[4], ratio, t_full, passes_per_iteration)}
+
+
+def c5_arm(args, torch, E, dev, local):
+    """BASELINE.json config 5 (n = 4096, m = 16384, 1024 inequalities + 8192 bounds) on ONE GPU ("replicas only",
+    SURVEY.md 8e): one step = one complete solve from x0."""
+    d = E.synth.gen_single_index(C5_M, C5_N, C5_NB, seed=5, ineq=True)
+    lo, up = np.full(C5_N, -2.0), np.full(C5_N, 2.0)
+    W = torch.from_numpy(d["W"]).to(dev)
+    y = torch.from_numpy(d["y"]).to(dev)
+    mod = E.LargeCnlsModel("single_index", d["x0"], {"W": W, "y": y, "rho": d["rho"]}, ineq=True, x_low=lo, x_upp=up, device=local)
+    for _ in range(max(1, args.large_warmup)):
+        E.solve(mod, trace_cap=40)
+    ts = [int(v) for v in mod.trace[0][: int(mod.iterations[0]) + 1, 1]]
+    st0 = mod.stats()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"]), wallclock=False)
+    its = 0
+    for _ in range(args.c5_steps):
+        E.solve(mod)
+        its += int(mod.iterations[0])
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    v = r.iterations / dt * sample_rows / m_global
-    return {"value": v, "unit": "iters/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "%d of the %d rows (n=256, 64 equalities): %d oracle iterations in %.2f s, scaled linearly in m; "
-                      "oracle = numpy + SciPy LAPACK restatement of Enlsip.jl (Julia itself is absent from this image)"
-                      % (sample_rows, m_global, r.iterations, dt)}
+    st1 = mod.stats()
+    dst = {k: st1[k] - st0[k] for k in st1 if k != "rows_pad"}
+    nfac = max(dst["factorisations"], 1.0)
+    flops_it = [c5_flops(C5_N, C5_M, t) for t in ts if t > 0]
+    flops_mean = float(np.mean(flops_it)) if flops_it else c5_flops(C5_N, C5_M, 511)
+    peak, peak_src = fp64_tensor_peak()
+    per_pass_s = dt / max(dst["points"] - args.c5_steps, 1.0)          # passes of the loop = points evaluated - 1 per solve
+    achieved = flops_mean / per_pass_s / 1e12
+    res = {"metric": C5_METRIC, "value": its / dt, "unit": "iters/s", "n_gpus": 1, "steps": args.c5_steps,
+           "warmup": max(1, args.large_warmup), "scaling": "replicas only (SURVEY.md 8e)", "higher_is_better": True, "dtype": "f64",
+           "ms_per_iteration": dt * 1e3 / max(its, 1), "iterations_reported_by_solver_per_solve": its / args.c5_steps,
+           "passes_of_the_loop_per_solve": (dst["points"] - args.c5_steps) / args.c5_steps,
+           "working_set_sizes": ts, "exit_code": int(mod.exit_code[0]), "objective": float(mod.obj_value[0]),
+           "config": {"workload": "C5 single-index n=4096 m=16384, 1024 inequalities + 8192 bounds (BASELINE.json config 5)",
+                      "l2": "W is 0.54 GB, [J | r] 0.54 GB, the compressed problem 0.13 GB: larger than L2"},
+           "phases_ms_per_pass": {"build_J_r_grad": dst["build_ms"] / max(dst["points"], 1.0), "tsqr": dst["tsqr_ms"] / nfac,
+                                  "small_stage_device": dst["small_stage_ms"] / nfac,
+                                  "host_other": (dst["solve_wall_ms"] - dst["build_ms"] - dst["tsqr_ms"] - dst["small_stage_ms"]
+                                                 - dst["linesearch_ms"]) / nfac},
+           "device_qrcp_per_solve": dst["device_qrcp"] / args.c5_steps, "gpu_launches": int(dst["launches"]),
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src,
+                        "kernel": "one pass of the iteration: TSQR of [J | r] (tsqr_*), blocked QRCP of A_act', R_A' and J2 "
+                                  "(qr_panel_* + DMMA trailing update), compact-WY J~ Q1 (gemm_dmma_*)",
+                        "algorithmic_flops_per_pass": flops_mean,
+                        "note": "algorithmic flops of the REFERENCE's math per pass (SURVEY.md 8d formula at the measured working-set "
+                                "sizes) / wall time of a pass; the engine itself executes fewer flops (it pivots on the compressed "
+                                "(n+1) x (n+1) problem), and the pivoted panels are BLAS-2 (L2-bandwidth bound) by nature"}}
+    if args.large_e2e_steps > 0:
+        W_h = torch.from_numpy(d["W"]).pin_memory()
+        y_h = torch.from_numpy(d["y"]).pin_memory()
+        mod.close()
+        del W, y, mod
+        hm = E.LargeCnlsModel("single_index", d["x0"], {"W": W_h.numpy(), "y": y_h.numpy(), "rho": d["rho"]}, ineq=True,
+                              x_low=lo, x_upp=up, device=local)
+        E.solve(hm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        it2 = 0
+        for _ in range(args.large_e2e_steps):
+            hm.set_data(0, W_h.numpy())
+            hm.set_data(1, y_h.numpy())
+            E.solve(hm)
+            it2 += int(hm.iterations[0])
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+        res["e2e"] = {"value": it2 / dt2, "unit": "iters/s", "h2d_bytes_per_step": int(C5_M * (C5_N + 1) * 8 + C5_N * 8),
+                      "d2h_bytes_per_step": C5_N * 8 + 8 + 16}
+        hm.close()
+    else:
+        mod.close()
+    return res
 
 
 def large_arm(args, torch, dist, E, rank, world, local, dev):
@@ -230,24 +359,29 @@ def large_arm(args, torch, dist, E, rank, world, local, dev):
     dst = {k: st1[k] - st0[k] for k in st1 if k != "rows_pad"}
     nfac = max(dst["factorisations"], 1.0)
     npts = max(dst["points"], 1.0)
-    # executed Gauss-Newton iterations: every pass of the `while exit_code == 0` loop (EF:2776-2878) ends with one
-    # new_point!, and one more precedes the loop; the solver's own counter does not count the terminating pass.
-    # The point at which the solve terminates is evaluated (r, J'r, c) but not factored: factorisations = iterations.
-    iters = int(npts) - args.large_steps
+    # `value` counts the iterations the solver reports (length of iterations_detail, 3 for this problem) -- the same
+    # count in both arms.  Every pass of the `while exit_code == 0` loop (EF:2776-2878) ends with one new_point!, one
+    # more precedes the loop, so passes = points - solves (4: the last pass terminates); the point at which the solve
+    # terminates is evaluated (r, J'r, c) but not factored: factorisations = passes.
+    iters = iters_solver
+    passes = int(npts) - args.large_steps
     tsqr_ms = dst["tsqr_ms"] / nfac
     flops = 2.0 * m_global * (LARGE_N + 1) ** 2          # Householder R factor of the augmented [J | r]
     peak, peak_src = fp64_tensor_peak()
     achieved = flops / world / (tsqr_ms * 1e-3) / 1e12  # per GPU: its m/world rows in its own tsqr time
     res = {"metric": LARGE_METRIC, "value": iters / dt, "unit": "iters/s", "n_gpus": world, "steps": args.large_steps,
            "warmup": max(1, args.large_warmup), "scaling": "strong", "higher_is_better": True, "dtype": "f64",
-           "ms_per_iteration": dt * 1e3 / iters, "iterations_per_solve": iters / args.large_steps,
-           "iterations_reported_by_solver_per_solve": iters_solver / args.large_steps,
+           "ms_per_iteration": dt * 1e3 / iters, "iterations_reported_by_solver_per_solve": iters_solver / args.large_steps,
+           "passes_of_the_loop_per_solve": passes / args.large_steps, "ms_per_pass": dt * 1e3 / max(passes, 1),
            "exit_code": int(mod.exit_code[0]), "status": int(mod.status_code[0]), "objective": float(mod.obj_value[0]),
            "config": {"workload": "C4 single-index m=%d n=256 q=64 (BASELINE.json config 4), analytic Jacobian" % m_global,
                       "rows_per_gpu": rows, "sharding": "row blocks; all-gather of R factors + all-reduce of linesearch sums (NCCL)",
                       "l2": "[J | r] is %.1f GB per GPU, larger than L2" % (rows * (LARGE_N + 8) * 8 / 1e9)},
            "phases_ms_per_factorisation": {"build_J_r_grad": dst["build_ms"] / npts, "tsqr": tsqr_ms},
            "phases_ms_per_solve": {"linesearch_kernels": dst["linesearch_ms"] / args.large_steps,
+                                   "small_stage_device": dst["small_stage_ms"] / args.large_steps,
+                                   "host_other": (dst["solve_wall_ms"] - dst["build_ms"] - dst["tsqr_ms"] - dst["small_stage_ms"]
+                                                  - dst["linesearch_ms"]) / args.large_steps,
                                    "total": dst["solve_wall_ms"] / args.large_steps,
                                    "factorisations": nfac / args.large_steps,
                                    "points_evaluated": npts / args.large_steps,
@@ -276,13 +410,13 @@ def large_arm(args, torch, dist, E, rank, world, local, dev):
         E.solve(hm)
         barrier()
         t0 = time.perf_counter()
-        f0 = hm.stats()["points"]
+        it2 = 0
         for _ in range(args.large_e2e_steps):
             hm.set_data(0, W_h.numpy())          # H2D of the step's inputs inside the timed region
             hm.set_data(1, y_h.numpy())
             E.solve(hm)                          # x, f, exit code come back to host arrays
+            it2 += int(hm.iterations[0])
         barrier()
-        it2 = int(hm.stats()["points"] - f0) - args.large_e2e_steps
         dt2 = time.perf_counter() - t0
         t = torch.tensor([dt2], dtype=torch.float64, device=dev)
         if world > 1:
@@ -319,15 +453,31 @@ def reference_arm(args):
             "config": {"workload": "C3 gauss-peaks n=6 m=128 q=1 l=13 FD-jacobian (BASELINE.json config 3)",
                        "problems_per_step": sample, "note": "bounded sample of the 4M-problem workload"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d problems (seed 128 stream, first chunk), compiled C++ port of the oracle, "
-                                       "OpenMP over problems" % sample},
+                             "sample": "%d problems (seed 128 stream, first chunk), compiled C++ port of the oracle, OpenMP "
+                                       "over problems, every qr(., ColumnNorm()) in OpenBLAS dgeqp3: %s" % (sample, cpu_port.lapack)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mean_iterations": float(np.mean(iters))}
     if not args.skip_large:
-        lb = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
+        # the reference arm has minutes, not seconds: the C4 pass runs on ALL rows when the host has the memory for W, J
+        # and the LAPACK workspace (3 x 8.6 GB), otherwise on the bounded sample
+        rows = args.large_rows
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 3.5 * rows * LARGE_N * 8:
+                rows = args.large_cpu_rows
+        except Exception:
+            rows = args.large_cpu_rows
+        if args.large_ref_rows > 0:
+            rows = args.large_ref_rows
+        lb = large_cpu_baseline(rows, args.large_rows)
         line["large"] = {"impl": "reference", "metric": LARGE_METRIC, "value": lb["value"], "unit": "iters/s",
                          "higher_is_better": True, "cpu_baseline": lb,
                          "config": {"workload": "C4 single-index m=%d n=256 q=64 (BASELINE.json config 4)" % args.large_rows}}
+        if not args.skip_c5:
+            cb = c5_cpu_baseline(scale=1 if args.c5_ref_full else 2)
+            line["large5"] = {"impl": "reference", "metric": C5_METRIC, "value": cb["value"], "unit": "iters/s",
+                              "higher_is_better": True, "cpu_baseline": cb,
+                              "config": {"workload": "C5 single-index n=4096 m=16384, 1024 inequalities + 8192 bounds (BASELINE.json config 5)"}}
     print(json.dumps(line))
 
 
@@ -347,7 +497,12 @@ def main():
     ap.add_argument("--large-steps", type=int, default=3)
     ap.add_argument("--large-warmup", type=int, default=1)
     ap.add_argument("--large-e2e-steps", type=int, default=1)
-    ap.add_argument("--large-cpu-rows", type=int, default=65536)
+    ap.add_argument("--large-cpu-rows", type=int, default=1 << 19,
+                    help="rows of the C4 problem the cpu_baseline leg of the default run times (scaled linearly to --large-rows)")
+    ap.add_argument("--large-ref-rows", type=int, default=0, help="--impl reference: rows to time (0 = all rows if memory allows)")
+    ap.add_argument("--skip-c5", action="store_true", help="skip BASELINE.json config 5 (one GPU, replicas only)")
+    ap.add_argument("--c5-steps", type=int, default=2)
+    ap.add_argument("--c5-ref-full", action="store_true", help="--impl reference: time the C5 pass at the named size (minutes)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -462,6 +617,10 @@ def main():
         del hmodel, model, y_d, S_d, x0_d, y_h, S_h, x0_h, x_h, f_h, out, hout
         torch.cuda.empty_cache()
         large = large_arm(args, torch, dist, E, rank, world, local, dev)
+    large5 = None
+    if not args.skip_large and not args.skip_c5 and world == 1:
+        torch.cuda.empty_cache()
+        large5 = c5_arm(args, torch, E, dev, local)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -499,14 +658,20 @@ def main():
             dt = min(run() for _ in range(2))
             line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d problems of the same stream, compiled C++ port of the oracle "
-                                              "(oracle/hostport), OpenMP over problems; Enlsip.jl itself needs Julia, "
-                                              "absent from this image" % args.cpu_sample,
+                                              "(oracle/hostport), OpenMP over problems, every qr(., ColumnNorm()) in OpenBLAS "
+                                              "dgeqp3 (%s); Enlsip.jl itself needs Julia, absent from this image"
+                                              % (args.cpu_sample, cpu_port.lapack),
                                     "mean_iterations": float(np.mean(cit))}
         if large is not None:
             if not args.skip_cpu and world == 1:
                 large["cpu_baseline"] = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
             line["large"] = large
             line["gpu_launches"] = int(launches) + large["gpu_launches"]
+        if large5 is not None:
+            if not args.skip_cpu:
+                large5["cpu_baseline"] = c5_cpu_baseline()
+            line["large5"] = large5
+            line["gpu_launches"] += large5["gpu_launches"]
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

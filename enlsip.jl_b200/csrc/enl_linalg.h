@@ -11,6 +11,23 @@
 
 namespace enl {
 
+#if defined(ENL_HOST_BUILD)
+// CPU reference arm only (oracle/hostport, bench.py --impl reference): when a LAPACK dgeqp3 has been bound (OpenBLAS,
+// the library Julia's `qr(., ColumnNorm())` calls), the two pivoted QR routines below hand the matrix to it instead of
+// running the engine's own restatement -- the CPU baseline then executes the reference's algorithm, not the engine's.
+// Never compiled into the CUDA library.
+typedef void (*host_dgeqp3_fn)(const int*, const int*, double*, const int*, int*, double*, double*, const int*, int*);
+inline host_dgeqp3_fn& host_dgeqp3() { static host_dgeqp3_fn fn = nullptr; return fn; }
+inline void host_lapack_qrcp(double* a, int ld, int rows, int cols, double* tau, int* jpvt) {
+    static thread_local double work[8192];
+    for (int j = 0; j < cols; ++j) jpvt[j] = 0;
+    int info = 0;
+    const int lwork = 8192;
+    host_dgeqp3()(&rows, &cols, a, &ld, jpvt, tau, work, &lwork, &info);
+    for (int j = 0; j < cols; ++j) jpvt[j] -= 1;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // small (replicated) routines.  Matrices are column major: a(r,c) = a[c*ld + r].
 // ------------------------------------------------------------------------------------------
@@ -25,6 +42,9 @@ ENL_NOINL double nrm2_small(V a, int n) {
 // dlaqp2 on a rows x cols matrix; returns nothing, fills tau[min(rows,cols)], jpvt[cols] (0-based)
 template <class V, class VI>
 ENL_NOINL void qrcp_small(V a, int ld, int rows, int cols, V tau, VI jpvt, V vn1, V vn2) {
+#if defined(ENL_HOST_BUILD)
+    if (host_dgeqp3() && rows > 0 && cols > 0) { host_lapack_qrcp(&a[0], ld, rows, cols, &tau[0], &jpvt[0]); return; }
+#endif
 #pragma unroll 1
     for (int j = 0; j < cols; ++j) {
         jpvt[j] = j;
@@ -225,6 +245,15 @@ struct Dist {
     // Rout (column major, ld = ldr) where kk = min(M, ncols).
     template <class V, class VI>
     ENL_NOINL void qrcp(DM<G, MS, NT> a, int M, int ncols, V tau2, VI jpvt, V vn1, V vn2, V Rout, int ldr) const {
+#if defined(ENL_HOST_BUILD)
+        if (host_dgeqp3() && G == 1 && NT == 1 && M > 0 && ncols > 0) {   // host layout: column major, ld = MS
+            host_lapack_qrcp(&a.at(0, 0), MS, M, ncols, &tau2[0], &jpvt[0]);
+            const int kk = imin(M, ncols);
+            for (int c = 0; c < ncols; ++c)
+                for (int r = 0; r < kk; ++r) Rout[c * ldr + r] = (r <= c) ? a.row(r, c) : 0.0;
+            return;
+        }
+#endif
 #pragma unroll 1
         for (int j = 0; j < ncols; ++j) {
             jpvt[j] = j;

@@ -611,119 +611,6 @@ __global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f
     }
 }
 
-// ---- the whole factorisation in ONE CTA (dlaqp2 semantics): matrices of up to QR_ONE_CTA_MAX entries, i.e. the small
-// stage of an n ~ 256 problem (config 4: 256 x 64, 64 x 64, 257 x 192), where a kernel launch per column step costs more
-// than the step.  32 warps: pivot search and dlarfg by the whole CTA, one warp per trailing column for H_i and the
-// partial-norm downdate (recompute rule applied on the spot, the trailing matrix is always up to date).
-constexpr long long QR_ONE_CTA_MAX = 160 * 1024;   // entries (1.25 MB): beyond this the L2 round trips of a single SM lose
-__global__ void __launch_bounds__(1024) qr_one_cta_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau,
-                                                          int* __restrict__ jpvt) {
-    extern __shared__ double sm[];          // vn1[cols] | vn2[cols] | v[rows]
-    __shared__ double sh[32];
-    __shared__ double s_best[32];
-    __shared__ int s_idx[32];
-    __shared__ int s_pvt;
-    double* vn1 = sm;
-    double* vn2 = sm + cols;
-    double* v = sm + 2 * cols;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int k = rows < cols ? rows : cols;
-    for (int c = w; c < cols; c += 32) {
-        const double* cc = f + (size_t)c * rows;
-        double s = 0.0;
-        for (int r = lane; r < rows; r += 32) s = fma(cc[r], cc[r], s);
-        s = s_warp_sum(s);
-        if (lane == 0) { vn1[c] = vn2[c] = sqrt(s); jpvt[c] = c; }
-    }
-    __syncthreads();
-    for (int i = 0; i < k; ++i) {
-        double best = -1.0; int idx = cols;
-        for (int j = i + tid; j < cols; j += 1024) {
-            const double x = vn1[j];
-            if (x > best) { best = x; idx = j; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
-        }
-        if (lane == 0) { s_best[w] = best; s_idx[w] = idx; }
-        __syncthreads();
-        if (tid == 0) {
-            double b = s_best[0]; int bi = s_idx[0];
-            for (int q = 1; q < 32; ++q)
-                if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
-            if (bi >= cols) bi = i;
-            s_pvt = bi;
-            if (bi != i) {
-                const int tp = jpvt[bi]; jpvt[bi] = jpvt[i]; jpvt[i] = tp;
-                vn1[bi] = vn1[i]; vn2[bi] = vn2[i];
-            }
-        }
-        __syncthreads();
-        const int pvt = s_pvt;
-        double* ci = f + (size_t)i * rows;
-        double* cp = f + (size_t)pvt * rows;
-        // swap (rows above i too: they are finished rows of R) and stage the new column i (rows i..) in shared memory
-        double part = 0.0;
-        for (int r = tid; r < rows; r += 1024) {
-            const double a = cp[r];
-            if (pvt != i) { cp[r] = ci[r]; ci[r] = a; }
-            if (r >= i) v[r] = a;
-            if (r > i) part = fma(a, a, part);
-        }
-        double tau_i = 0.0;
-        if (i < rows - 1) {
-            const double xn = sqrt(s_block_sum(part, sh));     // syncs inside: v[] is visible afterwards
-            if (xn != 0.0) {
-                const double alpha = v[i];
-                const double beta = -copysign(s_lapy2(alpha, xn), alpha);
-                tau_i = (beta - alpha) / beta;
-                const double sc = 1.0 / (alpha - beta);
-                __syncthreads();
-                for (int r = i + 1 + tid; r < rows; r += 1024) { const double x = v[r] * sc; v[r] = x; ci[r] = x; }
-                if (tid == 0) ci[i] = beta;
-            }
-        }
-        if (tid == 0) tau[i] = tau_i;
-        __syncthreads();
-        // H_i on the trailing columns + dlaqp2 norm downdate, one warp per column
-        const int len = rows - i - 1;
-        for (int c = i + 1 + w; c < cols; c += 32) {
-            double* cc = f + (size_t)c * rows + i;
-            double c0 = cc[0];
-            if (tau_i != 0.0) {
-                double s = 0.0;
-                for (int r = lane; r < len; r += 32) s = fma(v[i + 1 + r], cc[1 + r], s);
-                s = s_warp_sum(s);
-                const double wv = (c0 + s) * tau_i;
-                for (int r = lane; r < len; r += 32) cc[1 + r] = fma(-wv, v[i + 1 + r], cc[1 + r]);
-                c0 -= wv;
-                if (lane == 0) cc[0] = c0;
-                __syncwarp();
-            }
-            const double v1 = vn1[c];
-            if (v1 != 0.0) {
-                const double tq = fabs(c0) / v1;
-                const double temp = fmax(1.0 - tq * tq, 0.0);
-                const double rq = v1 / vn2[c];
-                if (temp * (rq * rq) <= S_TOL3Z) {
-                    double s = 0.0;
-                    if (i < rows - 1) {
-                        for (int r = lane; r < len; r += 32) s = fma(cc[1 + r], cc[1 + r], s);
-                        s = s_warp_sum(s);
-                    }
-                    if (lane == 0) vn1[c] = vn2[c] = sqrt(s);
-                } else if (lane == 0) {
-                    vn1[c] = v1 * sqrt(temp);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ---- the whole factorisation in ONE THREAD-BLOCK CLUSTER (dlaqp2 semantics), the matrix resident in shared memory ----
 // Column c of the matrix lives in the shared memory of CTA c % 8 (slot c / 8).  Per column step: every CTA proposes its
 // best remaining column (first maximum of the partial norms by current position), the proposals are exchanged through
@@ -940,17 +827,10 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
 inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
-    if (qc_smem_bytes(rows, cols) <= QC_MAX_SMEM && !getenv("ENLSIP_QR_NO_CLUSTER")) {
+    if (qc_smem_bytes(rows, cols) <= QC_MAX_SMEM) {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM); attr_set = true; }
         qr_cluster_kernel<<<QC_CTAS, QC_THREADS, qc_smem_bytes(rows, cols), st>>>(f, rows, cols, tau, jpvt);
-        return 1;
-    }
-    if ((long long)rows * cols <= QR_ONE_CTA_MAX && (size_t)(2 * cols + rows) * sizeof(double) <= 200 * 1024) {
-        const size_t shb = sizeof(double) * (size_t)(2 * cols + rows);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(qr_one_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-        qr_one_cta_kernel<<<1, 1024, shb, st>>>(f, rows, cols, tau, jpvt);
         return 1;
     }
     // dgeqp3: blocked (dlaqps) while j <= topbmn = minmn - nx, if nb < minmn and nx < minmn
@@ -1271,6 +1151,32 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ 
     const double s = (s0 + s1) + (s2 + s3);
     y[r] = alpha * s + (y0 ? beta * y0[r] : 0.0);
 }
+// the same for short matrices (rows of a few hundred): CTA = 32 rows (lane = row), its 8 warps split the columns and
+// their partial sums are added in warp order -- 8x the parallelism of a thread per row
+__global__ void __launch_bounds__(256) gemv_n_split_kernel(const double* __restrict__ A, int lda, int rows, int cols,
+                                                           const double* __restrict__ x, double alpha,
+                                                           const double* __restrict__ y0, double beta, double* __restrict__ y) {
+    __shared__ double part[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + lane;
+    const int per = (cols + 7) / 8, c0 = w * per, c1 = (c0 + per < cols) ? c0 + per : cols;
+    double s0 = 0.0, s1 = 0.0;
+    if (r < rows) {
+        int c = c0;
+        for (; c + 2 <= c1; c += 2) {
+            s0 = fma(A[(size_t)c * lda + r], x[c], s0);
+            s1 = fma(A[(size_t)(c + 1) * lda + r], x[c + 1], s1);
+        }
+        if (c < c1) s0 = fma(A[(size_t)c * lda + r], x[c], s0);
+    }
+    part[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0 && r < rows) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += part[q][lane];
+        y[r] = alpha * s + (y0 ? beta * y0[r] : 0.0);
+    }
+}
 // y (cols) = A' x : one warp per column
 __global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ A, int lda, int rows, int cols,
                                                      const double* __restrict__ x, double* __restrict__ y) {
@@ -1287,7 +1193,8 @@ __global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ 
 inline int gemv_n(const double* A, int lda, int rows, int cols, const double* x, double alpha, const double* y0, double beta,
                   double* y, cudaStream_t st) {
     if (rows <= 0) return 0;
-    gemv_n_kernel<<<(rows + 255) / 256, 256, sizeof(double) * (size_t)(cols > 0 ? cols : 1), st>>>(A, lda, rows, cols, x, alpha, y0, beta, y);
+    if (rows <= 2048) gemv_n_split_kernel<<<(rows + 31) / 32, 256, 0, st>>>(A, lda, rows, cols, x, alpha, y0, beta, y);
+    else gemv_n_kernel<<<(rows + 255) / 256, 256, sizeof(double) * (size_t)(cols > 0 ? cols : 1), st>>>(A, lda, rows, cols, x, alpha, y0, beta, y);
     return 1;
 }
 inline int gemv_t(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st) {

@@ -10,6 +10,8 @@
 // fallback.  Parity claims rest on the independent Python oracle (oracle/enlsip_oracle.py).
 //
 // Build: g++ -O2 -ffp-contract=off -mfma -std=c++17 -shared -fPIC -fopenmp hostport.cpp -o ../_build/libhostport.so
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cstring>
 #include <type_traits>
@@ -80,4 +82,22 @@ extern "C" void hostport_det_exp(const double* x, double* y, long long n) {
 extern "C" void hostport_qrcp(int rows, int cols, double* f, double* tau, int* jpvt) {
     std::vector<double> vn1(cols), vn2(cols);
     qrcp_small(SV<1>{f}, rows, rows, cols, SV<1>{tau}, SI<1>{jpvt}, SV<1>{vn1.data()}, SV<1>{vn2.data()});
+}
+
+// Reference-arm switch (bench.py --impl reference): bind LAPACK dgeqp3 from an OpenBLAS shared library (the SciPy wheel's
+// libscipy_openblas: symbols scipy_dgeqp3_, scipy_openblas_set_num_threads) so that every `qr(., ColumnNorm())` of the
+// solve (EF:223, 700, 769) is executed by the routine Julia itself calls.  path == NULL unbinds.  Returns 0 on success.
+extern "C" int hostport_use_lapack(const char* path) {
+    if (!path) { enl::host_dgeqp3() = nullptr; return 0; }
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    void* fn = dlsym(h, "scipy_dgeqp3_");
+    if (!fn) fn = dlsym(h, "dgeqp3_");
+    if (!fn) return -2;
+    typedef void (*setthr_fn)(int);
+    setthr_fn st = (setthr_fn)dlsym(h, "scipy_openblas_set_num_threads");
+    if (!st) st = (setthr_fn)dlsym(h, "openblas_set_num_threads");
+    if (st) st(1);       // problems are independent: parallelism is OpenMP over problems, BLAS stays single-threaded
+    enl::host_dgeqp3() = (enl::host_dgeqp3_fn)fn;
+    return 0;
 }

@@ -247,3 +247,130 @@ extern "C" void largeport_qrcp(int rows, int cols, double* f, double* tau, int* 
     for (int i = 0; i < F.k; ++i) tau[i] = F.tau[i];
     for (int j = 0; j < cols; ++j) jpvt[j] = F.p[j];
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// CPU reference arm of the large regime (bench.py cpu_baseline "reference-algorithm" / --impl reference): ONE
+// Gauss-Newton iteration's dense work done the way Enlsip.jl does it, with the LAPACK/BLAS routines Julia calls, bound at
+// run time from an OpenBLAS shared library (the SciPy wheel's libscipy_openblas; Julia ships OpenBLAS_jll):
+//     new_point!                      r, J = diag(1 - tanh^2) W (m x n, column major), c, A          EF:34-52
+//     qr(A_active', ColumnNorm())     dgeqp3 (n x t)                                                  EF:700
+//     J * F_A.Q                       dormqr('R', 'N') on the full m x n Jacobian                     EF:219
+//     qr(J2, ColumnNorm())            dgeqp3 (m x (n - t))                                            EF:223
+//     p1 = L11 \ (-P'c), d = Q3'(-J1 p1 - r), p2 = R22 \ d, p = Q1 [p1; p2]   dtrtrs / dgemv / dormqr  EF:133-152
+// for the single-index problem at x: working set = the equalities (config 4) or the inequalities / bounds with c <= 0
+// (init_working_set, EF:826-859; config 5), assumed of full rank (method code 1).  The multiplier estimates and the
+// linesearch are left out, so the figure flatters the CPU slightly.  secs: {total, new_point,
+// J*Q1, qr(J2), rest}.  Returns 0, or a negative code when the library / a symbol cannot be bound.
+// ------------------------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+#include <chrono>
+
+namespace {
+struct Lapack {
+    typedef void (*geqp3_t)(const int*, const int*, double*, const int*, int*, double*, double*, const int*, int*);
+    typedef void (*ormqr_t)(const char*, const char*, const int*, const int*, const int*, const double*, const int*,
+                            const double*, double*, const int*, double*, const int*, int*);
+    typedef void (*trtrs_t)(const char*, const char*, const char*, const int*, const int*, const double*, const int*,
+                            double*, const int*, int*);
+    typedef void (*gemv_t)(const char*, const int*, const int*, const double*, const double*, const int*, const double*,
+                           const int*, const double*, double*, const int*);
+    typedef void (*setthr_t)(int);
+    geqp3_t geqp3 = nullptr; ormqr_t ormqr = nullptr; trtrs_t trtrs = nullptr; gemv_t gemv = nullptr; setthr_t setthr = nullptr;
+    int bind(const char* path) {
+        void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) return -1;
+        auto sym = [&](const char* a, const char* b) { void* p = dlsym(h, a); return p ? p : dlsym(h, b); };
+        geqp3 = (geqp3_t)sym("scipy_dgeqp3_", "dgeqp3_");
+        ormqr = (ormqr_t)sym("scipy_dormqr_", "dormqr_");
+        trtrs = (trtrs_t)sym("scipy_dtrtrs_", "dtrtrs_");
+        gemv = (gemv_t)sym("scipy_dgemv_", "dgemv_");
+        setthr = (setthr_t)sym("scipy_openblas_set_num_threads", "openblas_set_num_threads");
+        return (geqp3 && ormqr && trtrs && gemv) ? 0 : -2;
+    }
+};
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+extern "C" int largeport_ref_iteration(const char* blas_path, int n, long long m, int nb, int ineq, const double* x_low,
+                                       const double* x_upp, const double* W, const double* y, const double* rho,
+                                       const double* x, int nthreads, double* secs, double* p_out, int* t_out) {
+    Lapack L;
+    int rc = L.bind(blas_path);
+    if (rc != 0) return rc;
+    if (L.setthr) L.setthr(nthreads < 1 ? 1 : nthreads);
+    const int mi = (int)m;
+    int info = 0;
+    const double t0 = now_s();
+    // ---- new_point! ----
+    std::vector<double> J((size_t)m * n), r(m), sv(m);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long long i = 0; i < m; ++i) {
+        double th = enl::det_tanh(dot_n(W + (size_t)i * n, x, n));
+        r[i] = th - y[i];
+        sv[i] = 1.0 - th * th;
+    }
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int j = 0; j < n; ++j) {
+        double* cj = J.data() + (size_t)j * m;
+        for (long long i = 0; i < m; ++i) cj[i] = sv[i] * W[(size_t)i * n + j];
+    }
+    SingleIndexConstraints sc;
+    sc.n = n; sc.nb = nb; sc.ineq = ineq != 0;
+    sc.rho.assign(rho, rho + nb);
+    sc.set_bounds(x_low, x_upp);
+    const int l = sc.l();
+    std::vector<double> call(l), Aall((size_t)l * n, 0.0);
+    sc.cons(x, call.data());
+    sc.jac(x, Aall.data());                                // l x n column major
+    std::vector<int> act;
+    for (int i = 0; i < l; ++i)
+        if (i < sc.q() || call[i] <= 0.0) act.push_back(i);
+    const int t = (int)act.size(), k2 = n - t;
+    if (t_out) *t_out = t;
+    if (t < 1 || k2 < 1) return -20;
+    std::vector<double> c(t), At((size_t)n * t);
+    for (int i = 0; i < t; ++i) {
+        c[i] = call[act[i]];
+        for (int j = 0; j < n; ++j) At[(size_t)i * n + j] = Aall[(size_t)j * l + act[i]];
+    }
+    const double t1 = now_s();
+    // ---- qr(A', ColumnNorm()) ----
+    std::vector<int> pA(t, 0), p2(k2, 0);
+    std::vector<double> tauA(t), tau2(k2), wq(1);
+    int lwork = -1;
+    L.geqp3(&mi, &k2, J.data() + (size_t)t * m, &mi, p2.data(), tau2.data(), wq.data(), &lwork, &info);
+    size_t need = (size_t)wq[0];
+    L.ormqr("R", "N", &mi, &n, &t, At.data(), &n, tauA.data(), J.data(), &mi, wq.data(), &lwork, &info);
+    need = std::max(need, (size_t)wq[0]);
+    std::vector<double> work(std::max<size_t>(need, (size_t)8 * n + 64) + 1024);
+    lwork = (int)work.size();
+    L.geqp3(&n, &t, At.data(), &n, pA.data(), tauA.data(), work.data(), &lwork, &info);
+    if (info != 0) return -10;
+    // ---- J * Q1 ----
+    L.ormqr("R", "N", &mi, &n, &t, At.data(), &n, tauA.data(), J.data(), &mi, work.data(), &lwork, &info);
+    if (info != 0) return -11;
+    const double t2 = now_s();
+    // ---- qr(J2, ColumnNorm()) ----
+    std::fill(p2.begin(), p2.end(), 0);
+    L.geqp3(&mi, &k2, J.data() + (size_t)t * m, &mi, p2.data(), tau2.data(), work.data(), &lwork, &info);
+    if (info != 0) return -12;
+    const double t3 = now_s();
+    // ---- p1 = L11 \ (-P'c) ; d = Q3'(-J1 p1 - r) ; p2 = R22 \ d[1:k2] ; p = Q1 [p1; p2[invperm]] ----
+    std::vector<double> p1(t), d(m), pv(n, 0.0);
+    for (int i = 0; i < t; ++i) p1[i] = -c[pA[i] - 1];
+    const int one = 1;
+    L.trtrs("U", "T", "N", &t, &one, At.data(), &n, p1.data(), &t, &info);
+    const double neg1 = -1.0;
+    for (long long i = 0; i < m; ++i) d[i] = r[i];
+    L.gemv("N", &mi, &t, &neg1, J.data(), &mi, p1.data(), &one, &neg1, d.data(), &one);        // d = -J1 p1 - r
+    L.ormqr("L", "T", &mi, &one, &k2, J.data() + (size_t)t * m, &mi, tau2.data(), d.data(), &mi, work.data(), &lwork, &info);
+    L.trtrs("U", "N", "N", &k2, &one, J.data() + (size_t)t * m, &mi, d.data(), &mi, &info);
+    for (int i = 0; i < t; ++i) pv[i] = p1[i];
+    for (int j = 0; j < k2; ++j) pv[t + p2[j] - 1] = d[j];
+    L.ormqr("L", "N", &n, &one, &t, At.data(), &n, tauA.data(), pv.data(), &n, work.data(), &lwork, &info);
+    const double t4 = now_s();
+    if (p_out) std::memcpy(p_out, pv.data(), sizeof(double) * n);
+    secs[0] = t4 - t0; secs[1] = t1 - t0; secs[2] = t2 - t1; secs[3] = t3 - t2; secs[4] = t4 - t3;
+    return info == 0 ? 0 : -13;
+}

@@ -20,8 +20,10 @@ class Opt(ctypes.Structure):
                 ("eps_rank", ctypes.c_double)]
 
 
-def run(family, x0, d0, d1, xl, xu, jac_mode, trace_cap=40, nthreads=2, time_limit=1e3, max_iter=100):
+def run(family, x0, d0, d1, xl, xu, jac_mode, trace_cap=40, nthreads=2, time_limit=1e3, max_iter=100, lapack=False):
     lib = ctypes.CDLL(ge.build_hostport())
+    lib.hostport_use_lapack.argtypes = [ctypes.c_char_p]
+    assert lib.hostport_use_lapack(ge.openblas_path().encode() if lapack else None) == 0
     se = math.sqrt(np.finfo(float).eps)
     opt = Opt(max_iter, 0, jac_mode, 1, time_limit, 1e-10, se, se, se, se)
     B, n = x0.shape
@@ -59,6 +61,19 @@ def test_gauss_peaks_vs_golden(golden_dir, mode, fixture, jac):
     y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B)
     out = run(1, x0, y, S, E.synth.GP_LOW, E.synth.GP_UPP, jac)
     parity.compare(gold, out, mode, 6)
+
+
+@pytest.mark.parametrize("mode,fixture,jac", [("analytic", "c3_gp_analytic.npz", 0), ("fd", "c3_gp_fd.npz", 1)])
+def test_reference_arm_with_openblas_dgeqp3_vs_golden(golden_dir, mode, fixture, jac):
+    """The CPU reference arm of bench.py: every `qr(., ColumnNorm())` of the solve goes to OpenBLAS' dgeqp3 (the routine
+    Julia calls) instead of the engine's restatement; same parity bars against the oracle fixtures."""
+    import enlsip_jl_b200 as E
+    gold = np.load(golden_dir + "/" + fixture)
+    B = gold["x"].shape[0]
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B)
+    out = run(1, x0, y, S, E.synth.GP_LOW, E.synth.GP_UPP, jac, lapack=True)
+    parity.compare(gold, out, mode, 6)
+    run(1, x0[:1], y[:1], S[:1], E.synth.GP_LOW, E.synth.GP_UPP, jac, lapack=False)      # unbind for the tests that follow
 
 
 def test_time_limit_and_max_iter():
