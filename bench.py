@@ -581,6 +581,35 @@ def main():
     iters = out["iters"].cpu().numpy()
     conv = float(np.mean(status == 1))
 
+    # ---- the evaluation phase alone (last row): forward-difference Jacobian + residuals of every problem,
+    #      written to HBM (enlsipb200_eval_batch); the one phase of the solve with no replicated work ----------------
+    fdj = None
+    if rank == 0:
+        Bf = min(B, 1_000_000)
+        xs = x0_d[:Bf].contiguous()
+        fm = E.CnlsModel("gauss_peaks", xs, data={"y": y_d[:Bf].contiguous(), "S": S_d[:Bf].contiguous()}, x_low=E.synth.GP_LOW,
+                         x_upp=E.synth.GP_UPP, jacobian="forward_diff", device=local)
+        E.evaluate(fm, xs, want=("r", "J"))
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(3):
+            E.evaluate(fm, xs, want=("r", "J"))
+            torch.cuda.synchronize()
+            ms.append(last_kernel_ms(fm))
+        t_ms = float(np.median(ms))
+        # algorithmic work of jac_forward_diff + res_eval! (cnls_model.jl:40-82): n + 1 = 7 evaluations of the 128 residuals,
+        # each 2 exponentials (det_exp: 15 FMA + 7 other FP64 instructions = 37 flop) + 12 flop of model arithmetic
+        flop = 7 * 128 * (2 * 37 + 12) * float(Bf)
+        wbytes = Bf * (128 * 6 + 128) * 8.0
+        fdj = {"problems": Bf, "kernel_ms": t_ms, "kernel": "enlsip_eval_batch_kernel<GaussPeaks> (r and J of every problem to HBM)",
+               "achieved_tflops": flop / (t_ms * 1e-3) / 1e12, "peak_tflops": fp64_fma_peak(),
+               "frac_of_fp64_fma_peak": flop / (t_ms * 1e-3) / 1e12 / fp64_fma_peak(),
+               "algorithmic_flop_per_problem": flop / Bf, "hbm_write_gbs": wbytes / (t_ms * 1e-3) / 1e9,
+               "note": "the engine's FD kernel re-uses the unperturbed exponentials (6 instead of 14 det_exp per row, bit-identical "
+                       "values), so it executes fewer flops than the algorithmic count it is credited with"}
+        fm.close()
+        del fm
+
     # ---- end to end through the C ABI with pinned host buffers -------------------------------------
     x_h = torch.empty(B, 6, dtype=torch.float64).pin_memory()
     f_h = torch.empty(B, dtype=torch.float64).pin_memory()
@@ -649,6 +678,7 @@ def main():
                                   "algorithmic_flop_per_solve": ALG_FLOP_PER_SOLVE,
                                   "note": "algorithmic flops (SURVEY.md 8d: ~2e5 per Gauss-Newton iteration x the mean iteration "
                                           "count); ncu: FP64 pipe 12.7 % active, issue slots 34 % (profiles/r1_c3_v4_ncu.txt)"},
+                "fd_jacobian_phase": fdj,
                 "quality": {"converged_fraction": conv, "mean_iterations": float(iters.mean()),
                             "kernel_info": kernel_info}}
         if not args.skip_cpu and world == 1:      # cpu_baseline: rank 0 at N = 1 only

@@ -1687,6 +1687,44 @@ struct Solver {
         rdot_x1 = cdot_x1 = 0.0;
     }
 
+    // new_point! (EF:34-52) as an operator of its own: r, J (forward differences of cnls_model.jl:65-82 or analytic),
+    // c and A at xin -- the evaluation layer without the iteration around it (enlsipb200_eval_batch)
+    ENL_NOINL void eval_only(const double* xin, const FamilyData& fd, long long bidx) {
+        Fam::template load<Grp, MS>(fctx(), fd, bidx, grp());
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) x[j] = xin[j];
+        l = NNL + bnd.nlo + bnd.nup;
+        double xv[N], rn[MS];
+        load_x(x, xv);
+        eval_point(xv, rn, cx);
+#pragma unroll
+        for (int sl = 0; sl < MS; ++sl) dR.at(sl, 0) = rn[sl];
+        grp().sync();
+        init_bound_rows();
+        eval_res_jacobian();
+        eval_cons_jacobian();
+    }
+    // r [M], J [N][M] (column major m x n, the reference's layout), c [LMAX], A [LMAX][N] (row i = gradient of c_i)
+    ENL_NOINL void store_eval(double* r_out, double* J_out, double* c_out, double* A_out, long long bidx) {
+#pragma unroll
+        for (int sl = 0; sl < MS; ++sl) {
+            const int row = sl * G + grp().lane;
+            if (row < M) {
+                if (r_out) r_out[bidx * M + row] = dR.at(sl, 0);
+                if (J_out)
+#pragma unroll
+                    for (int j = 0; j < N; ++j) J_out[(bidx * N + j) * M + row] = dJ.at(sl, j);
+            }
+        }
+        if (grp().lane != 0) return;
+        if (c_out)
+#pragma unroll 1
+            for (int i = 0; i < LMAX; ++i) c_out[bidx * LMAX + i] = (i < l) ? cx[i] : 0.0;
+        if (A_out)
+#pragma unroll 1
+            for (int i = 0; i < LMAX * N; ++i) A_out[bidx * LMAX * N + i] = (i < l * N) ? A[i] : 0.0;
+    }
+
     // one ENLSIP iteration; sets exit_code != 0 when the solve is over
     ENL_NOINL void step(double now, double* trace_row) {
         evaluate_scaling();

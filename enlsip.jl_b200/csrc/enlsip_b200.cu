@@ -124,6 +124,48 @@ __global__ void __launch_bounds__(NT) enlsip_solve_batch_kernel(const __grid_con
     }
 }
 
+// The evaluation layer alone (new_point!, EF:34-52; jac_forward_diff, cnls_model.jl:65-82): every group takes problems
+// from the work counter, evaluates r, J, c, A at the given point and writes them to HBM.
+struct EvalArgs {
+    long long B;
+    unsigned long long* counter;
+    const double* x;
+    FamilyData fd;
+    Options opt;
+    Bounds bnd;
+    double *r, *J, *c, *A;
+};
+template <class Fam, int G, int NT>
+__global__ void __launch_bounds__(NT) enlsip_eval_batch_kernel(const __grid_constant__ EvalArgs a) {
+    using LY = Layout<Fam, G, NT>;
+    using SolverT = Solver<Fam, DevGroup<G>, NT>;
+    constexpr int SOLVER_DOUBLES = (int)((sizeof(SolverT) + 7) / 8) | 1;
+    const int tid = threadIdx.x;
+    const int pid = tid / G;
+    constexpr int CFG_DOUBLES = (int)((sizeof(Options) + sizeof(Bounds) + 15) / 16) * 2;
+    Options* s_opt = reinterpret_cast<Options*>(enl_smem);
+    Bounds* s_bnd = reinterpret_cast<Bounds*>(reinterpret_cast<char*>(enl_smem) + sizeof(Options));
+    if (tid == 0) { *s_opt = a.opt; *s_bnd = a.bnd; }
+    __syncthreads();
+    double* objs = enl_smem + CFG_DOUBLES;
+    double* small = objs + (size_t)SOLVER_DOUBLES * LY::PPC;
+    double* distb = small + (size_t)LY::nD * LY::PPC;
+    int* ints = reinterpret_cast<int*>(distb + (size_t)LY::DCOLS * LY::MS * NT);
+    DevGroup<G> g;
+    SolverT& S = *new (objs + (size_t)SOLVER_DOUBLES * pid) SolverT(small, ints, distb, pid, *s_opt, *s_bnd);
+    g.sync();
+    for (;;) {
+        unsigned long long nb = 0;
+        if (g.lane == 0) nb = atomicAdd(a.counter, 1ULL);
+        if (G > 1) nb = __shfl_sync(g.mask, nb, 0, G);
+        const long long b = (long long)nb;
+        if (b >= a.B) break;
+        S.eval_only(a.x + b * Fam::N, a.fd, b);
+        S.store_eval(a.r, a.J, a.c, a.A, b);
+        g.sync();
+    }
+}
+
 __global__ void det_exp_kernel(const double* x, double* y, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) y[i] = det_exp(x[i]);
@@ -531,6 +573,47 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     }
     for (int sl = 0; sl < 3; ++sl) h->host_pending[sl] = false;
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
+                          double* J, double* c, double* A, int on_device, void* stream) {
+    if (!h) return fail(ENLSIPB200_EINVAL, "null handle");
+    if (B < 0 || !x) return fail(ENLSIPB200_EINVAL, "x is required");
+    if (B == 0) return 0;
+    if (!on_device) return fail(ENLSIPB200_EINVAL, "enlsipb200_eval_batch works on device buffers (the outputs are B x m x n)");
+    if ((h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS || h->family == ENLSIPB200_FAMILY_OSBORNE2) && (!h->data[0] || !h->data[1]))
+        return fail(ENLSIPB200_EINVAL, "this family needs data slots 0 and 1");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rcf = flush_pending(h, st, -1);
+    if (rcf != 0) return rcf;
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.counter = h->counter; a.x = x;
+    a.fd = FamilyData{h->data[0], h->data[1], h->data[2]};
+    a.opt = make_options(opt, h->fi.n, h->fi.m);
+    a.bnd = h->bnd;
+    a.r = r; a.J = J; a.c = c; a.A = A;
+    int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
+        using Fm = decltype(fam);
+        constexpr int G = decltype(g_)::value, NT = decltype(nt_)::value;
+        auto kern = enlsip_eval_batch_kernel<Fm, G, NT>;
+        const size_t smem = smem_total<Fm, G, NT>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long need = (B + NT / G - 1) / (NT / G);
+        int grid = (int)(need < (long long)h->grid ? need : (long long)h->grid);
+        CU(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+        CU(cudaEventRecord(h->ev0, st));
+        kern<<<grid < 1 ? 1 : grid, NT, smem, st>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+        h->launches += 1;
+        return 0;
+    });
+    if (rc != 0) return rc;
+    if (!stream) CU(cudaStreamSynchronize(st));
     return 0;
 }
 

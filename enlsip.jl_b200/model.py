@@ -234,6 +234,30 @@ def solve(model: CnlsModel, silent=True, max_iter=100, scaling=False, time_limit
 solve_b = solve   # `solve!`
 
 
+def evaluate(model: CnlsModel, x=None, want=("r", "J", "c", "A")):
+    """new_point! (enlsip_functions.jl:34-52) for the whole batch: residuals r [B, m], Jacobians J [B, n, m] (per problem
+    m x n column major; forward differences of cnls_model.jl:65-82 when the model was built with
+    jacobian="forward_diff"), constraint values c [B, lmax] and constraint Jacobians A [B, lmax, n] at `x` (default:
+    the model's current solution).  Device tensors in, device tensors out."""
+    import torch
+    x = model.sol if x is None else x
+    if not (_is_torch(x) and x.is_cuda):
+        x = torch.as_tensor(np.ascontiguousarray(_to_numpy(x), dtype=np.float64)).cuda()
+    x = x.contiguous()
+    assert x.dtype == torch.float64 and x.shape == (model.B, model.nb_parameters)
+    B, n, m, lmax = model.B, model.nb_parameters, model.nb_residuals, model.lmax
+    mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=x.device)
+    out = {"r": mk(B, m) if "r" in want else None, "J": mk(B, n, m) if "J" in want else None,
+           "c": mk(B, lmax) if "c" in want else None, "A": mk(B, lmax, n) if "A" in want else None}
+    o = capi.default_options()
+    o.jac_mode = _JAC[model.jacobian]
+    p = model._ptr
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(model._lib.enlsipb200_eval_batch(model._h, B, p(x), ctypes.byref(o), p(out["r"]), p(out["J"]), p(out["c"]),
+                                                p(out["A"]), 1, st), model._lib)
+    return out
+
+
 def last_kernel_ms(model: CnlsModel) -> float:
     ms = ctypes.c_float()
     capi.check(model._lib.enlsipb200_last_kernel_ms(model._h, ctypes.byref(ms)), model._lib)

@@ -92,6 +92,14 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
 int enlsipb200_last_kernel_ms(enlsipb200_handle h, float* ms);
 int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_bytes_per_cta, int* threads_per_cta,
                            int* ctas_per_sm, int* grid, int* lanes_per_problem);
+/* The evaluation layer as an operator of its own: new_point! (src/enlsip_functions.jl:34-52) through the wrappers
+ * res_eval! / jacres_eval! / cons_eval! / jaccons_eval! (src/cnls_model.jl:40-62), with jac_forward_diff
+ * (src/cnls_model.jl:65-82) when opt->jac_mode = ENLSIPB200_JAC_FORWARD_DIFF.  DEVICE buffers only:
+ *   x [B, n] in;  r [B, m];  J [B, n, m] (per problem the m x n Jacobian, column major as in the reference);
+ *   c [B, lmax];  A [B, lmax, n] (row i = gradient of constraint i, bound rows +-e_j included).  Any output may be NULL.
+ * enlsipb200_last_kernel_ms reports the kernel time. */
+int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
+                          double* J, double* c, double* A, int on_device, void* stream);
 long long enlsipb200_launch_count(enlsipb200_handle h);
 
 /* Run-time compiled problem family: the replacement of the reference's plugin surface -- `residuals`,

@@ -142,6 +142,30 @@ def test_batched_row_scaling_vs_live_oracle(E):
         assert same >= 0.95 * B, (n, same, B)
 
 
+@pytest.mark.parametrize("jac", ["analytic", "forward_diff"])
+def test_evaluation_layer_bit_parity(E, jac):
+    """enlsipb200_eval_batch (new_point!, EF:34-52; jac_forward_diff, cnls_model.jl:65-82) against the oracle's
+    evaluation surface on the same inputs: r, J, c, A bit for bit (the families are defined through det_exp, and the
+    forward differences use the same rounded operations in the same order)."""
+    import torch
+    from oracle import problems as P
+    B = 96
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B, start=3_000_000)
+    dev = torch.device("cuda", 0)
+    m = E.CnlsModel("gauss_peaks", torch.from_numpy(x0).to(dev), data={"y": torch.from_numpy(y).to(dev), "S": torch.from_numpy(S).to(dev)},
+                    x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian=jac)
+    out = {k: v.cpu().numpy() for k, v in E.evaluate(m).items()}
+    for b in range(B):
+        pb = P.gauss_peaks(y[b], S[b], x0[b], fd=(jac == "forward_diff"))
+        assert np.array_equal(out["r"][b].view(np.uint64), pb.res(x0[b]).view(np.uint64)), b
+        Jo = np.asarray(pb.jac_res(x0[b]))                         # m x n
+        assert np.array_equal(out["J"][b].T.copy().view(np.uint64), np.ascontiguousarray(Jo).view(np.uint64)), b
+        co, Ao = np.asarray(pb.cons(x0[b])), np.asarray(pb.jac_cons(x0[b]))
+        assert np.array_equal(out["c"][b][:pb.l].view(np.uint64), co.view(np.uint64)), b
+        assert np.array_equal(out["A"][b][:pb.l].copy().view(np.uint64), np.ascontiguousarray(Ao).view(np.uint64)), b
+    assert m.launch_count() == 1
+
+
 def test_device_buffers_and_determinism(E):
     """torch CUDA tensors (zero copy) give bit-identical results to host buffers; re-solving is idempotent; results do
     not depend on the position of a problem in the batch (the work queue hands problems to arbitrary warps)."""
