@@ -30,6 +30,10 @@
 #include "enl_large_host.h"
 #include "enl_tsqr.cuh"
 #include "enl_small.cuh"
+#include "enl_large_generic.cuh"
+#if defined(ENL_LARGE_USER_FAMILY)
+#include "enl_large_user.h"
+#endif
 
 using namespace enl_large;
 
@@ -321,6 +325,15 @@ struct LargeHandle : LargeOps, SmallBackend {
     long long n_dev_qrcp = 0, n_dev_mulq = 0;
     double ms_small = 0;              // host wall clock inside the small-stage calls (kernels + waits)
 
+    // general row families (enl_large_generic.cuh): gv != nullptr; [J | r] column major in dQ, factored without pivoting
+    const GenericVt* gv = nullptr;
+    int ncu = 0;                      // the family's own constraints (equalities + inequalities); bounds follow
+    double *dQ = nullptr, *dJkeep = nullptr, *dtauQ = nullptr, *dcu = nullptr;
+    int* dpQ = nullptr;
+    const double* gd[2] = {nullptr, nullptr};     // family data slots
+    double* gown[2] = {nullptr, nullptr};
+    int jac_fd = 0;                   // forward-difference Jacobians requested (cnls_model.jl:65-82)
+    std::vector<double> hxcur;        // the point of the last eval (linesearch trial points are x + alpha p)
     long long m_local = 0, rows_pad = 0, dT_subtiles = 0;
     int ld = 0, rr_rows = 0;
     SingleIndexConstraints sc;
@@ -351,6 +364,10 @@ struct LargeHandle : LargeOps, SmallBackend {
                           dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, qw.pbest, qw.psum, ww.Vb, ww.T, ww.W, ww.W2, ww.part})
             if (p) cudaFree(p);
         for (double*& p : dvec) { if (p) cudaFree(p); p = nullptr; }
+        for (double* p : {dQ, dJkeep, dtauQ, dcu, gown[0], gown[1]})
+            if (p) cudaFree(p);
+        if (dpQ) cudaFree(dpQ);
+        dQ = dJkeep = dtauQ = dcu = nullptr; dpQ = nullptr; gown[0] = gown[1] = nullptr;
         for (int* p : {dpA, dipA, dpL, dipL, dp2, dip2, dact, dbidx, qw.flags, qw.pidx})
             if (p) cudaFree(p);
         qw.drop_graphs();
@@ -389,6 +406,15 @@ struct LargeHandle : LargeOps, SmallBackend {
         rows_pad = ((m_local + TS_B - 1) / TS_B) * TS_B;
         if (rows_pad < TS_B) rows_pad = TS_B;
         rr_rows = n + TS_B;   // rows of an R factor padded to a multiple of 32
+        if (gv) {
+            const size_t mm = (size_t)(m_local > 0 ? m_local : 1);
+            LCU(cudaMalloc(&dQ, sizeof(double) * mm * (n + 1)));
+            LCU(cudaMalloc(&dJkeep, sizeof(double) * mm * n));
+            LCU(cudaMalloc(&dtauQ, sizeof(double) * (n + 1)));
+            LCU(cudaMalloc(&dpQ, sizeof(int) * (n + 1)));
+            LCU(cudaMalloc(&dcu, sizeof(double) * (ncu > 0 ? ncu : 1)));
+            rows_pad = TS_B;      // no TSQR work matrix
+        }
         LCU(cudaMalloc(&dA, sizeof(double) * rows_pad * ld));
         LCU(cudaMemsetAsync(dA, 0, sizeof(double) * rows_pad * ld, st));
         for (double** p : {&du, &dr, &ds, &dv, &dJp}) LCU(cudaMalloc(p, sizeof(double) * (m_local > 0 ? m_local : 1)));
@@ -455,7 +481,7 @@ struct LargeHandle : LargeOps, SmallBackend {
             idx.insert(idx.end(), sc.up_idx.begin(), sc.up_idx.end());
             LCU(cudaMalloc(&dbidx, sizeof(int) * idx.size()));
             LCU(cudaMemcpyAsync(dbidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
-            si_jac_bounds_kernel<<<(nlo + nup + 255) / 256, 256, 0, st>>>(dbidx, nlo, nup, sc.nb, n, dArow);
+            si_jac_bounds_kernel<<<(nlo + nup + 255) / 256, 256, 0, st>>>(dbidx, nlo, nup, gv ? ncu : sc.nb, n, dArow);
             LCU(cudaStreamSynchronize(st));
         }
         LCU(cudaGetLastError());
@@ -486,8 +512,38 @@ struct LargeHandle : LargeOps, SmallBackend {
     long long n_factor = 0;
 
     // r, s, u and [J | r] at x (li_build_kernel), gradient J'r and r'r reduced over CTAs and ranks -> hgrad (pinned)
+    int eval_at_generic(const double* x) {
+        hxcur.assign(x, x + n);
+        LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        jq1_valid = false;
+        LCU(cudaEventRecord(e0, st));
+        gv->build(grid_rows(), st, n, m_local, dx, gd[0], gd[1], jac_fd, dQ, dr);
+        LCU(cudaMemcpyAsync(dJkeep, dQ, sizeof(double) * (size_t)m_local * n, cudaMemcpyDeviceToDevice, st));
+        // [J'r ; r'r] = [J | r]' r
+        launches += 1 + enl_small::gemv_t(dQ, (int)m_local, (int)m_local, n + 1, dQ + (size_t)n * m_local, dgrad, st);
+        // constraints and their Jacobian rows (bound rows of A are constant)
+        gv->cons(st, n, ncu, dx, gd[0], gd[1], dcu);
+        gv->jac_cons(st, n, ncu, dx, gd[0], gd[1], jac_fd, dcu, dArow);
+        launches += 2;
+        LCU(cudaEventRecord(e1, st));
+        LCU(cudaMemcpyAsync(hgrad, dgrad, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, st));
+        if (ncu > 0) LCU(cudaMemcpyAsync(hst, dcu, sizeof(double) * ncu, cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        LCU(cudaGetLastError());
+        LCU(cudaEventElapsedTime(&last_build_ms, e0, e1));
+        ms_build += last_build_ms;
+        ++n_newpoint;
+        point_factored = false;
+        return 0;
+    }
+    // c (l) from the family's constraints (already in hst[0..ncu)) followed by the bound rows
+    void finish_cons(const double* x, double* cx) {
+        for (int k = 0; k < ncu; ++k) cx[k] = hst[k];
+        sc.cons(x, cx + ncu);          // sc.nb == 0 for general families: only [x - x_low ; x_upp - x]
+    }
     int eval_at(const double* x) {
         LCU(cudaSetDevice(device));
+        if (gv) return eval_at_generic(x);
         LCU(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         if (sc.nb > 0) {   // constraint Jacobian A(x): only the block rows depend on x
             si_jac_blocks_kernel<<<(4 * sc.nb + 255) / 256, 256, 0, st>>>(dx, sc.nb, sc.ineq ? 1 : 0, n, dArow);
@@ -533,6 +589,23 @@ struct LargeHandle : LargeOps, SmallBackend {
     int factor_point(bool want_host_R = true) {
         if (point_factored) return lfail(ENLSIPB200_EINVAL, "point already factored");
         LCU(cudaSetDevice(device));
+        if (gv) {      // plain Householder QR of the column-major [J | r] (dgeqrf order), R -> [J~ | r~]
+            LCU(cudaEventRecord(e1, st));
+            launches += enl_small::qrcp_device(dQ, (int)m_local, n + 1, dtauQ, dpQ, qw, st, 1);
+            const long long ne = (long long)(n + 1) * (n + 1);
+            enl_small::upper_to_square_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dQ, (int)m_local, n + 1, dJc);
+            ++launches;
+            jq1_valid = false;
+            point_factored = true;
+            LCU(cudaEventRecord(e2, st));
+            if (want_host_R) LCU(cudaMemcpyAsync(hR.data(), dJc, sizeof(double) * (size_t)(n + 1) * (n + 1), cudaMemcpyDeviceToHost, st));
+            LCU(cudaStreamSynchronize(st));
+            LCU(cudaGetLastError());
+            LCU(cudaEventElapsedTime(&last_tsqr_ms, e1, e2));
+            ms_tsqr += last_tsqr_ms;
+            ++n_factor;
+            return 0;
+        }
         LCU(cudaEventRecord(e1, st));
         LCU(cudaMemsetAsync(dR, 0, sizeof(double) * rr_rows * ld, st));
         launches += tsqr_factor(dA, ld, rows_pad, n, dR, ld, dT, dpart, st);
@@ -638,7 +711,8 @@ struct LargeHandle : LargeOps, SmallBackend {
         if (rc != 0) return rc;
         for (int j = 0; j < n; ++j) gradf[j] = hgrad[j];
         *rr = hgrad[n];
-        sc.cons(x, cx);
+        if (gv) finish_cons(x, cx);
+        else sc.cons(x, cx);
         return 0;
     }
     int new_point_compress(double* rt, double* gradf) override {
@@ -900,7 +974,12 @@ struct LargeHandle : LargeOps, SmallBackend {
         auto t0 = std::chrono::steady_clock::now();
         LCU(cudaMemcpyAsync(dp, p, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         cur_parts = grid_rows();
-        li_dir_kernel<<<cur_parts, 256, sizeof(double) * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart);
+        if (gv) {
+            launches += enl_small::gemv_n(dJkeep, (int)m_local, (int)m_local, n, dp, 1.0, nullptr, 0.0, dJp, st);
+            lg_dir_sums_kernel<<<cur_parts, 256, 0, st>>>(dr, dJp, m_local, dpart);
+        } else {
+            li_dir_kernel<<<cur_parts, 256, sizeof(double) * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart);
+        }
         ++launches;
         double o[4];
         int rc = finish4(o);
@@ -914,7 +993,8 @@ struct LargeHandle : LargeOps, SmallBackend {
         auto t0 = std::chrono::steady_clock::now();
         long long want = (m_local + 255) / 256;
         cur_parts = (int)(want < LI_PARTS ? (want > 0 ? want : 1) : LI_PARTS);
-        li_ls_kernel<<<cur_parts, 256, 0, st>>>(du, dv, dy, dr, dJp, m_local, alpha, with_coeffs, dpart);
+        if (gv) gv->ls(cur_parts, st, n, m_local, dx, dp, alpha, gd[0], gd[1], dr, dJp, with_coeffs, dpart);
+        else li_ls_kernel<<<cur_parts, 256, 0, st>>>(du, dv, dy, dr, dJp, m_local, alpha, with_coeffs, dpart);
         ++launches;
         int rc = finish4(o);
         if (rc != 0) return rc;
@@ -929,7 +1009,17 @@ struct LargeHandle : LargeOps, SmallBackend {
         return rc;
     }
     int ls_coeffs(double alpha, double out[4]) override { return ls_eval(alpha, 1, out); }
-    int cons(const double* x, double* cx) override { sc.cons(x, cx); return 0; }
+    int cons(const double* x, double* cx) override {
+        if (!gv) { sc.cons(x, cx); return 0; }
+        LCU(cudaSetDevice(device));
+        LCU(cudaMemcpyAsync(dvec[6], x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        gv->cons(st, n, ncu, dvec[6], gd[0], gd[1], dcu);
+        ++launches;
+        if (ncu > 0) LCU(cudaMemcpyAsync(hst, dcu, sizeof(double) * ncu, cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        finish_cons(x, cx);
+        return 0;
+    }
 };
 
 LargeHandle* LH(enlsipb200_large h) { return reinterpret_cast<LargeHandle*>(h); }
@@ -966,8 +1056,22 @@ int enlsipb200_large_create(int family, int n, long long m_local, long long m_gl
                             enlsipb200_large* out) {
     if (!out) return lfail(ENLSIPB200_EINVAL, "out is NULL");
     *out = nullptr;
-    if (family != ENLSIPB200_FAMILY_SINGLE_INDEX) return lfail(ENLSIPB200_EINVAL, "unknown large-regime family");
-    if (n < TS_B || n % TS_B != 0) return lfail(ENLSIPB200_EINVAL, "n must be a positive multiple of 32");
+    const GenericVt* gv = nullptr;
+#if defined(ENL_LARGE_USER_FAMILY)
+    if (family == ENLSIPB200_FAMILY_USER) gv = generic_vt<LFamUser>();
+    else return lfail(ENLSIPB200_EINVAL, "this library was compiled for ENLSIPB200_FAMILY_USER only");
+#else
+    if (family == ENLSIPB200_FAMILY_LARGE_CHAINED_ROSENBROCK) gv = generic_vt<LFamChainedRosenbrock>();
+    else if (family != ENLSIPB200_FAMILY_SINGLE_INDEX) return lfail(ENLSIPB200_EINVAL, "unknown large-regime family");
+#endif
+    if (gv) {
+        if (n < 3) return lfail(ENLSIPB200_EINVAL, "n >= 3 required");
+        if (m_local != gv->m_of(n) || m_global != m_local)
+            return lfail(ENLSIPB200_EINVAL, "general families are not row-sharded: m_local = m_global = the family's m(n)");
+        nb = 0; ineq = 0; rho = nullptr;
+    } else if (n < TS_B || n % TS_B != 0) {
+        return lfail(ENLSIPB200_EINVAL, "n must be a positive multiple of 32");
+    }
     if (m_local < 0 || m_global < m_local || nb < 0 || 4 * nb > n) return lfail(ENLSIPB200_EINVAL, "bad sizes");
     if ((long long)n + m_global < 1000)
         return lfail(ENLSIPB200_EINVAL, "n + m < 1000: second derivatives stay on in the reference (EF:2658); use the batched engine");
@@ -981,9 +1085,15 @@ int enlsipb200_large_create(int family, int n, long long m_local, long long m_gl
     h->device = device;
     h->n = n; h->m = m_global; h->m_local = m_local;
     h->sc.n = n; h->sc.nb = nb; h->sc.ineq = ineq != 0;
-    h->sc.rho.assign(rho, rho + nb);
+    if (nb > 0) h->sc.rho.assign(rho, rho + nb);
     h->sc.set_bounds(x_low, x_upp);
     h->l = h->sc.l(); h->q = h->sc.q();
+    h->gv = gv;
+    if (gv) {
+        h->q = gv->q_of(n);
+        h->ncu = h->q + gv->ni_of(n);
+        h->l = h->ncu + h->sc.l();
+    }
     if (h->l == 0) { delete h; return lfail(ENLSIPB200_EINVAL, "There must be at least one constraint (cnls_model.jl:367)"); }
     int rc = h->alloc();
     if (rc != 0) { delete h; return rc; }
@@ -1001,6 +1111,15 @@ int enlsipb200_large_set_data(enlsipb200_large hh, int slot, const double* ptr, 
     LargeHandle* h = LH(hh);
     if (!h || !ptr) return lfail(ENLSIPB200_EINVAL, "NULL argument");
     LCU(cudaSetDevice(h->device));
+    if (h->gv) {     // general families: two free-form data slots handed to the family's functions
+        if (slot < 0 || slot > 1 || count < 0) return lfail(ENLSIPB200_EINVAL, "bad slot / count");
+        if (on_device) { h->gd[slot] = ptr; return 0; }
+        if (h->gown[slot]) { cudaFree(h->gown[slot]); h->gown[slot] = nullptr; }
+        LCU(cudaMalloc(&h->gown[slot], sizeof(double) * (count > 0 ? count : 1)));
+        LCU(cudaMemcpy(h->gown[slot], ptr, sizeof(double) * count, cudaMemcpyHostToDevice));
+        h->gd[slot] = h->gown[slot];
+        return 0;
+    }
     long long want = slot == 0 ? h->m_local * h->n : h->m_local;
     if (slot < 0 || slot > 1 || count != want) return lfail(ENLSIPB200_EINVAL, "bad slot / count");
     const double** dst = slot == 0 ? &h->dW : &h->dy;
@@ -1053,7 +1172,8 @@ int enlsipb200_large_solve(enlsipb200_large hh, const double* x0, const enlsipb2
                            int trace_cap) {
     LargeHandle* h = LH(hh);
     if (!h || !x0 || !o || !x || !f) return lfail(ENLSIPB200_EINVAL, "NULL argument");
-    if (!h->dW || !h->dy) return lfail(ENLSIPB200_EINVAL, "family data (W, y) not set");
+    if (!h->gv && (!h->dW || !h->dy)) return lfail(ENLSIPB200_EINVAL, "family data (W, y) not set");
+    h->jac_fd = (o->jac_mode == ENLSIPB200_JAC_FORWARD_DIFF) ? 1 : 0;
     LargeOptions opt;
     opt.max_iter = o->max_iter;
     opt.scaling = o->scaling;
@@ -1100,7 +1220,7 @@ int enlsipb200_large_solve(enlsipb200_large hh, const double* x0, const enlsipb2
 int enlsipb200_large_factor(enlsipb200_large hh, const double* x, double* R, float* build_ms, float* tsqr_ms) {
     LargeHandle* h = LH(hh);
     if (!h || !x) return lfail(ENLSIPB200_EINVAL, "NULL argument");
-    if (!h->dW || !h->dy) return lfail(ENLSIPB200_EINVAL, "family data (W, y) not set");
+    if (!h->gv && (!h->dW || !h->dy)) return lfail(ENLSIPB200_EINVAL, "family data (W, y) not set");
     int rc = h->factor_at(x);
     if (rc != 0) return rc;
     const int nc = h->n + 1;

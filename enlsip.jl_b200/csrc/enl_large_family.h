@@ -66,3 +66,71 @@ struct SingleIndexConstraints {
 };
 
 }  // namespace enl_large
+
+// =====================================================================================================================
+// General problem families of the large regime ("row families"): the reference accepts ANY closure for residuals /
+// constraints / Jacobians (src/cnls_model.jl:11-62, 345-359); here a family is a set of device functions over a point
+// accessor X (x[j]), so that the same source serves the plain evaluation, the forward-difference Jacobian
+// (cnls_model.jl:65-82: X adds delta_j to one coordinate) and the linesearch trial points (X = x + alpha p):
+//     template <class X> double residual(long long i, int n, const X& x, const double* d0, const double* d1);
+//     template <class X> double constraint(int k, int n, const X& x, const double* d0, const double* d1);   // eq first, then ineq
+//     double jac_residual(long long i, int j, int n, const double* x, ...);      // optional (HAS_JAC)
+//     double jac_constraint(int k, int j, int n, const double* x, ...);
+// plus the sizes as functions of n.  Built in: chained Rosenbrock (test/problems/chained_rosenbrock.jl:8-53, the
+// reference's own large test: n = 1000, m = 1998, 998 equalities); user source is bound to the same interface by
+// enl_large_user.h (enlsipb200_large_compile_family).
+// =====================================================================================================================
+#if defined(__CUDACC__)
+namespace enl_large {
+
+struct XPlain {
+    const double* x;
+    __device__ __forceinline__ double operator[](int j) const { return x[j]; }
+};
+struct XPert {          // x + delta e_jp
+    const double* x; int jp; double delta;
+    __device__ __forceinline__ double operator[](int j) const { return j == jp ? __dadd_rn(x[j], delta) : x[j]; }
+};
+struct XStep {          // x + alpha p, rounded like the host's x[j] + alpha * p[j]
+    const double* x; const double* p; double alpha;
+    __device__ __forceinline__ double operator[](int j) const { return __dadd_rn(x[j], __dmul_rn(alpha, p[j])); }
+};
+
+struct LFamChainedRosenbrock {
+    static constexpr bool HAS_JAC = true;
+    __host__ __device__ static long long m_of(int n) { return 2LL * (n - 1); }
+    __host__ __device__ static int q_of(int n) { return n - 2; }
+    __host__ __device__ static int ni_of(int) { return 0; }
+    // r_i = 10 (x_i^2 - x_{i+1}), i < n-1 ; r_{n-1+i} = x_i - 1        (chained_rosenbrock.jl:8-19)
+    template <class X>
+    __device__ static double residual(long long i, int n, const X& x, const double*, const double*) {
+        if (i < n - 1) { const double a = x[(int)i]; return __dmul_rn(10.0, __dsub_rn(__dmul_rn(a, a), x[(int)i + 1])); }
+        return __dsub_rn(x[(int)(i - (n - 1))], 1.0);
+    }
+    __device__ static double jac_residual(long long i, int j, int n, const double* x, const double*, const double*) {
+        if (i < n - 1) return j == i ? __dmul_rn(20.0, x[j]) : (j == i + 1 ? -10.0 : 0.0);
+        return j == i - (n - 1) ? 1.0 : 0.0;
+    }
+    // c_k = 3 b^3 + 2 c - 5 + sin(b - c) sin(b + c) + 4 b - a exp(a - b) - 3, (a, b, c) = x[k..k+2]   (:21-24)
+    template <class X>
+    __device__ static double constraint(int k, int, const X& x, const double*, const double*) {
+        const double a = x[k], b = x[k + 1], c = x[k + 2];
+        double v = __dadd_rn(__dmul_rn(3.0, __dmul_rn(__dmul_rn(b, b), b)), __dmul_rn(2.0, c));
+        v = __dsub_rn(v, 5.0);
+        v = __dadd_rn(v, __dmul_rn(sin(__dsub_rn(b, c)), sin(__dadd_rn(b, c))));
+        v = __dadd_rn(v, __dmul_rn(4.0, b));
+        v = __dsub_rn(v, __dmul_rn(a, exp(__dsub_rn(a, b))));
+        return __dsub_rn(v, 3.0);
+    }
+    __device__ static double jac_constraint(int k, int j, int, const double* x, const double*, const double*) {   // (:26-51)
+        if (j < k || j > k + 2) return 0.0;
+        const double a = x[k], b = x[k + 1], c = x[k + 2];
+        const double e = exp(a - b), sm = sin(b - c), cm = cos(b - c), sp = sin(b + c), cp = cos(b + c);
+        if (j == k) return -(a + 1.0) * e;
+        if (j == k + 1) return 9.0 * b * b + cm * sp + sm * cp + 4.0 + a * e;
+        return 2.0 - cm * sp + sm * cp;
+    }
+};
+
+}  // namespace enl_large
+#endif

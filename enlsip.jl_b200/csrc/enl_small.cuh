@@ -192,6 +192,7 @@ struct QrState {
     int active;    // the blocked phase still has work
     int pvt;       // pivot column chosen for the panel column in flight
     int anyflag;   // some column was flagged by the norm downdate of the column just finished
+    int nopivot;   // plain Householder QR (dgeqrf order): columns stay where they are
     unsigned int ticket1, ticket2;
     double tau_k, sc_k, beta_k;   // dlarfg scalars of the panel column in flight (the column itself is stored unscaled
                                   // until the next finish kernel scales it in place)
@@ -199,7 +200,7 @@ struct QrState {
 constexpr int QR_MAXPART = 1024;   // partial results of the multi-CTA reductions
 
 __global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols, double* vn1, double* vn2, int* jpvt,
-                               QrState* stt, int topbmn) {
+                               QrState* stt, int topbmn, int nopivot) {
     __shared__ double sh[32];
     const int c = blockIdx.x;
     const double* cc = f + (size_t)c * rows;
@@ -213,7 +214,7 @@ __global__ void qr_init_kernel(const double* __restrict__ f, int rows, int cols,
             stt->j0 = 0; stt->k = 0; stt->stop = 0;
             stt->jb = topbmn < QR_NB ? topbmn : QR_NB;
             stt->active = topbmn > 0 ? 1 : 0;
-            stt->pvt = 0; stt->anyflag = 0; stt->ticket1 = 0; stt->ticket2 = 0;
+            stt->pvt = 0; stt->anyflag = 0; stt->ticket1 = 0; stt->ticket2 = 0; stt->nopivot = nopivot;
             stt->tau_k = 0.0; stt->sc_k = 1.0; stt->beta_k = 0.0;
         }
     }
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __re
                 double temp = fabs(a) / v1;
                 temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
                 const double rq = v1 / vn2[j];
-                if (temp * (rq * rq) <= S_TOL3Z) { any = 1; if (lane == 0) flags[j] = 1; }
+                if (temp * (rq * rq) <= S_TOL3Z && !stt->nopivot) { any = 1; if (lane == 0) flags[j] = 1; }
                 else { v1 = v1 * sqrt(temp); if (lane == 0) vn1[j] = v1; }
             }
             if (lane == 0) *ap = a;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(256) qr_panel_finish_pivot_kernel(double* __re
             if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
         }
         const int flagged = __ldcg(&stt->anyflag);
-        if (bi >= cols) bi = jc;
+        if (bi >= cols || stt->nopivot) bi = jc;
         const bool pivoting = !flagged && k < jb;
         if (pivoting && bi != jc && lane < k) {          // swap the rows of F (k <= 32 entries)
             const double t = __ldcg(F + (size_t)bi * QR_NB + lane);
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(256) qr_panel_close_kernel(const double* __res
 
 // ---- unblocked dlaqp2 steps (the last min(m,n) - topbmn columns; host-driven column index i) ----
 __global__ void __launch_bounds__(1024) qr_p2_pivot_house_kernel(double* __restrict__ f, int rows, int cols, int i,
-                                                                  double* vn1, double* vn2, int* jpvt, double* tau) {
+                                                                  double* vn1, double* vn2, int* jpvt, double* tau, int nopivot) {
     __shared__ double sh[32];
     __shared__ double s_best[32];
     __shared__ int s_idx[32];
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(1024) qr_p2_pivot_house_kernel(double* __restr
         double b = s_best[0]; int bi = s_idx[0];
         for (int q = 1; q < nw; ++q)
             if (s_best[q] > b || (s_best[q] == b && s_idx[q] < bi)) { b = s_best[q]; bi = s_idx[q]; }
-        if (bi >= cols) bi = i;
+        if (bi >= cols || nopivot) bi = i;
         s_pvt = bi;
         if (bi != i) {
             const int tp = jpvt[bi]; jpvt[bi] = jpvt[i]; jpvt[i] = tp;
@@ -625,7 +626,7 @@ inline size_t qc_smem_bytes(int rows, int cols) {
     return sizeof(double) * ((size_t)ncl * rows + rows + 2 + 2 * (size_t)ncl + QC_CTAS) + sizeof(int) * ((size_t)ncl + cols + 2 * QC_CTAS + 2);
 }
 __global__ void __cluster_dims__(QC_CTAS, 1, 1) __launch_bounds__(QC_THREADS)
-qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau, int* __restrict__ jpvt) {
+qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau, int* __restrict__ jpvt, int nopivot) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -692,7 +693,7 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
             double b = -1.0; int bp = 0x7fffffff, bph = -1;
             for (int q = 0; q < QC_CTAS; ++q)
                 if (cphys[q] >= 0 && (cval[q] > b || (cval[q] == b && cpos[q] < bp))) { b = cval[q]; bp = cpos[q]; bph = cphys[q]; }
-            if (bph < 0) { bp = i; bph = l2p[i]; }          // nothing comparable (NaN norms): keep the column in place
+            if (bph < 0 || nopivot) { bp = i; bph = l2p[i]; }   // nothing comparable (NaN norms) / plain QR: the column stays
             const int q = l2p[i];                           // the column sitting at position i moves to the winner's place
             l2p[bp] = q; l2p[i] = bph;
             if (q % QC_CTAS == rank) pos[q / QC_CTAS] = bp;
@@ -779,6 +780,15 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
     }
 }
 
+// R of a factored rows x nc matrix (dgeqrf layout, column major) -> out (nc x nc column major), zeros below the diagonal
+// and in rows >= rows
+__global__ void upper_to_square_kernel(const double* __restrict__ f, int rows, int nc, double* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)nc * nc) return;
+    const int r = (int)(e % nc), c = (int)(e / nc);
+    out[e] = (r <= c && r < rows) ? f[(size_t)c * rows + r] : 0.0;
+}
+
 // diag(R) and the inverse permutation of a finished factorisation
 __global__ void qr_finish_kernel(const double* __restrict__ f, int rows, int cols, const int* __restrict__ jpvt,
                                  double* diag, int* ipvt) {
@@ -824,13 +834,13 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
 
 // f: rows x cols column major on the device, factored in place (dgeqp3 layout); tau [min(rows, cols)]; jpvt [cols]
 // (0-based).  Returns the number of kernels launched.  At most one host synchronisation (blocked phase only).
-inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st) {
+inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st, int nopivot = 0) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
     if (qc_smem_bytes(rows, cols) <= QC_MAX_SMEM) {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM); attr_set = true; }
-        qr_cluster_kernel<<<QC_CTAS, QC_THREADS, qc_smem_bytes(rows, cols), st>>>(f, rows, cols, tau, jpvt);
+        qr_cluster_kernel<<<QC_CTAS, QC_THREADS, qc_smem_bytes(rows, cols), st>>>(f, rows, cols, tau, jpvt, nopivot);
         return 1;
     }
     // dgeqp3: blocked (dlaqps) while j <= topbmn = minmn - nx, if nb < minmn and nx < minmn
@@ -838,7 +848,7 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
     int launches = 0;
     cudaMemsetAsync(wk.flags, 0, sizeof(int) * cols, st);
     cudaMemsetAsync(wk.ticket, 0, sizeof(unsigned int), st);
-    qr_init_kernel<<<cols, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.state, topbmn);
+    qr_init_kernel<<<cols, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.state, topbmn, nopivot);
     ++launches;
     if (topbmn > 0) {
         // A panel that stops early (a norm to recompute) re-opens at its next column, so more than ceil(topbmn / nb)
@@ -881,7 +891,7 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
         }
     }
     for (int i = topbmn; i < minmn; ++i) {
-        qr_p2_pivot_house_kernel<<<1, 1024, 0, st>>>(f, rows, cols, i, wk.vn1, wk.vn2, jpvt, tau);
+        qr_p2_pivot_house_kernel<<<1, 1024, 0, st>>>(f, rows, cols, i, wk.vn1, wk.vn2, jpvt, tau, nopivot);
         ++launches;
         if (i < cols - 1) {
             const int len = rows - i - 1;

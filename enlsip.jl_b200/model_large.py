@@ -26,14 +26,31 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
+# general "row families" (csrc/enl_large_family.h): name -> (family id, m(n), nb_eq(n), nb_ineq(n), data slots)
+_ROW_FAMILIES = {
+    "chained_rosenbrock": (capi.FAMILY_LARGE_CHAINED_ROSENBROCK, lambda n: 2 * (n - 1), lambda n: n - 2, lambda n: 0, ()),
+}
+
+
 class LargeCnlsModel:
-    def __init__(self, family, starting_point, data, ineq=False, x_low=None, x_upp=None, m_global=None, device=-1):
-        if family != "single_index":
-            raise AssertionError("large-regime families: ['single_index']")
+    def __init__(self, family, starting_point, data=None, ineq=False, x_low=None, x_upp=None, m_global=None, device=-1,
+                 jacobian="analytic"):
+        if jacobian not in ("analytic", "forward_diff"):
+            raise AssertionError("jacobian must be 'analytic' or 'forward_diff'")
+        self.jacobian = jacobian
         self.family = family
         self.B = 1
         self.starting_point = np.ascontiguousarray(starting_point, dtype=np.float64).reshape(-1)
         n = self.starting_point.size
+        self._keep = {}
+        if family in _ROW_FAMILIES:
+            fam_id, m_of, q_of, ni_of, keys = _ROW_FAMILIES[family]
+            self._init_row_family(fam_id, n, int(m_of(n)), int(q_of(n)), int(ni_of(n)), keys, data or {}, x_low, x_upp, device)
+            return
+        if family != "single_index":
+            raise AssertionError("large-regime families: %s" % (["single_index"] + sorted(_ROW_FAMILIES)))
+        if jacobian != "analytic":
+            raise AssertionError("the single_index family is built with its analytic Jacobian")
         W, y = data["W"], data["y"]
         rho = np.ascontiguousarray(data["rho"], dtype=np.float64)
         rows = int(W.shape[0])
@@ -52,9 +69,28 @@ class LargeCnlsModel:
                                                             1 if ineq else 0, rho.ctypes.data, self.x_low.ctypes.data,
                                                             self.x_upp.ctypes.data, device, ctypes.byref(h)))
         self._h = h
-        self._keep = {}
         self.set_data(0, W)
         self.set_data(1, y)
+        self._reset_results()
+
+    def _init_row_family(self, fam_id, n, m, q, ni, keys, data, x_low, x_upp, device):
+        """A general family: residual rows / constraints as device functions of the point (csrc/enl_large_family.h), the
+        counterpart of CnlsModel(residuals, n, m; eq_constraints, nb_eqcons, ...) for an arbitrary model."""
+        self.nb_parameters, self.rows, self.nb_residuals = n, m, m
+        self.x_low = np.full(n, -np.inf) if x_low is None else np.ascontiguousarray(x_low, dtype=np.float64)
+        self.x_upp = np.full(n, np.inf) if x_upp is None else np.ascontiguousarray(x_upp, dtype=np.float64)
+        self.nb_eqcons = q
+        self.nb_constraints = q + ni + int(np.isfinite(self.x_low).sum()) + int(np.isfinite(self.x_upp).sum())
+        self.lmax = self.nb_constraints
+        h = ctypes.c_void_p()
+        capi.check_large(capi.lib().enlsipb200_large_create(fam_id, n, m, m, 0, 0, None, self.x_low.ctypes.data,
+                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)))
+        self._h = h
+        for slot, key in enumerate(keys):
+            self.set_data(slot, data[key])
+        self._reset_results()
+
+    def _reset_results(self):
         self.status_code = None
         self.sol = self.starting_point
         self.obj_value = None
@@ -141,6 +177,7 @@ def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False,
     o = capi.default_options()
     o.max_iter = int(max_iter)
     o.scaling = 1 if scaling else 0
+    o.jac_mode = capi.JAC_FORWARD_DIFF if model.jacobian == "forward_diff" else capi.JAC_ANALYTIC
     o.time_limit = float(time_limit)
     nan = float("nan")
     o.abs_tol = nan if abs_tol is None else float(abs_tol)
@@ -159,7 +196,7 @@ def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False,
     model.iterations, model.nb_active, model.active, model.trace = it, na, act, tr
     if not silent:
         from .model import iteration_table, status
-        print("single_index problem (n=%d, m=%d, constraints=%d)" % (n, model.nb_residuals, model.nb_constraints))
+        print("%s problem (n=%d, m=%d, constraints=%d)" % (model.family, n, model.nb_residuals, model.nb_constraints))
         print(iteration_table(model, 0))
         print("Number of iterations...................: %4d" % int(it[0]))
         print("Square sum of residuals................: %.7e" % float(f[0]))

@@ -140,6 +140,12 @@ int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
                                              parameters: equalities sum x_j^2 - rho_k (ineq = 0) or
                                              inequalities rho_k - sum x_j^2 >= 0 (ineq = 1); optional bounds */
 
+#define ENLSIPB200_FAMILY_LARGE_CHAINED_ROSENBROCK 17 /* test/problems/chained_rosenbrock.jl:8-53 at ANY n (the reference
+                                             runs n = 1000: m = 2(n-1) = 1998 residuals, q = n-2 = 998 nonlinear
+                                             equalities); a general "row family": no restriction on n, not row-sharded
+                                             (m_local = m_global = 2(n-1); nb / ineq / rho are ignored); analytic or
+                                             forward-difference Jacobians (opt->jac_mode)                              */
+
 typedef struct enlsipb200_large_s* enlsipb200_large;
 
 const char* enlsipb200_large_last_error(void);

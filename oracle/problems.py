@@ -119,8 +119,8 @@ def osborne2(golden_dir=None) -> Problem:
     return make_problem(11, 65, r, jac_r, x_low=d["x_low"], x_upp=d["x_upp"], x0=d["x0"], name="osborne2")
 
 
-def chained_rosenbrock(n=1000) -> Problem:
-    """test/problems/chained_rosenbrock.jl:8-53."""
+def chained_rosenbrock(n=1000, fd=False) -> Problem:
+    """test/problems/chained_rosenbrock.jl:8-53.  ``fd``: forward-difference Jacobians (cnls_model.jl:65-82)."""
     m = 2 * (n - 1)
 
     def r(x):
@@ -151,7 +151,8 @@ def chained_rosenbrock(n=1000) -> Problem:
         return A
 
     x0 = np.array([-1.2 if (i % 2 == 1) else 1.0 for i in range(1, n + 1)])
-    return make_problem(n, m, r, jac_r, eq=c, jac_eq=jac_c, nb_eq=n - 2, x0=x0, name="chained_rosenbrock_%d" % n)
+    return make_problem(n, m, r, None if fd else jac_r, eq=c, jac_eq=None if fd else jac_c, nb_eq=n - 2, x0=x0,
+                        name="chained_rosenbrock_%d" % n, fd=fd)
 
 
 def chained_wood(n=20) -> Problem:

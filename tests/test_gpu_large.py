@@ -281,3 +281,32 @@ def test_large_solve_seed_sweep_vs_oracle(E):
         mod.close()
         done += 1
     assert done == 12
+
+
+@pytest.mark.parametrize("n,jac", [(1000, "analytic"), (1000, "forward_diff"), (333, "analytic"), (40, "analytic")])
+def test_chained_rosenbrock_reference_size_vs_oracle(E, n, jac):
+    """The reference's own large test problem, test/problems/chained_rosenbrock.jl:3-53, at ITS size: n = 1000,
+    m = 1998 residuals, 998 nonlinear equalities (n + m >= 1000: Newton off, EF:2658 -> the large regime), as a general
+    row family (csrc/enl_large_family.h) -- no multiple-of-32 restriction, [J | r] factored by the plain-Householder
+    mode of the device QR, the whole small stage (998 active constraints of 1000 parameters) on the device.  Checked
+    against the oracle: status, exit code, iteration count, active set, per-iteration trace identical, f to 1e-10."""
+    from oracle import enlsip_oracle as O, problems as P
+    from tests.test_large_host import compare_with_oracle
+    pb = P.chained_rosenbrock(n, fd=(jac == "forward_diff"))
+    mod = E.LargeCnlsModel("chained_rosenbrock", pb.x0, jacobian=jac)
+    assert (mod.nb_parameters, mod.nb_residuals, mod.nb_eqcons, mod.nb_constraints) == (n, 2 * (n - 1), n - 2, n - 2)
+    E.solve(mod, trace_cap=60)
+    r = O.solve(pb, wallclock=False)
+    assert int(mod.status_code[0]) == r.status == 1
+    assert int(mod.exit_code[0]) == r.exit_code and int(mod.iterations[0]) == r.iterations
+    assert [int(v) for v in mod.active[0] if v > 0] == r.active
+    if jac == "analytic":
+        out = dict(x=mod.sol[0], f=mod.obj_value, exit_code=mod.exit_code, status=mod.status_code, iters=mod.iterations,
+                   nact=mod.nb_active, active=mod.active[0], trace=mod.trace[0])
+        compare_with_oracle(out, r, n)
+    else:      # forward differences: noise floor eps |r| / delta ~ 1e-8 in J (DESIGN.md section 4)
+        assert abs(float(mod.obj_value[0]) - r.f) <= 1e-8 * r.f
+        assert np.linalg.norm(mod.sol[0] - r.x) <= 1e-6 * np.linalg.norm(r.x)
+    st = mod.stats()
+    assert st["device_qrcp"] > 0 and st["launches"] > 0
+    mod.close()
