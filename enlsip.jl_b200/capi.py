@@ -34,7 +34,7 @@ EXIT_WOULD_THROW, EXIT_WOULD_HANG, EXIT_CAPACITY = -99, -98, -97
 EXPORTS = ["enlsipb200_version", "enlsipb200_last_error", "enlsipb200_default_options", "enlsipb200_create",
            "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data", "enlsipb200_solve_batch", "enlsipb200_eval_batch",
            "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count", "enlsipb200_det_exp",
-           "enlsipb200_compile_family",
+           "enlsipb200_compile_family", "enlsipb200_large_compile_family",
            "enlsipb200_large_last_error", "enlsipb200_large_create", "enlsipb200_large_destroy",
            "enlsipb200_large_set_data", "enlsipb200_large_comm_id", "enlsipb200_large_comm_init",
            "enlsipb200_large_solve", "enlsipb200_large_factor", "enlsipb200_large_stats",
@@ -99,6 +99,8 @@ def _bind(L, large=True):
     L.enlsipb200_launch_count.restype = ctypes.c_longlong
     L.enlsipb200_det_exp.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_int]
     L.enlsipb200_compile_family.argtypes = [cs, ci, ci, ci, ci, ci, ci, ci, cs, cs]
+    if hasattr(L, "enlsipb200_large_compile_family"):
+        L.enlsipb200_large_compile_family.argtypes = [cs, ll, ci, ci, ci, cs, cs]
     if large:
         L.enlsipb200_large_last_error.restype = ctypes.c_char_p
         L.enlsipb200_large_create.argtypes = [ci, ci, ll, ll, ci, ci, vp, vp, vp, ci, ctypes.POINTER(vp)]
@@ -142,14 +144,56 @@ def compile_family(source, n, m, nb_eq=0, nb_ineq=0, stride0=0, stride1=0, has_j
     tag = (name or "family") + "_" + hsh.hexdigest()[:16]
     if tag in _user_libs:
         return _user_libs[tag]
-    work = os.path.join(USER_LIB_DIR, tag)
     out = os.path.join(USER_LIB_DIR, "libenlsip_b200_%s.so" % tag)
     if not os.path.exists(out):
+        # one-process-per-GPU launches build the same family concurrently: per-process work directory and library name,
+        # renamed into place when complete (os.replace is atomic), so nobody loads a half-written file
+        work = os.path.join(USER_LIB_DIR, "%s.%d" % (tag, os.getpid()))
         os.makedirs(work, exist_ok=True)
+        tmp = os.path.join(work, "lib.so")
         rc = lib().enlsipb200_compile_family(source.encode(), n, m, nb_eq, nb_ineq, stride0, stride1,
-                                             1 if has_jacobians else 0, out.encode(), work.encode())
+                                             1 if has_jacobians else 0, tmp.encode(), work.encode())
         check(rc)
+        os.replace(tmp, out)
     L = _bind(ctypes.CDLL(out), large=False)
+    _user_libs[tag] = L
+    return L
+
+
+def _bind_large_only(L):
+    """Prototypes of a library built by enlsipb200_large_compile_family (large-regime symbols only)."""
+    vp, ll, ci = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    L.enlsipb200_large_last_error.restype = ctypes.c_char_p
+    L.enlsipb200_large_create.argtypes = [ci, ci, ll, ll, ci, ci, vp, vp, vp, ci, ctypes.POINTER(vp)]
+    L.enlsipb200_large_destroy.argtypes = [vp]
+    L.enlsipb200_large_set_data.argtypes = [vp, ci, vp, ll, ci]
+    L.enlsipb200_large_solve.argtypes = [vp, vp, ctypes.POINTER(Options)] + [vp] * 8 + [ci]
+    L.enlsipb200_large_factor.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    L.enlsipb200_large_stats.argtypes = [vp, vp, ci]
+    return L
+
+
+def large_compile_family(source, m, nb_eq=0, nb_ineq=0, has_jacobians=False, name=None):
+    """enlsipb200_large_compile_family: the large-regime solver compiled around user CUDA source (row functors over a
+    point accessor, csrc/enl_large_user.h).  Cached in lib/user/ by a hash of (source, sizes, solver sources); built under a
+    per-process temporary name and renamed into place, so concurrent builders never load a half-written library."""
+    import hashlib
+    hsh = hashlib.sha256()
+    hsh.update(repr((source, int(m), nb_eq, nb_ineq, bool(has_jacobians))).encode())
+    for p in [SRC_LARGE] + HEADERS_LARGE + [os.path.join(_HERE, "csrc", "enl_large_user.h")]:
+        hsh.update(open(p, "rb").read())
+    tag = (name or "large_family") + "_" + hsh.hexdigest()[:16]
+    if tag in _user_libs:
+        return _user_libs[tag]
+    out = os.path.join(USER_LIB_DIR, "libenlsip_b200_%s.so" % tag)
+    if not os.path.exists(out):
+        work = os.path.join(USER_LIB_DIR, "%s.%d" % (tag, os.getpid()))
+        os.makedirs(work, exist_ok=True)
+        tmp = os.path.join(work, "lib.so")
+        check(lib().enlsipb200_large_compile_family(source.encode(), int(m), nb_eq, nb_ineq, 1 if has_jacobians else 0,
+                                                    tmp.encode(), work.encode()))
+        os.replace(tmp, out)
+    L = _bind_large_only(ctypes.CDLL(out))
     _user_libs[tag] = L
     return L
 
@@ -163,9 +207,9 @@ def check(rc, L=None):
         raise EngineError("enlsip_b200 error %d: %s" % (rc, (L or lib()).enlsipb200_last_error().decode()))
 
 
-def check_large(rc):
+def check_large(rc, L=None):
     if rc != 0:
-        raise EngineError("enlsip_b200 (large regime) error %d: %s" % (rc, lib().enlsipb200_large_last_error().decode()))
+        raise EngineError("enlsip_b200 (large regime) error %d: %s" % (rc, (L or lib()).enlsipb200_large_last_error().decode()))
 
 
 def default_options() -> Options:

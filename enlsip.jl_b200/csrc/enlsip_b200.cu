@@ -665,6 +665,49 @@ int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int n
     return 0;
 }
 
+// The same for the large regime (one problem, n + m >= 1000): the user's residual rows / constraints as device functions
+// over a point accessor (csrc/enl_large_user.h) are compiled with csrc/enl_large.cu into a library that exports the
+// enlsipb200_large_* API with family = ENLSIPB200_FAMILY_USER.
+int enlsipb200_large_compile_family(const char* source, long long m, int nb_eq, int nb_ineq, int has_jacobians,
+                                    const char* out_lib_path, const char* work_dir) {
+    if (!source || !out_lib_path || !work_dir) return fail(ENLSIPB200_EINVAL, "NULL argument");
+    if (m < 1 || nb_eq < 0 || nb_ineq < 0) return fail(ENLSIPB200_EINVAL, "bad sizes");
+    Dl_info info;
+    if (!dladdr((void*)&enlsipb200_version, &info) || !info.dli_fname) return fail(ENLSIPB200_EINVAL, "cannot locate the library on disk");
+    std::string lib = info.dli_fname;
+    const size_t slash = lib.rfind('/');
+    const std::string libdir = slash == std::string::npos ? "." : lib.substr(0, slash);
+    const std::string csrc = libdir + "/../csrc";
+    const std::string unit = csrc + "/enl_large.cu";
+    if (access(unit.c_str(), R_OK) != 0) return fail(ENLSIPB200_EINVAL, "solver sources not found at " + csrc);
+    const std::string wd = work_dir;
+    const std::string pre = wd + "/enl_large_user_prelude.h";
+    FILE* fp = fopen(pre.c_str(), "w");
+    if (!fp) return fail(ENLSIPB200_EINVAL, "cannot write " + pre);
+    fprintf(fp, "// generated by enlsipb200_large_compile_family\n#pragma once\n#define ENL_LARGE_USER_FAMILY 1\n"
+                "#define ENL_LUSER_M %lldLL\n#define ENL_LUSER_Q %d\n#define ENL_LUSER_NI %d\n#define ENL_LUSER_HAS_JAC %d\n"
+                "#include <cuda_runtime.h>\n#include <math.h>\n#line 1 \"user_family_source\"\n%s\n",
+            m, nb_eq, nb_ineq, has_jacobians ? 1 : 0, source);
+    fclose(fp);
+    const std::string log = wd + "/enl_large_user_build.log";
+    const char* nvcc = getenv("ENLSIP_NVCC");
+    std::string cmd = std::string(nvcc ? nvcc : "nvcc") +
+                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fopenmp"
+                      " -shared -include \"" + pre + "\" \"" + unit + "\" -o \"" + out_lib_path + "\" -lgomp -ldl > \"" + log + "\" 2>&1";
+    const int rc = system(cmd.c_str());
+    if (rc != 0) {
+        std::string msg = "nvcc failed (" + cmd + "):\n";
+        if (FILE* lf = fopen(log.c_str(), "r")) {
+            char buf[512];
+            size_t got;
+            while (msg.size() < 6000 && (got = fread(buf, 1, sizeof(buf), lf)) > 0) msg.append(buf, got);
+            fclose(lf);
+        }
+        return fail(ENLSIPB200_EINVAL, msg);
+    }
+    return 0;
+}
+
 int enlsipb200_last_kernel_ms(enlsipb200_handle h, float* ms) {
     if (!h || !ms) return fail(ENLSIPB200_EINVAL, "null argument");
     if (!h->timed) return fail(ENLSIPB200_EINVAL, "no solve has been launched");

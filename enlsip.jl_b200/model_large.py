@@ -32,6 +32,22 @@ _ROW_FAMILIES = {
 }
 
 
+class LargeUserFamily:
+    """A problem of the large regime defined by user CUDA source: the replacement of the reference's closure arguments
+    (residuals, eq_constraints, ineq_constraints, jacobian_*; cnls_model.jl:345-359) when n + m >= 1000.  `source` defines
+    enl_user::residual / constraint as templates over a point accessor and, with has_jacobians, jac_residual /
+    jac_constraint (include/enlsip_b200.h, enlsipb200_large_compile_family).  `data`: names of up to two data arrays."""
+
+    def __init__(self, source, m, nb_eqcons=0, nb_ineqcons=0, has_jacobians=False, data=(), name="large_user"):
+        self.source, self.m, self.q, self.ni = source, int(m), int(nb_eqcons), int(nb_ineqcons)
+        self.has_jacobians, self.data, self.name = bool(has_jacobians), tuple(data), name
+        if len(self.data) > 2:
+            raise ValueError("at most two data slots")
+
+    def library(self):
+        return capi.large_compile_family(self.source, self.m, self.q, self.ni, self.has_jacobians, self.name)
+
+
 class LargeCnlsModel:
     def __init__(self, family, starting_point, data=None, ineq=False, x_low=None, x_upp=None, m_global=None, device=-1,
                  jacobian="analytic"):
@@ -43,6 +59,14 @@ class LargeCnlsModel:
         self.starting_point = np.ascontiguousarray(starting_point, dtype=np.float64).reshape(-1)
         n = self.starting_point.size
         self._keep = {}
+        self._lib = capi.lib()
+        if isinstance(family, LargeUserFamily):
+            self._lib = family.library()
+            self.family = family.name
+            if jacobian == "analytic" and not family.has_jacobians:
+                self.jacobian = "forward_diff"     # no jacobian_* given: the reference differentiates for the user as well
+            self._init_row_family(capi.FAMILY_USER, n, family.m, family.q, family.ni, family.data, data or {}, x_low, x_upp, device)
+            return
         if family in _ROW_FAMILIES:
             fam_id, m_of, q_of, ni_of, keys = _ROW_FAMILIES[family]
             self._init_row_family(fam_id, n, int(m_of(n)), int(q_of(n)), int(ni_of(n)), keys, data or {}, x_low, x_upp, device)
@@ -65,9 +89,9 @@ class LargeCnlsModel:
         self.nb_constraints = nb + int(np.isfinite(self.x_low).sum()) + int(np.isfinite(self.x_upp).sum())
         self.lmax = self.nb_constraints
         h = ctypes.c_void_p()
-        capi.check_large(capi.lib().enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, n, rows, self.nb_residuals, nb,
+        capi.check_large(self._lib.enlsipb200_large_create(capi.FAMILY_SINGLE_INDEX, n, rows, self.nb_residuals, nb,
                                                             1 if ineq else 0, rho.ctypes.data, self.x_low.ctypes.data,
-                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)))
+                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)), self._lib)
         self._h = h
         self.set_data(0, W)
         self.set_data(1, y)
@@ -83,8 +107,8 @@ class LargeCnlsModel:
         self.nb_constraints = q + ni + int(np.isfinite(self.x_low).sum()) + int(np.isfinite(self.x_upp).sum())
         self.lmax = self.nb_constraints
         h = ctypes.c_void_p()
-        capi.check_large(capi.lib().enlsipb200_large_create(fam_id, n, m, m, 0, 0, None, self.x_low.ctypes.data,
-                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)))
+        capi.check_large(self._lib.enlsipb200_large_create(fam_id, n, m, m, 0, 0, None, self.x_low.ctypes.data,
+                                                            self.x_upp.ctypes.data, device, ctypes.byref(h)), self._lib)
         self._h = h
         for slot, key in enumerate(keys):
             self.set_data(slot, data[key])
@@ -113,7 +137,7 @@ class LargeCnlsModel:
             arr = np.ascontiguousarray(arr, dtype=np.float64)
             ptr, count = arr.ctypes.data, arr.size
         self._keep[slot] = arr if dev else None
-        capi.check_large(capi.lib().enlsipb200_large_set_data(self._h, slot, ctypes.c_void_p(ptr), count, 1 if dev else 0))
+        capi.check_large(self._lib.enlsipb200_large_set_data(self._h, slot, ctypes.c_void_p(ptr), count, 1 if dev else 0), self._lib)
 
     def join(self, rank, world, broadcast=None):
         """Join the row shards of `world` processes (one per GPU).  `broadcast(buf: np.uint8[128])` must
@@ -134,7 +158,7 @@ class LargeCnlsModel:
                     dist.broadcast(t, 0)
             else:
                 broadcast(buf)
-        capi.check_large(capi.lib().enlsipb200_large_comm_init(self._h, buf.ctypes.data, int(rank), int(world)))
+        capi.check_large(self._lib.enlsipb200_large_comm_init(self._h, buf.ctypes.data, int(rank), int(world)), self._lib)
 
     def factor(self, x, want_R=True):
         """Measurement / test hook: one evaluation + QR of [J | r] at x.  Returns (R or None, build_ms, tsqr_ms)."""
@@ -142,13 +166,13 @@ class LargeCnlsModel:
         n = self.nb_parameters
         R = np.zeros((n + 1, n + 1)) if want_R else None
         b, t = ctypes.c_float(), ctypes.c_float()
-        capi.check_large(capi.lib().enlsipb200_large_factor(self._h, x.ctypes.data, None if R is None else R.ctypes.data,
-                                                            ctypes.byref(b), ctypes.byref(t)))
+        capi.check_large(self._lib.enlsipb200_large_factor(self._h, x.ctypes.data, None if R is None else R.ctypes.data,
+                                                            ctypes.byref(b), ctypes.byref(t)), self._lib)
         return R, float(b.value), float(t.value)
 
     def stats(self):
         v = np.zeros(12)
-        capi.check_large(capi.lib().enlsipb200_large_stats(self._h, v.ctypes.data, 12))
+        capi.check_large(self._lib.enlsipb200_large_stats(self._h, v.ctypes.data, 12), self._lib)
         keys = ("points", "build_ms", "tsqr_ms", "linesearch_ms", "solve_wall_ms", "linesearch_evals",
                 "launches", "rows_pad", "device_qrcp", "device_mulq", "small_stage_ms", "factorisations")
         return dict(zip(keys, [float(a) for a in v]))
@@ -158,7 +182,7 @@ class LargeCnlsModel:
 
     def close(self):
         if getattr(self, "_h", None):
-            capi.lib().enlsipb200_large_destroy(self._h)
+            self._lib.enlsipb200_large_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -190,8 +214,8 @@ def solve_large(model: LargeCnlsModel, silent=True, max_iter=100, scaling=False,
     act = np.zeros((1, max(model.lmax, 1)), dtype=np.int32)
     tr = np.zeros((1, trace_cap, capi.TRACE_HDR + n)) if trace_cap > 0 else None
     p = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
-    capi.check_large(capi.lib().enlsipb200_large_solve(model._h, p(model.starting_point), ctypes.byref(o), p(x), p(f),
-                                                       p(ec), p(st), p(it), p(na), p(act), p(tr), int(trace_cap)))
+    capi.check_large(model._lib.enlsipb200_large_solve(model._h, p(model.starting_point), ctypes.byref(o), p(x), p(f),
+                                                       p(ec), p(st), p(it), p(na), p(act), p(tr), int(trace_cap)), model._lib)
     model.status_code, model.exit_code, model.sol, model.obj_value = st, ec, x, f
     model.iterations, model.nb_active, model.active, model.trace = it, na, act, tr
     if not silent:

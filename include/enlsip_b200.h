@@ -121,6 +121,20 @@ long long enlsipb200_launch_count(enlsipb200_handle h);
 int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
                               int has_jacobians, const char* out_lib_path, const char* work_dir);
 
+/* The same plugin surface for the large regime (one problem, n + m >= 1000).  `source` defines, in namespace enl_user,
+ *     template <class X> __device__ double residual(long long i, int n, const X& x, const double* d0, const double* d1);
+ *     template <class X> __device__ double constraint(int k, int n, const X& x, const double* d0, const double* d1);
+ *         k < nb_eq: equalities, then the inequalities (>= 0); X is a point accessor, x[j]
+ * and, if has_jacobians != 0,
+ *     __device__ double jac_residual(long long i, int j, int n, const double* x, const double* d0, const double* d1);
+ *     __device__ double jac_constraint(int k, int j, int n, const double* x, const double* d0, const double* d1);
+ * (entry (i, j) of the dense Jacobian).  d0 / d1: the two data slots of enlsipb200_large_set_data (any length).
+ * The resulting library exports the enlsipb200_large_* API; create the handle with family = ENLSIPB200_FAMILY_USER,
+ * m_local = m_global = m, any n >= 3 (nb / ineq / rho ignored), bounds through x_low / x_upp.  Without Jacobians the
+ * solve differentiates by forward differences (cnls_model.jl:65-82). */
+int enlsipb200_large_compile_family(const char* source, long long m, int nb_eq, int nb_ineq, int has_jacobians,
+                                    const char* out_lib_path, const char* work_dir);
+
 /* deterministic exp used by the synthetic families, exposed for bit-parity tests vs oracle/detmath.c */
 int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
 

@@ -283,7 +283,7 @@ def test_large_solve_seed_sweep_vs_oracle(E):
     assert done == 12
 
 
-@pytest.mark.parametrize("n,jac", [(1000, "analytic"), (1000, "forward_diff"), (333, "analytic"), (40, "analytic")])
+@pytest.mark.parametrize("n,jac", [(1000, "analytic"), (1000, "forward_diff"), (334, "analytic"), (400, "forward_diff")])
 def test_chained_rosenbrock_reference_size_vs_oracle(E, n, jac):
     """The reference's own large test problem, test/problems/chained_rosenbrock.jl:3-53, at ITS size: n = 1000,
     m = 1998 residuals, 998 nonlinear equalities (n + m >= 1000: Newton off, EF:2658 -> the large regime), as a general
