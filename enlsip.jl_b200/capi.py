@@ -48,7 +48,7 @@ class Options(ctypes.Structure):
 
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-Xcompiler", "-fvisibility=hidden"]
 
 
 def build(force=False, verbose=False):
@@ -180,7 +180,7 @@ def large_compile_family(source, m, nb_eq=0, nb_ineq=0, has_jacobians=False, nam
     import hashlib
     hsh = hashlib.sha256()
     hsh.update(repr((source, int(m), nb_eq, nb_ineq, bool(has_jacobians))).encode())
-    for p in [SRC_LARGE] + HEADERS_LARGE + [os.path.join(_HERE, "csrc", "enl_large_user.h")]:
+    for p in [SRC, SRC_LARGE] + HEADERS_LARGE + [os.path.join(_HERE, "csrc", "enl_large_user.h")]:
         hsh.update(open(p, "rb").read())
     tag = (name or "large_family") + "_" + hsh.hexdigest()[:16]
     if tag in _user_libs:

@@ -648,7 +648,7 @@ int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int n
     const std::string log = wd + "/enl_user_build.log";
     const char* nvcc = getenv("ENLSIP_NVCC");
     std::string cmd = std::string(nvcc ? nvcc : "nvcc") +
-                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
+                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared"
                       " -DENL_COMPACT_CODE=1 -include \"" + pre + "\" \"" + unit + "\" -o \"" + out_lib_path +
                       "\" -ldl > \"" + log + "\" 2>&1";
     const int rc = system(cmd.c_str());
@@ -692,7 +692,7 @@ int enlsipb200_large_compile_family(const char* source, long long m, int nb_eq, 
     const std::string log = wd + "/enl_large_user_build.log";
     const char* nvcc = getenv("ENLSIP_NVCC");
     std::string cmd = std::string(nvcc ? nvcc : "nvcc") +
-                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fopenmp"
+                      " -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -fopenmp"
                       " -shared -include \"" + pre + "\" \"" + unit + "\" -o \"" + out_lib_path + "\" -lgomp -ldl > \"" + log + "\" 2>&1";
     const int rc = system(cmd.c_str());
     if (rc != 0) {

@@ -20,6 +20,15 @@
  */
 #ifndef ENLSIP_B200_H
 #define ENLSIP_B200_H
+/* Every entry point is exported explicitly; the libraries are built with -fvisibility=hidden so that nothing else (template
+ * instantiations, inline functions with static state) is shared between the stock library and the libraries that
+ * enlsipb200_compile_family / enlsipb200_large_compile_family build -- several of them live in one process. */
+#if defined(__GNUC__)
+#define ENLSIPB200_API __attribute__((visibility("default")))
+#else
+#define ENLSIPB200_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -59,22 +68,22 @@ typedef struct enlsipb200_options {
 
 typedef struct enlsipb200_handle_s* enlsipb200_handle;
 
-int enlsipb200_version(void);
-const char* enlsipb200_last_error(void);
-void enlsipb200_default_options(enlsipb200_options* opt);
+ENLSIPB200_API int enlsipb200_version(void);
+ENLSIPB200_API const char* enlsipb200_last_error(void);
+ENLSIPB200_API void enlsipb200_default_options(enlsipb200_options* opt);
 
 /* problem family + bounds (replaces CnlsModel(...) + instantiate_constraints_*; cnls_model.jl:345-496).
  * x_low / x_upp: host arrays of length n, +-Inf = no bound.  device < 0 = current device. */
-int enlsipb200_create(int family, const double* x_low, const double* x_upp, int device, enlsipb200_handle* out);
-int enlsipb200_destroy(enlsipb200_handle h);
-int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_constraints, int* lmax);
+ENLSIPB200_API int enlsipb200_create(int family, const double* x_low, const double* x_upp, int device, enlsipb200_handle* out);
+ENLSIPB200_API int enlsipb200_destroy(enlsipb200_handle h);
+ENLSIPB200_API int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_constraints, int* lmax);
 
 /* family data arrays (GAUSS_PEAKS: slot 0 = y [B,128], slot 1 = S [B]; OSBORNE2: slot 0 = t [65], slot 1 = y [65],
  * shared by the whole batch).  `on_device` != 0: ptr is a device pointer that must stay valid for the solve.
  * Otherwise ptr is a HOST buffer that must stay valid until the next enlsipb200_solve_batch returns: the upload
  * happens inside that call -- with host-buffer solves chunk by chunk, overlapped with the solves of the previous
  * chunk (pinned host memory makes the copies asynchronous). */
-int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream);
+ENLSIPB200_API int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream);
 
 /* solve B independent problems (replaces B calls of solve!).  All array arguments are host or
  * device pointers according to `on_device`; optional outputs may be NULL.
@@ -83,14 +92,14 @@ int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long l
  *   counters [B,2] nb_function_evaluations, nb_jacobian_evaluations (reference counting formula);
  *   trace [B,trace_cap,TRACE_HDR+n] per-iteration records (tests only).
  * Blocking unless on_device != 0 and a stream is given (then enqueued on that stream). */
-int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, const enlsipb200_options* opt,
+ENLSIPB200_API int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, const enlsipb200_options* opt,
                            double* x, double* f, int* exit_code, int* status, int* iters, int* nact, int* active,
                            int* counters, double* trace, int trace_cap, int on_device, void* stream);
 
 /* measurement hooks: device time of the last solve kernel (CUDA events on its stream), launch
  * geometry, number of kernels launched by this handle so far */
-int enlsipb200_last_kernel_ms(enlsipb200_handle h, float* ms);
-int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_bytes_per_cta, int* threads_per_cta,
+ENLSIPB200_API int enlsipb200_last_kernel_ms(enlsipb200_handle h, float* ms);
+ENLSIPB200_API int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_bytes_per_cta, int* threads_per_cta,
                            int* ctas_per_sm, int* grid, int* lanes_per_problem);
 /* The evaluation layer as an operator of its own: new_point! (src/enlsip_functions.jl:34-52) through the wrappers
  * res_eval! / jacres_eval! / cons_eval! / jaccons_eval! (src/cnls_model.jl:40-62), with jac_forward_diff
@@ -98,9 +107,9 @@ int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thread, int* smem_
  *   x [B, n] in;  r [B, m];  J [B, n, m] (per problem the m x n Jacobian, column major as in the reference);
  *   c [B, lmax];  A [B, lmax, n] (row i = gradient of constraint i, bound rows +-e_j included).  Any output may be NULL.
  * enlsipb200_last_kernel_ms reports the kernel time. */
-int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
+ENLSIPB200_API int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
                           double* J, double* c, double* A, int on_device, void* stream);
-long long enlsipb200_launch_count(enlsipb200_handle h);
+ENLSIPB200_API long long enlsipb200_launch_count(enlsipb200_handle h);
 
 /* Run-time compiled problem family: the replacement of the reference's plugin surface -- `residuals`,
  * `eq_constraints`, `ineq_constraints` and their optional `jacobian_*` closures handed to CnlsModel(...)
@@ -118,7 +127,7 @@ long long enlsipb200_launch_count(enlsipb200_handle h);
  * and uses this same API with family = ENLSIPB200_FAMILY_USER.  `work_dir`: writable directory for the generated
  * prelude and the build log.  Limits: n <= 16, m <= 4096, nb_eq + nb_ineq <= 16. */
 #define ENLSIPB200_FAMILY_USER 64
-int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
+ENLSIPB200_API int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
                               int has_jacobians, const char* out_lib_path, const char* work_dir);
 
 /* The same plugin surface for the large regime (one problem, n + m >= 1000).  `source` defines, in namespace enl_user,
@@ -132,11 +141,11 @@ int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int n
  * The resulting library exports the enlsipb200_large_* API; create the handle with family = ENLSIPB200_FAMILY_USER,
  * m_local = m_global = m, any n >= 3 (nb / ineq / rho ignored), bounds through x_low / x_upp.  Without Jacobians the
  * solve differentiates by forward differences (cnls_model.jl:65-82). */
-int enlsipb200_large_compile_family(const char* source, long long m, int nb_eq, int nb_ineq, int has_jacobians,
+ENLSIPB200_API int enlsipb200_large_compile_family(const char* source, long long m, int nb_eq, int nb_ineq, int has_jacobians,
                                     const char* out_lib_path, const char* work_dir);
 
 /* deterministic exp used by the synthetic families, exposed for bit-parity tests vs oracle/detmath.c */
-int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
+ENLSIPB200_API int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
 
 /* ===========================================================================================
  * Large-Jacobian regime (BASELINE.json configs 4/5): ONE problem whose m x n residual Jacobian is
@@ -162,32 +171,32 @@ int enlsipb200_det_exp(const double* x, double* y, long long n, int on_device);
 
 typedef struct enlsipb200_large_s* enlsipb200_large;
 
-const char* enlsipb200_large_last_error(void);
+ENLSIPB200_API const char* enlsipb200_large_last_error(void);
 
 /* n: parameters (multiple of 32); m_local: residual rows held by this handle; m_global: all rows;
  * nb: number of 4-parameter blocks with a constraint; rho [nb]; x_low / x_upp [n] or NULL (+-Inf = none). */
-int enlsipb200_large_create(int family, int n, long long m_local, long long m_global, int nb, int ineq,
+ENLSIPB200_API int enlsipb200_large_create(int family, int n, long long m_local, long long m_global, int nb, int ineq,
                             const double* rho, const double* x_low, const double* x_upp, int device,
                             enlsipb200_large* out);
-int enlsipb200_large_destroy(enlsipb200_large h);
+ENLSIPB200_API int enlsipb200_large_destroy(enlsipb200_large h);
 /* slot 0 = W [m_local, n] row major, slot 1 = y [m_local].  on_device != 0: device pointer that must stay
  * valid (and resident on the handle's device) for the solves; otherwise copied host -> device. */
-int enlsipb200_large_set_data(enlsipb200_large h, int slot, const double* ptr, long long count, int on_device);
+ENLSIPB200_API int enlsipb200_large_set_data(enlsipb200_large h, int slot, const double* ptr, long long count, int on_device);
 /* multi-GPU: rank 0 creates a 128-byte NCCL unique id, the host layer distributes it, every rank joins */
-int enlsipb200_large_comm_id(void* id128);
-int enlsipb200_large_comm_init(enlsipb200_large h, const void* id128, int rank, int nranks);
+ENLSIPB200_API int enlsipb200_large_comm_id(void* id128);
+ENLSIPB200_API int enlsipb200_large_comm_init(enlsipb200_large h, const void* id128, int rank, int nranks);
 /* blocking solve; outputs as in enlsipb200_solve_batch for B = 1 (active [l], trace [trace_cap, TRACE_HDR + n]) */
-int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb200_options* opt, double* x, double* f,
+ENLSIPB200_API int enlsipb200_large_solve(enlsipb200_large h, const double* x0, const enlsipb200_options* opt, double* x, double* f,
                            int* exit_code, int* status, int* iters, int* nact, int* active, double* trace,
                            int trace_cap);
 /* measurement / test hook: evaluate [J | r] at x and factor it; R [(n+1) x (n+1)] row major (may be NULL);
  * device times of the two stages (CUDA events on the handle's stream) */
-int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
+ENLSIPB200_API int enlsipb200_large_factor(enlsipb200_large h, const double* x, double* R, float* build_ms, float* tsqr_ms);
 /* cumulative counters: {points evaluated (new_point!), build ms, tsqr ms, linesearch ms, solve wall ms, linesearch
  * evaluations (host clock around launch..result), kernels launched, padded local rows, device QRCPs, device M*Q products,
  * ms inside the small-stage calls (host clock: kernels + the waits for their results), factorisations of [J | r] (one per
  * point from which the iteration continued)} */
-int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
+ENLSIPB200_API int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
 
 /* Known-answer hooks of the small stage's dense kernels (csrc/enl_small.cuh), host buffers, column major:
  *   enlsipb200_dense_qrcp : `qr(M, ColumnNorm())` of src/enlsip_functions.jl:223 / :700 / :769 = LAPACK dgeqp3
@@ -195,10 +204,10 @@ int enlsipb200_large_stats(enlsipb200_large h, double* out, int count);
  *       jpvt [cols] 0-based;
  *   enlsipb200_dense_mulq : `J * F_A.Q` of src/enlsip_functions.jl:219: M [mr x nq] <- M * H(0) ... H(k-1), the
  *       reflectors in f [nq x k] / tau [k] (dgeqp3 layout). */
-int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device);
-int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device);
+ENLSIPB200_API int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device);
+ENLSIPB200_API int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device);
 /* device time (CUDA events around the kernels, transfers excluded) of the last enlsipb200_dense_* call, in ms */
-float enlsipb200_dense_last_ms(void);
+ENLSIPB200_API float enlsipb200_dense_last_ms(void);
 
 #ifdef __cplusplus
 }

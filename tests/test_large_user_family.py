@@ -108,7 +108,7 @@ def test_user_data_family_vs_oracle():
     assert mod.jacobian == "forward_diff" and mod.nb_constraints == 9
     E.solve(mod, trace_cap=100)
     r = O.solve(pb, wallclock=False)
-    assert int(mod.status_code[0]) == r.status == 1
+    assert int(mod.status_code[0]) == r.status == 1, (mod.exit_code, mod.iterations, mod.obj_value, mod.sol, r.exit_code)
     assert sorted(int(v) for v in mod.active[0] if v > 0) == sorted(r.active)
     assert abs(int(mod.iterations[0]) - r.iterations) <= 1
     assert abs(float(mod.obj_value[0]) - r.f) <= 1e-8 * max(r.f, 1e-300)
