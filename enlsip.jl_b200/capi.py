@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -155,6 +156,7 @@ def compile_family(source, n, m, nb_eq=0, nb_ineq=0, stride0=0, stride1=0, has_j
                                              1 if has_jacobians else 0, tmp.encode(), work.encode())
         check(rc)
         os.replace(tmp, out)
+        shutil.rmtree(work, ignore_errors=True)
     L = _bind(ctypes.CDLL(out), large=False)
     _user_libs[tag] = L
     return L
@@ -193,6 +195,7 @@ def large_compile_family(source, m, nb_eq=0, nb_ineq=0, has_jacobians=False, nam
         check(lib().enlsipb200_large_compile_family(source.encode(), int(m), nb_eq, nb_ineq, 1 if has_jacobians else 0,
                                                     tmp.encode(), work.encode()))
         os.replace(tmp, out)
+        shutil.rmtree(work, ignore_errors=True)
     L = _bind_large_only(ctypes.CDLL(out))
     _user_libs[tag] = L
     return L
