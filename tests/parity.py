@@ -20,6 +20,7 @@ TRACE_HDR = 16
 
 def compare(gold, eng, mode, n):
     """gold: npz fixture; eng: dict(x, f, exit_code, status, iters, active, trace[B,cap,16+n])."""
+    gold = {k: gold[k] for k in getattr(gold, "files", gold)}     # an NpzFile decompresses an array on EVERY access
     B = gold["x"].shape[0]
     x, f = np.asarray(eng["x"])[:B], np.asarray(eng["f"])[:B]
     ec, st, it = (np.asarray(eng[k])[:B] for k in ("exit_code", "status", "iters"))
@@ -60,3 +61,48 @@ def compare(gold, eng, mode, n):
         assert frel[ok].max() <= 1e-9, stats
         assert xrel[ok].max() <= 1e-8, stats
     return stats
+
+
+def histogram(gold, eng, n, start=None):
+    """Full mismatch histogram of a large sample: how many problems differ in status / raw exit
+    code / iteration count / final working set / per-iteration trace, the distribution of the iteration-count
+    differences, and quantiles of the relative errors of x and f over the problems whose discrete outputs agree."""
+    gold = {k: gold[k] for k in getattr(gold, "files", gold)}     # an NpzFile decompresses an array on EVERY access
+    B = gold["x"].shape[0]
+    x, f = np.asarray(eng["x"])[:B], np.asarray(eng["f"])[:B]
+    ec, st, it = (np.asarray(eng[k])[:B] for k in ("exit_code", "status", "iters"))
+    act = np.asarray(eng["active"])[:B]
+    same_status = st == gold["status"]
+    same_exit = ec == gold["exit_code"]
+    same_iters = it == gold["iters"]
+    same_active = np.all(act == gold["active"], axis=1)
+    agree = same_status & same_exit & same_iters & same_active
+    h = {"problems": int(B), "status_mismatch": int((~same_status).sum()), "exit_code_mismatch": int((~same_exit).sum()),
+         "iteration_count_mismatch": int((~same_iters).sum()), "working_set_mismatch": int((~same_active).sum()),
+         "all_discrete_outputs_identical": int(agree.sum())}
+    d = (it.astype(np.int64) - gold["iters"].astype(np.int64))
+    vals, cnt = np.unique(d, return_counts=True)
+    h["iteration_difference_histogram"] = {int(v): int(c) for v, c in zip(vals, cnt)}
+    vals, cnt = np.unique(gold["exit_code"], return_counts=True)
+    h["oracle_exit_codes"] = {int(v): int(c) for v, c in zip(vals, cnt)}
+    if "trace" in eng and eng["trace"] is not None:
+        tr = np.asarray(eng["trace"])[:B]
+        cap = min(tr.shape[1], gold["trace"].shape[1])
+        same_trace = np.zeros(B, dtype=bool)
+        for b in np.nonzero(agree)[0]:
+            nt = min(int(gold["ntrace"][b]), cap)
+            same_trace[b] = np.array_equal(tr[b, :nt][:, [1, 2, 3, 4, 5, 6, 9, 10]].astype(np.int64), gold["trace"][b, :nt])
+        h["trace_identical"] = int(same_trace.sum())
+    ok = agree & (gold["exit_code"] > -90)
+    xn = np.maximum(np.linalg.norm(gold["x"], axis=1), 1e-300)
+    xrel = np.linalg.norm(x - gold["x"], axis=1) / xn
+    frel = np.abs(f - gold["f"]) / np.maximum(np.abs(gold["f"]), 1e-300)
+    q = [0.5, 0.9, 0.99, 0.999, 1.0]
+    h["x_rel_error_quantiles"] = {str(k): float(np.quantile(xrel[ok], k)) for k in q} if ok.any() else {}
+    h["f_rel_error_quantiles"] = {str(k): float(np.quantile(frel[ok], k)) for k in q} if ok.any() else {}
+    h["x_rel_error_over_1e-10"] = int((xrel[ok] > 1e-10).sum())
+    h["x_rel_error_over_1e-8"] = int((xrel[ok] > 1e-8).sum())
+    # the final move of a converged solve is bounded by 3 ||p_last|| (flat merit function): excess over that bound
+    excess = np.linalg.norm(x - gold["x"], axis=1) - (1e-10 * xn + 1.05 * gold["last_step"])
+    h["x_beyond_last_step_bound"] = int((excess[ok] > 0).sum())
+    return h

@@ -80,6 +80,32 @@ def test_c3_gauss_peaks_vs_golden(E, golden_dir, mode, fixture, jac):
     print("C3 parity", mode, st)
 
 
+@pytest.mark.parametrize("fixture,family,jac,n", [("c2_hs65_10k.npz", "hs65", "analytic", 3),
+                                                   ("c3_gp_analytic_10k.npz", "gauss_peaks", "analytic", 6),
+                                                   ("c3_gp_fd_10k.npz", "gauss_peaks", "forward_diff", 6)])
+def test_10k_sample_histogram(E, golden_dir, fixture, family, jac, n):
+    """10^4-problem oracle samples of C2 / C3 (tests/golden/make_golden_10k.py): the full
+    histogram of status / exit-code / iteration / working-set / trace mismatches and of the x, f errors, printed and
+    written to gpurun_out/ (committed under profiles/); bars as for the small fixtures."""
+    import json
+    import os
+    from tests.test_hostport import check_10k_bars
+    gold = np.load(golden_dir + "/" + fixture)
+    B, start = gold["x"].shape[0], int(gold["start"])
+    if family == "hs65":
+        m = E.CnlsModel("hs65", E.synth.gen_hs65_batch(B, start=start), x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP)
+    else:
+        y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B, start=start)
+        m = E.CnlsModel("gauss_peaks", x0, data={"y": y, "S": S}, x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian=jac)
+    E.solve(m, trace_cap=40)
+    h = parity.histogram(gold, _outputs(m), n)
+    print("\n10k histogram (B200)", fixture, json.dumps(h))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    json.dump(h, open(os.path.join(out_dir, "parity_hist_" + fixture.replace(".npz", ".json")), "w"), indent=1)
+    check_10k_bars(h, 0 if jac == "analytic" else 1)
+
+
 def test_c3_fresh_samples_vs_live_oracle(E):
     """Problems beyond the committed fixtures, checked against the oracle run on the box."""
     from oracle import enlsip_oracle as O, problems as P

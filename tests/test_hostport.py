@@ -156,3 +156,35 @@ def test_reference_suite_families_vs_oracle():
             check_against_oracle(out, b, o, n, name)
         if name == "chained_wood20":
             assert np.any(out["trace"][:, :, 6] == 2)        # the Newton path runs (the reference's purpose for this test)
+
+
+# ---- 10^4-problem samples (tests/golden/*_10k.npz, made by make_golden_10k.py): the full mismatch histogram ----
+@pytest.mark.parametrize("fixture,family,jac,n", [("c2_hs65_10k.npz", 0, 0, 3), ("c3_gp_analytic_10k.npz", 1, 0, 6),
+                                                   ("c3_gp_fd_10k.npz", 1, 1, 6)])
+def test_10k_sample_histogram(golden_dir, fixture, family, jac, n):
+    import enlsip_jl_b200 as E
+    gold = np.load(golden_dir + "/" + fixture)
+    B, start = gold["x"].shape[0], int(gold["start"])
+    if family == 0:
+        out = run(0, E.synth.gen_hs65_batch(B, start=start), None, None, E.synth.HS65_LOW, E.synth.HS65_UPP, 0, nthreads=8)
+    else:
+        y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B, start=start)
+        out = run(1, x0, y, S, E.synth.GP_LOW, E.synth.GP_UPP, jac, nthreads=8)
+    h = parity.histogram(gold, out, n)
+    print("\n10k histogram (host port)", fixture, h)
+    check_10k_bars(h, jac)
+
+
+def check_10k_bars(h, jac):
+    B = h["problems"]
+    if jac == 0:      # analytic Jacobians: everything identical except knife-edge ties
+        assert h["status_mismatch"] <= 0.002 * B, h
+        assert h["all_discrete_outputs_identical"] >= 0.97 * B, h
+        assert h["trace_identical"] >= 0.97 * B, h
+        assert h["f_rel_error_quantiles"]["1.0"] <= 1e-9 and h["f_rel_error_quantiles"]["0.999"] <= 1e-10, h
+        assert h["x_beyond_last_step_bound"] <= 0.001 * B, h
+    else:             # forward differences: the oracle's own 1-ulp sensitivity (test_oracle.py::test_fd_noise_floor)
+        assert h["status_mismatch"] <= 0.05 * B, h
+        assert h["iteration_count_mismatch"] <= 0.10 * B, h
+        assert h["f_rel_error_quantiles"]["0.99"] <= 1e-9, h
+        assert h["x_rel_error_quantiles"]["0.99"] <= 1e-8, h
