@@ -183,6 +183,7 @@ struct enlsipb200_handle_s {
     int l;
     unsigned long long* counter = nullptr;
     const double* data[3] = {nullptr, nullptr, nullptr};
+    long long slot_count[3] = {-1, -1, -1};      // values bound to each data slot (enlsipb200_set_data)
     double* owned[3] = {nullptr, nullptr, nullptr};
     long long owned_count[3] = {0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -436,6 +437,7 @@ int enlsipb200_dims(enlsipb200_handle h, int* n, int* m, int* nb_eq, int* nb_con
 int enlsipb200_set_data(enlsipb200_handle h, int slot, const double* ptr, long long count, int on_device, void* stream) {
     if (!h || slot < 0 || slot > 2) return fail(ENLSIPB200_EINVAL, "bad handle/slot");
     CU(cudaSetDevice(h->device));
+    h->slot_count[slot] = count;
     if (on_device) { h->data[slot] = ptr; h->host_pending[slot] = false; return 0; }
     if (h->owned_count[slot] < count) {
         if (h->owned[slot]) CU(cudaFree(h->owned[slot]));
@@ -465,7 +467,12 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     if (!FamUser::HAS_ANALYTIC && (!opt || opt->jac_mode != ENLSIPB200_JAC_FORWARD_DIFF))
         return fail(ENLSIPB200_EINVAL, "this user family was compiled without Jacobians: set jac_mode = ENLSIPB200_JAC_FORWARD_DIFF");
 #endif
-    if (B == 0) return 0;
+    for (int sl = 0; sl < 3; ++sl) {      // a per-problem data slot shorter than the batch would be read out of bounds
+        const int sd = slot_stride(h->family, sl);
+        if (sd > 0 && h->data[sl] && h->slot_count[sl] >= 0 && h->slot_count[sl] < B * sd)
+            return fail(ENLSIPB200_EINVAL, "data slot " + std::to_string(sl) + " holds " + std::to_string(h->slot_count[sl]) +
+                                               " values, the batch needs " + std::to_string(B * sd));
+    }
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n = h->fi.n, lmax = h->fi.q + h->fi.ni + h->fi.maxb;

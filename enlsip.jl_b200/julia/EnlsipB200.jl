@@ -90,6 +90,8 @@ mutable struct CnlsModel{T<:Float64}
     iterations::Vector{Cint}
     nb_active::Vector{Cint}
     active::Matrix{Cint}             # lmax x B, 1-based constraint ids of the final working set, 0 padded
+    data::Vector{Any}                # the family's data arrays: enlsipb200_set_data with host pointers only RECORDS the pointer
+                                     # (the upload happens inside the next solve), so the model must keep the arrays alive
 end
 
 """
@@ -118,13 +120,14 @@ function CnlsModel(lib::Ptr{Cvoid}, fam::Cint, family::Symbol, starting_point::M
                 h[], n, m, q, l, lmax))
     @assert size(starting_point, 1) == n[] "starting_point must be n x B"
     B = size(starting_point, 2)
-    for (slot, arr) in enumerate(data)
+    kept = Any[arr for arr in data]
+    for (slot, arr) in enumerate(kept)
         check(ccall(fsym(lib, :enlsipb200_set_data), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint, Ptr{Cvoid}),
                     h[], Cint(slot - 1), arr, length(arr), Cint(0), C_NULL))
     end
     model = CnlsModel{Float64}(h[], lib, family, n[], m[], q[], l[], lmax[], starting_point, x_low, x_upp, jacobian,
                                zeros(Cint, B), zeros(Cint, B), copy(starting_point), fill(NaN, B), zeros(Cint, B),
-                               zeros(Cint, B), zeros(Cint, lmax[], B))
+                               zeros(Cint, B), zeros(Cint, lmax[], B), kept)
     finalizer(m -> ccall(fsym(m.lib, :enlsipb200_destroy), Cint, (Ptr{Cvoid},), m.handle), model)
     return model
 end
@@ -141,11 +144,14 @@ function solve!(model::CnlsModel; silent::Bool=true, max_iter::Int=100, scaling:
     B = size(model.starting_point, 2)
     opt = Ref(Options(max_iter, scaling, model.jacobian === :forward_diff ? JAC_FORWARD_DIFF : JAC_ANALYTIC, 0,
                       time_limit, abs_tol, rel_tol, c_tol, x_tol))
-    check(ccall(fsym(model.lib, :enlsipb200_solve_batch), Cint,
-                (Ptr{Cvoid}, Clonglong, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
-                 Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
-                model.handle, B, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,
-                model.iterations, model.nb_active, model.active, C_NULL, C_NULL, Cint(0), Cint(0), C_NULL))
+    data = model.data
+    GC.@preserve data begin          # the recorded host pointers of the data slots are read inside this call
+        check(ccall(fsym(model.lib, :enlsipb200_solve_batch), Cint,
+                    (Ptr{Cvoid}, Clonglong, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
+                     Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
+                    model.handle, B, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,
+                    model.iterations, model.nb_active, model.active, C_NULL, C_NULL, Cint(0), Cint(0), C_NULL))
+    end
     silent || println("solved $B problems: ", count(==(1), model.status_code), " converged")
     return
 end
@@ -160,9 +166,28 @@ total_nb_constraints(model::CnlsModel) = model.nb_constraints                   
 # the same `solve!` / `status` / `solution` / `sum_sq_residuals` surface for B = 1.
 # ---------------------------------------------------------------------------------------------------
 const FAMILY_SINGLE_INDEX = Cint(16)
+const FAMILY_LARGE_CHAINED_ROSENBROCK = Cint(17)
+
+"""
+    large_compile_family(source; m, nb_eqcons=0, nb_ineqcons=0, has_jacobians=false) -> library handle
+
+User problems of the large regime (n + m >= 1000): `source` defines `enl_user::residual` / `enl_user::constraint` as
+templates over a point accessor (and optionally `jac_residual` / `jac_constraint`), see include/enlsip_b200.h.  Pass the
+handle to `LargeCnlsModel(lib, starting_point; m=..., nb_eqcons=..., nb_ineqcons=..., data=(...))`.
+"""
+function large_compile_family(source::String; m::Integer, nb_eqcons::Integer=0, nb_ineqcons::Integer=0,
+                              has_jacobians::Bool=false, work_dir::String=mktempdir(),
+                              out::String=joinpath(work_dir, "libenlsip_b200_large_user.so"))
+    check(ccall((:enlsipb200_large_compile_family, libenlsip), Cint,
+                (Cstring, Clonglong, Cint, Cint, Cint, Cstring, Cstring),
+                source, m, nb_eqcons, nb_ineqcons, has_jacobians ? 1 : 0, out, work_dir))
+    return Libdl.dlopen(out)
+end
 
 mutable struct LargeCnlsModel{T<:AbstractFloat}
     handle::Ptr{Cvoid}
+    lib::Ptr{Cvoid}                 # C_NULL: stock library; else the library of a user row family
+    jacobian::Symbol                # :analytic | :forward_diff (general row families)
     nb_parameters::Int
     nb_residuals::Int               # global m (all row shards)
     nb_eqcons::Int
@@ -199,9 +224,46 @@ function LargeCnlsModel(family::Symbol, starting_point::Vector{Float64}; W::Matr
                      h[], Cint(slot), arr, length(arr), Cint(0)))
     end
     l = length(rho) + count(isfinite, x_low) + count(isfinite, x_upp)
-    model = LargeCnlsModel{Float64}(h[], n, m_global, ineq ? 0 : length(rho), l, starting_point, Ref(Cint(0)), Ref(Cint(0)),
-                                    copy(starting_point), Ref(NaN), Ref(Cint(0)), Ref(Cint(0)), zeros(Cint, max(l, 1)))
+    model = LargeCnlsModel{Float64}(h[], C_NULL, :analytic, n, m_global, ineq ? 0 : length(rho), l, starting_point, Ref(Cint(0)),
+                                    Ref(Cint(0)), copy(starting_point), Ref(NaN), Ref(Cint(0)), Ref(Cint(0)), zeros(Cint, max(l, 1)))
     finalizer(m -> ccall((:enlsipb200_large_destroy, libenlsip), Cint, (Ptr{Cvoid},), m.handle), model)
+    return model
+end
+
+"""
+    LargeCnlsModel(:chained_rosenbrock, starting_point; x_low, x_upp, jacobian=:analytic)
+    LargeCnlsModel(lib, starting_point; m, nb_eqcons=0, nb_ineqcons=0, data=(), x_low, x_upp, jacobian=:forward_diff)
+
+General row families: the reference's own chained Rosenbrock test (test/problems/chained_rosenbrock.jl, any n; the
+reference runs n = 1000), or a user family compiled by `large_compile_family`.  `data`: up to two Float64 arrays
+handed to the family's functions (copied to the device here).
+"""
+function LargeCnlsModel(family::Symbol, starting_point::Vector{Float64}; x_low=fill(-Inf, length(starting_point)),
+                        x_upp=fill(Inf, length(starting_point)), jacobian::Symbol=:analytic, device::Integer=-1)
+    family === :chained_rosenbrock || error("row families: :chained_rosenbrock, or a library from large_compile_family")
+    n = length(starting_point)
+    return _row_family_model(C_NULL, FAMILY_LARGE_CHAINED_ROSENBROCK, starting_point, 2 * (n - 1), n - 2, 0, (), x_low, x_upp,
+                             jacobian, device)
+end
+LargeCnlsModel(lib::Ptr{Cvoid}, starting_point::Vector{Float64}; m::Integer, nb_eqcons::Integer=0, nb_ineqcons::Integer=0,
+               data=(), x_low=fill(-Inf, length(starting_point)), x_upp=fill(Inf, length(starting_point)),
+               jacobian::Symbol=:forward_diff, device::Integer=-1) =
+    _row_family_model(lib, FAMILY_USER, starting_point, m, nb_eqcons, nb_ineqcons, data, x_low, x_upp, jacobian, device)
+
+function _row_family_model(lib, fam, starting_point, m, q, ni, data, x_low, x_upp, jacobian, device)
+    n = length(starting_point)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    checkl(ccall(fsym(lib, :enlsipb200_large_create), Cint,
+                 (Cint, Cint, Clonglong, Clonglong, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Ptr{Cvoid}}),
+                 fam, n, m, m, 0, 0, C_NULL, x_low, x_upp, Cint(device), h))
+    for (slot, arr) in enumerate(data)      # copied host -> device inside the call: nothing to keep alive
+        checkl(ccall(fsym(lib, :enlsipb200_large_set_data), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clonglong, Cint),
+                     h[], Cint(slot - 1), arr, length(arr), Cint(0)))
+    end
+    l = q + ni + count(isfinite, x_low) + count(isfinite, x_upp)
+    model = LargeCnlsModel{Float64}(h[], lib, jacobian, n, m, q, l, starting_point, Ref(Cint(0)), Ref(Cint(0)),
+                                    copy(starting_point), Ref(NaN), Ref(Cint(0)), Ref(Cint(0)), zeros(Cint, max(l, 1)))
+    finalizer(mm -> ccall(fsym(mm.lib, :enlsipb200_large_destroy), Cint, (Ptr{Cvoid},), mm.handle), model)
     return model
 end
 
@@ -215,8 +277,9 @@ join!(model::LargeCnlsModel, id::Vector{UInt8}, rank::Integer, nranks::Integer) 
 
 function solve!(model::LargeCnlsModel; silent::Bool=true, max_iter::Int=100, scaling::Bool=false, time_limit::Float64=1e3,
                 abs_tol::Float64=eps(Float64), rel_tol::Float64=sqrt(abs_tol), c_tol::Float64=rel_tol, x_tol::Float64=rel_tol)
-    opt = Ref(Options(max_iter, scaling, JAC_ANALYTIC, 0, time_limit, abs_tol, rel_tol, c_tol, x_tol))
-    checkl(ccall((:enlsipb200_large_solve, libenlsip), Cint,
+    opt = Ref(Options(max_iter, scaling, model.jacobian === :forward_diff ? JAC_FORWARD_DIFF : JAC_ANALYTIC, 0, time_limit,
+                      abs_tol, rel_tol, c_tol, x_tol))
+    checkl(ccall(fsym(model.lib, :enlsipb200_large_solve), Cint,
                  (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Options}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint},
                   Ptr{Cint}, Ptr{Cdouble}, Cint),
                  model.handle, model.starting_point, opt, model.sol, model.obj_value, model.exit_code, model.status_code,

@@ -89,6 +89,12 @@ class CnlsModel:
         self.B, n = int(starting_point.shape[0]), int(starting_point.shape[1])
         self.x_low = np.full(n, -np.inf) if x_low is None else np.ascontiguousarray(x_low, dtype=np.float64)
         self.x_upp = np.full(n, np.inf) if x_upp is None else np.ascontiguousarray(x_upp, dtype=np.float64)
+        if self.x_low.shape != (n,) or self.x_upp.shape != (n,):
+            raise ValueError("x_low / x_upp must have n = %d entries" % n)       # cnls_model.jl:363-365
+        if _is_torch(starting_point):
+            import torch
+            if starting_point.dtype != torch.float64:
+                raise ValueError("starting_point must be float64")
         h = ctypes.c_void_p()
         capi.check(self._lib.enlsipb200_create(fam_id, self.x_low.ctypes.data, self.x_upp.ctypes.data,
                                                device, ctypes.byref(h)), self._lib)
@@ -124,10 +130,17 @@ class CnlsModel:
         return None
 
     def _ptr(self, a):
+        """Raw pointer of a zero-copy buffer.  Torch tensors are checked here (CUDA, contiguous, float64 or int32):
+        the library reads and writes them by address, a float32 tensor would be a silent out-of-bounds access."""
         if a is None:
             return None
         if _is_torch(a):
+            import torch
+            if not a.is_cuda or not a.is_contiguous() or a.dtype not in (torch.float64, torch.int32):
+                raise ValueError("device buffers must be contiguous CUDA tensors of dtype float64 (int32 for the integer outputs)")
             return ctypes.c_void_p(a.data_ptr())
+        if a.dtype not in (np.float64, np.int32) or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("host buffers must be C-contiguous float64 (int32 for the integer outputs) arrays")
         return ctypes.c_void_p(a.ctypes.data)
 
     def set_data(self, slot, arr):
