@@ -796,6 +796,206 @@ tsqr_trail_staged_kernel(double* __restrict__ A, int ld, long long nblk, long lo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// trailing update fed by TMA: the staged kernel above with its operand traffic taken out of the math warps
+// ---------------------------------------------------------------------------------------------
+// A ninth warp is the producer: it moves V (once per CTA) and every 256 x 32 block of B from the row-major work matrix
+// into the padded shared-memory tiles with bulk asynchronous copies (cp.async.bulk.shared::cluster.global with
+// mbarrier::complete_tx::bytes: the TMA unit, UBLKCP in SASS), one 256-byte row per copy so that the conflict-free
+// leading dimension of 36 doubles survives; an mbarrier per buffer carries the byte count.  The eight math warps issue
+// LDS + DMMA (+ the stores of their result rows) and wait on the mbarrier instead of cp.async.wait_group + a block
+// barrier.  Schedule, tiles and results are those of tsqr_trail_staged_kernel (bit-identical output).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+constexpr int TR_TMA_SMEM = TR_SMEM + 64;
+
+template <int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
+tsqr_trail_tma_kernel(double* __restrict__ A, int ld, long long nblk, long long stride, int col0, int ncb, int cbpc,
+                      const double* __restrict__ Tbuf) {
+    constexpr int NTH = 32 * NW;          // math threads
+    constexpr int KS = NW / 4;
+    constexpr int KROWS = TR_ROWS / KS;
+    constexpr int RW = TR_ROWS / NW;
+    constexpr int RT = RW / 8;
+    extern __shared__ __align__(16) double smem[];
+    double* Vs = smem;
+    double* Bs = Vs + TR_ROWS * TR_LD;
+    double* Ts = Bs + TR_ROWS * TR_LD;
+    double* Ws = Ts + TS_B * TR_LD;
+    double* Gs = Ws + TS_B * TR_LD;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Gs + KS * TS_B * TR_LD);   // [0]: V, [1]: B
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const bool producer = (w == NW);
+    const int nchunks = (ncb + cbpc - 1) / cbpc;
+    const long long sub = blockIdx.x / (unsigned)nchunks;
+    const int chunk = (int)(blockIdx.x % (unsigned)nchunks);
+    const int cb_begin = chunk * cbpc;
+    const int cb_end = (cb_begin + cbpc < ncb) ? cb_begin + cbpc : ncb;
+    int nvalid = 0;                        // 32-row blocks of this subtile that exist
+#pragma unroll
+    for (int b = 0; b < TS_FAN; ++b) nvalid += ((sub * TS_FAN + b) * stride < nblk) ? 1 : 0;
+    const unsigned tile_bytes = (unsigned)nvalid * TS_B * TS_B * (unsigned)sizeof(double);
+    // producer: 256 x 32 tile at column c0 -> dst, one bulk copy per existing row (lane owns rows lane, lane + 32, ...)
+    auto tma_stage = [&](double* dst, int c0, unsigned long long* bar) {
+        if (lane == 0) mbar_expect_tx(bar, tile_bytes);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < TS_FAN; ++q) {
+            const int row = lane + 32 * q;
+            const long long blk = (sub * TS_FAN + q) * stride;
+            if (blk < nblk) bulk_g2s(dst + row * TR_LD, A + (blk * TS_B + lane) * (long long)ld + c0, TS_B * sizeof(double), bar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // rows of missing blocks are never written by a copy: zero them once (both tiles)
+    for (int idx = tid; idx < TR_ROWS * TS_B; idx += 32 * (NW + 1)) {
+        const int row = idx >> 5, c = idx & 31;
+        if ((sub * TS_FAN + (row >> 5)) * stride >= nblk) { Vs[row * TR_LD + c] = 0.0; Bs[row * TR_LD + c] = 0.0; }
+    }
+    __syncthreads();
+    if (producer) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tma_stage(Vs, col0, &bars[0]);
+        tma_stage(Bs, col0 + TS_B * (cb_begin + 1), &bars[1]);
+    } else {
+        const double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+        for (int q = 0; q < 1024 / NTH; ++q) {
+            const int idx = tid + NTH * q;
+            Ts[(idx >> 5) * TR_LD + (idx & 31)] = Tg[idx];
+        }
+        mbar_wait(&bars[0], 0);
+    }
+    __syncthreads();
+    // the top block of V is a unit lower trapezoid (R of the panel sits on and above its diagonal)
+    if (!producer) {
+#pragma unroll
+        for (int q = 0; q < 1024 / NTH; ++q) {
+            const int idx = tid + NTH * q;
+            const int r = idx >> 5, c = idx & 31;
+            if (r <= c) Vs[r * TR_LD + c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    const int wm = producer ? 0 : w;
+    const long long myblk = (sub * TS_FAN + ((wm * RW) >> 5)) * stride;
+    const bool valid = myblk < nblk;
+    const int kh = wm >> 2, qd = wm & 3;
+    const int ti0 = (qd >> 1) * 2, tj0 = (qd & 1) * 2;
+    double* Gk = Gs + kh * (TS_B * TR_LD);
+    unsigned phase = 0;
+    for (int cb = cb_begin; cb < cb_end; ++cb) {
+        if (producer) {
+            __syncthreads();                  // (a) the math warps have taken the block out of Bs
+            if (cb + 1 < cb_end) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_stage(Bs, col0 + TS_B * (cb + 2), &bars[1]);
+            }
+            __syncthreads();                  // (b) W stage done
+            continue;
+        }
+        mbar_wait(&bars[1], phase);
+        phase ^= 1u;
+        // ---- pass 1: this warp's quadrant of G over its share of the rows ----
+        double acc[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        {
+            const double* vp = Vs + (kh * KROWS + t) * TR_LD + ti0 * 8 + g;
+            const double* bp = Bs + (kh * KROWS + t) * TR_LD + tj0 * 8 + g;
+#pragma unroll 8
+            for (int kk = 0; kk < KROWS / 4; ++kk) {
+                const double a0 = vp[kk * 4 * TR_LD], a1 = vp[kk * 4 * TR_LD + 8];
+                const double b0 = bp[kk * 4 * TR_LD], b1 = bp[kk * 4 * TR_LD + 8];
+                dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+                dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+                dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+                dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(Gk + ((ti0 + i) * 8 + g) * TR_LD + (tj0 + j) * 8 + 2 * t) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+        double b2[RT][4][2];
+#pragma unroll
+        for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < 4; ++cj) {
+                const double2 v = *reinterpret_cast<const double2*>(Bs + (w * RW + ri * 8 + g) * TR_LD + cj * 8 + 2 * t);
+                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
+            }
+        __syncthreads();                      // (a) Bs is free: the producer streams the next block in
+        // ---- W = -T' G ----
+#pragma unroll
+        for (int id = w; id < 16; id += NW) {
+            const int ti = id >> 2, tj = id & 3;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int o = (kk * 4 + t) * TR_LD + tj * 8 + g;
+                double gv;
+                if (KS == 2) gv = Gs[o] + Gs[TS_B * TR_LD + o];
+                else gv = (Gs[o] + Gs[TS_B * TR_LD + o]) + (Gs[2 * TS_B * TR_LD + o] + Gs[3 * TS_B * TR_LD + o]);
+                dmma884(c0, c1, Ts[(kk * 4 + t) * TR_LD + ti * 8 + g], gv);
+            }
+            *reinterpret_cast<double2*>(Ws + (ti * 8 + g) * TR_LD + tj * 8 + 2 * t) = make_double2(-c0, -c1);
+        }
+        __syncthreads();                      // (b)
+        // ---- pass 2: B_w += V_w W ----
+        {
+            const double* vp = Vs + (w * RW + g) * TR_LD + t;
+            const double* wp = Ws + t * TR_LD + g;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                double av[RT], bw[4];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri) av[ri] = vp[ri * 8 * TR_LD + kk * 4];
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj) bw[cj] = wp[kk * 4 * TR_LD + cj * 8];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                    for (int cj = 0; cj < 4; ++cj) dmma884(b2[ri][cj][0], b2[ri][cj][1], av[ri], bw[cj]);
+            }
+        }
+        if (valid) {
+            double* Bb = A + (myblk * TS_B + ((w * RW) & 31)) * (long long)ld + col0 + TS_B * (cb + 1);
+#pragma unroll
+            for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj)
+                    *reinterpret_cast<double2*>(Bb + (long long)(ri * 8 + g) * ld + cj * 8 + 2 * t) =
+                        make_double2(b2[ri][cj][0], b2[ri][cj][1]);
+        }
+    }
+}
+
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
 // (one CTA per row: at n = 4096 a single CTA needed 140 us per panel)
 __global__ void tsqr_extract_kernel(double* __restrict__ A, int ld, int col0, int ncols, double* __restrict__ Rout,
@@ -847,10 +1047,12 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     // > 48 KB of dynamic shared memory needs the opt-in (per device, so it is simply set on every call)
     cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     cudaFuncSetAttribute(tsqr_trail_staged_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
+    cudaFuncSetAttribute(tsqr_trail_tma_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_TMA_SMEM);
     // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
     // development switch: ENLSIP_PANEL=1 selects the row-tile panel kernel (kept for A/B measurements)
     static const int panel_mode = [] { const char* e = getenv("ENLSIP_PANEL"); return (e && e[0] == '1') ? 1 : 3; }();
-    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : 2; }();
+    // ENLSIP_TRAIL=2: the cp.async staged kernel; default (3): the TMA-fed kernel (bulk copies + mbarrier, producer warp)
+    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }();
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
@@ -862,13 +1064,17 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             if (panel_mode == 1) tsqr_panel_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             else tsqr_panel_cg_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             ++launches;
-            if (ncb32 > 0 && trail_mode == 2) {
+            if (ncb32 > 0 && trail_mode >= 2) {
                 // chunk = all column blocks of the subtile while there are enough subtiles to fill the machine
                 int cbpc = ncb32;
                 while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
                 const int nchunks = (ncb32 + cbpc - 1) / cbpc;
-                tsqr_trail_staged_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * TR_NW, TR_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32,
-                                                                                          cbpc, Tbuf);
+                if (trail_mode == 3)
+                    tsqr_trail_tma_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * (TR_NW + 1), TR_TMA_SMEM, st>>>(A, ld, nblk, stride, col0,
+                                                                                                        ncb32, cbpc, Tbuf);
+                else
+                    tsqr_trail_staged_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * TR_NW, TR_SMEM, st>>>(A, ld, nblk, stride, col0, ncb32,
+                                                                                              cbpc, Tbuf);
                 ++launches;
             } else if (ncb32 > 0) {
                 constexpr int CBW = TS_TRAIL_CB;
