@@ -805,6 +805,8 @@ tsqr_trail_staged_kernel(double* __restrict__ A, int ld, long long nblk, long lo
 // leading dimension of 36 doubles survives; an mbarrier per buffer carries the byte count.  The eight math warps issue
 // LDS + DMMA (+ the stores of their result rows) and wait on the mbarrier instead of cp.async.wait_group + a block
 // barrier.  Schedule, tiles and results are those of tsqr_trail_staged_kernel (bit-identical output).
+// MEASURED SLOWER than the cp.async kernel (see tsqr_factor) and therefore not the default: selectable with
+// ENLSIP_TRAIL=3, covered by test_tsqr_tma_trailing_kernel_matches.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -1051,8 +1053,11 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
     // development switch: ENLSIP_PANEL=1 selects the row-tile panel kernel (kept for A/B measurements)
     static const int panel_mode = [] { const char* e = getenv("ENLSIP_PANEL"); return (e && e[0] == '1') ? 1 : 3; }();
-    // ENLSIP_TRAIL=2: the cp.async staged kernel; default (3): the TMA-fed kernel (bulk copies + mbarrier, producer warp)
-    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }();
+    // ENLSIP_TRAIL=3: the TMA-fed kernel (bulk copies + mbarrier, producer warp).  Measured on B200 at m = 4M, n = 256:
+    // TSQR 80.1 ms against 52.2 ms with the cp.async kernel -- a copy per 256-byte row is 4.3e8 copy operations per
+    // factorisation and the TMA unit does not sustain that rate; 8 KB tensor-map boxes need a swizzled tile layout
+    // (DESIGN.md 5.3 item 12).  Default (2): the cp.async staged kernel.
+    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2); }();
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;

@@ -310,3 +310,22 @@ def test_chained_rosenbrock_reference_size_vs_oracle(E, n, jac):
     st = mod.stats()
     assert st["device_qrcp"] > 0 and st["launches"] > 0
     mod.close()
+
+
+def test_tsqr_tma_trailing_kernel_matches():
+    """The TMA-fed trailing update (ENLSIP_TRAIL=3: producer warp, cp.async.bulk + mbarrier) returns the bits of the
+    default cp.async kernel.  The switch is read once per process, so the variant runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import enlsip_jl_b200 as E\n"
+            "d = E.synth.gen_single_index(70000, 128, 32, seed=2)\n"
+            "mod = E.LargeCnlsModel('single_index', d['x0'], d, m_global=70000)\n"
+            "R, _, _ = mod.factor(d['x0']); sys.stdout.buffer.write(R.tobytes())\n" % root)
+    outs = []
+    for mode in ("2", "3"):
+        env = dict(os.environ, ENLSIP_TRAIL=mode)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True).stdout)
+    a, b = (np.frombuffer(o, dtype=np.float64) for o in outs)
+    assert a.size == 129 * 129 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
