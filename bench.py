@@ -584,6 +584,7 @@ def main():
     # ---- the evaluation phase alone (last row): forward-difference Jacobian + residuals of every problem,
     #      written to HBM (enlsipb200_eval_batch); the one phase of the solve with no replicated work ----------------
     fdj = None
+    stepk = None
     if rank == 0:
         Bf = min(B, 1_000_000)
         xs = x0_d[:Bf].contiguous()
@@ -607,6 +608,26 @@ def main():
                "algorithmic_flop_per_problem": flop / Bf, "hbm_write_gbs": wbytes / (t_ms * 1e-3) / 1e9,
                "note": "the engine's FD kernel re-uses the unperturbed exponentials (6 instead of 14 det_exp per row, bit-identical "
                        "values), so it executes fewer flops than the algorithmic count it is credited with"}
+        # ---- the batched STEP kernel from materialised inputs (the HBM-roofline row): reads J, r, A, c of
+        #      every problem from HBM (written by the evaluation kernel above), one update_working_set each ----
+        ev = E.evaluate(fm, xs)
+        E.gn_step(fm, xs, ev)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(3):
+            E.gn_step(fm, xs, ev)
+            torch.cuda.synchronize()
+            ms.append(last_kernel_ms(fm))
+        s_ms = float(np.median(ms))
+        step_bytes = 8.0 * (128 * 6 + 128 + 13 * 6 + 13 + 2 * 6)          # 8 (mn + m + ln + l + 2n) = 7992 B
+        hbm_peak, hbm_src = measured_peaks()
+        stepk = {"problems": Bf, "kernel_ms": s_ms, "kernel": "enlsip_eval_batch_kernel<GaussPeaks> in step mode (enlsipb200_step_batch)",
+                 "algorithmic_bytes_per_problem": step_bytes, "steps_per_s": Bf / (s_ms * 1e-3),
+                 "roofline": {"bound": "hbm", "achieved": step_bytes * Bf / (s_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": step_bytes * Bf / (s_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": None},
+                 "note": "one warp per problem with the n = 6 logic replicated over its lanes (the solve kernel's building blocks): "
+                         "latency / instruction bound, far from the HBM roofline the survey assigns to this kernel"}
+        del ev
         fm.close()
         del fm
 
@@ -679,6 +700,7 @@ def main():
                                   "note": "algorithmic flops (SURVEY.md 8d: ~2e5 per Gauss-Newton iteration x the mean iteration "
                                           "count); ncu: FP64 pipe 12.7 % active, issue slots 34 % (profiles/r1_c3_v4_ncu.txt)"},
                 "fd_jacobian_phase": fdj,
+                "step_kernel": stepk if rank == 0 else None,
                 "quality": {"converged_fraction": conv, "mean_iterations": float(iters.mean()),
                             "kernel_info": kernel_info}}
         if not args.skip_cpu and world == 1:      # cpu_baseline: rank 0 at N = 1 only

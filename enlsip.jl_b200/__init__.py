@@ -8,8 +8,8 @@ device is missing -- there is no CPU fallback.
 """
 from . import capi, synth
 from .model import (CnlsModel, UserFamily, solve, solve_b, status, solution, sum_sq_residuals, constraints_values,
-                    total_nb_constraints, dict_status_codes, evaluate)
+                    total_nb_constraints, dict_status_codes, evaluate, gn_step)
 from .model_large import LargeCnlsModel, LargeUserFamily, solve_large
 
 __all__ = ["capi", "synth", "CnlsModel", "UserFamily", "solve", "solve_b", "status", "solution", "sum_sq_residuals",
-           "constraints_values", "total_nb_constraints", "dict_status_codes", "evaluate", "LargeCnlsModel", "LargeUserFamily", "solve_large"]
+           "constraints_values", "total_nb_constraints", "dict_status_codes", "evaluate", "gn_step", "LargeCnlsModel", "LargeUserFamily", "solve_large"]

@@ -33,7 +33,7 @@ TRACE_HDR = 16
 EXIT_WOULD_THROW, EXIT_WOULD_HANG, EXIT_CAPACITY = -99, -98, -97
 
 EXPORTS = ["enlsipb200_version", "enlsipb200_last_error", "enlsipb200_default_options", "enlsipb200_create",
-           "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data", "enlsipb200_solve_batch", "enlsipb200_eval_batch",
+           "enlsipb200_destroy", "enlsipb200_dims", "enlsipb200_set_data", "enlsipb200_solve_batch", "enlsipb200_eval_batch", "enlsipb200_step_batch",
            "enlsipb200_last_kernel_ms", "enlsipb200_kernel_info", "enlsipb200_launch_count", "enlsipb200_det_exp",
            "enlsipb200_compile_family", "enlsipb200_large_compile_family",
            "enlsipb200_large_last_error", "enlsipb200_large_create", "enlsipb200_large_destroy",
@@ -94,6 +94,7 @@ def _bind(L, large=True):
     L.enlsipb200_solve_batch.argtypes = [vp, ctypes.c_longlong, vp, ctypes.POINTER(Options)] + [vp] * 9 + \
                                         [ctypes.c_int, ctypes.c_int, vp]
     L.enlsipb200_eval_batch.argtypes = [vp, ctypes.c_longlong, vp, ctypes.POINTER(Options)] + [vp] * 4 + [ctypes.c_int, vp]
+    L.enlsipb200_step_batch.argtypes = [vp, ctypes.c_longlong] + [vp] * 5 + [ctypes.POINTER(Options)] + [vp] * 4 + [ctypes.c_int, vp]
     L.enlsipb200_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.enlsipb200_kernel_info.argtypes = [vp, ip, ip, ip, ip, ip, ip]
     L.enlsipb200_launch_count.argtypes = [vp]

@@ -186,7 +186,19 @@ struct Solver {
     }
 
     // J(x) -> dJ  (x in the small state, r(x) in dR)
+    const double* mat_J = nullptr;       // step_only: the Jacobian is an input ([N][M] column major), not evaluated
     ENL_NOINL void eval_res_jacobian() {
+        if (mat_J) {
+#pragma unroll
+            for (int sl = 0; sl < MS; ++sl) {
+                const int row = sl * G + grp().lane;
+#pragma unroll
+                for (int j = 0; j < N; ++j) dJ.at(sl, j) = (row < M) ? mat_J[(size_t)j * M + row] : 0.0;
+            }
+            j2_factored = false;
+            grp().sync();
+            return;
+        }
         double xv[N];
         load_x(x, xv);
         double out[MS * N];
@@ -1723,6 +1735,71 @@ struct Solver {
         if (A_out)
 #pragma unroll 1
             for (int i = 0; i < LMAX * N; ++i) A_out[bidx * LMAX * N + i] = (i < l * N) ? A[i] : 0.0;
+    }
+
+    // One Gauss-Newton step from MATERIALISED inputs (the batched step kernel): r [M], J [N][M] column
+    // major, c [LMAX], A [LMAX][N] of one problem are read from global memory; the working set is the initial one of
+    // init_working_set (EF:826-859); update_working_set (EF:686-795) gives the multipliers, the (possibly reduced)
+    // working set and the Gauss-Newton direction -- no function evaluation anywhere.
+    ENL_NOINL void step_only(const double* xin, const double* r_in, const double* J_in, const double* c_in,
+                             const double* A_in) {
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) { double v = xin[j]; x[j] = v; xprev[j] = v; }
+        l = NNL + bnd.nlo + bnd.nup;
+        k_iter = 0; ndetail = 0; exit_code = 0; threw = false; hang = false;
+#pragma unroll
+        for (int sl = 0; sl < MS; ++sl) {
+            const int row = sl * G + grp().lane;
+            dR.at(sl, 0) = (row < M) ? r_in[row] : 0.0;
+        }
+#pragma unroll 1
+        for (int i = 0; i < l; ++i) cx[i] = c_in[i];
+#pragma unroll 1
+        for (int i = 0; i < l * N; ++i) A[i] = A_in[i];
+        mat_J = J_in;
+        grp().sync();
+        eval_res_jacobian();
+        grad_and_sumsq();
+        t = Q;
+        int lmt = 0;
+#pragma unroll 1
+        for (int i = 0; i < LMAX; ++i) { active[i] = 0; inactive[i] = 0; }
+#pragma unroll 1
+        for (int i = 1; i <= Q; ++i) active[i - 1] = i;
+#pragma unroll 1
+        for (int i = Q + 1; i <= l; ++i) {
+            if (cx[i - 1] <= 0.0) {
+                if (t < T) active[t] = i;
+                t += 1;
+            } else {
+                inactive[lmt++] = i;
+            }
+        }
+        cur = IterRec{};
+        cur.alpha = 1.0;
+        cur.code = 1;
+        if (t > T) { exit_code = EXIT_CAPACITY; t = T; return; }
+        cur.t = t;
+        gather_active();
+        evaluate_scaling();
+        update_working_set();
+        if (threw) exit_code = EXIT_WOULD_THROW;
+    }
+    // p [N], lam [T] (in working-set order, 0 padded), active [LMAX], info = {t, rankA, rankJ2, index_del, code}
+    ENL_NOINL void store_step(double* p_out, double* lam_out, int* active_out, int* info_out, long long bidx) {
+        if (grp().lane != 0) return;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) p_out[bidx * N + j] = p[j];
+        if (lam_out)
+#pragma unroll 1
+            for (int i = 0; i < T; ++i) lam_out[bidx * T + i] = (i < t) ? lam[i] : 0.0;
+        if (active_out)
+#pragma unroll 1
+            for (int i = 0; i < LMAX; ++i) active_out[bidx * LMAX + i] = (i < t) ? active[i] : 0;
+        if (info_out) {
+            info_out[bidx * 5 + 0] = t; info_out[bidx * 5 + 1] = cur.rankA; info_out[bidx * 5 + 2] = cur.rankJ2;
+            info_out[bidx * 5 + 3] = cur.index_del; info_out[bidx * 5 + 4] = exit_code;
+        }
     }
 
     // one ENLSIP iteration; sets exit_code != 0 when the solve is over

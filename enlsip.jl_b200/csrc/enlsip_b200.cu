@@ -134,6 +134,10 @@ struct EvalArgs {
     Options opt;
     Bounds bnd;
     double *r, *J, *c, *A;
+    // step mode (enlsipb200_step_batch): r, J, c, A are INPUTS; outputs:
+    int step;
+    double *p, *lam;
+    int *active, *info;
 };
 template <class Fam, int G, int NT>
 __global__ void __launch_bounds__(NT) enlsip_eval_batch_kernel(const __grid_constant__ EvalArgs a) {
@@ -160,8 +164,14 @@ __global__ void __launch_bounds__(NT) enlsip_eval_batch_kernel(const __grid_cons
         if (G > 1) nb = __shfl_sync(g.mask, nb, 0, G);
         const long long b = (long long)nb;
         if (b >= a.B) break;
-        S.eval_only(a.x + b * Fam::N, a.fd, b);
-        S.store_eval(a.r, a.J, a.c, a.A, b);
+        if (a.step) {
+            S.step_only(a.x + b * Fam::N, a.r + b * Fam::M, a.J + b * (long long)(Fam::N * Fam::M), a.c + b * LY::LMAX,
+                        a.A + b * (long long)(LY::LMAX * Fam::N));
+            S.store_step(a.p, a.lam, a.active, a.info, b);
+        } else {
+            S.eval_only(a.x + b * Fam::N, a.fd, b);
+            S.store_eval(a.r, a.J, a.c, a.A, b);
+        }
         g.sync();
     }
 }
@@ -583,6 +593,9 @@ int enlsipb200_solve_batch(enlsipb200_handle h, long long B, const double* x0, c
     return 0;
 }
 
+static int eval_or_step(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r, double* J,
+                        double* c, double* A, int step, double* p, double* lam, int* active, int* info, void* stream);
+
 int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
                           double* J, double* c, double* A, int on_device, void* stream) {
     if (!h) return fail(ENLSIPB200_EINVAL, "null handle");
@@ -591,6 +604,22 @@ int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, con
     if (!on_device) return fail(ENLSIPB200_EINVAL, "enlsipb200_eval_batch works on device buffers (the outputs are B x m x n)");
     if ((h->family == ENLSIPB200_FAMILY_GAUSS_PEAKS || h->family == ENLSIPB200_FAMILY_OSBORNE2) && (!h->data[0] || !h->data[1]))
         return fail(ENLSIPB200_EINVAL, "this family needs data slots 0 and 1");
+    return eval_or_step(h, B, x, opt, r, J, c, A, 0, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int enlsipb200_step_batch(enlsipb200_handle h, long long B, const double* x, const double* r, const double* J, const double* c,
+                          const double* A, const enlsipb200_options* opt, double* p, double* lam, int* active, int* info,
+                          int on_device, void* stream) {
+    if (!h) return fail(ENLSIPB200_EINVAL, "null handle");
+    if (B < 0 || !x || !r || !J || !c || !A || !p) return fail(ENLSIPB200_EINVAL, "x, r, J, c, A, p are required");
+    if (B == 0) return 0;
+    if (!on_device) return fail(ENLSIPB200_EINVAL, "enlsipb200_step_batch works on device buffers");
+    return eval_or_step(h, B, x, opt, const_cast<double*>(r), const_cast<double*>(J), const_cast<double*>(c),
+                        const_cast<double*>(A), 1, p, lam, active, info, stream);
+}
+
+static int eval_or_step(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r, double* J,
+                        double* c, double* A, int step, double* p, double* lam, int* active, int* info, void* stream) {
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rcf = flush_pending(h, st, -1);
@@ -602,6 +631,7 @@ int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, con
     a.opt = make_options(opt, h->fi.n, h->fi.m);
     a.bnd = h->bnd;
     a.r = r; a.J = J; a.c = c; a.A = A;
+    a.step = step; a.p = p; a.lam = lam; a.active = active; a.info = info;
     int rc = with_family(h->family, h->nt, [&](auto fam, auto g_, auto nt_) {
         using Fm = decltype(fam);
         constexpr int G = decltype(g_)::value, NT = decltype(nt_)::value;

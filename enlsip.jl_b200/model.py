@@ -271,6 +271,26 @@ def evaluate(model: CnlsModel, x=None, want=("r", "J", "c", "A")):
     return out
 
 
+def gn_step(model: CnlsModel, x, ev, scaling=False):
+    """One Gauss-Newton step of every problem from MATERIALISED r, J, c, A (the dict `evaluate` returns): the batched step
+    kernel (enlsipb200_step_batch; update_working_set, enlsip_functions.jl:686-795).  Returns dict(p [B, n], lam [B, T],
+    active [B, lmax], info [B, 5] = t, rankA, rankJ2, index_del, error)."""
+    import torch
+    B, n, lmax = model.B, model.nb_parameters, model.lmax
+    T = min(lmax, n)
+    dev = ev["r"].device
+    out = {"p": torch.empty(B, n, dtype=torch.float64, device=dev), "lam": torch.empty(B, T, dtype=torch.float64, device=dev),
+           "active": torch.empty(B, lmax, dtype=torch.int32, device=dev), "info": torch.empty(B, 5, dtype=torch.int32, device=dev)}
+    o = capi.default_options()
+    o.scaling = 1 if scaling else 0
+    p = model._ptr
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(model._lib.enlsipb200_step_batch(model._h, B, p(x.contiguous()), p(ev["r"]), p(ev["J"]), p(ev["c"]), p(ev["A"]),
+                                                ctypes.byref(o), p(out["p"]), p(out["lam"]), p(out["active"]), p(out["info"]), 1, st),
+               model._lib)
+    return out
+
+
 def last_kernel_ms(model: CnlsModel) -> float:
     ms = ctypes.c_float()
     capi.check(model._lib.enlsipb200_last_kernel_ms(model._h, ctypes.byref(ms)), model._lib)

@@ -109,6 +109,16 @@ ENLSIPB200_API int enlsipb200_kernel_info(enlsipb200_handle h, int* regs_per_thr
  * enlsipb200_last_kernel_ms reports the kernel time. */
 ENLSIPB200_API int enlsipb200_eval_batch(enlsipb200_handle h, long long B, const double* x, const enlsipb200_options* opt, double* r,
                           double* J, double* c, double* A, int on_device, void* stream);
+/* One Gauss-Newton step per problem from MATERIALISED inputs -- the batched step kernel of the coalesced-load design:
+ * update_working_set (src/enlsip_functions.jl:686-795: qr(A_active', ColumnNorm()), first-order multipliers, J*Q1,
+ * qr(J2, ColumnNorm()), the triangular solves of sub_search_direction :116-153, second-order multipliers :514-537 and a
+ * possible deletion) applied to r [B, m], J [B, n, m], c [B, lmax], A [B, lmax, n] in the layout enlsipb200_eval_batch
+ * writes, from the working set of init_working_set (:826-859).  Outputs: p [B, n] (Gauss-Newton direction), lam
+ * [B, min(lmax, n)] (multipliers in working-set order, 0 padded; may be NULL), active [B, lmax] (may be NULL),
+ * info [B, 5] = {t, rankA, rankJ2, index_del, error code (0, -99, -97)} (may be NULL).  DEVICE buffers only. */
+ENLSIPB200_API int enlsipb200_step_batch(enlsipb200_handle h, long long B, const double* x, const double* r, const double* J,
+                                         const double* c, const double* A, const enlsipb200_options* opt, double* p, double* lam,
+                                         int* active, int* info, int on_device, void* stream);
 ENLSIPB200_API long long enlsipb200_launch_count(enlsipb200_handle h);
 
 /* Run-time compiled problem family: the replacement of the reference's plugin surface -- `residuals`,

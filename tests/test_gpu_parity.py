@@ -192,6 +192,42 @@ def test_evaluation_layer_bit_parity(E, jac):
     assert m.launch_count() == 1
 
 
+def test_step_kernel_from_materialised_inputs(E):
+    """enlsipb200_step_batch (the batched step kernel that reads J, r, A, c from HBM) against the first
+    iteration of the full solve and of the oracle: same working-set size and ranks, the Gauss-Newton direction
+    p = (x1 - x0) / alpha to 1e-10."""
+    import torch
+    from oracle import enlsip_oracle as O, problems as P
+    B = 64
+    y, S, x0, _ = E.synth.gen_gauss_peaks_batch(B, start=4_000_000)
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(x0).to(dev)
+    m = E.CnlsModel("gauss_peaks", xd, data={"y": torch.from_numpy(y).to(dev), "S": torch.from_numpy(S).to(dev)},
+                    x_low=E.synth.GP_LOW, x_upp=E.synth.GP_UPP, jacobian="analytic")
+    ev = E.evaluate(m, xd)
+    st = {k: v.cpu().numpy() for k, v in E.gn_step(m, xd, ev).items()}
+    E.solve(m, trace_cap=4)
+    tr = m.trace.cpu().numpy()
+    checked = 0
+    for b in range(B):
+        row = tr[b, 0]
+        assert st["info"][b, 4] == 0
+        assert (int(row[1]), int(row[2]), int(row[3])) == tuple(int(v) for v in st["info"][b, :3]), b
+        if int(row[6]) == 1 and row[7] > 0:                      # first iteration took the Gauss-Newton direction
+            p_full = (row[16:22] - x0[b]) / row[7]
+            assert np.linalg.norm(st["p"][b] - p_full) <= 1e-9 * np.linalg.norm(p_full), b
+            assert abs(np.linalg.norm(st["p"][b]) - row[8]) <= 1e-12 * row[8], b
+            checked += 1
+        if b < 8:
+            o = O.solve(P.gauss_peaks(y[b], S[b], x0[b], fd=False), wallclock=False, max_iter=1)
+            t0 = o.trace[0]
+            assert (t0.t, t0.rankA, t0.rankJ2) == tuple(int(v) for v in st["info"][b, :3])
+            if t0.code == 1:
+                po = (t0.x_new - x0[b]) / t0.alpha
+                assert np.linalg.norm(st["p"][b] - po) <= 1e-9 * np.linalg.norm(po), b
+    assert checked >= B // 2
+
+
 def test_device_buffers_and_determinism(E):
     """torch CUDA tensors (zero copy) give bit-identical results to host buffers; re-solving is idempotent; results do
     not depend on the position of a problem in the batch (the work queue hands problems to arbitrary warps)."""
