@@ -1166,13 +1166,38 @@ public:
         }
         return pen;
     }
+    // ||r(x + alpha p)||^2 of the trial points of the current direction: the reference evaluates the same point several
+    // times (EF:2000 vs 2005, the accepted step again at EF:2281); every evaluation is an m-sized kernel (+ an all-reduce
+    // when row-sharded), so the values are kept for the life of the direction.  The kernels compute this sum with the
+    // same arithmetic whether or not the model coefficients are requested, so a cached value is the value.
+    double ls_alpha[8], ls_rs[8];
+    int ls_cached = 0, ls_next = 0;
+    void ls_cache_reset() { ls_cached = 0; ls_next = 0; }
+    bool ls_cache_get(double alpha, double& rs) const {
+        for (int i = 0; i < ls_cached; ++i)
+            if (ls_alpha[i] == alpha) { rs = ls_rs[i]; return true; }
+        return false;
+    }
+    void ls_cache_put(double alpha, double rs) {
+        double dummy;
+        if (ls_cache_get(alpha, dummy)) return;
+        ls_alpha[ls_next] = alpha; ls_rs[ls_next] = rs;
+        ls_next = (ls_next + 1) % 8;
+        if (ls_cached < 8) ++ls_cached;
+    }
+    double res_sq_cached(double alpha) {
+        double rs;
+        ++n_res_eval;
+        if (ls_cache_get(alpha, rs)) return rs;
+        check(ops.res_sq(alpha, &rs));
+        ls_cache_put(alpha, rs);
+        return rs;
+    }
     // psi(x + alpha p) with the direction fixed by ops.set_direction (EF:1307-1340)
     double psi(const Vec& x, double alpha, const Vec& p, const Vec& w, Vec& cbuf) {
         Vec xn(n);
         for (int j = 0; j < n; ++j) xn[j] = x[j] + alpha * p[j];
-        double rs;
-        check(ops.res_sq(alpha, &rs));
-        ++n_res_eval;
+        double rs = res_sq_cached(alpha);
         check(ops.cons(xn.data(), cbuf.data()));
         return 0.5 * (rs + penalty_part(cbuf, w));
     }
@@ -1460,6 +1485,7 @@ public:
         double o[4];
         check(ops.ls_coeffs(alpha_k, o));
         ++n_res_eval;
+        ls_cache_put(alpha_k, o[0]);
         Vec xn(n), cn(l), v0c(l), vbc(l);
         for (int j = 0; j < n; ++j) xn[j] = x[j] + alpha_k * p[j];
         check(ops.cons(xn.data(), cn.data()));
@@ -1500,10 +1526,10 @@ public:
             v1c[k] = (cx[k] > 0) ? 0.0 : sqrt(w[k]) * Ap[k];
         }
         auto PSI = [&](double a) { return psi(x, a, p, w, cbuf); };
+        double dd[6];
+        ls_dots(x, p, alpha_k, v1c, w, sums, dd);      // (before psi(alpha_k): its residual sum serves both, EF:2000 / 2005)
         double psi_k = PSI(alpha_k);
         double diff_psi = psi0 - psi_k;
-        double dd[6];
-        ls_dots(x, p, alpha_k, v1c, w, sums, dd);
         double x_min = (diff_psi >= 0) ? alpha_k : 0.0;
         double alpha_kp1, pk, beta, pbeta;
         minrm(dd, x_min, alpha_min, alpha_max, alpha_kp1, pk, beta, pbeta);
@@ -1620,6 +1646,7 @@ public:
                 double alpha0 = fmin(fmin(1.0, magfy * prev.alpha), alpha_upp);
                 double sums[3];
                 check(ops.set_direction(x.data(), p.data(), sums));
+                ls_cache_reset();
                 bool gac_error;
                 alpha = linesearch_constrained(x, alpha0, p, Ap, w, psi0, dpsi0, alpha_low, alpha_upp, sums, gac_error);
                 Vec cbuf(l);
@@ -1640,9 +1667,7 @@ public:
                 // progress at the accepted step (EF:2281-2287)
                 Vec xn(n), cn(l);
                 for (int j = 0; j < n; ++j) xn[j] = x[j] + alpha * p[j];
-                double rs;
-                check(ops.res_sq(alpha, &rs));
-                ++n_res_eval;
+                double rs = res_sq_cached(alpha);
                 check(ops.cons(xn.data(), cn.data()));
                 double whsum = 0.0;
                 for (int i = 0; i < W.t; ++i) {
