@@ -613,19 +613,20 @@ __global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f
 }
 
 // ---- the whole factorisation in ONE THREAD-BLOCK CLUSTER (dlaqp2 semantics), the matrix resident in shared memory ----
-// Column c of the matrix lives in the shared memory of CTA c % 8 (slot c / 8).  Per column step and ONE cluster barrier:
-// every CTA proposes its best remaining column (first maximum of the partial norms by current position) and ships the
-// proposal TOGETHER WITH that column to all eight CTAs through distributed shared memory; after the barrier every CTA
-// picks the same winner, runs dlarfg on its own copy of the winning column (identical arithmetic everywhere: no
-// reflector broadcast, no owner-only serial section), applies the reflector to its own columns (one warp per column)
-// and downdates their norms.  A 257 x 192 factorisation (config 4's J2) costs ~2 us per column with no L2 round trip.
+// Column c of the matrix lives in the shared memory of CTA c % 8 (slot c / 8).  Per column step: every CTA proposes its
+// best remaining column (first maximum of the partial norms by current position), the proposals are exchanged through
+// distributed shared memory, the owner of the winner runs dlarfg and stores the reflector into every CTA's shared
+// memory, then each CTA applies it to its own columns (one warp per column) and downdates their norms.  Two cluster
+// barriers per step and no L2 round trip: a 257 x 192 factorisation (config 4's J2) takes 1.04 ms (5 us per column).
+// (A variant with ONE barrier per step -- every CTA ships its candidate column with the proposal and runs dlarfg
+// redundantly -- was measured slower: 1.33 ms; the 8-fold column traffic through distributed shared memory costs more
+// than the barrier it saves.)
 // Columns are never moved: `pos` tracks the position dlaqp2's swaps would have given them.
-constexpr int QC_CTAS = 8, QC_THREADS = 1024;
+constexpr int QC_CTAS = 8, QC_THREADS = 512;
 constexpr size_t QC_MAX_SMEM = 200 * 1024;
 inline size_t qc_smem_bytes(int rows, int cols) {
     const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
-    return sizeof(double) * ((size_t)ncl * rows + (size_t)(2 * QC_CTAS + 1) * rows + 2 + 2 * (size_t)ncl + 2 * QC_CTAS) +
-           sizeof(int) * ((size_t)ncl + cols + 4 * QC_CTAS + 2);
+    return sizeof(double) * ((size_t)ncl * rows + rows + 2 + 2 * (size_t)ncl + QC_CTAS) + sizeof(int) * ((size_t)ncl + cols + 2 * QC_CTAS + 2);
 }
 __global__ void __cluster_dims__(QC_CTAS, 1, 1) __launch_bounds__(QC_THREADS)
 qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau, int* __restrict__ jpvt, int nopivot) {
@@ -634,21 +635,19 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
     const int rank = (int)cluster.block_rank();
     extern __shared__ double sm[];
     __shared__ double sh[32];
-    __shared__ double s_rb[32];
-    __shared__ int s_rp[32], s_rs[32];
-    __shared__ int s_wrank, s_wphys;
-    __shared__ double s_tau, s_sc, s_beta;
+    __shared__ double s_rb[16];
+    __shared__ int s_rp[16], s_rs[16];
+    __shared__ int s_wphys;
     const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
-    double* Al = sm;                                       // [ncl][rows]
-    double* cand = Al + (size_t)ncl * rows;                // [2][QC_CTAS][rows] candidate columns (double buffered)
-    double* vbuf = cand + (size_t)2 * QC_CTAS * rows;      // [rows] the scaled reflector of the step
-    double* vn1 = vbuf + rows + 2;                         // [ncl]
-    double* vn2 = vn1 + ncl;                               // [ncl]
-    double* cval = vn2 + ncl;                              // [2][QC_CTAS] proposals: value
-    int* pos = reinterpret_cast<int*>(cval + 2 * QC_CTAS); // [ncl] current position of the local column
-    int* l2p = pos + ncl;                                  // [cols] position -> column (replicated in every CTA)
-    int* cpos = l2p + cols;                                // [2][QC_CTAS] proposals: position
-    int* cphys = cpos + 2 * QC_CTAS;                       // [2][QC_CTAS] proposals: column (-1: none)
+    double* Al = sm;                                // [ncl][rows]
+    double* vbuf = Al + (size_t)ncl * rows;         // [rows] reflector (entries i+1..), [rows] = tau
+    double* vn1 = vbuf + rows + 2;                  // [ncl]
+    double* vn2 = vn1 + ncl;                        // [ncl]
+    double* cval = vn2 + ncl;                       // [QC_CTAS] proposals: value
+    int* pos = reinterpret_cast<int*>(cval + QC_CTAS);   // [ncl] current position of the local column
+    int* l2p = pos + ncl;                           // [cols] position -> column (replicated in every CTA)
+    int* cpos = l2p + cols;                         // [QC_CTAS] proposals: position
+    int* cphys = cpos + QC_CTAS;                    // [QC_CTAS] proposals: column
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = QC_THREADS / 32;
     const int nloc = (cols > rank) ? (cols - rank + QC_CTAS - 1) / QC_CTAS : 0;     // my columns: rank, rank + 8, ...
     const int k = rows < cols ? rows : cols;
@@ -661,16 +660,14 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
         if (lane == 0) { vn1[s] = vn2[s] = sqrt(acc); pos[s] = rank + s * QC_CTAS; }
     }
     for (int c = tid; c < cols; c += QC_THREADS) l2p[c] = c;
-    __syncthreads();
-    // proposal for step `step`: my best column among those at positions >= step (plain QR: the column AT position step),
-    // shipped with its rows [step, rows) to every CTA (buffer step & 1)
-    auto propose = [&](int step) {
-        const int par = step & 1;
+    cluster.sync();        // every CTA has read its input: the output may overwrite f at the end
+    for (int i = 0; i < k; ++i) {
+        // ---- 1. local proposal: largest vn1 among my columns still to the right of i, ties -> smallest position
         double best = -1.0; int bpos = 0x7fffffff, bslot = -1;
         for (int s = tid; s < nloc; s += QC_THREADS) {
             const int p = pos[s];
-            if (nopivot ? (p == step) : (p >= step)) {
-                const double x = nopivot ? 1.0 : vn1[s];
+            if (p >= i) {
+                const double x = vn1[s];
                 if (x > best || (x == best && p < bpos)) { best = x; bpos = p; bslot = s; }
             }
         }
@@ -683,77 +680,62 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
         }
         if (lane == 0) { s_rb[w] = best; s_rp[w] = bpos; s_rs[w] = bslot; }
         __syncthreads();
-        double b = s_rb[0]; int bp = s_rp[0], bs = s_rs[0];
-        for (int q = 1; q < nw; ++q)
-            if (s_rb[q] > b || (s_rb[q] == b && s_rp[q] < bp)) { b = s_rb[q]; bp = s_rp[q]; bs = s_rs[q]; }
-        if (tid < QC_CTAS) {                                // thread t delivers the proposal to CTA t
+        if (tid < QC_CTAS) {
+            double b = s_rb[0]; int bp = s_rp[0], bs = s_rs[0];
+            for (int q = 1; q < nw; ++q)
+                if (s_rb[q] > b || (s_rb[q] == b && s_rp[q] < bp)) { b = s_rb[q]; bp = s_rp[q]; bs = s_rs[q]; }
+            // thread t delivers this CTA's proposal to CTA t
             double* rv = cluster.map_shared_rank(cval, tid);
             int* rp = cluster.map_shared_rank(cpos, tid);
             int* rph = cluster.map_shared_rank(cphys, tid);
-            rv[par * QC_CTAS + rank] = b; rp[par * QC_CTAS + rank] = bp;
-            rph[par * QC_CTAS + rank] = (bs >= 0) ? (rank + bs * QC_CTAS) : -1;
+            rv[rank] = b; rp[rank] = bp; rph[rank] = (bs >= 0) ? (rank + bs * QC_CTAS) : -1;
         }
-        if (bs >= 0) {
-            const double* col = Al + (size_t)bs * rows;
-            const int len = rows - step;
-            for (int e = tid; e < len * QC_CTAS; e += QC_THREADS) {
-                const int dstr = e % QC_CTAS, r = step + e / QC_CTAS;
-                double* rc = cluster.map_shared_rank(cand, dstr);
-                rc[((size_t)par * QC_CTAS + rank) * rows + r] = col[r];
-            }
-        }
-        __syncthreads();                                    // s_rb .. are reused by the next call
-    };
-    if (k > 0) propose(0);
-    cluster.sync();
-    for (int i = 0; i < k; ++i) {
-        const int par = i & 1;
-        // ---- the winner, identically in every CTA; position bookkeeping of dlaqp2's column swap ----
+        cluster.sync();
+        // ---- 2. the winner, identically in every CTA; position bookkeeping of dlaqp2's column swap
         if (tid == 0) {
-            double b = -1.0; int bp = 0x7fffffff, bph = -1, br = -1;
-            for (int q = 0; q < QC_CTAS; ++q) {
-                const int ph = cphys[par * QC_CTAS + q];
-                const double v = cval[par * QC_CTAS + q];
-                const int pp = cpos[par * QC_CTAS + q];
-                if (ph >= 0 && (v > b || (v == b && pp < bp))) { b = v; bp = pp; bph = ph; br = q; }
-            }
-            s_wrank = br; s_wphys = bph;
-            if (bph >= 0) {
-                const int q = l2p[i];                       // the column sitting at position i moves to the winner's place
-                l2p[bp] = q; l2p[i] = bph;
-                if (q % QC_CTAS == rank) pos[q / QC_CTAS] = bp;
-                if (bph % QC_CTAS == rank) pos[bph / QC_CTAS] = i;
-            }
+            double b = -1.0; int bp = 0x7fffffff, bph = -1;
+            for (int q = 0; q < QC_CTAS; ++q)
+                if (cphys[q] >= 0 && (cval[q] > b || (cval[q] == b && cpos[q] < bp))) { b = cval[q]; bp = cpos[q]; bph = cphys[q]; }
+            if (bph < 0 || nopivot) { bp = i; bph = l2p[i]; }   // nothing comparable (NaN norms) / plain QR: the column stays
+            const int q = l2p[i];                           // the column sitting at position i moves to the winner's place
+            l2p[bp] = q; l2p[i] = bph;
+            if (q % QC_CTAS == rank) pos[q / QC_CTAS] = bp;
+            if (bph % QC_CTAS == rank) pos[bph / QC_CTAS] = i;
+            s_wphys = bph;
         }
         __syncthreads();
-        const int wrank = s_wrank, wphys = s_wphys;
-        // ---- dlarfg on my copy of the winning column (every CTA: identical data, identical arithmetic) ----
-        double tau_i = 0.0;
-        if (wrank >= 0) {                                   // (no candidate at all: NaN norms -- H_i = I, nothing moves)
-            const double* vr = cand + ((size_t)par * QC_CTAS + wrank) * rows;
-            double beta = vr[i], sc = 1.0;
+        const int wphys = s_wphys;
+        // ---- 3. owner: dlarfg, reflector into every CTA
+        if (wphys % QC_CTAS == rank) {
+            double* col = Al + (size_t)(wphys / QC_CTAS) * rows;
+            double tau_i = 0.0;
             if (i < rows - 1) {
                 double part = 0.0;
-                for (int r = i + 1 + tid; r < rows; r += QC_THREADS) part = fma(vr[r], vr[r], part);
+                for (int r = i + 1 + tid; r < rows; r += QC_THREADS) part = fma(col[r], col[r], part);
                 const double xn = sqrt(s_block_sum(part, sh));
                 if (xn != 0.0) {
-                    const double alpha = vr[i];
-                    beta = -copysign(s_lapy2(alpha, xn), alpha);
+                    const double alpha = col[i];
+                    const double beta = -copysign(s_lapy2(alpha, xn), alpha);
                     tau_i = (beta - alpha) / beta;
-                    sc = 1.0 / (alpha - beta);
+                    const double sc = 1.0 / (alpha - beta);
+                    __syncthreads();
+                    for (int r = i + 1 + tid; r < rows; r += QC_THREADS) col[r] *= sc;
+                    if (tid == 0) col[i] = beta;
+                    __syncthreads();
                 }
             }
-            for (int r = i + 1 + tid; r < rows; r += QC_THREADS) vbuf[r] = vr[r] * sc;
-            if (wphys % QC_CTAS == rank) {                  // the owner keeps the factored column
-                double* col = Al + (size_t)(wphys / QC_CTAS) * rows;
-                for (int r = i + 1 + tid; r < rows; r += QC_THREADS) col[r] = vr[r] * sc;
-                if (tid == 0) { col[i] = beta; tau[i] = tau_i; }
+            const int len = rows - i - 1;
+            for (int e = tid; e < (len + 1) * QC_CTAS; e += QC_THREADS) {
+                const int dstr = e % QC_CTAS, r = e / QC_CTAS;       // r == len: the tau slot
+                double* rv = cluster.map_shared_rank(vbuf, dstr);
+                if (r < len) rv[i + 1 + r] = col[i + 1 + r];
+                else rv[rows] = tau_i;
             }
-        } else if (tid == 0 && l2p[i] % QC_CTAS == rank) {
-            tau[i] = 0.0;
+            if (tid == 0) tau[i] = tau_i;
         }
-        __syncthreads();
-        // ---- H_i on my remaining columns + dlaqp2 norm downdate, one warp per column ----
+        cluster.sync();
+        // ---- 4. H_i on my remaining columns + dlaqp2 norm downdate, one warp per column
+        const double tau_i = vbuf[rows];
         const int len = rows - i - 1;
         for (int s = w; s < nloc; s += nw) {
             if (pos[s] <= i) continue;
@@ -789,9 +771,8 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
             }
         }
         __syncthreads();
-        if (i + 1 < k) propose(i + 1);
-        cluster.sync();
     }
+    cluster.sync();
     // output in dgeqp3 layout: the column now at position p goes to column p of f
     for (int s = w; s < nloc; s += nw) {
         const int p = pos[s];
