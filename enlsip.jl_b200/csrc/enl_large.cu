@@ -102,14 +102,25 @@ __device__ __forceinline__ double warp_sum(double v) {
 // pairs) and of r'r; the CTA folds its 8 warps in a fixed order into gpart[blockIdx][0..n] ([n] = r'r).  The gradient is
 // what the termination test of the new point reads (EF:2838, 2411), so that the factorisation can wait until the
 // iteration is known to continue.  NC == 0 (n > 64 * 8): no gradient here, li_grad_kernel does it.
-template <int NC>
+// FD: the Jacobian row by forward differences (jac_forward_diff, cnls_model.jl:65-82) instead of s * w_i: entry j is
+// (r_i(x + delta_j e_j) - r_i(x)) / delta_j with delta_j = max(|x_j|, 1) sqrt(eps); for this family
+// w_i . (x + delta_j e_j) = u_i + delta_j w_ij, so the perturbed residual costs one det_tanh and no second pass over W.
+__device__ __forceinline__ double li_fd_entry(double uu, double wij, double dj, double yi, double rr) {
+    const double rj = __dsub_rn(enl::det_tanh(fma(dj, wij, uu)), yi);
+    return __ddiv_rn(__dsub_rn(rj, rr), dj);
+}
+template <int NC, bool FD = false>
 __global__ void __launch_bounds__(256) li_build_kernel(const double* __restrict__ W, const double* __restrict__ y,
                                                        const double* __restrict__ x, long long m, int n, int ld,
                                                        double* __restrict__ A, double* __restrict__ u,
                                                        double* __restrict__ r, double* __restrict__ s,
                                                        double* __restrict__ gpart) {
-    extern __shared__ double xs[];   // x [n]; then, NC > 0: 8 x (n + 1) partial gradients
-    for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = x[j];
+    extern __shared__ double xs[];   // x [n]; then, NC > 0: 8 x (n + 1) partial gradients; FD: then delta [n]
+    double* dls = xs + n + (NC > 0 ? 8 * (n + 1) : 0);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        xs[j] = x[j];
+        if (FD) dls[j] = __dmul_rn(fmax(fabs(x[j]), 1.0), 1.4901161193847656e-08);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -137,7 +148,8 @@ __global__ void __launch_bounds__(256) li_build_kernel(const double* __restrict_
                 const int c = 2 * lane + 64 * k;
                 if (c < n) {
                     double2 wv = *reinterpret_cast<const double2*>(wr + c);
-                    const double j0 = __dmul_rn(ss, wv.x), j1 = __dmul_rn(ss, wv.y);
+                    const double j0 = FD ? li_fd_entry(uu, wv.x, dls[c], y[i], rr) : __dmul_rn(ss, wv.x);
+                    const double j1 = FD ? li_fd_entry(uu, wv.y, dls[c + 1], y[i], rr) : __dmul_rn(ss, wv.y);
                     *reinterpret_cast<double2*>(ar + c) = make_double2(j0, j1);
                     ga[2 * k] = fma(j0, rr, ga[2 * k]);
                     ga[2 * k + 1] = fma(j1, rr, ga[2 * k + 1]);
@@ -147,7 +159,9 @@ __global__ void __launch_bounds__(256) li_build_kernel(const double* __restrict_
         } else {
             for (int c = 2 * lane; c < n; c += 64) {
                 double2 wv = *reinterpret_cast<const double2*>(wr + c);
-                *reinterpret_cast<double2*>(ar + c) = make_double2(__dmul_rn(ss, wv.x), __dmul_rn(ss, wv.y));
+                const double j0 = FD ? li_fd_entry(uu, wv.x, dls[c], y[i], rr) : __dmul_rn(ss, wv.x);
+                const double j1 = FD ? li_fd_entry(uu, wv.y, dls[c + 1], y[i], rr) : __dmul_rn(ss, wv.y);
+                *reinterpret_cast<double2*>(ar + c) = make_double2(j0, j1);
             }
         }
         if (lane < ld - n) ar[n + lane] = (lane == 0) ? rr : 0.0;
@@ -212,12 +226,20 @@ __device__ __forceinline__ void block_reduce4(double (&v)[4], double* part) {
 }
 
 // v = W p (one warp per row), Jp = s .* v; partial sums {r.r, r.Jp, Jp.Jp, 0}
+// fd != 0: Jp is the product with the forward-difference Jacobian of li_build_kernel<., true> (entries recomputed on the fly
+// from u, y, r and the point xcur), so that the linesearch model sees the Jacobian the iteration was built on
 __global__ void __launch_bounds__(256) li_dir_kernel(const double* __restrict__ W, const double* __restrict__ p,
                                                      const double* __restrict__ r, const double* __restrict__ s,
                                                      long long m, int n, double* __restrict__ v,
-                                                     double* __restrict__ Jp, double* __restrict__ part) {
-    extern __shared__ double xs[];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = p[j];
+                                                     double* __restrict__ Jp, double* __restrict__ part, int fd,
+                                                     const double* __restrict__ xcur, const double* __restrict__ u,
+                                                     const double* __restrict__ y) {
+    extern __shared__ double xs[];      // p [n]; fd: then delta [n]
+    double* dls = xs + n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        xs[j] = p[j];
+        if (fd) dls[j] = __dmul_rn(fmax(fabs(xcur[j]), 1.0), 1.4901161193847656e-08);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -225,15 +247,21 @@ __global__ void __launch_bounds__(256) li_dir_kernel(const double* __restrict__ 
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long i = warp0; i < m; i += nwarps) {
         const double* wr = W + i * n;
-        double acc = 0.0;
+        double acc = 0.0, accj = 0.0;
+        const double ui = fd ? u[i] : 0.0, yi = fd ? y[i] : 0.0, rri = fd ? r[i] : 0.0;
         for (int c = 2 * lane; c < n; c += 64) {
             double2 wv = *reinterpret_cast<const double2*>(wr + c);
             acc = fma(wv.x, xs[c], acc);
             acc = fma(wv.y, xs[c + 1], acc);
+            if (fd) {
+                accj = fma(li_fd_entry(ui, wv.x, dls[c], yi, rri), xs[c], accj);
+                accj = fma(li_fd_entry(ui, wv.y, dls[c + 1], yi, rri), xs[c + 1], accj);
+            }
         }
         const double vv = warp_sum(acc);
+        const double jfd = fd ? warp_sum(accj) : 0.0;
         if (lane == 0) {
-            const double jp = s[i] * vv, ri = r[i];
+            const double jp = fd ? jfd : s[i] * vv, ri = r[i];
             v[i] = vv; Jp[i] = jp;
             sums[0] = fma(ri, ri, sums[0]); sums[1] = fma(ri, jp, sums[1]); sums[2] = fma(jp, jp, sums[2]);
         }
@@ -554,8 +582,18 @@ struct LargeHandle : LargeOps, SmallBackend {
         int parts = grid_rows();
         if (m_local > 0) {
             const int nc = (n + 63) / 64;
-            const size_t sh = sizeof(double) * (n + 8 * (size_t)(n + 1));
-            if (nc <= 1) li_build_kernel<1><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+            const size_t sh = sizeof(double) * (2 * (size_t)n + 8 * (size_t)(n + 1));
+            if (jac_fd) {
+                if (nc <= 1) li_build_kernel<1, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                else if (nc <= 2) li_build_kernel<2, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                else if (nc <= 4) li_build_kernel<4, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                else if (nc <= 8) li_build_kernel<8, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                else {
+                    li_build_kernel<0, true><<<parts, 256, sizeof(double) * 2 * n, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                    li_grad_kernel<<<parts, 256, 0, st>>>(dA, ld, m_local, n, dgpart);
+                    ++launches;
+                }
+            } else if (nc <= 1) li_build_kernel<1><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
             else if (nc <= 2) li_build_kernel<2><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
             else if (nc <= 4) li_build_kernel<4><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
             else if (nc <= 8) li_build_kernel<8><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
@@ -978,7 +1016,7 @@ struct LargeHandle : LargeOps, SmallBackend {
             launches += enl_small::gemv_n(dJkeep, (int)m_local, (int)m_local, n, dp, 1.0, nullptr, 0.0, dJp, st);
             lg_dir_sums_kernel<<<cur_parts, 256, 0, st>>>(dr, dJp, m_local, dpart);
         } else {
-            li_dir_kernel<<<cur_parts, 256, sizeof(double) * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart);
+            li_dir_kernel<<<cur_parts, 256, sizeof(double) * 2 * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart, jac_fd, dx, du, dy);
         }
         ++launches;
         double o[4];

@@ -73,8 +73,6 @@ class LargeCnlsModel:
             return
         if family != "single_index":
             raise AssertionError("large-regime families: %s" % (["single_index"] + sorted(_ROW_FAMILIES)))
-        if jacobian != "analytic":
-            raise AssertionError("the single_index family is built with its analytic Jacobian")
         W, y = data["W"], data["y"]
         rho = np.ascontiguousarray(data["rho"], dtype=np.float64)
         rows = int(W.shape[0])

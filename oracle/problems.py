@@ -255,12 +255,13 @@ def gauss_peaks(y, S, x0, fd=True) -> Problem:
                         x_low=GP_LOW, x_upp=GP_UPP, x0=x0, name="gauss_peaks", fd=fd)
 
 
-def single_index(Wm, y, rho, x0, ineq=False, bounds=None) -> Problem:
+def single_index(Wm, y, rho, x0, ineq=False, bounds=None, fd_res=False) -> Problem:
     """C4/C5 family: r_i = det_tanh(w_i . x) - y_i ; block constraints on groups of 4 parameters.
 
     ``ineq=False``: equalities h_k = sum_{j in block k} x_j^2 - rho_k  (C4)
     ``ineq=True`` : inequalities g_k = rho_k - sum x_j^2 >= 0, optional bounds (C5)
-    Analytic Jacobians: J = diag(1 - tanh^2) W.
+    Analytic Jacobians: J = diag(1 - tanh^2) W; ``fd_res``: forward-difference residual Jacobian (cnls_model.jl:65-82;
+    the constraint Jacobian stays analytic, as in the engine's FD variant of this family).
     """
     Wm = np.asarray(Wm, dtype=np.float64)
     m, n = Wm.shape
@@ -283,6 +284,8 @@ def single_index(Wm, y, rho, x0, ineq=False, bounds=None) -> Problem:
             A[k, 4 * k: 4 * k + 4] = 2.0 * x[4 * k: 4 * k + 4]
         return A
 
+    if fd_res:
+        jac_r = lambda x: jac_forward_diff(r, x)        # noqa: E731
     if not ineq:
         return make_problem(n, m, r, jac_r, eq=lambda x: blocks(x) - rho, jac_eq=jb, nb_eq=nb, x0=x0, name="single_index_eq")
     lo, up = (None, None) if bounds is None else (np.full(n, bounds[0]), np.full(n, bounds[1]))

@@ -329,3 +329,25 @@ def test_tsqr_tma_trailing_kernel_matches():
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True).stdout)
     a, b = (np.frombuffer(o, dtype=np.float64) for o in outs)
     assert a.size == 129 * 129 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("m,n,nb,seed", [(3000, 32, 8, 41), (5000, 64, 16, 42)])
+def test_single_index_forward_difference_jacobian_vs_oracle(E, m, n, nb, seed):
+    """The FD-Jacobian variant of the tall family (SURVEY.md 8d, C4 inputs; jac_forward_diff, cnls_model.jl:65-82): the
+    residual Jacobian by forward differences inside the build kernel (one det_tanh per entry, no second pass over W)
+    against the oracle with the same differencing: same status / iteration count / working set, f and x to the FD noise
+    floor.  The analytic solve of the same problem lands on the same point to 1e-6."""
+    from oracle import enlsip_oracle as O, problems as P
+    d = E.synth.gen_single_index(m, n, nb, seed=seed)
+    mod = E.LargeCnlsModel("single_index", d["x0"], d, jacobian="forward_diff")
+    E.solve(mod, trace_cap=60)
+    r = O.solve(P.single_index(d["W"], d["y"], d["rho"], d["x0"], fd_res=True), wallclock=False)
+    assert int(mod.status_code[0]) == r.status == 1
+    assert abs(int(mod.iterations[0]) - r.iterations) <= 1
+    assert sorted(int(v) for v in mod.active[0] if v > 0) == sorted(r.active)
+    assert abs(float(mod.obj_value[0]) - r.f) <= 1e-8 * r.f
+    assert np.linalg.norm(mod.sol[0] - r.x) <= 1e-6 * np.linalg.norm(r.x)
+    ma = E.LargeCnlsModel("single_index", d["x0"], d)
+    E.solve(ma)
+    assert np.linalg.norm(mod.sol[0] - ma.sol[0]) <= 1e-6 * np.linalg.norm(ma.sol[0])
+    mod.close(); ma.close()
