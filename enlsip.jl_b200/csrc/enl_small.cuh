@@ -622,12 +622,13 @@ __global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f
 // redundantly -- was measured slower: 1.33 ms; the 8-fold column traffic through distributed shared memory costs more
 // than the barrier it saves.)
 // Columns are never moved: `pos` tracks the position dlaqp2's swaps would have given them.
-constexpr int QC_CTAS = 8, QC_THREADS = 512;
+constexpr int QC_MAXCTAS = 8, QC_THREADS = 512;
 constexpr size_t QC_MAX_SMEM = 200 * 1024;
-inline size_t qc_smem_bytes(int rows, int cols) {
-    const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
-    return sizeof(double) * ((size_t)ncl * rows + rows + 2 + 2 * (size_t)ncl + QC_CTAS) + sizeof(int) * ((size_t)ncl + cols + 2 * QC_CTAS + 2);
+inline size_t qc_smem_bytes(int rows, int cols, int nctas) {
+    const int ncl = (cols + nctas - 1) / nctas;
+    return sizeof(double) * ((size_t)ncl * rows + rows + 2 + 2 * (size_t)ncl + QC_MAXCTAS) + sizeof(int) * ((size_t)ncl + cols + 2 * QC_MAXCTAS + 2);
 }
+template <int QC_CTAS>
 __global__ void __cluster_dims__(QC_CTAS, 1, 1) __launch_bounds__(QC_THREADS)
 qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict__ tau, int* __restrict__ jpvt, int nopivot) {
     namespace cg = cooperative_groups;
@@ -644,10 +645,10 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
     double* vn1 = vbuf + rows + 2;                  // [ncl]
     double* vn2 = vn1 + ncl;                        // [ncl]
     double* cval = vn2 + ncl;                       // [QC_CTAS] proposals: value
-    int* pos = reinterpret_cast<int*>(cval + QC_CTAS);   // [ncl] current position of the local column
+    int* pos = reinterpret_cast<int*>(cval + QC_MAXCTAS);   // [ncl] current position of the local column
     int* l2p = pos + ncl;                           // [cols] position -> column (replicated in every CTA)
     int* cpos = l2p + cols;                         // [QC_CTAS] proposals: position
-    int* cphys = cpos + QC_CTAS;                    // [QC_CTAS] proposals: column
+    int* cphys = cpos + QC_MAXCTAS;                    // [QC_CTAS] proposals: column
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = QC_THREADS / 32;
     const int nloc = (cols > rank) ? (cols - rank + QC_CTAS - 1) / QC_CTAS : 0;     // my columns: rank, rank + 8, ...
     const int k = rows < cols ? rows : cols;
@@ -840,11 +841,31 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
 inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st, int nopivot = 0) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
-    if (qc_smem_bytes(rows, cols) <= QC_MAX_SMEM) {
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM); attr_set = true; }
-        qr_cluster_kernel<<<QC_CTAS, QC_THREADS, qc_smem_bytes(rows, cols), st>>>(f, rows, cols, tau, jpvt, nopivot);
-        return 1;
+    // cluster size: the smallest of 2 / 4 / 8 CTAs whose shared memory holds the matrix with <= 32 columns per CTA (two
+    // rounds of the warp-per-column update with 16 warps); ENLSIP_QC_NC overrides it (measurements)
+    {
+        static const int forced = [] { const char* e = getenv("ENLSIP_QC_NC"); return e ? atoi(e) : 0; }();
+        int nc = 0;
+        for (int c : {2, 4, 8})
+            if (!nc && qc_smem_bytes(rows, cols, c) <= QC_MAX_SMEM && (cols + c - 1) / c <= 32) nc = c;
+        if (!nc && qc_smem_bytes(rows, cols, 8) <= QC_MAX_SMEM) nc = 8;
+        if (forced && qc_smem_bytes(rows, cols, forced) <= QC_MAX_SMEM) nc = forced;
+        if (nc) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(qr_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM);
+                cudaFuncSetAttribute(qr_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM);
+                cudaFuncSetAttribute(qr_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM);
+                cudaFuncSetAttribute(qr_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC_MAX_SMEM);
+                attr_set = true;
+            }
+            const size_t shb = qc_smem_bytes(rows, cols, nc);
+            if (nc == 1) qr_cluster_kernel<1><<<1, QC_THREADS, shb, st>>>(f, rows, cols, tau, jpvt, nopivot);
+            else if (nc == 2) qr_cluster_kernel<2><<<2, QC_THREADS, shb, st>>>(f, rows, cols, tau, jpvt, nopivot);
+            else if (nc == 4) qr_cluster_kernel<4><<<4, QC_THREADS, shb, st>>>(f, rows, cols, tau, jpvt, nopivot);
+            else qr_cluster_kernel<8><<<8, QC_THREADS, shb, st>>>(f, rows, cols, tau, jpvt, nopivot);
+            return 1;
+        }
     }
     // dgeqp3: blocked (dlaqps) while j <= topbmn = minmn - nx, if nb < minmn and nx < minmn
     int topbmn = (QR_NB < minmn && QR_NX < minmn) ? (minmn - QR_NX) : 0;
