@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) qr_p2_apply_kernel(double* __restrict__ f
 // redundantly -- was measured slower: 1.33 ms; the 8-fold column traffic through distributed shared memory costs more
 // than the barrier it saves.)
 // Columns are never moved: `pos` tracks the position dlaqp2's swaps would have given them.
-constexpr int QC_MAXCTAS = 8, QC_THREADS = 512;
+constexpr int QC_MAXCTAS = 8, QC_THREADS = 512;   // (1024 threads: 0.43 / 0.38 / 1.34 ms instead of 0.30 / 0.26 / 1.05: wider barriers cost more than the second round of column updates)
 constexpr size_t QC_MAX_SMEM = 200 * 1024;
 inline size_t qc_smem_bytes(int rows, int cols, int nctas) {
     const int ncl = (cols + nctas - 1) / nctas;
@@ -636,8 +636,8 @@ qr_cluster_kernel(double* __restrict__ f, int rows, int cols, double* __restrict
     const int rank = (int)cluster.block_rank();
     extern __shared__ double sm[];
     __shared__ double sh[32];
-    __shared__ double s_rb[16];
-    __shared__ int s_rp[16], s_rs[16];
+    __shared__ double s_rb[32];
+    __shared__ int s_rp[32], s_rs[32];
     __shared__ int s_wphys;
     const int ncl = (cols + QC_CTAS - 1) / QC_CTAS;
     double* Al = sm;                                // [ncl][rows]
@@ -841,13 +841,16 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
 inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, cudaStream_t st, int nopivot = 0) {
     const int minmn = rows < cols ? rows : cols;
     if (minmn <= 0) return 0;
-    // cluster size: the smallest of 2 / 4 / 8 CTAs whose shared memory holds the matrix with <= 32 columns per CTA (two
-    // rounds of the warp-per-column update with 16 warps); ENLSIP_QC_NC overrides it (measurements)
+    // cluster size: the smallest of 2 / 4 / 8 CTAs whose shared memory holds the matrix with at most one column per warp
+    // (a single round of the warp-per-column update), else 8; ENLSIP_QC_NC overrides it.  Measured (B200, 512 threads):
+    // 256 x 64: 0.43 / 0.34 / 0.30 / 0.34 ms with 1 / 2 / 4 / 8 CTAs, 64 x 64: 0.34 / 0.29 / 0.26 / 0.27 ms -- a column step
+    // costs 4-5 us whatever the cluster size: the dependent chain inside a step (reductions, IEEE divisions and square
+    // roots of dlarfg and of the norm downdate), not the cluster barrier, sets the pace
     {
         static const int forced = [] { const char* e = getenv("ENLSIP_QC_NC"); return e ? atoi(e) : 0; }();
         int nc = 0;
         for (int c : {2, 4, 8})
-            if (!nc && qc_smem_bytes(rows, cols, c) <= QC_MAX_SMEM && (cols + c - 1) / c <= 32) nc = c;
+            if (!nc && qc_smem_bytes(rows, cols, c) <= QC_MAX_SMEM && (cols + c - 1) / c <= QC_THREADS / 32) nc = c;
         if (!nc && qc_smem_bytes(rows, cols, 8) <= QC_MAX_SMEM) nc = 8;
         if (forced && qc_smem_bytes(rows, cols, forced) <= QC_MAX_SMEM) nc = forced;
         if (nc) {
