@@ -153,11 +153,13 @@ def compile_family(source, n, m, nb_eq=0, nb_ineq=0, stride0=0, stride1=0, has_j
         work = os.path.join(USER_LIB_DIR, "%s.%d" % (tag, os.getpid()))
         os.makedirs(work, exist_ok=True)
         tmp = os.path.join(work, "lib.so")
-        rc = lib().enlsipb200_compile_family(source.encode(), n, m, nb_eq, nb_ineq, stride0, stride1,
-                                             1 if has_jacobians else 0, tmp.encode(), work.encode())
-        check(rc)
-        os.replace(tmp, out)
-        shutil.rmtree(work, ignore_errors=True)
+        try:
+            rc = lib().enlsipb200_compile_family(source.encode(), n, m, nb_eq, nb_ineq, stride0, stride1,
+                                                 1 if has_jacobians else 0, tmp.encode(), work.encode())
+            check(rc)
+            os.replace(tmp, out)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
     L = _bind(ctypes.CDLL(out), large=False)
     _user_libs[tag] = L
     return L
@@ -193,10 +195,12 @@ def large_compile_family(source, m, nb_eq=0, nb_ineq=0, has_jacobians=False, nam
         work = os.path.join(USER_LIB_DIR, "%s.%d" % (tag, os.getpid()))
         os.makedirs(work, exist_ok=True)
         tmp = os.path.join(work, "lib.so")
-        check(lib().enlsipb200_large_compile_family(source.encode(), int(m), nb_eq, nb_ineq, 1 if has_jacobians else 0,
-                                                    tmp.encode(), work.encode()))
-        os.replace(tmp, out)
-        shutil.rmtree(work, ignore_errors=True)
+        try:
+            check(lib().enlsipb200_large_compile_family(source.encode(), int(m), nb_eq, nb_ineq, 1 if has_jacobians else 0,
+                                                        tmp.encode(), work.encode()))
+            os.replace(tmp, out)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
     L = _bind_large_only(ctypes.CDLL(out))
     _user_libs[tag] = L
     return L

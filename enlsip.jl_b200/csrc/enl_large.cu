@@ -589,7 +589,7 @@ struct LargeHandle : LargeOps, SmallBackend {
                 else if (nc <= 4) li_build_kernel<4, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
                 else if (nc <= 8) li_build_kernel<8, true><<<parts, 256, sh, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
                 else {
-                    li_build_kernel<0, true><<<parts, 256, sizeof(double) * 2 * n, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);
+                    li_build_kernel<0, true><<<parts, 256, sizeof(double) * 2 * n, st>>>(dW, dy, dx, m_local, n, ld, dA, du, dr, ds, dgpart);   // (n <= 3072: 48 KB)
                     li_grad_kernel<<<parts, 256, 0, st>>>(dA, ld, m_local, n, dgpart);
                     ++launches;
                 }
@@ -1016,7 +1016,7 @@ struct LargeHandle : LargeOps, SmallBackend {
             launches += enl_small::gemv_n(dJkeep, (int)m_local, (int)m_local, n, dp, 1.0, nullptr, 0.0, dJp, st);
             lg_dir_sums_kernel<<<cur_parts, 256, 0, st>>>(dr, dJp, m_local, dpart);
         } else {
-            li_dir_kernel<<<cur_parts, 256, sizeof(double) * 2 * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart, jac_fd, dx, du, dy);
+            li_dir_kernel<<<cur_parts, 256, sizeof(double) * (jac_fd ? 2 : 1) * n, st>>>(dW, dp, dr, ds, m_local, n, dv, dJp, dpart, jac_fd, dx, du, dy);
         }
         ++launches;
         double o[4];
@@ -1212,6 +1212,8 @@ int enlsipb200_large_solve(enlsipb200_large hh, const double* x0, const enlsipb2
     if (!h || !x0 || !o || !x || !f) return lfail(ENLSIPB200_EINVAL, "NULL argument");
     if (!h->gv && (!h->dW || !h->dy)) return lfail(ENLSIPB200_EINVAL, "family data (W, y) not set");
     h->jac_fd = (o->jac_mode == ENLSIPB200_JAC_FORWARD_DIFF) ? 1 : 0;
+    if (h->jac_fd && !h->gv && h->n > 3072)
+        return lfail(ENLSIPB200_EINVAL, "forward-difference Jacobians of the single-index family: n <= 3072 (x and the steps are staged in 48 KB of shared memory)");
     LargeOptions opt;
     opt.max_iter = o->max_iter;
     opt.scaling = o->scaling;
