@@ -25,7 +25,9 @@
 // price is 1/7 more flops than a flat tree (each level re-factors 1/8 of the rows).
 // Algorithmic flops: 2 m n^2 (n = number of columns).  See DESIGN.md for the roofline accounting.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <stdlib.h>
 
 namespace enl_large {
@@ -998,6 +1000,211 @@ tsqr_trail_tma_kernel(double* __restrict__ A, int ld, long long nblk, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// trailing update fed by TMA, tensor-map form: one cp.async.bulk.tensor.2d per 32 x 16 box (4 KB), 128-byte swizzle
+// ---------------------------------------------------------------------------------------------
+// The work matrix is described once by a 2-D tensor map (row major, inner dimension = ld doubles); a 256 x 32 tile is
+// 8 row blocks x 2 column halves = 16 boxes of 32 rows x 16 doubles, each landing as 32 rows of 128 bytes whose 16-byte
+// chunks are XOR-swizzled with the row number (CU_TENSOR_MAP_SWIZZLE_128B).  Row blocks beyond the matrix are
+// out-of-bounds boxes: the TMA unit zero-fills them and still delivers their byte count.  The fragment loads are
+// re-assigned so that the swizzled tiles are read without bank conflicts:
+//   pass 1 (G = V'B: lanes = 4 k-rows x 8 columns): the four k-rows of a DMMA step are rows b, b+2, b+4, b+6 of an
+//          8-row group (distinct (row >> 1) & 3 => their 16-byte chunk pairs fall into disjoint bank groups);
+//   pass 2 (B += V W: lanes = 8 rows x 4 k-columns) and the accumulator tiles: fragment row g is row
+//          QROW(g) = {0,4,2,6,1,5,3,7}[g] of its 8-row tile, for the same reason.
+// Same schedule as tsqr_trail_staged_kernel; the summation order inside G differs (other row grouping), results agree
+// to rounding.
+constexpr int TM_BOX_ROWS = 32, TM_BOX_COLS = 16;
+constexpr int TM_BOX_DOUBLES = TM_BOX_ROWS * TM_BOX_COLS;                 // 512 doubles = 4 KB
+constexpr int TM_TILE_DOUBLES = 16 * TM_BOX_DOUBLES;                      // 256 x 32
+// element (r, c) of a swizzled 256 x 32 tile, r < 256, c < 32
+__device__ __forceinline__ int tm_off(int r, int c) {
+    const int box = ((r >> 5) << 1) | (c >> 4), rr = r & 31, cc = c & 15;
+    return box * TM_BOX_DOUBLES + rr * 16 + ((((cc >> 1) ^ (rr & 7)) << 1) | (cc & 1));
+}
+__device__ __forceinline__ int tm_qrow(int g) { return ((g & 1) << 2) | (g & 2) | (g >> 2); }   // 0,4,2,6,1,5,3,7
+__device__ __forceinline__ void tma_load_2d(double* smem_dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+constexpr int TM_SMEM = (2 * TM_TILE_DOUBLES + (2 + TR_KS) * TS_B * TR_LD) * (int)sizeof(double) + 64 + 1024;
+
+template <int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
+tsqr_trail_tmap_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ A, int ld, long long nblk, long long stride,
+                       int col0, int ncb, int cbpc, const double* __restrict__ Tbuf) {
+    constexpr int NTH = 32 * NW;
+    constexpr int KS = NW / 4;
+    constexpr int KROWS = TR_ROWS / KS;
+    constexpr int RW = TR_ROWS / NW;
+    constexpr int RT = RW / 8;
+    extern __shared__ __align__(1024) double smem_raw[];
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    double* Vs = smem;
+    double* Bs = Vs + TM_TILE_DOUBLES;
+    double* Ts = Bs + TM_TILE_DOUBLES;
+    double* Ws = Ts + TS_B * TR_LD;
+    double* Gs = Ws + TS_B * TR_LD;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Gs + KS * TS_B * TR_LD);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const bool producer = (w == NW);
+    const int nchunks = (ncb + cbpc - 1) / cbpc;
+    const long long sub = blockIdx.x / (unsigned)nchunks;
+    const int chunk = (int)(blockIdx.x % (unsigned)nchunks);
+    const int cb_begin = chunk * cbpc;
+    const int cb_end = (cb_begin + cbpc < ncb) ? cb_begin + cbpc : ncb;
+    // producer: lanes 0..15 each issue one box of the tile at column c0 (row block lane >> 1, column half lane & 1)
+    auto tma_stage = [&](double* dst, int c0, unsigned long long* bar) {
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)(TM_TILE_DOUBLES * sizeof(double)));
+        __syncwarp();
+        if (lane < 16) {
+            const long long blk = (sub * TS_FAN + (lane >> 1)) * stride;
+            // a block index past the matrix is an out-of-bounds box (zero filled); keep the coordinate in int range
+            const long long row = blk < nblk ? blk * TS_B : (long long)nblk * TS_B;
+            tma_load_2d(dst + lane * TM_BOX_DOUBLES, &tmap, c0 + (lane & 1) * TM_BOX_COLS, (int)row, bar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (producer) {
+        tma_stage(Vs, col0, &bars[0]);
+        tma_stage(Bs, col0 + TS_B * (cb_begin + 1), &bars[1]);
+    } else {
+        const double* Tg = Tbuf + sub * (TS_B * TS_B);
+#pragma unroll
+        for (int q = 0; q < 1024 / NTH; ++q) {
+            const int idx = tid + NTH * q;
+            Ts[(idx >> 5) * TR_LD + (idx & 31)] = Tg[idx];
+        }
+        mbar_wait(&bars[0], 0);
+    }
+    __syncthreads();
+    // the top block of V is a unit lower trapezoid (R of the panel sits on and above its diagonal)
+    if (!producer) {
+#pragma unroll
+        for (int q = 0; q < 1024 / NTH; ++q) {
+            const int idx = tid + NTH * q;
+            const int r = idx >> 5, c = idx & 31;
+            if (r <= c) Vs[tm_off(r, c)] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    const int wm = producer ? 0 : w;
+    const long long myblk = (sub * TS_FAN + ((wm * RW) >> 5)) * stride;
+    const bool valid = myblk < nblk;
+    const int kh = wm >> 2, qd = wm & 3;
+    const int ti0 = (qd >> 1) * 2, tj0 = (qd & 1) * 2;
+    double* Gk = Gs + kh * (TS_B * TR_LD);
+    const int qg = tm_qrow(g);
+    unsigned phase = 0;
+    for (int cb = cb_begin; cb < cb_end; ++cb) {
+        if (producer) {
+            __syncthreads();                  // (a) the math warps have taken the block out of Bs
+            if (cb + 1 < cb_end) tma_stage(Bs, col0 + TS_B * (cb + 2), &bars[1]);
+            __syncthreads();                  // (b) W stage done
+            continue;
+        }
+        mbar_wait(&bars[1], phase);
+        phase ^= 1u;
+        // ---- pass 1: this warp's quadrant of G over its share of the rows; k-rows of step kk: base + 2 t ----
+        double acc[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 8
+        for (int kk = 0; kk < KROWS / 4; ++kk) {
+            const int r = kh * KROWS + ((kk >> 1) << 3) + (kk & 1) + 2 * t;
+            const double a0 = Vs[tm_off(r, ti0 * 8 + g)], a1 = Vs[tm_off(r, ti0 * 8 + 8 + g)];
+            const double b0 = Bs[tm_off(r, tj0 * 8 + g)], b1 = Bs[tm_off(r, tj0 * 8 + 8 + g)];
+            dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(Gk + ((ti0 + i) * 8 + g) * TR_LD + (tj0 + j) * 8 + 2 * t) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+        // accumulators of pass 2: this warp's rows of the staged block (fragment row g = tile row QROW(g))
+        double b2[RT][4][2];
+#pragma unroll
+        for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+            for (int cj = 0; cj < 4; ++cj) {
+                const double2 v = *reinterpret_cast<const double2*>(Bs + tm_off(w * RW + ri * 8 + qg, cj * 8 + 2 * t));
+                b2[ri][cj][0] = v.x; b2[ri][cj][1] = v.y;
+            }
+        __syncthreads();                      // (a) Bs is free: the producer streams the next block in
+        // ---- W = -T' G ----
+#pragma unroll
+        for (int id = w; id < 16; id += NW) {
+            const int ti = id >> 2, tj = id & 3;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int o = (kk * 4 + t) * TR_LD + tj * 8 + g;
+                double gv;
+                if (KS == 2) gv = Gs[o] + Gs[TS_B * TR_LD + o];
+                else gv = (Gs[o] + Gs[TS_B * TR_LD + o]) + (Gs[2 * TS_B * TR_LD + o] + Gs[3 * TS_B * TR_LD + o]);
+                dmma884(c0, c1, Ts[(kk * 4 + t) * TR_LD + ti * 8 + g], gv);
+            }
+            *reinterpret_cast<double2*>(Ws + (ti * 8 + g) * TR_LD + tj * 8 + 2 * t) = make_double2(-c0, -c1);
+        }
+        __syncthreads();                      // (b)
+        // ---- pass 2: B_w += V_w W ----
+        {
+            const double* wp = Ws + t * TR_LD + g;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                double av[RT], bw[4];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri) av[ri] = Vs[tm_off(w * RW + ri * 8 + qg, kk * 4 + t)];
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj) bw[cj] = wp[kk * 4 * TR_LD + cj * 8];
+#pragma unroll
+                for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                    for (int cj = 0; cj < 4; ++cj) dmma884(b2[ri][cj][0], b2[ri][cj][1], av[ri], bw[cj]);
+            }
+        }
+        if (valid) {
+            double* Bb = A + (myblk * TS_B + ((w * RW) & 31)) * (long long)ld + col0 + TS_B * (cb + 1);
+#pragma unroll
+            for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+                for (int cj = 0; cj < 4; ++cj)
+                    *reinterpret_cast<double2*>(Bb + (long long)(ri * 8 + qg) * ld + cj * 8 + 2 * t) =
+                        make_double2(b2[ri][cj][0], b2[ri][cj][1]);
+        }
+    }
+}
+
+// host side: the tensor map of a row-major work matrix (rows_pad x ld doubles), boxes of 32 rows x 16 doubles
+inline bool tsqr_make_tensor_map(CUtensorMap* tm, double* A, int ld, long long rows_pad) {
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (PFN_cuTensorMapEncodeTiled)fn;
+    }();
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows_pad};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {TM_BOX_COLS, TM_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, A, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // rows 0..31 of the matrix now hold rows col0..col0+31 of R: copy them out and clear them in place
 // (one CTA per row: at n = 4096 a single CTA needed 140 us per panel)
 __global__ void tsqr_extract_kernel(double* __restrict__ A, int ld, int col0, int ncols, double* __restrict__ Rout,
@@ -1050,6 +1257,7 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     cudaFuncSetAttribute(tsqr_trail_staged_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
     cudaFuncSetAttribute(tsqr_trail_tma_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_TMA_SMEM);
+    cudaFuncSetAttribute(tsqr_trail_tmap_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM);
     // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
     // development switch: ENLSIP_PANEL=1 selects the row-tile panel kernel (kept for A/B measurements)
     static const int panel_mode = [] { const char* e = getenv("ENLSIP_PANEL"); return (e && e[0] == '1') ? 1 : 3; }();
@@ -1057,7 +1265,11 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     // TSQR 80.1 ms against 52.2 ms with the cp.async kernel -- a copy per 256-byte row is 4.3e8 copy operations per
     // factorisation and the TMA unit does not sustain that rate; 8 KB tensor-map boxes need a swizzled tile layout
     // (DESIGN.md 5.3 item 12).  Default (2): the cp.async staged kernel.
-    static const int trail_mode = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2); }();
+    //                 4: tensor-map TMA kernel (4 KB boxes, 128-byte swizzle).
+    static const int trail_mode_env = [] { const char* e = getenv("ENLSIP_TRAIL"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }();
+    int trail_mode = trail_mode_env;
+    CUtensorMap tmap;
+    if (trail_mode == 4 && ((ld * (int)sizeof(double)) % 16 != 0 || !tsqr_make_tensor_map(&tmap, A, ld, rows_pad))) trail_mode = 2;
     for (int j = 0; j < npanels; ++j) {
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
@@ -1074,7 +1286,10 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
                 int cbpc = ncb32;
                 while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
                 const int nchunks = (ncb32 + cbpc - 1) / cbpc;
-                if (trail_mode == 3)
+                if (trail_mode == 4)
+                    tsqr_trail_tmap_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * (TR_NW + 1), TM_SMEM, st>>>(tmap, A, ld, nblk, stride,
+                                                                                                      col0, ncb32, cbpc, Tbuf);
+                else if (trail_mode == 3)
                     tsqr_trail_tma_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * (TR_NW + 1), TR_TMA_SMEM, st>>>(A, ld, nblk, stride, col0,
                                                                                                         ncb32, cbpc, Tbuf);
                 else
