@@ -1027,7 +1027,7 @@ __device__ __forceinline__ void tma_load_2d(double* smem_dst, const CUtensorMap*
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
-constexpr int TM_SMEM = (2 * TM_TILE_DOUBLES + (2 + TR_KS) * TS_B * TR_LD) * (int)sizeof(double) + 64 + 1024;
+constexpr int tm_smem_bytes(int nw) { return (2 * TM_TILE_DOUBLES + (2 + nw / 4) * TS_B * TR_LD) * (int)sizeof(double) + 64 + 1024; }
 
 template <int NW>
 __global__ void __launch_bounds__(32 * (NW + 1), 1)
@@ -1257,7 +1257,9 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     cudaFuncSetAttribute(tsqr_trail_kernel<TS_TRAIL_CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_TRAIL_SMEM);
     cudaFuncSetAttribute(tsqr_trail_staged_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
     cudaFuncSetAttribute(tsqr_trail_tma_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_TMA_SMEM);
-    cudaFuncSetAttribute(tsqr_trail_tmap_kernel<TR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM);
+    cudaFuncSetAttribute(tsqr_trail_tmap_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(8));
+    cudaFuncSetAttribute(tsqr_trail_tmap_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem_bytes(16));
+    static const int tmap_nw = [] { const char* e = getenv("ENLSIP_TMAP_NW"); return (e && atoi(e) == 16) ? 16 : 8; }();
     // development switch: ENLSIP_TRAIL=1 selects the direct-from-global trailing kernel (kept for A/B measurements)
     // development switch: ENLSIP_PANEL=1 selects the row-tile panel kernel (kept for A/B measurements)
     static const int panel_mode = [] { const char* e = getenv("ENLSIP_PANEL"); return (e && e[0] == '1') ? 1 : 3; }();
@@ -1286,9 +1288,12 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
                 int cbpc = ncb32;
                 while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
                 const int nchunks = (ncb32 + cbpc - 1) / cbpc;
-                if (trail_mode == 4)
-                    tsqr_trail_tmap_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * (TR_NW + 1), TM_SMEM, st>>>(tmap, A, ld, nblk, stride,
-                                                                                                      col0, ncb32, cbpc, Tbuf);
+                if (trail_mode == 4 && tmap_nw == 16)
+                    tsqr_trail_tmap_kernel<16><<<(unsigned)(nsub * nchunks), 32 * 17, tm_smem_bytes(16), st>>>(tmap, A, ld, nblk, stride, col0,
+                                                                                                   ncb32, cbpc, Tbuf);
+                else if (trail_mode == 4)
+                    tsqr_trail_tmap_kernel<8><<<(unsigned)(nsub * nchunks), 32 * 9, tm_smem_bytes(8), st>>>(tmap, A, ld, nblk, stride, col0,
+                                                                                                ncb32, cbpc, Tbuf);
                 else if (trail_mode == 3)
                     tsqr_trail_tma_kernel<TR_NW><<<(unsigned)(nsub * nchunks), 32 * (TR_NW + 1), TR_TMA_SMEM, st>>>(A, ld, nblk, stride, col0,
                                                                                                         ncb32, cbpc, Tbuf);
