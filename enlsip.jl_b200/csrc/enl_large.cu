@@ -492,11 +492,11 @@ struct LargeHandle : LargeOps, SmallBackend {
         LCU(cudaMalloc(&qw.F, sizeof(double) * (size_t)maxc * enl_small::QR_NB));
         LCU(cudaMalloc(&qw.auxv, sizeof(double) * enl_small::QR_NB));
         LCU(cudaMalloc(&qw.pbest, sizeof(double) * enl_small::QR_MAXPART));
-        LCU(cudaMalloc(&qw.psum, sizeof(double) * enl_small::QR_MAXPART));
-        LCU(cudaMalloc(&qw.pidx, sizeof(int) * enl_small::QR_MAXPART));
+        LCU(cudaMalloc(&qw.psum, sizeof(double) * enl_small::QR_PSUM_LEN));
+        LCU(cudaMalloc(&qw.pidx, sizeof(int) * enl_small::QR_PIDX_LEN));
         LCU(cudaMalloc(&qw.flags, sizeof(int) * maxc));
         LCU(cudaMalloc(&qw.state, sizeof(enl_small::QrState)));
-        LCU(cudaMalloc(&qw.ticket, sizeof(unsigned int)));
+        LCU(cudaMalloc(&qw.ticket, sizeof(unsigned int) * enl_small::QR_TICKET_LEN));
         LCU(cudaMalloc(&ww.Vb, sizeof(double) * mt * 32));
         LCU(cudaMalloc(&ww.T, sizeof(double) * 32 * 32));
         LCU(cudaMalloc(&ww.W, sizeof(double) * mt * 32));
@@ -1295,9 +1295,9 @@ int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt,
     const int k = rows < cols ? rows : cols;
     bool ok = S.get(&df, (size_t)rows * cols) && S.get(&dtau, k) && S.get(&dp, cols) && S.get(&S.qw.vn1, cols) &&
               S.get(&S.qw.vn2, cols) && S.get(&S.qw.F, (size_t)cols * enl_small::QR_NB) && S.get(&S.qw.auxv, enl_small::QR_NB) &&
-              S.get(&S.qw.flags, cols) && S.get(&S.qw.state, 1) && S.get(&S.qw.ticket, 1) &&
-              S.get(&S.qw.pbest, enl_small::QR_MAXPART) && S.get(&S.qw.psum, enl_small::QR_MAXPART) &&
-              S.get(&S.qw.pidx, enl_small::QR_MAXPART);
+              S.get(&S.qw.flags, cols) && S.get(&S.qw.state, 1) && S.get(&S.qw.ticket, enl_small::QR_TICKET_LEN) &&
+              S.get(&S.qw.pbest, enl_small::QR_MAXPART) && S.get(&S.qw.psum, enl_small::QR_PSUM_LEN) &&
+              S.get(&S.qw.pidx, enl_small::QR_PIDX_LEN);
     if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
     S.qw.cap_cols = cols;
     LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice));

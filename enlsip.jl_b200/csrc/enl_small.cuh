@@ -509,6 +509,382 @@ __global__ void __launch_bounds__(256) qr_panel_close_kernel(const double* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One dlaqps panel as ONE persistent cooperative kernel (default; the three-kernels-per-column form above stays selectable
+// with ENLSIP_QR_PANEL=graph).  A pivoted column step is a chain of grid-wide dependencies (pivot -> column -> norm ->
+// F column -> row / norm downdate -> next pivot); as separate kernels that chain costs three launches and three
+// last-CTA tails per column.  Here it is two grid barriers per column:
+//   phase P  every CTA combines the per-CTA pivot candidates (same result everywhere); the CTAs that own a slice of rows
+//            (slices are fixed for the whole panel, the panel columns of a slice stay in shared memory) bring the pivot
+//            column in, scale the previous reflector in place, apply the panel's reflectors to the new column and leave
+//            partial sums of squares and partial dot products of the panel columns with it (for auxv);
+//   phase Q  every CTA adds the partials in a fixed order and forms the dlarfg scalars and auxv (same bits everywhere);
+//            then, on its own chunk of the trailing columns, 16 at a time: the dots with the new reflector (streaming
+//            pass over the trailing matrix), and straight away -- one warp per column -- the F entry, the correction of
+//            the F column, the pivot-row entry, the partial-norm downdate with its tol3z flag and the pivot candidate
+//            of the next column.
+// The F row of the column that a pivot exchange moves away from position jc is dead after phase P (only rows behind the
+// panel are read later), so the exchange of F rows is a one-way move done by the warp that finishes column `pvt`.
+constexpr int QP_THREADS = 512, QP_NW = QP_THREADS / 32, QP_GC = 16, QP_MAXG = 160, QP_MAXRW = 512, QP_MINRW = 128;
+
+__device__ __forceinline__ unsigned int qp_ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Barrier over all CTAs of the (co-resident) grid.  bar[0]: epoch reached by the previous launches, bar[1]: exit ticket,
+// bar[4 + 8 c]: arrival flag of CTA c (one 32-byte sector each).  A CTA publishes its epoch with a release store to
+// its own flag and warp 0 polls all flags.  Measured on B200 (tools/qp_probe.cu, 148 CTAs): SLOWER than one counter
+// that every CTA increments and polls (QP_BARRIER_FLAGS=0: bar[2]) -- 5.4 k / 9.5 k cycles for the two barriers of a
+// column against 2.7 k / 5.0 k (arrival skew included); the counter is the default.
+#ifndef QP_BARRIER_FLAGS
+#define QP_BARRIER_FLAGS 0
+#endif
+__device__ __forceinline__ void qp_grid_barrier(unsigned int* bar, unsigned int& epoch) {
+    __syncthreads();
+#if QP_BARRIER_FLAGS
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, G = gridDim.x;
+        ++epoch;
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 4 + 8 * blockIdx.x), "r"(epoch) : "memory");
+        }
+        bool ok;
+        do {
+            ok = true;
+            for (int q = lane; q < G; q += 32) ok = ok && ((int)(qp_ld_acquire(bar + 4 + 8 * q) - epoch) >= 0);
+        } while (!__all_sync(0xffffffffu, ok));
+        __threadfence();
+    }
+#else
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(bar + 2, 1u);
+        while (qp_ld_acquire(bar + 2) < epoch) { }
+        __threadfence();
+    }
+#endif
+    __syncthreads();
+}
+__device__ __forceinline__ void qp_first_max(double& b, int& bi, double ob, int oi) {
+    if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+}
+__host__ __device__ inline int qp_rows_per_slice(int rows, int G) {
+    const int rw = (rows + G - 1) / G;
+    return rw < QP_MINRW ? QP_MINRW : rw;
+}
+inline size_t qp_smem_bytes(int rows, int G) {
+    return sizeof(double) * ((size_t)qp_rows_per_slice(rows, G) * (QR_NB + 2) + (size_t)QP_GC * QP_THREADS);
+}
+
+#ifdef QP_PROF
+__device__ unsigned long long qp_prof[8];      // cycles of CTA 0 per phase, summed over the columns (tools/qp_probe.cu)
+#define QP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); qp_prof[i] += (unsigned long long)(t_ - qp_t); qp_t = t_; } } while (0)
+#else
+#define QP_STAMP(i) do { } while (0)
+#endif
+__global__ void __launch_bounds__(QP_THREADS, 1)
+qr_panel_persist_kernel(double* f, int rows, int cols, double* vn1, double* vn2, int* jpvt, double* tau, double* F,
+                        int* flags, QrState* stt, double* pbest, int* pidx, int* pany, double* ppart, unsigned int* bar) {
+    extern __shared__ double qp_dyn[];
+    __shared__ double s_tot[QR_NB + 1];
+    __shared__ double s_aux[QR_NB], s_frow[QR_NB], s_prow[QR_NB];
+    __shared__ double s_best[QP_NW];
+    __shared__ int s_idx[QP_NW], s_any[QP_NW];
+    __shared__ double s_scal[3];
+    __shared__ int s_pv[2];
+    if (!stt->active) return;
+    const int j0 = stt->j0, jb = stt->jb, nopivot = stt->nopivot;
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int rw = qp_rows_per_slice(rows, G), Gp = (rows + rw - 1) / rw;
+    const int r0 = c * rw, nr = (c < Gp) ? ((rows - r0 < rw) ? rows - r0 : rw) : 0;
+    double* Vs = qp_dyn;                          // [rw][QR_NB + 1]: this slice of the panel columns
+    double* s_a = qp_dyn + (size_t)rw * (QR_NB + 1);   // [rw]: the new column
+    double* s_acc = s_a + rw;                          // [QP_GC][QP_THREADS]: partial dot products of a column group
+    constexpr int VL = QR_NB + 1;
+#if QP_BARRIER_FLAGS
+    unsigned int epoch = __ldcg(bar);             // continues where the previous launch stopped (flags are never reset)
+#else
+    unsigned int epoch = 0;
+#endif
+    int kb = jb;
+
+    // pivot candidates of the first column: first maximum of vn1 over this CTA's chunk of [j0, cols)
+    {
+        const int nt = cols - j0, cw = (nt + G - 1) / G;
+        const int jbeg = j0 + c * cw, jend = (jbeg + cw < cols) ? jbeg + cw : cols;
+        double b = -1.0; int bi = cols;
+        for (int j = jbeg + tid; j < jend; j += QP_THREADS) qp_first_max(b, bi, __ldcg(vn1 + j), j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            qp_first_max(b, bi, __shfl_xor_sync(0xffffffffu, b, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (lane == 0) { s_best[w] = b; s_idx[w] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < QP_NW; ++q) qp_first_max(b, bi, s_best[q], s_idx[q]);
+            pbest[c] = b; pidx[c] = bi; pany[c] = 0;
+        }
+        qp_grid_barrier(bar, epoch);
+    }
+
+#ifdef QP_PROF
+    long long qp_t = clock64();
+#endif
+    for (int k = 0; k < jb; ++k) {
+        const int jc = j0 + k, rk = jc;
+        // ---------------- phase P ----------------
+        QP_STAMP(7);
+        if (w == 0) {
+            double b = -1.0; int bi = cols, any = 0;
+            {
+                constexpr int NU = (QP_MAXG + 31) / 32;
+                double cb[NU]; int ci[NU], ca[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {            // all loads in flight together
+                    const int q = lane + 32 * u;
+                    cb[u] = (q < G) ? __ldcg(pbest + q) : -1.0;
+                    ci[u] = (q < G) ? __ldcg(pidx + q) : cols;
+                    ca[u] = (q < G) ? __ldcg(pany + q) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) { qp_first_max(b, bi, cb[u], ci[u]); any |= ca[u]; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                qp_first_max(b, bi, __shfl_xor_sync(0xffffffffu, b, o), __shfl_xor_sync(0xffffffffu, bi, o));
+            any = __any_sync(0xffffffffu, any);
+            if (bi >= cols || nopivot) bi = jc;
+            if (lane == 0) { s_pv[0] = bi; s_pv[1] = any; }
+        }
+        __syncthreads();
+        const int pvt = s_pv[0];
+        if (s_pv[1]) { kb = k; break; }               // a norm has to be recomputed: the panel ends (dlaqps lsticc)
+        QP_STAMP(0);
+        {
+            // every load that depends on the pivot only goes out before the block barrier (QP_MAXRW == QP_THREADS:
+            // a thread owns at most one row of the slice)
+            const bool has_row = tid < nr;
+            const int r = r0 + tid;
+            double* cj = f + (size_t)jc * rows;
+            double* cp = f + (size_t)pvt * rows;
+            double a = 0.0, oldj = 0.0;
+            if (has_row) { a = __ldcg(cp + r); if (pvt != jc) oldj = __ldcg(cj + r); }
+            if (tid < QR_NB) s_frow[tid] = (tid < k) ? __ldcg(F + (size_t)pvt * QR_NB + tid) : 0.0;
+            if (c == 0 && tid == 0 && pvt != jc) {
+                const int tp = __ldcg(jpvt + pvt); jpvt[pvt] = __ldcg(jpvt + jc); jpvt[jc] = tp;
+                vn1[pvt] = __ldcg(vn1 + jc); vn2[pvt] = __ldcg(vn2 + jc);
+            }
+            __syncthreads();
+            if (nr > 0) {
+                const double sc_prev = s_scal[1], beta_prev = s_scal[2];
+                if (has_row) {
+                    double* vrow = Vs + (size_t)tid * VL;
+                    if (pvt != jc) cp[r] = oldj;
+                    if (k > 0) {                          // the previous reflector: v = [1; x * sc], R(rk-1, jc-1) = beta
+                        double* cq = f + (size_t)(jc - 1) * rows;
+                        if (r > rk - 1) {
+                            if (sc_prev != 1.0) { const double v = vrow[k - 1] * sc_prev; cq[r] = v; vrow[k - 1] = v; }
+                        } else if (r == rk - 1) {
+                            cq[r] = beta_prev;
+                        }
+                    }
+                    if (r >= rk) {
+                        double s = 0.0;
+#pragma unroll 8
+                        for (int i = 0; i < k; ++i) s = fma(vrow[i], s_frow[i], s);
+                        a -= s;
+                        vrow[k] = a;
+                    }
+                    s_a[tid] = (r > rk) ? a : 0.0;
+                    cj[r] = a;
+                }
+                __syncthreads();
+                // partial sums over this slice: warp per quantity (i < k: panel column i . a ; i == k: a . a), fixed order
+                for (int i = w; i <= k; i += QP_NW) {
+                    double t = 0.0;
+                    if (i < k) { for (int rl = lane; rl < nr; rl += 32) if (r0 + rl > rk) t = fma(Vs[rl * VL + i], s_a[rl], t); }
+                    else { for (int rl = lane; rl < nr; rl += 32) t = fma(s_a[rl], s_a[rl], t); }
+                    t = s_warp_sum(t);
+                    if (lane == 0) ppart[(size_t)c * VL + (i < k ? i : QR_NB)] = t;
+                }
+            }
+        }
+        QP_STAMP(1);
+        qp_grid_barrier(bar, epoch);
+        QP_STAMP(2);
+
+        // ---------------- phase Q ----------------
+        {
+            double alpha = 0.0, prow = 0.0;
+            if (w == 0) {                             // in flight during the reduction of the partials
+                alpha = __ldcg(f + (size_t)jc * rows + rk);
+                if (lane < k) prow = __ldcg(f + (size_t)(j0 + lane) * rows + rk);
+                else if (lane == k) prow = 1.0;
+            }
+            {
+                // 16 threads per quantity (i < k: dot of panel column i with the new column; i == k: its sum of squares);
+                // all loads of a thread are in flight together, sums in a fixed order
+                const int i = tid >> 4, sub = tid & 15;
+                const int slot = (i < k) ? i : QR_NB;
+                double part[(QP_MAXG + 15) / 16];
+#pragma unroll
+                for (int u = 0; u < (QP_MAXG + 15) / 16; ++u) {
+                    const int q = sub + 16 * u;
+                    part[u] = (i <= k && q < Gp) ? __ldcg(ppart + (size_t)q * VL + slot) : 0.0;
+                }
+                double t = 0.0;
+#pragma unroll
+                for (int u = 0; u < (QP_MAXG + 15) / 16; ++u) t += part[u];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (sub == 0 && i <= k) s_tot[slot] = t;
+            }
+            __syncthreads();
+            if (w == 0) {
+                double beta = alpha, tau_k = 0.0, sc = 1.0;
+                if (rk < rows - 1) {
+                    const double xn = sqrt(s_tot[QR_NB]);
+                    if (xn != 0.0) {
+                        beta = -copysign(s_lapy2(alpha, xn), alpha);
+                        tau_k = (beta - alpha) / beta;
+                        sc = 1.0 / (alpha - beta);
+                    }
+                }
+                if (lane == 0) {
+                    s_scal[0] = tau_k; s_scal[1] = sc; s_scal[2] = beta;
+                    if (c == 0) tau[jc] = tau_k;
+                }
+                s_prow[lane] = prow;
+                s_aux[lane] = (lane < k) ? -tau_k * (prow + sc * s_tot[lane]) : 0.0;
+            }
+            __syncthreads();
+        }
+        QP_STAMP(3);
+        {
+            const double tau_k = s_scal[0], sc = s_scal[1];
+            const int ntrail = cols - jc - 1, cw = (ntrail + G - 1) / G;
+            const int jbeg = jc + 1 + c * cw, jend = (jbeg + cw < cols) ? jbeg + cw : cols;
+            const int ncol = jend > jbeg ? jend - jbeg : 0;
+            const int ngrp = (ncol + QP_GC - 1) / QP_GC, gsz = ngrp ? (ncol + ngrp - 1) / ngrp : 0;   // even groups of <= 16
+            const double* x = f + (size_t)jc * rows;
+            const double aux_l = s_aux[lane], prow_l = s_prow[lane];
+            double best = -1.0; int bidx = cols, any = 0;
+            for (int g0 = jbeg; g0 < jend; g0 += gsz) {
+                const int nc = (jend - g0 < gsz) ? jend - g0 : gsz;
+                // what the finishing warp of column g0 + w needs, in flight during the streaming pass
+                const int j = g0 + w;
+                const bool fin = w < nc;
+                const bool moved = fin && (j == pvt && pvt != jc);
+                double fl = 0.0, arkj = 0.0, v1 = 0.0, v2 = 1.0;
+                if (fin) {
+                    if (lane < k) fl = __ldcg(F + (size_t)(moved ? jc : j) * QR_NB + lane);
+                    if (lane == 0) { arkj = __ldcg(f + (size_t)j * rows + rk); v1 = __ldcg(vn1 + j); v2 = __ldcg(vn2 + j); }
+                }
+                double acc[QP_GC];
+#pragma unroll
+                for (int q = 0; q < QP_GC; ++q) acc[q] = 0.0;
+                const double* base = f + (size_t)g0 * rows;
+                if (nc == QP_GC) {
+#pragma unroll 2
+                    for (int r = rk + 1 + tid; r < rows; r += QP_THREADS) {
+                        const double xv = __ldcg(x + r);
+#pragma unroll
+                        for (int q = 0; q < QP_GC; ++q) acc[q] = fma(__ldcg(base + (size_t)q * rows + r), xv, acc[q]);
+                    }
+                } else if (nc <= QP_GC / 2) {        // few columns per CTA: latency bound, deeper unrolling
+#pragma unroll 4
+                    for (int r = rk + 1 + tid; r < rows; r += QP_THREADS) {
+                        const double xv = __ldcg(x + r);
+#pragma unroll
+                        for (int q = 0; q < QP_GC / 2; ++q)
+                            if (q < nc) acc[q] = fma(__ldcg(base + (size_t)q * rows + r), xv, acc[q]);
+                    }
+                } else {
+#pragma unroll 2
+                    for (int r = rk + 1 + tid; r < rows; r += QP_THREADS) {
+                        const double xv = __ldcg(x + r);
+#pragma unroll
+                        for (int q = 0; q < QP_GC; ++q)
+                            if (q < nc) acc[q] = fma(__ldcg(base + (size_t)q * rows + r), xv, acc[q]);
+                    }
+                }
+                // the per-thread partial sums go through shared memory; the finishing warp of a column adds the 512 partials
+                // of its column (16 per lane in a fixed order, then the lane tree): 10 shuffles per warp instead of 62
+#pragma unroll
+                for (int q = 0; q < QP_GC; ++q)
+                    if (q < nc) s_acc[q * QP_THREADS + tid] = acc[q];
+                __syncthreads();
+                if (fin) {                          // finish column j: one warp, lane = panel index
+                    double t = 0.0;
+#pragma unroll
+                    for (int u = 0; u < QP_NW; ++u) t += s_acc[w * QP_THREADS + lane + 32 * u];
+                    t = s_warp_sum(t);
+                    arkj = __shfl_sync(0xffffffffu, arkj, 0);
+                    v1 = __shfl_sync(0xffffffffu, v1, 0);
+                    v2 = __shfl_sync(0xffffffffu, v2, 0);
+                    const double dotv = arkj + sc * t;                       // head of v is 1
+                    const double s = s_warp_sum(fl * aux_l);
+                    const double fjk = tau_k * dotv + s;
+                    if (lane == k) fl = fjk;
+                    if (moved ? (lane <= k) : (lane == k)) F[(size_t)j * QR_NB + lane] = fl;
+                    const double ru = s_warp_sum(prow_l * fl);            // sum_{i <= k} A(rk, j0 + i) F(j, i)
+                    const double a = arkj - ru;
+                    if (v1 != 0.0) {
+                        double temp = fabs(a) / v1;
+                        temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+                        const double rq = v1 / v2;
+                        if (temp * (rq * rq) <= S_TOL3Z && !nopivot) { any = 1; if (lane == 0) flags[j] = 1; }
+                        else { v1 = v1 * sqrt(temp); if (lane == 0) vn1[j] = v1; }
+                    }
+                    if (lane == 0) f[(size_t)j * rows + rk] = a;
+                    if (v1 > best) { best = v1; bidx = j; }
+                }
+                __syncthreads();
+            }
+            if (lane == 0) { s_best[w] = best; s_idx[w] = bidx; s_any[w] = any; }
+            __syncthreads();
+            if (w == 0) {
+                double b = (lane < QP_NW) ? s_best[lane] : -1.0;
+                int bi = (lane < QP_NW) ? s_idx[lane] : cols;
+                const int an = __any_sync(0xffffffffu, (lane < QP_NW) ? s_any[lane] : 0);
+#pragma unroll
+                for (int o = QP_NW / 2; o > 0; o >>= 1)
+                    qp_first_max(b, bi, __shfl_xor_sync(0xffffffffu, b, o), __shfl_xor_sync(0xffffffffu, bi, o));
+                if (lane == 0) { pbest[c] = b; pidx[c] = bi; pany[c] = an; }
+            }
+        }
+        QP_STAMP(4);
+        qp_grid_barrier(bar, epoch);
+        QP_STAMP(5);
+    }
+    // the last reflector of the panel: scale in place, store beta
+    if (kb > 0 && nr > 0) {
+        const int kl = kb - 1, rkl = j0 + kl;
+        const double sc = s_scal[1], beta = s_scal[2];
+        double* cq = f + (size_t)rkl * rows;
+        for (int rl = tid; rl < nr; rl += QP_THREADS) {
+            const int r = r0 + rl;
+            if (r > rkl) { if (sc != 1.0) cq[r] = Vs[rl * VL + kl] * sc; }
+            else if (r == rkl) cq[r] = beta;
+        }
+    }
+    if (tid == 0) {
+        if (c == 0) { stt->k = kb; stt->stop = 0; }
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == (unsigned int)G - 1) {     // last CTA out: nobody polls any more
+#if QP_BARRIER_FLAGS
+            bar[0] = epoch;
+#else
+            bar[2] = 0;
+#endif
+            bar[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ---- unblocked dlaqp2 steps (the last min(m,n) - topbmn columns; host-driven column index i) ----
 __global__ void __launch_bounds__(1024) qr_p2_pivot_house_kernel(double* __restrict__ f, int rows, int cols, int i,
                                                                   double* vn1, double* vn2, int* jpvt, double* tau, int nopivot) {
@@ -806,11 +1182,14 @@ struct QrGraph {          // one dlaqps panel (3 x 32 + 3 kernels) captured as a
     cudaGraphExec_t exec = nullptr;
     const void* f = nullptr; int rows = 0, cols = 0; const void* tau = nullptr; const void* jpvt = nullptr; int topbmn = 0;
 };
+constexpr int QR_PSUM_LEN = QP_MAXG * (QR_NB + 1) > QR_MAXPART ? QP_MAXG * (QR_NB + 1) : QR_MAXPART;   // doubles in QrWork::psum
+constexpr int QR_PIDX_LEN = QR_MAXPART + QP_MAXG;                                                    // ints in QrWork::pidx
+constexpr int QR_TICKET_LEN = 8 + 8 * QP_MAXG;   // [0] close ticket; from [1]: the grid barrier of the persistent panel (qp_grid_barrier)
 struct QrWork {          // scratch of one factorisation (sized for the largest matrix of the solve)
-    double *vn1 = nullptr, *vn2 = nullptr, *F = nullptr, *auxv = nullptr, *pbest = nullptr, *psum = nullptr;
-    int *flags = nullptr, *pidx = nullptr;
+    double *vn1 = nullptr, *vn2 = nullptr, *F = nullptr, *auxv = nullptr, *pbest = nullptr, *psum = nullptr;   // psum: QR_PSUM_LEN
+    int *flags = nullptr, *pidx = nullptr;                                                                     // pidx: QR_PIDX_LEN
     QrState* state = nullptr;
-    unsigned int* ticket = nullptr;
+    unsigned int* ticket = nullptr;                                                                            // QR_TICKET_LEN
     int cap_cols = 0;
     QrGraph graphs[6];
     int next_graph = 0;
@@ -819,6 +1198,43 @@ struct QrWork {          // scratch of one factorisation (sized for the largest 
         for (QrGraph& g : graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = QrGraph(); }
     }
 };
+
+// grid of the persistent panel kernel (one CTA per SM, co-resident: cooperative launch); 0 = not available
+inline int qp_grid() {
+    static const int g = [] {
+        const char* e = getenv("ENLSIP_QR_PANEL");
+        if (e && e[0] == 'g') return 0;                        // "graph": the three-kernels-per-column form
+        int dev = 0, sms = 0, coop = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop || sms <= 0) return 0;
+        const int max_dyn = (int)(sizeof(double) * (QP_MAXRW * (QR_NB + 2) + QP_GC * QP_THREADS));
+        if (cudaFuncSetAttribute(qr_panel_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_persist_kernel, QP_THREADS, max_dyn) != cudaSuccess ||
+            per_sm < 1) {
+            cudaGetLastError();
+            return 0;
+        }
+        return sms < QP_MAXG ? sms : QP_MAXG;
+    }();
+    return g;
+}
+inline int qr_enqueue_panel_persist(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, int topbmn, int G,
+                                    cudaStream_t st) {
+    double *vn1 = wk.vn1, *vn2 = wk.vn2, *F = wk.F, *pbest = wk.pbest, *ppart = wk.psum;
+    int *flags = wk.flags, *pidx = wk.pidx, *pany = wk.pidx + QR_MAXPART;
+    QrState* stt = wk.state;
+    unsigned int* bar = wk.ticket + 1;
+    void* args[] = {&f, &rows, &cols, &vn1, &vn2, &jpvt, &tau, &F, &flags, &stt, &pbest, &pidx, &pany, &ppart, &bar};
+    cudaLaunchCooperativeKernel((const void*)qr_panel_persist_kernel, dim3(G), dim3(QP_THREADS), args, qp_smem_bytes(rows, G), st);
+    qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+    qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
+    return 3;
+}
 
 inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpvt, QrWork& wk, int topbmn, cudaStream_t st) {
     const int g_fin = imin_host((cols + 7) / 8, QR_MAXPART), g_col = imin_host((rows + 255) / 256, QR_MAXPART);
@@ -874,7 +1290,7 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
     int topbmn = (QR_NB < minmn && QR_NX < minmn) ? (minmn - QR_NX) : 0;
     int launches = 0;
     cudaMemsetAsync(wk.flags, 0, sizeof(int) * cols, st);
-    cudaMemsetAsync(wk.ticket, 0, sizeof(unsigned int), st);
+    cudaMemsetAsync(wk.ticket, 0, sizeof(unsigned int) * QR_TICKET_LEN, st);
     qr_init_kernel<<<cols, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.state, topbmn, nopivot);
     ++launches;
     if (topbmn > 0) {
@@ -883,7 +1299,9 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
         // margin, then (rarely) top up after looking at the state.
         const int per_panel = 3 * QR_NB + 3;
         cudaGraphExec_t exec = nullptr;
-        if (wk.use_graphs && st != nullptr) {
+        const int G = qp_grid();
+        const bool persist = G > 0 && qp_rows_per_slice(rows, G) <= QP_MAXRW;
+        if (!persist && wk.use_graphs && st != nullptr) {
             for (QrGraph& g : wk.graphs)
                 if (g.exec && g.f == f && g.rows == rows && g.cols == cols && g.tau == tau && g.jpvt == jpvt && g.topbmn == topbmn) exec = g.exec;
             if (!exec) {
@@ -907,7 +1325,8 @@ inline int qrcp_device(double* f, int rows, int cols, double* tau, int* jpvt, Qr
         int budget = (topbmn + QR_NB - 1) / QR_NB + 2;
         for (;;) {
             for (int pnl = 0; pnl < budget; ++pnl) {
-                if (exec) { cudaGraphLaunch(exec, st); launches += per_panel; }
+                if (persist) launches += qr_enqueue_panel_persist(f, rows, cols, tau, jpvt, wk, topbmn, G, st);
+                else if (exec) { cudaGraphLaunch(exec, st); launches += per_panel; }
                 else launches += qr_enqueue_panel(f, rows, cols, tau, jpvt, wk, topbmn, st);
             }
             QrState h;
