@@ -343,6 +343,10 @@ struct LargeHandle : LargeOps, SmallBackend {
     int *dpA = nullptr, *dipA = nullptr, *dpL = nullptr, *dipL = nullptr, *dp2 = nullptr, *dip2 = nullptr, *dact = nullptr, *dbidx = nullptr;
     double* dvec[8] = {nullptr};      // scratch vectors
     double* dscal = nullptr;
+    // compact-WY T factors of the three factorisations (all panels; built on first use after a factorisation) and the
+    // scratch of the cooperative vector kernels
+    double *dTA = nullptr, *dTL = nullptr, *dT2 = nullptr, *dwpart = nullptr;
+    bool ta_valid = false, tl_valid = false, t2_valid = false;
     double* hst = nullptr;            // pinned staging, 4 * lv doubles
     int* hsti = nullptr;              // pinned staging for permutations
     enl_small::QrWork qw;
@@ -392,6 +396,8 @@ struct LargeHandle : LargeOps, SmallBackend {
                           dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, qw.pbest, qw.psum, ww.Vb, ww.T, ww.W, ww.W2, ww.part})
             if (p) cudaFree(p);
         for (double*& p : dvec) { if (p) cudaFree(p); p = nullptr; }
+        for (double** p : {&dTA, &dTL, &dT2, &dwpart}) { if (*p) cudaFree(*p); *p = nullptr; }
+        ta_valid = tl_valid = t2_valid = false;
         for (double* p : {dQ, dJkeep, dtauQ, dcu, gown[0], gown[1]})
             if (p) cudaFree(p);
         if (dpQ) cudaFree(dpQ);
@@ -497,6 +503,12 @@ struct LargeHandle : LargeOps, SmallBackend {
         LCU(cudaMalloc(&qw.flags, sizeof(int) * maxc));
         LCU(cudaMalloc(&qw.state, sizeof(enl_small::QrState)));
         LCU(cudaMalloc(&qw.ticket, sizeof(unsigned int) * enl_small::QR_TICKET_LEN));
+        LCU(cudaMemsetAsync(qw.ticket, 0, sizeof(unsigned int) * enl_small::QR_TICKET_LEN, st));
+        {
+            const size_t tlen = ((size_t)mt / 32 + 2) * 1024;
+            for (double** p : {&dTA, &dTL, &dT2}) LCU(cudaMalloc(p, sizeof(double) * tlen));
+            LCU(cudaMalloc(&dwpart, sizeof(double) * enl_small::RW_WPART_LEN));
+        }
         LCU(cudaMalloc(&ww.Vb, sizeof(double) * mt * 32));
         LCU(cudaMalloc(&ww.T, sizeof(double) * 32 * 32));
         LCU(cudaMalloc(&ww.W, sizeof(double) * mt * 32));
@@ -703,20 +715,46 @@ struct LargeHandle : LargeOps, SmallBackend {
         sm_check(cudaStreamSynchronize(st), "synchronize");
         sm_check(cudaGetLastError(), "kernel");
     }
+    // T factors of a factorisation (dFA / dFL / dF2), built once per factorisation
+    double* wy_t_of(const double* f, int frows, int k, const double* tau) {
+        double* T = nullptr; bool* valid = nullptr;
+        if (f == dFA) { T = dTA; valid = &ta_valid; }
+        else if (f == dFL) { T = dTL; valid = &tl_valid; }
+        else if (f == dF2) { T = dT2; valid = &t2_valid; }
+        if (!T) return nullptr;
+        if (!*valid) {
+            const int rc = enl_small::wy_build_t_all(f, frows, k, tau, T, ww.part, (size_t)(n + 1) * 32 * enl_small::GEMM_MAX_SPLITS, st);
+            if (rc < 0) return nullptr;
+            launches += rc;
+            *valid = true;
+        }
+        return T;
+    }
     void k_reflect(const double* f, int frows, int k, const double* tau, double* v, int transpose) {
-        if (frows <= 0) return;
-        if (frows <= enl_small::VEC_WARP_MAX) enl_small::reflect_vec_warp_kernel<<<1, 32, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
-        else enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
+        if (frows <= 0 || k <= 0) return;
+        if (frows <= enl_small::VEC_WARP_MAX) {
+            enl_small::reflect_vec_warp_kernel<<<1, 32, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
+            ++launches;
+            return;
+        }
+        // long vectors: the compact-WY panels in one cooperative kernel (one grid barrier per 32 reflectors)
+        if (double* T = wy_t_of(f, frows, k, tau)) {
+            const int rc = enl_small::reflect_vec_wy(f, frows, k, T, v, transpose, dwpart, qw.ticket + 1, st);
+            if (rc > 0) { launches += rc; return; }
+        }
+        enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
         ++launches;
     }
     void k_trsv_upper(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
+        if (k > 32 && enl_small::trsv_coop(f, ldf, k, x, false, qw.ticket + 1, st) > 0) { ++launches; return; }
         if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upper_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         else enl_small::trsv_upper_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;
     }
     void k_trsv_upperT(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
+        if (k > 32 && enl_small::trsv_coop(f, ldf, k, x, true, qw.ticket + 1, st) > 0) { ++launches; return; }
         if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upperT_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         else enl_small::trsv_upperT_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;
@@ -811,6 +849,7 @@ struct LargeHandle : LargeOps, SmallBackend {
         if (t > 0) {
             sm_check(cudaMemcpyAsync(dFA, dCA, sizeof(double) * (size_t)n * t, cudaMemcpyDeviceToDevice, st), "D2D");
             launches += enl_small::qrcp_device(dFA, n, t, dtauA, dpA, qw, st);
+            ta_valid = false;
             ++n_dev_qrcp;
         }
         finish_factor(dFA, n, t, dpA, dipA, F, hpA);
@@ -824,6 +863,7 @@ struct LargeHandle : LargeOps, SmallBackend {
             enl_small::build_rt_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dFA, n, t, kr, dFL);
             ++launches;
             launches += enl_small::qrcp_device(dFL, t, kr, dtauL, dpL, qw, st);
+            tl_valid = false;
             ++n_dev_qrcp;
         }
         finish_factor(dFL, t, kr, dpL, dipL, F, hpL);
@@ -833,7 +873,8 @@ struct LargeHandle : LargeOps, SmallBackend {
         const int mt = n + 1;
         sm_check(cudaMemcpyAsync(dJQ1, dJc, sizeof(double) * (size_t)mt * n, cudaMemcpyDeviceToDevice, st), "D2D");
         if (fa_k > 0) {
-            launches += enl_small::mulq_device(dJQ1, mt, n, dFA, n, fa_k, dtauA, ww, st);
+            launches += enl_small::mulq_device(dJQ1, mt, n, dFA, n, fa_k, dtauA, ww, st, dTA, !ta_valid);
+            ta_valid = true;
             ++n_dev_mulq;
         }
         jq1_valid = true;
@@ -846,6 +887,7 @@ struct LargeHandle : LargeOps, SmallBackend {
         if (cols2 > 0) {
             sm_check(cudaMemcpyAsync(dF2, dJQ1 + (size_t)rankA * mt, sizeof(double) * (size_t)mt * cols2, cudaMemcpyDeviceToDevice, st), "D2D");
             launches += enl_small::qrcp_device(dF2, mt, cols2, dtau2, dp2, qw, st);
+            t2_valid = false;
             ++n_dev_qrcp;
         }
         finish_factor(dF2, mt, cols2, dp2, dip2, F, hp2);
@@ -1330,8 +1372,9 @@ int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* 
     if (device < 0) LCU(cudaGetDevice(&device));
     LCU(cudaSetDevice(device));
     DenseScratch S;
-    double *df = nullptr, *dtau = nullptr, *dM = nullptr;
+    double *df = nullptr, *dtau = nullptr, *dM = nullptr, *dTall = nullptr;
     bool ok = S.get(&df, (size_t)nq * (k > 0 ? k : 1)) && S.get(&dtau, k) && S.get(&dM, (size_t)mr * nq) &&
+              S.get(&dTall, ((size_t)nq / 32 + 2) * 1024) &&
               S.get(&S.ww.Vb, (size_t)nq * 32) && S.get(&S.ww.T, 32 * 32) && S.get(&S.ww.W, (size_t)mr * 32) &&
               S.get(&S.ww.W2, (size_t)mr * 32) && S.get(&S.ww.part, (size_t)mr * 32 * enl_small::GEMM_MAX_SPLITS);
     if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
@@ -1341,7 +1384,7 @@ int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     LCU(cudaEventCreate(&ev0)); LCU(cudaEventCreate(&ev1));
     LCU(cudaEventRecord(ev0, nullptr));
-    enl_small::mulq_device(dM, mr, nq, df, nq, k, dtau, S.ww, nullptr);
+    enl_small::mulq_device(dM, mr, nq, df, nq, k, dtau, S.ww, nullptr, dTall, true);
     LCU(cudaEventRecord(ev1, nullptr));
     cudaError_t es = cudaDeviceSynchronize();
     if (es == cudaSuccess) es = cudaGetLastError();
@@ -1349,6 +1392,49 @@ int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* 
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     LCU(es);
     LCU(cudaMemcpy(M, dM, sizeof(double) * (size_t)mr * nq, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Known-answer hook for the vector kernels of the small stage (tests/test_gpu_kat.py).  kind 0: v <- Q' v, 1: v <- Q v
+// (f: frows x k reflectors in dgeqrf layout, tau [k], v [frows]; compact-WY cooperative kernel);
+// kind 2: v <- UpperTriangular(f[0:k, 0:k]) \ v, 3: v <- UpperTriangular(f[0:k, 0:k])' \ v (f: frows x k, v [k]).
+int enlsipb200_dense_vecop(int kind, int frows, int k, const double* f, const double* tau, double* v, int device) {
+    if (kind < 0 || kind > 3 || frows < 1 || k < 1 || k > frows || !f || !v || (kind < 2 && !tau)) return lfail(ENLSIPB200_EINVAL, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return lfail(ENLSIPB200_ENOGPU, "no CUDA device");
+    if (device < 0) LCU(cudaGetDevice(&device));
+    LCU(cudaSetDevice(device));
+    DenseScratch S;
+    const int vlen = kind < 2 ? frows : k;
+    double *df = nullptr, *dtau = nullptr, *dv = nullptr, *dTall = nullptr, *dscr = nullptr, *dwp = nullptr;
+    unsigned int* dbar = nullptr;
+    const size_t scr = (size_t)1024 * ((frows + enl_small::WY_SLAB - 1) / enl_small::WY_SLAB) * 8;
+    bool ok = S.get(&df, (size_t)frows * k) && S.get(&dtau, k) && S.get(&dv, vlen) && S.get(&dTall, ((size_t)k / 32 + 2) * 1024) &&
+              S.get(&dscr, scr) && S.get(&dwp, enl_small::RW_WPART_LEN) && S.get(&dbar, 16);
+    if (!ok) return lfail(ENLSIPB200_ENOMEM, "cudaMalloc");
+    LCU(cudaMemcpy(df, f, sizeof(double) * (size_t)frows * k, cudaMemcpyHostToDevice));
+    if (kind < 2) LCU(cudaMemcpy(dtau, tau, sizeof(double) * k, cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(dv, v, sizeof(double) * vlen, cudaMemcpyHostToDevice));
+    LCU(cudaMemset(dbar, 0, sizeof(unsigned int) * 16));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    LCU(cudaEventCreate(&ev0)); LCU(cudaEventCreate(&ev1));
+    int rc = 0;
+    if (kind < 2) {
+        rc = enl_small::wy_build_t_all(df, frows, k, dtau, dTall, dscr, scr, nullptr);
+        LCU(cudaEventRecord(ev0, nullptr));
+        if (rc >= 0) rc = enl_small::reflect_vec_wy(df, frows, k, dTall, dv, kind == 0 ? 1 : 0, dwp, dbar, nullptr);
+    } else {
+        LCU(cudaEventRecord(ev0, nullptr));
+        rc = enl_small::trsv_coop(df, frows, k, dv, kind == 3, dbar, nullptr);
+    }
+    LCU(cudaEventRecord(ev1, nullptr));
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es == cudaSuccess) es = cudaGetLastError();
+    cudaEventElapsedTime(&g_dense_ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    LCU(es);
+    if (rc < 0) return lfail(ENLSIPB200_EINVAL, "shape not supported by the cooperative kernel");
+    LCU(cudaMemcpy(v, dv, sizeof(double) * vlen, cudaMemcpyDeviceToHost));
     return 0;
 }
 

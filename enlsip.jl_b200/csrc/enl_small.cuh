@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) qr_panel_close_kernel(const double* __res
 //            of the next column.
 // The F row of the column that a pivot exchange moves away from position jc is dead after phase P (only rows behind the
 // panel are read later), so the exchange of F rows is a one-way move done by the warp that finishes column `pvt`.
-constexpr int QP_THREADS = 512, QP_NW = QP_THREADS / 32, QP_GC = 16, QP_MAXG = 160, QP_MAXRW = 512, QP_MINRW = 128;
+constexpr int QP_THREADS = 512, QP_NW = QP_THREADS / 32, QP_GC = 16, QP_MAXG = 160, QP_MAXRW = 512, QP_MINRW = 128, QP_MAXSLICES = 64;
 
 __device__ __forceinline__ unsigned int qp_ld_acquire(const unsigned int* p) {
     unsigned int v;
@@ -571,8 +571,9 @@ __device__ __forceinline__ void qp_grid_barrier(unsigned int* bar, unsigned int&
 __device__ __forceinline__ void qp_first_max(double& b, int& bi, double ob, int oi) {
     if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
 }
-__host__ __device__ inline int qp_rows_per_slice(int rows, int G) {
-    const int rw = (rows + G - 1) / G;
+__host__ __device__ inline int qp_rows_per_slice(int rows, int G) {          // at most QP_MAXSLICES slices
+    const int ns = G < QP_MAXSLICES ? G : QP_MAXSLICES;
+    const int rw = (rows + ns - 1) / ns;
     return rw < QP_MINRW ? QP_MINRW : rw;
 }
 inline size_t qp_smem_bytes(int rows, int G) {
@@ -716,31 +717,31 @@ qr_panel_persist_kernel(double* f, int rows, int cols, double* vn1, double* vn2,
         QP_STAMP(2);
 
         // ---------------- phase Q ----------------
-        {
-            double alpha = 0.0, prow = 0.0;
-            if (w == 0) {                             // in flight during the reduction of the partials
-                alpha = __ldcg(f + (size_t)jc * rows + rk);
-                if (lane < k) prow = __ldcg(f + (size_t)(j0 + lane) * rows + rk);
-                else if (lane == k) prow = 1.0;
-            }
-            {
-                // 16 threads per quantity (i < k: dot of panel column i with the new column; i == k: its sum of squares);
-                // all loads of a thread are in flight together, sums in a fixed order
-                const int i = tid >> 4, sub = tid & 15;
-                const int slot = (i < k) ? i : QR_NB;
-                double part[(QP_MAXG + 15) / 16];
+        // (Deferring this block behind the first streaming pass -- the dots need none of the dlarfg scalars -- was
+        // measured: no gain, the values held across the pass cost the streaming loop its registers.)
+        double alpha = 0.0, prow = 0.0;
+        if (w == 0) {
+            alpha = __ldcg(f + (size_t)jc * rows + rk);
+            if (lane < k) prow = __ldcg(f + (size_t)(j0 + lane) * rows + rk);
+            else if (lane == k) prow = 1.0;
+        }
+        // 16 threads per quantity (i < k: dot of panel column i with the new column; i == k: its sum of squares)
+        constexpr int NPU = QP_MAXSLICES / 16;
+        const int qi = tid >> 4, qsub = tid & 15;
+        const int qslot = (qi < k) ? qi : QR_NB;
+        double part[NPU];
 #pragma unroll
-                for (int u = 0; u < (QP_MAXG + 15) / 16; ++u) {
-                    const int q = sub + 16 * u;
-                    part[u] = (i <= k && q < Gp) ? __ldcg(ppart + (size_t)q * VL + slot) : 0.0;
-                }
-                double t = 0.0;
+        for (int u = 0; u < NPU; ++u) {
+            const int q = qsub + 16 * u;
+            part[u] = (qi <= k && q < Gp) ? __ldcg(ppart + (size_t)q * VL + qslot) : 0.0;
+        }
+        auto scalars = [&]() {                       // all threads; fixed summation order, the same bits in every CTA
+            double t = 0.0;
 #pragma unroll
-                for (int u = 0; u < (QP_MAXG + 15) / 16; ++u) t += part[u];
+            for (int u = 0; u < NPU; ++u) t += part[u];
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (sub == 0 && i <= k) s_tot[slot] = t;
-            }
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (qsub == 0 && qi <= k) s_tot[qslot] = t;
             __syncthreads();
             if (w == 0) {
                 double beta = alpha, tau_k = 0.0, sc = 1.0;
@@ -760,16 +761,16 @@ qr_panel_persist_kernel(double* f, int rows, int cols, double* vn1, double* vn2,
                 s_aux[lane] = (lane < k) ? -tau_k * (prow + sc * s_tot[lane]) : 0.0;
             }
             __syncthreads();
-        }
+        };
+        scalars();
         QP_STAMP(3);
         {
-            const double tau_k = s_scal[0], sc = s_scal[1];
+            const double tau_k = s_scal[0], sc = s_scal[1], aux_l = s_aux[lane], prow_l = s_prow[lane];
             const int ntrail = cols - jc - 1, cw = (ntrail + G - 1) / G;
             const int jbeg = jc + 1 + c * cw, jend = (jbeg + cw < cols) ? jbeg + cw : cols;
             const int ncol = jend > jbeg ? jend - jbeg : 0;
             const int ngrp = (ncol + QP_GC - 1) / QP_GC, gsz = ngrp ? (ncol + ngrp - 1) / ngrp : 0;   // even groups of <= 16
             const double* x = f + (size_t)jc * rows;
-            const double aux_l = s_aux[lane], prow_l = s_prow[lane];
             double best = -1.0; int bidx = cols, any = 0;
             for (int g0 = jbeg; g0 < jend; g0 += gsz) {
                 const int nc = (jend - g0 < gsz) ? jend - g0 : gsz;
@@ -1403,20 +1404,102 @@ __global__ void __launch_bounds__(1024) wy_build_t_kernel(const double* __restri
     T[b * 32 + a] = (a < pw && b < pw) ? Ts[a][b] : 0.0;    // column major, ld = 32
 }
 
+// ---- the T factors of ALL panels of a factorisation in two launches (dlarft, forward columnwise) ----
+// wy_gram_kernel: grid (slabs of 256 rows, panels); gpart[(panel * nslab + slab) * 1024 + b * 32 + a] = the slab's share of
+// V(:, a)' V(:, b) (a < b), V = the panel's reflectors read from f (unit diagonal, zeros above).
+constexpr int WY_SLAB = 256;
+__global__ void __launch_bounds__(1024) wy_gram_kernel(const double* __restrict__ f, int frows, int k, int p0,
+                                                       double* __restrict__ gpart, int nslab) {
+    __shared__ double Vs[128][33];
+    const int panel = p0 + blockIdx.y, j0 = panel * 32;
+    const int pw = (k - j0) < 32 ? (k - j0) : 32, len = frows - j0;
+    const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int half = 0; half < WY_SLAB / 128; ++half) {
+        const int r0 = blockIdx.x * WY_SLAB + half * 128;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 128 * 32; e += 1024) {
+            const int rr = e & 127, c = e >> 7, r = r0 + rr;
+            double v = 0.0;
+            if (r < len && c < pw) v = (r < c) ? 0.0 : (r == c ? 1.0 : f[(size_t)(j0 + c) * frows + j0 + r]);
+            Vs[rr][c] = v;
+        }
+        __syncthreads();
+        if (a < b && r0 < len)
+#pragma unroll 8
+            for (int rr = 0; rr < 128; ++rr) s = fma(Vs[rr][a], Vs[rr][b], s);
+    }
+    gpart[((size_t)blockIdx.y * nslab + blockIdx.x) * 1024 + threadIdx.x] = s;
+}
+// wy_t_kernel: one CTA per panel; adds the slab shares in slab order, then T(0:i, i) = -tau_i T(0:i, 0:i) G(0:i, i)
+__global__ void __launch_bounds__(1024) wy_t_kernel(const double* __restrict__ gpart, int nslab, int frows, int k, int p0,
+                                                    const double* __restrict__ tau, double* __restrict__ Tall) {
+    __shared__ double G[32][33];
+    __shared__ double Ts[32][33];
+    __shared__ double tmp[32];
+    const int panel = p0 + blockIdx.x, j0 = panel * 32;
+    const int pw = (k - j0) < 32 ? (k - j0) : 32, len = frows - j0;
+    const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+    const int ns = (len + WY_SLAB - 1) / WY_SLAB;
+    double s = 0.0;
+    const double* gp = gpart + (size_t)blockIdx.x * nslab * 1024 + threadIdx.x;
+#pragma unroll 4
+    for (int q = 0; q < ns; ++q) s += gp[(size_t)q * 1024];
+    G[a][b] = s;
+    Ts[a][b] = 0.0;
+    __syncthreads();
+    for (int i = 0; i < pw; ++i) {
+        const double ti = tau[j0 + i];
+        if (threadIdx.x < 32) {
+            double acc = 0.0;
+            if ((int)threadIdx.x < i)
+                for (int c = threadIdx.x; c < i; ++c) acc = fma(Ts[threadIdx.x][c], G[c][i], acc);
+            tmp[threadIdx.x] = -ti * acc;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < i) Ts[threadIdx.x][i] = tmp[threadIdx.x];
+        if (threadIdx.x == 0) Ts[i][i] = ti;
+        __syncthreads();
+    }
+    Tall[(size_t)panel * 1024 + b * 32 + a] = (a < pw && b < pw) ? Ts[a][b] : 0.0;    // column major, ld = 32
+}
+// Tall: ceil(k / 32) x 1024 doubles; scratch: cap doubles (>= 1024 * ceil(frows / 256))
+inline int wy_build_t_all(const double* f, int frows, int k, const double* tau, double* Tall, double* scratch, size_t cap,
+                          cudaStream_t st) {
+    const int np = (k + 31) / 32, nslab = (frows + WY_SLAB - 1) / WY_SLAB;
+    int per = (int)(cap / ((size_t)nslab * 1024));
+    if (per < 1) return -1;
+    int launches = 0;
+    for (int p0 = 0; p0 < np; p0 += per) {
+        const int cnt = (np - p0) < per ? (np - p0) : per;
+        wy_gram_kernel<<<dim3(nslab, cnt), 1024, 0, st>>>(f, frows, k, p0, scratch, nslab);
+        wy_t_kernel<<<cnt, 1024, 0, st>>>(scratch, nslab, frows, k, p0, tau, Tall);
+        launches += 2;
+    }
+    return launches;
+}
+
 struct WyWork { double *Vb = nullptr, *T = nullptr, *W = nullptr, *W2 = nullptr, *part = nullptr; };   // Vb: frows x 32, T: 32 x 32, W/W2: mr x 32, part: GEMM_MAX_SPLITS x mr x 32
 
 // M: mr x nq column major (ld = mr); f: frows (= nq) x k
+// Tall (optional): the T factors of all panels (wy_build_t_all) -- built here if `build_t`, reusable by reflect_vec_wy
 inline int mulq_device(double* M, int mr, int nq, const double* f, int frows, int k, const double* tau, WyWork& wk,
-                       cudaStream_t st) {
+                       cudaStream_t st, double* Tall = nullptr, bool build_t = true) {
     int launches = 0;
+    if (Tall && build_t) {
+        const int rc = wk.part ? wy_build_t_all(f, frows, k, tau, Tall, wk.part, (size_t)mr * 32 * GEMM_MAX_SPLITS, st) : -1;
+        if (rc < 0) Tall = nullptr; else launches += rc;
+    }
     for (int j0 = 0; j0 < k; j0 += 32) {
         const int pw = (k - j0) < 32 ? (k - j0) : 32;
         const int len = frows - j0;
         if (len <= 0) break;
         const long long ne = (long long)len * pw;
         wy_build_v_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(f, frows, j0, pw, wk.Vb);
-        wy_build_t_kernel<<<1, 1024, 0, st>>>(wk.Vb, len, pw, tau + j0, wk.T);
-        launches += 2;
+        const double* Tp = wk.T;
+        if (Tall) Tp = Tall + (size_t)(j0 / 32) * 1024;
+        else { wy_build_t_kernel<<<1, 1024, 0, st>>>(wk.Vb, len, pw, tau + j0, wk.T); ++launches; }
+        ++launches;
         // W = M(:, j0:) Vb ; W2 = W T ; M(:, j0:) -= W2 Vb'
         int splits = len / 256;                                   // W = M V: N = 32, K = len
         if (splits > GEMM_MAX_SPLITS) splits = GEMM_MAX_SPLITS;
@@ -1431,7 +1514,7 @@ inline int mulq_device(double* M, int mr, int nq, const double* f, int frows, in
         } else {
             launches += gemm<false>(M + (size_t)j0 * mr, mr, wk.Vb, len, wk.W, mr, mr, pw, len, 1.0, 0.0, st);
         }
-        launches += gemm<false>(wk.W, mr, wk.T, 32, wk.W2, mr, mr, pw, pw, 1.0, 0.0, st);
+        launches += gemm<false>(wk.W, mr, Tp, 32, wk.W2, mr, mr, pw, pw, 1.0, 0.0, st);
         launches += gemm<true>(wk.W2, mr, wk.Vb, len, M + (size_t)j0 * mr, mr, mr, len, pw, -1.0, 1.0, st);
     }
     return launches;
@@ -1521,6 +1604,237 @@ __global__ void __launch_bounds__(32) trsv_upperT_warp_kernel(const double* __re
     }
     for (int r = lane; r < k; r += 32) x[r] = xs[r];
 }
+// ---- v <- Q' v / Q v with the compact-WY panels (dormqr's blocked form), ONE cooperative kernel ----
+// CTA c keeps rows [c rw, (c+1) rw) of v in shared memory for the whole sweep.  Per panel (32 reflectors): the slice
+// of V goes to shared memory, the CTA leaves its share of w = V' v (32 numbers), ONE grid barrier, every CTA adds the
+// shares in CTA order, forms z = T' w (Q') or T w (Q) and updates its rows v -= V z.  T comes from wy_build_t_all.
+constexpr int RW_THREADS = 256, RW_ROWS = 128, RW_MAXG = 148;
+constexpr int RW_WPART_LEN = 2 * RW_MAXG * 32;      // doubles of the wpart scratch
+__global__ void __launch_bounds__(RW_THREADS, 1)
+reflect_vec_wy_kernel(const double* __restrict__ f, int frows, int k, const double* __restrict__ Tall, double* v,
+                      int transpose, double* wpart, unsigned int* bar) {
+    extern __shared__ double rw_dyn[];
+    __shared__ double Ts[32][33];
+    __shared__ double s_w[32], s_z[32];
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int rw = ((frows + G - 1) / G + 31) / 32 * 32;
+    const int r0 = c * rw, nr = (frows - r0) < rw ? (frows - r0 > 0 ? frows - r0 : 0) : rw;
+    double* vs = rw_dyn;                         // [rw]
+    double* Vs = rw_dyn + rw;                    // [rw][33]
+    for (int rl = tid; rl < nr; rl += RW_THREADS) vs[rl] = v[r0 + rl];
+    const int np = (k + 31) / 32;
+    unsigned int epoch = 0;
+    for (int sp = 0; sp < np; ++sp) {
+        const int p = transpose ? sp : (np - 1 - sp), j0 = p * 32;
+        const int pw = (k - j0) < 32 ? (k - j0) : 32;
+        // the shares are double-buffered: a CTA can be at most one barrier ahead of the slowest reader
+        double* wbuf = wpart + (size_t)(sp & 1) * RW_MAXG * 32;
+        __syncthreads();
+        // slice of V (unit diagonal, zeros above) and T of the panel
+        for (int e = tid; e < rw * 32; e += RW_THREADS) {
+            const int rl = e % rw, cc = e / rw, r = r0 + rl, d = j0 + cc;
+            double x = 0.0;
+            if (rl < nr && cc < pw) x = (r < d) ? 0.0 : (r == d ? 1.0 : f[(size_t)d * frows + r]);
+            Vs[rl * 33 + cc] = x;
+        }
+        for (int e = tid; e < 1024; e += RW_THREADS) Ts[e & 31][e >> 5] = Tall[(size_t)p * 1024 + e];   // Ts[a][b] = T(a, b)
+        __syncthreads();
+        // share of w_cc = sum_r V(r, cc) v(r): warp per 4 columns, lanes over the rows
+        for (int cc = w; cc < 32; cc += RW_THREADS / 32) {
+            double t = 0.0;
+            for (int rl = lane; rl < nr; rl += 32) t = fma(Vs[rl * 33 + cc], vs[rl], t);
+            t = s_warp_sum(t);
+            if (lane == 0) wbuf[(size_t)c * 32 + cc] = t;
+        }
+        qp_grid_barrier(bar, epoch);
+        {
+            // 8 threads per column; all loads of a thread in flight together, sums in a fixed order
+            constexpr int NU = (RW_MAXG + 7) / 8;
+            const int cc = tid >> 3, sub = tid & 7;
+            double part[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int q = sub + 8 * u;
+                part[u] = (q < G) ? __ldcg(wbuf + (size_t)q * 32 + cc) : 0.0;
+            }
+            double t = 0.0;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) t += part[u];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (sub == 0) s_w[cc] = t;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double z = 0.0;
+            if (transpose) { for (int j = 0; j <= tid; ++j) z = fma(Ts[j][tid], s_w[j], z); }      // (T' w)_c
+            else { for (int j = tid; j < 32; ++j) z = fma(Ts[tid][j], s_w[j], z); }                // (T w)_c
+            s_z[tid] = z;
+        }
+        __syncthreads();
+        for (int rl = tid; rl < nr; rl += RW_THREADS) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int cc = 0; cc < 32; ++cc) t = fma(Vs[rl * 33 + cc], s_z[cc], t);
+            vs[rl] -= t;
+        }
+    }
+    __syncthreads();
+    for (int rl = tid; rl < nr; rl += RW_THREADS) v[r0 + rl] = vs[rl];
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == (unsigned int)G - 1) { bar[2] = 0; bar[1] = 0; __threadfence(); }
+    }
+}
+inline int rw_grid(int frows) {
+    int g = (frows + RW_ROWS - 1) / RW_ROWS;
+    return g < 1 ? 1 : (g > RW_MAXG ? RW_MAXG : g);
+}
+inline size_t rw_smem_bytes(int frows, int G) {
+    const int rw = ((frows + G - 1) / G + 31) / 32 * 32;
+    return sizeof(double) * (size_t)rw * 34;
+}
+// returns the number of launches, or -1 when the shape does not fit (caller falls back to the reflector sweep)
+inline int reflect_vec_wy(const double* f, int frows, int k, const double* Tall, double* v, int transpose, double* wpart,
+                          unsigned int* bar, cudaStream_t st) {
+    const int G = rw_grid(frows);
+    const size_t shb = rw_smem_bytes(frows, G);
+    if (shb > 200 * 1024) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(reflect_vec_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    void* args[] = {&f, &frows, &k, &Tall, &v, &transpose, &wpart, &bar};
+    if (cudaLaunchCooperativeKernel((const void*)reflect_vec_wy_kernel, dim3(G), dim3(RW_THREADS), args, shb, st) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return 1;
+}
+
+// ---- triangular solves over many CTAs: one WARP per diagonal block of 32, blocks solved in sequence, a solved block is
+// announced through a counter (release / acquire) and every warp folds it into its own rows while the next block is
+// being solved.  The arithmetic (order of every sum) is that of trsv_upper_kernel / trsv_upperT_kernel below. ----
+__device__ __forceinline__ void ts_wait(const unsigned int* flag, unsigned int need, int lane) {
+    if (lane == 0) while (qp_ld_acquire(flag) < need) { }
+    __syncwarp();
+}
+__device__ __forceinline__ void ts_post(unsigned int* flag, unsigned int val, int lane) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(val) : "memory");
+}
+// x <- UpperTriangular(f[0:k, 0:k]) \ x.  Blocks are aligned to the bottom (block t = rows [k - 32 (t+1), k - 32 t)).
+__global__ void trsv_upper_coop_kernel(const double* __restrict__ f, int ldf, int k, double* x, int bpc, unsigned int* bar) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nblk = (k + 31) / 32, t = blockIdx.x * bpc + w;
+    unsigned int* solved = bar + 3;
+    if (t < nblk && w < bpc) {
+        const int b1 = k - 32 * t, b0 = (b1 - 32 > 0) ? b1 - 32 : 0, nb = b1 - b0;
+        const int r = b0 + lane;
+        const bool live = lane < nb;
+        double xr = live ? x[r] : 0.0;
+        double Rv[32];
+        for (int s = 0; s < t; ++s) {                   // fold in the blocks below, in the order they are solved
+            const int cb0 = k - 32 * (s + 1);
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) Rv[cc] = live ? f[(size_t)(cb0 + cc) * ldf + r] : 0.0;   // in flight while waiting
+            ts_wait(solved, (unsigned int)(s + 1), lane);
+            const double xb = __ldcg(x + cb0 + lane);
+            double sum = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) sum = fma(Rv[cc], __shfl_sync(0xffffffffu, xb, cc), sum);
+            xr -= sum;
+        }
+        // back substitution inside the block: lane = row, Rv[cc] = R(b0 + lane, b0 + cc)
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) Rv[cc] = (live && cc < nb) ? f[(size_t)(b0 + cc) * ldf + r] : 1.0;
+#pragma unroll
+        for (int i = 31; i >= 0; --i) {
+            if (i < nb) {
+                const double xi = __shfl_sync(0xffffffffu, xr / Rv[i], i);      // lane i: x_i / R(i, i)
+                if (lane == i) xr = xi;
+                else if (lane < i) xr = fma(-Rv[i], xi, xr);
+            }
+        }
+        if (live) x[r] = xr;
+        ts_post(solved, (unsigned int)(t + 1), lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) { bar[3] = 0; bar[1] = 0; __threadfence(); }
+    }
+}
+// x <- LowerTriangular(f[0:k, 0:k]') \ x (forward).  Blocks from the top (block t = [32 t, min(32 t + 32, k))).
+__global__ void trsv_upperT_coop_kernel(const double* __restrict__ f, int ldf, int k, double* x, int bpc, unsigned int* bar) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nblk = (k + 31) / 32, t = blockIdx.x * bpc + w;
+    unsigned int* solved = bar + 3;
+    if (t < nblk && w < bpc) {
+        const int b0 = 32 * t, b1 = (b0 + 32 < k) ? b0 + 32 : k, nb = b1 - b0;
+        double acc[32], Rv[32];
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) acc[cc] = 0.0;
+        for (int s = 0; s < t; ++s) {                   // rows of block s: lane = row, one accumulator per column of this block
+            const int rr = 32 * s + lane;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) Rv[cc] = (cc < nb) ? f[(size_t)(b0 + cc) * ldf + rr] : 0.0;
+            ts_wait(solved, (unsigned int)(s + 1), lane);
+            const double xr = __ldcg(x + rr);
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) acc[cc] = fma(Rv[cc], xr, acc[cc]);
+        }
+        // column sums over the lanes (the pairing of s_warp_sum), lane cc ends with the sum of column cc
+#pragma unroll
+        for (int h = 16; h > 0; h >>= 1) {
+            const bool up = (lane & h) != 0;
+#pragma unroll
+            for (int q = 0; q < h; ++q) {
+                const double keep = up ? acc[q + h] : acc[q];
+                const double send = up ? acc[q] : acc[q + h];
+                acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+        }
+        const bool live = lane < nb;
+        double xc = live ? (x[b0 + lane] - acc[0]) : 0.0;
+        // forward recurrence inside the block: lane = column c, Rv[ii] = R(b0 + ii, b0 + c)
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) Rv[ii] = (live && ii < nb) ? f[(size_t)(b0 + lane) * ldf + b0 + ii] : 1.0;
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) {
+            if (ii < nb) {
+                const double xi = __shfl_sync(0xffffffffu, xc / Rv[ii], ii);    // lane ii: x_ii / R(ii, ii)
+                if (lane == ii) xc = xi;
+                else if (lane > ii) xc = fma(-Rv[ii], xi, xc);
+            }
+        }
+        if (live) x[b0 + lane] = xc;
+        ts_post(solved, (unsigned int)(t + 1), lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) { bar[3] = 0; bar[1] = 0; __threadfence(); }
+    }
+}
+// returns 1 (launched) or -1 (shape does not fit / launch refused: caller falls back)
+inline int trsv_coop(const double* f, int ldf, int k, double* x, bool transposed, unsigned int* bar, cudaStream_t st) {
+    const int nblk = (k + 31) / 32;
+    int G = nblk < 148 ? nblk : 148;
+    int bpc = (nblk + G - 1) / G;
+    if (bpc > 8) return -1;                    // k > 37888
+    G = (nblk + bpc - 1) / bpc;
+    void* args[] = {&f, &ldf, &k, &x, &bpc, &bar};
+    const void* fn = transposed ? (const void*)trsv_upperT_coop_kernel : (const void*)trsv_upper_coop_kernel;
+    if (cudaLaunchCooperativeKernel(fn, dim3(G), dim3(32 * bpc), args, 0, st) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return 1;
+}
+
 constexpr int VEC_WARP_MAX = 640;     // up to this many entries the one-warp kernels are used
 
 // x (k entries) <- UpperTriangular(f[0:k, 0:k]) \ x ; one CTA of 1024 threads, blocks of 32 from the bottom

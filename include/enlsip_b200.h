@@ -216,6 +216,11 @@ ENLSIPB200_API int enlsipb200_large_stats(enlsipb200_large h, double* out, int c
  *       reflectors in f [nq x k] / tau [k] (dgeqp3 layout). */
 ENLSIPB200_API int enlsipb200_dense_qrcp(int rows, int cols, double* f, double* tau, int* jpvt, int device);
 ENLSIPB200_API int enlsipb200_dense_mulq(int mr, int nq, int k, const double* f, const double* tau, double* M, int device);
+/*   enlsipb200_dense_vecop : the vector products and triangular solves of src/enlsip_functions.jl:133-152, 484-500 as the
+ *       engine runs them for long vectors (cooperative multi-CTA kernels).  kind 0: v [frows] <- Q' v, 1: v <- Q v with
+ *       Q = H(0) ... H(k-1) from f [frows x k] / tau [k] (LAPACK dormqr); kind 2: v [k] <- R \ v, 3: v [k] <- R' \ v with
+ *       R = the upper triangle of the leading k x k block of f [frows x k] (LAPACK dtrtrs). */
+ENLSIPB200_API int enlsipb200_dense_vecop(int kind, int frows, int k, const double* f, const double* tau, double* v, int device);
 /* device time (CUDA events around the kernels, transfers excluded) of the last enlsipb200_dense_* call, in ms */
 ENLSIPB200_API float enlsipb200_dense_last_ms(void);
 

@@ -96,3 +96,41 @@ def test_mulq_vs_dormqr(L, mr, nq, k):
     rc = L.enlsipb200_dense_mulq(mr, nq, k, np.asfortranarray(qr).ctypes.data_as(vp), tau.ctypes.data_as(vp), out.ctypes.data_as(vp), -1)
     assert rc == 0, L.enlsipb200_large_last_error()
     assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("frows,k", [(700, 33), (1000, 257), (4097, 520), (2000, 1999)])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_reflect_vec_wy_vs_dormqr(L, frows, k, kind):
+    """v <- Q' v / Q v by the cooperative compact-WY kernel (batched dlarft T factors) against LAPACK dormqr."""
+    rng = np.random.default_rng(frows + k + kind)
+    qr, tau, _, info = lapack.dgeqrf(np.asfortranarray(rng.standard_normal((frows, k))))
+    v = rng.standard_normal(frows)
+    ref, _, info = lapack.dormqr("L", "T" if kind == 0 else "N", qr, tau, np.asfortranarray(v.reshape(-1, 1)), max(1, 64 * frows))
+    assert info == 0
+    out = v.copy()
+    vp = ctypes.c_void_p
+    rc = L.enlsipb200_dense_vecop(kind, frows, k, np.asfortranarray(qr).ctypes.data_as(vp), tau.ctypes.data_as(vp), out.ctypes.data_as(vp), -1)
+    assert rc == 0, L.enlsipb200_large_last_error()
+    assert np.abs(out - ref[:, 0]).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("frows,k", [(40, 33), (300, 64), (700, 511), (3600, 3587), (5000, 4999)])
+@pytest.mark.parametrize("kind", [2, 3])
+def test_trsv_coop_vs_dtrtrs(L, frows, k, kind):
+    """R \\ v and R' \\ v by the one-warp-per-block cooperative kernels against LAPACK dtrtrs (R well conditioned: a QR factor of
+    a random matrix; the entries below the diagonal of f hold reflector data and must be ignored)."""
+    rng = np.random.default_rng(frows + k + kind)
+    qr, tau, _, info = lapack.dgeqrf(np.asfortranarray(rng.standard_normal((frows, k))))
+    R = np.triu(qr[:k, :k])
+    v = rng.standard_normal(k)
+    ref, info = lapack.dtrtrs(np.asfortranarray(R), np.asfortranarray(v.reshape(-1, 1)), lower=0, trans=0 if kind == 2 else 1)
+    assert info == 0
+    out = v.copy()
+    vp = ctypes.c_void_p
+    rc = L.enlsipb200_dense_vecop(kind, frows, k, np.asfortranarray(qr).ctypes.data_as(vp), None, out.ctypes.data_as(vp), -1)
+    assert rc == 0, L.enlsipb200_large_last_error()
+    # forward error of a triangular solve scales with the condition number: compare residuals and a cond-scaled difference
+    cond = np.linalg.cond(R)
+    assert np.abs(out - ref[:, 0]).max() <= 1e-13 * cond * np.abs(ref).max()
+    res = (R @ out - v) if kind == 2 else (R.T @ out - v)
+    assert np.abs(res).max() <= 1e-12 * (np.abs(R).max() * np.abs(out).max() * k ** 0.5 + np.abs(v).max())
