@@ -22,6 +22,7 @@
 
 #include <chrono>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/enlsip_b200.h"
@@ -392,6 +393,11 @@ struct LargeHandle : LargeOps, SmallBackend {
     ~LargeHandle() override { release(); }
     void release() {
         cudaSetDevice(device);
+        if (small_prof_on() && !small_prof.empty()) {
+            for (const auto& kv : small_prof)
+                fprintf(stderr, "[small stage] %-24s %6lld calls %10.3f ms\n", kv.first.c_str(), kv.second.second, kv.second.first);
+            small_prof.clear();
+        }
         for (double* p : {ownW, owny, dA, du, dr, ds, dv, dJp, dx, dp, dT, dpart, dout, dR, dStack, dR2, dJc, dArow, dCA, dCA2, dFA,
                           dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, qw.pbest, qw.psum, ww.Vb, ww.T, ww.W, ww.W2, ww.part})
             if (p) cudaFree(p);
@@ -694,10 +700,23 @@ struct LargeHandle : LargeOps, SmallBackend {
     // matrices never leave HBM.
     // =========================================================================================
     std::vector<int> hpA, hpL, hp2;     // host copies of the three permutations
+    // ENLSIP_SMALL_PROF=1: per-call breakdown of the small stage (each call is followed by a stream synchronisation, so
+    // the figures include what the call left in flight), printed when the handle is released
+    std::map<std::string, std::pair<double, long long>> small_prof;
+    static bool small_prof_on() {
+        static const bool v = [] { const char* e = getenv("ENLSIP_SMALL_PROF"); return e && e[0] == '1'; }();
+        return v;
+    }
     struct SmallScope {
-        LargeHandle* h; std::chrono::steady_clock::time_point t0;
-        explicit SmallScope(LargeHandle* hh) : h(hh), t0(std::chrono::steady_clock::now()) { cudaSetDevice(hh->device); }
-        ~SmallScope() { h->ms_small += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+        LargeHandle* h; std::chrono::steady_clock::time_point t0; const char* name;
+        explicit SmallScope(LargeHandle* hh, const char* nm = __builtin_FUNCTION())
+            : h(hh), t0(std::chrono::steady_clock::now()), name(nm) { cudaSetDevice(hh->device); }
+        ~SmallScope() {
+            if (small_prof_on()) cudaStreamSynchronize(h->st);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            h->ms_small += ms;
+            if (small_prof_on()) { auto& e = h->small_prof[name]; e.first += ms; e.second += 1; }
+        }
     };
     void sm_check(cudaError_t e, const char* what) {
         if (e != cudaSuccess) throw std::runtime_error(std::string("device small stage: ") + what + ": " + cudaGetErrorString(e));
@@ -745,16 +764,20 @@ struct LargeHandle : LargeOps, SmallBackend {
         enl_small::reflect_vec_kernel<<<1, 1024, sizeof(double) * (size_t)frows, st>>>(f, frows, k, tau, v, transpose);
         ++launches;
     }
+    static int coop_min() {          // smallest triangle solved by the multi-CTA kernels (ENLSIP_TRSV_COOP_MIN overrides)
+        static const int v = [] { const char* e = getenv("ENLSIP_TRSV_COOP_MIN"); return e ? atoi(e) : 320; }();
+        return v;
+    }
     void k_trsv_upper(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
-        if (k > 32 && enl_small::trsv_coop(f, ldf, k, x, false, qw.ticket + 1, st) > 0) { ++launches; return; }
+        if (k >= coop_min() && enl_small::trsv_coop(f, ldf, k, x, false, qw.ticket + 1, st) > 0) { ++launches; return; }
         if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upper_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         else enl_small::trsv_upper_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;
     }
     void k_trsv_upperT(const double* f, int ldf, int k, double* x) {
         if (k <= 0) return;
-        if (k > 32 && enl_small::trsv_coop(f, ldf, k, x, true, qw.ticket + 1, st) > 0) { ++launches; return; }
+        if (k >= coop_min() && enl_small::trsv_coop(f, ldf, k, x, true, qw.ticket + 1, st) > 0) { ++launches; return; }
         if (k <= enl_small::VEC_WARP_MAX) enl_small::trsv_upperT_warp_kernel<<<1, 32, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         else enl_small::trsv_upperT_kernel<<<1, 1024, sizeof(double) * (size_t)k, st>>>(f, ldf, k, x);
         ++launches;

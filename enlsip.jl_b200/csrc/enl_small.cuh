@@ -476,6 +476,62 @@ __global__ void __launch_bounds__(256) qr_panel_trail_kernel(double* __restrict_
         gemm_tile<false>(A, rows, B, QR_NB, C, rows, M, N, kb, -1.0, 1.0, t % tmn, t / tmn, As, Bs);
 }
 
+// The same rank-kb update on the FP64 FMA pipe with coalesced accesses to the trailing matrix (default).  At K = 32 the
+// update is bound by reading and writing C (2 x 8 bytes against 64 flops per element), not by the tensor pipe, and the
+// DMMA fragment layout touches C in 8 x 8 patches (half-used sectors; measured 1.0 TB/s, profiles/r2_qr_panel_trail_ncu.txt).
+// Here a thread owns one row of a 128 x 32 tile (its 32 panel entries in registers) and 16 of its columns; the lanes of
+// a warp are 32 consecutive rows of one column (256-byte segments), F is read from shared memory as 16-byte broadcasts.
+constexpr int QT_ROWS = 128, QT_COLS = 32;
+__global__ void __launch_bounds__(256) qr_panel_trail_fma_kernel(double* __restrict__ f, int rows, int cols,
+                                                                 const double* __restrict__ F, const QrState* stt) {
+    __shared__ __align__(16) double Bs[QT_COLS][QR_NB + 2];
+    if (!stt->active) return;
+    const int j0 = stt->j0, kb = stt->k;
+    if (kb <= 0) return;
+    const int r0 = j0 + kb, c0 = j0 + kb;
+    const int M = rows - r0, N = cols - c0;
+    if (M <= 0 || N <= 0) return;
+    const int tm = (M + QT_ROWS - 1) / QT_ROWS, tn = (N + QT_COLS - 1) / QT_COLS;
+    const int tid = threadIdx.x, rl = tid & (QT_ROWS - 1), cg = tid >> 7;          // cg: columns [16 cg, 16 cg + 16) of the tile
+    for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+        const int ti = t % tm, tj = t / tm;
+        const int r = r0 + ti * QT_ROWS + rl, cbase = c0 + tj * QT_COLS;
+        const bool rok = r < rows;
+        __syncthreads();
+        for (int e = tid; e < QT_COLS * QR_NB; e += 256) {
+            const int cc = e >> 5, kk = e & 31;
+            Bs[cc][kk] = (cbase + cc < cols && kk < kb) ? F[(size_t)(cbase + cc) * QR_NB + kk] : 0.0;
+        }
+        double a[QR_NB];
+#pragma unroll
+        for (int kk = 0; kk < QR_NB; ++kk) a[kk] = (rok && kk < kb) ? f[(size_t)(j0 + kk) * rows + r] : 0.0;
+        double acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int cc = cbase + cg * 16 + q;
+            acc[q] = (rok && cc < cols) ? f[(size_t)cc * rows + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const double2* bp = reinterpret_cast<const double2*>(&Bs[cg * 16 + q][0]);
+            double c = acc[q];
+#pragma unroll
+            for (int kk = 0; kk < QR_NB / 2; ++kk) {
+                const double2 b = bp[kk];
+                c = fma(-a[2 * kk], b.x, c);
+                c = fma(-a[2 * kk + 1], b.y, c);
+            }
+            acc[q] = c;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int cc = cbase + cg * 16 + q;
+            if (rok && cc < cols) f[(size_t)cc * rows + r] = acc[q];
+        }
+    }
+}
+
 // After the trailing update: recompute the flagged norms (dlaqps: the lsticc list), one CTA per candidate column;
 // the last CTA to finish (atomic ticket) opens the next panel.
 __global__ void __launch_bounds__(256) qr_panel_close_kernel(const double* __restrict__ f, int rows, int cols, double* vn1,
@@ -1200,6 +1256,12 @@ struct QrWork {          // scratch of one factorisation (sized for the largest 
     }
 };
 
+// trailing update of a finished panel: FMA kernel with coalesced C accesses (default) or the DMMA tile kernel (ENLSIP_QR_TRAIL=dmma)
+inline void qr_launch_trail(double* f, int rows, int cols, QrWork& wk, cudaStream_t st) {
+    static const bool dmma = [] { const char* e = getenv("ENLSIP_QR_TRAIL"); return e && e[0] == 'd'; }();
+    if (dmma) qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+    else qr_panel_trail_fma_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+}
 // grid of the persistent panel kernel (one CTA per SM, co-resident: cooperative launch); 0 = not available
 inline int qp_grid() {
     static const int g = [] {
@@ -1232,7 +1294,7 @@ inline int qr_enqueue_panel_persist(double* f, int rows, int cols, double* tau, 
     unsigned int* bar = wk.ticket + 1;
     void* args[] = {&f, &rows, &cols, &vn1, &vn2, &jpvt, &tau, &F, &flags, &stt, &pbest, &pidx, &pany, &ppart, &bar};
     cudaLaunchCooperativeKernel((const void*)qr_panel_persist_kernel, dim3(G), dim3(QP_THREADS), args, qp_smem_bytes(rows, G), st);
-    qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+    qr_launch_trail(f, rows, cols, wk, st);
     qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
     return 3;
 }
@@ -1248,7 +1310,7 @@ inline int qr_enqueue_panel(double* f, int rows, int cols, double* tau, int* jpv
         launches += 3;
     }
     qr_panel_finish_pivot_kernel<<<g_fin, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, jpvt, wk.F, wk.auxv, wk.flags, wk.state, wk.pbest, wk.pidx, QR_NB);
-    qr_panel_trail_kernel<<<148 * 4, 256, 0, st>>>(f, rows, cols, wk.F, wk.state);
+    qr_launch_trail(f, rows, cols, wk, st);
     qr_panel_close_kernel<<<148, 256, 0, st>>>(f, rows, cols, wk.vn1, wk.vn2, wk.flags, wk.state, topbmn, wk.ticket);
     return launches + 3;
 }
