@@ -292,7 +292,8 @@ def c5_arm(args, torch, E, dev, local):
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                         "traffic": None, "peak_source": peak_src,
                         "kernel": "one pass of the iteration: TSQR of [J | r] (tsqr_*), blocked QRCP of A_act', R_A' and J2 "
-                                  "(qr_panel_* + DMMA trailing update), compact-WY J~ Q1 (gemm_dmma_*)",
+                                  "(qr_panel_persist_kernel: one cooperative kernel per dlaqps panel, + rank-32 trailing update), "
+                                  "compact-WY J~ Q1 (gemm_dmma_*), cooperative WY vector products and triangular solves",
                         "algorithmic_flops_per_pass": flops_mean,
                         "note": "algorithmic flops of the REFERENCE's math per pass (SURVEY.md 8d formula at the measured working-set "
                                 "sizes) / wall time of a pass; the engine itself executes fewer flops (it pivots on the compressed "
@@ -319,11 +320,13 @@ def c5_arm(args, torch, E, dev, local):
         hbm_peak, hbm_src = measured_peaks()
         res["roofline_qrcp"] = {"bound": "hbm", "achieved": qbytes / (best * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": qbytes / (best * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": None,
-                                "kernel": "qrcp_device on %d x %d (qr_panel_gemv_kernel + the per-column finish / column kernels + "
-                                          "DMMA trailing updates)" % (rows_q, cols_q), "kernel_ms": best, "algorithmic_bytes": qbytes,
-                                "note": "whole factorisation: the trailing matrix streamed once per blocked column; the gemv kernel alone "
-                                        "runs at 4.6 TB/s = 71 % of the HBM peak on the full-size panels (profiles/r2_qr_panel_gemv_ncu.txt: "
-                                        "116 MB in 25.1 us, L2 hit rate 13 %), the rest of a column step is latency bound"}
+                                "kernel": "qrcp_device on %d x %d (qr_panel_persist_kernel: one cooperative kernel per dlaqps panel, "
+                                          "two grid barriers per pivoted column; rank-32 trailing updates; dlaqp2 tail)" % (rows_q, cols_q),
+                                "kernel_ms": best, "algorithmic_bytes": qbytes,
+                                "note": "whole factorisation: the trailing matrix streamed once per blocked column (dlaqps is BLAS-2 by "
+                                        "construction); per column about half of the time is that streaming pass, the rest the "
+                                        "latency chain pivot -> column -> norm -> F column across two grid barriers "
+                                        "(profiles/r2_qr_panel_persist_phases.txt)"}
     except Exception as ex:       # measurement aid only
         res["roofline_qrcp"] = {"error": str(ex)}
     if args.large_e2e_steps > 0:

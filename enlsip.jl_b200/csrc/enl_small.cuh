@@ -3,14 +3,19 @@
 // The ENLSIP iteration on the compressed problem [J~ | r~] ((n+1) x (n+1), enl_large.cu) needs, per iteration
 // (reference: src/enlsip_functions.jl = EF):
 //   * qr(C.A', ColumnNorm())  (EF:700), qr(F_A.R', ColumnNorm()) (EF:769), qr(J2, ColumnNorm()) (EF:223)
-//         -> qrcp_device(): LAPACK dgeqp3 restated for the GPU -- blocked dlaqps panels (nb = 32, the trailing
-//            rank-nb update on FP64 tensor cores, mma.sync.m8n8k4.f64) for the leading min(m,n) - 128 columns,
-//            unblocked dlaqp2 steps for the rest (dgeqp3's crossover nx = 128), first-max pivot, dlarfg with
-//            beta = -sign(alpha) dlapy2, partial-norm downdate with the tol3z recompute rule (deferred to the end of a
-//            panel in the blocked part exactly like dlaqps' lsticc list);
-//   * J * F_A.Q                (EF:219)  -> mulq_device(): compact-WY panels (dlarft T factors), three DMMA GEMMs each;
-//   * F.Q' v, F.Q v            (EF:137, 143, 152, 484)  -> reflect_vec_kernel;
-//   * R \ v, R' \ v            (EF:133-147, 486-500)    -> trsv_upper_kernel, trsv_upperT_kernel (blocked by 32);
+//         -> qrcp_device(): LAPACK dgeqp3 restated for the GPU -- blocked dlaqps panels (nb = 32) for the leading
+//            min(m,n) - 128 columns, each panel ONE persistent cooperative kernel (qr_panel_persist_kernel: two grid
+//            barriers per pivoted column) followed by the rank-nb trailing update; unblocked dlaqp2 steps for the rest
+//            (dgeqp3's crossover nx = 128); matrices that fit the shared memory of a thread-block cluster are factored
+//            by one cluster kernel (qr_cluster_kernel).  First-max pivot, dlarfg with beta = -sign(alpha) dlapy2,
+//            partial-norm downdate with the tol3z recompute rule (deferred to the end of a panel in the blocked part
+//            exactly like dlaqps' lsticc list);
+//   * J * F_A.Q                (EF:219)  -> mulq_device(): compact-WY panels (dlarft T factors of all panels in two
+//            launches, wy_build_t_all), three DMMA GEMMs (mma.sync.m8n8k4.f64) per panel;
+//   * F.Q' v, F.Q v            (EF:137, 143, 152, 484)  -> reflect_vec_wy_kernel (long vectors: the compact-WY panels in
+//            one cooperative kernel, one grid barrier per 32 reflectors) / reflect_vec_warp_kernel (short vectors);
+//   * R \ v, R' \ v            (EF:133-147, 486-500)    -> trsv_upper(T)_coop_kernel (one warp per diagonal block of 32
+//            spread over the SMs, solved blocks announced through a release/acquire counter) / the one-warp kernels;
 //   * J p, A p, J1 p1, J1' s, C.A' c (EF:2222-2224, 526, 2497) -> gemv_n_kernel / gemv_t_kernel.
 // Column-major storage everywhere (a row-major l x n matrix is the column-major n x l matrix of its transpose).
 // Everything is enqueued on one stream; indices that depend on the data (where a dlaqps panel stops) live in a device
