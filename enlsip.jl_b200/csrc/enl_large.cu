@@ -379,6 +379,9 @@ struct LargeHandle : LargeOps, SmallBackend {
     double *dA = nullptr, *du = nullptr, *dr = nullptr, *ds = nullptr, *dv = nullptr, *dJp = nullptr;
     double *dx = nullptr, *dp = nullptr, *dT = nullptr, *dpart = nullptr, *dout = nullptr;
     double *dR = nullptr, *dStack = nullptr, *dR2 = nullptr;
+    double* dP = nullptr;            // cross-rank level of the TSQR tree: max(nranks, 8) * 32 rows x ld (enl_tsqr.cuh, TsqrDist)
+    double* dPscal = nullptr;
+    bool tree_dist = false;          // every rank has at least 32 rows and ENLSIP_TSQR_DIST != stack
     double* dJc = nullptr;          // [J~ | r~] column major (n+1) x (n+1): stays resident for enl_dense.cuh
     std::vector<double> hR;         // host copy of dJc
     // comm
@@ -402,7 +405,8 @@ struct LargeHandle : LargeOps, SmallBackend {
                           dtauA, dFL, dtauL, dJQ1, dF2, dtau2, dscal, qw.vn1, qw.vn2, qw.F, qw.auxv, qw.pbest, qw.psum, ww.Vb, ww.T, ww.W, ww.W2, ww.part})
             if (p) cudaFree(p);
         for (double*& p : dvec) { if (p) cudaFree(p); p = nullptr; }
-        for (double** p : {&dTA, &dTL, &dT2, &dwpart}) { if (*p) cudaFree(*p); *p = nullptr; }
+        for (double** p : {&dTA, &dTL, &dT2, &dwpart, &dP, &dPscal}) { if (*p) cudaFree(*p); *p = nullptr; }
+        tree_dist = false;
         ta_valid = tl_valid = t2_valid = false;
         for (double* p : {dQ, dJkeep, dtauQ, dcu, gown[0], gown[1]})
             if (p) cudaFree(p);
@@ -664,9 +668,25 @@ struct LargeHandle : LargeOps, SmallBackend {
         }
         LCU(cudaEventRecord(e1, st));
         LCU(cudaMemsetAsync(dR, 0, sizeof(double) * rr_rows * ld, st));
-        launches += tsqr_factor(dA, ld, rows_pad, n, dR, ld, dT, dpart, st);
         double* dfinal = dR;
-        if (nranks > 1) {
+        if (nranks > 1 && tree_dist) {
+            TsqrDist td;
+            td.nranks = nranks; td.rank = rank; td.P = dP; td.scal = dPscal; td.ctx = this;
+            td.allgather = [](void* c, const double* send, double* recv, size_t count, cudaStream_t s) {
+                LargeHandle* h = static_cast<LargeHandle*>(c);
+                return g_nccl.AllGather(send, recv, count, NCCL_FLOAT64, h->comm, s);
+            };
+            td.allreduce_sum = [](void* c, double* buf, size_t count, cudaStream_t s) {
+                LargeHandle* h = static_cast<LargeHandle*>(c);
+                return g_nccl.AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, h->comm, s);
+            };
+            const int rc = tsqr_factor(dA, ld, rows_pad, n, dR, ld, dT, dpart, st, &td);
+            if (rc < 0) return lfail(ENLSIPB200_ECUDA, "NCCL collective inside the row-sharded TSQR failed");
+            launches += rc;
+        } else {
+            launches += tsqr_factor(dA, ld, rows_pad, n, dR, ld, dT, dpart, st);
+        }
+        if (nranks > 1 && !tree_dist) {
             int rc = g_nccl.AllGather(dR, dStack, (size_t)rr_rows * ld, NCCL_FLOAT64, comm, st);
             if (rc != 0) return lfail(ENLSIPB200_ECUDA, std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc));
             LCU(cudaMemsetAsync(dR2, 0, sizeof(double) * rr_rows * ld, st));
@@ -1258,6 +1278,20 @@ int enlsipb200_large_comm_init(enlsipb200_large hh, const void* id128, int rank,
     h->rank = rank; h->nranks = nranks;
     LCU(cudaMalloc(&h->dStack, sizeof(double) * (size_t)nranks * h->rr_rows * h->ld));
     LCU(cudaMalloc(&h->dR2, sizeof(double) * (size_t)h->rr_rows * h->ld));
+    {   // the cross-rank stage as one more level of every panel's tree (TsqrDist) needs a 32-row block on every rank
+        const size_t prow = (size_t)(nranks > 8 ? nranks : 8) * TS_B;
+        LCU(cudaMalloc(&h->dP, sizeof(double) * prow * h->ld));
+        LCU(cudaMemset(h->dP, 0, sizeof(double) * prow * h->ld));
+        LCU(cudaMalloc(&h->dPscal, sizeof(double) * 2));
+        const double mine = (h->rows_pad < TS_B || h->gv) ? 1.0 : 0.0;
+        LCU(cudaMemcpy(h->dPscal, &mine, sizeof(double), cudaMemcpyHostToDevice));
+        rc = g_nccl.AllReduce(h->dPscal, h->dPscal, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, nullptr);
+        if (rc != 0) return lfail(ENLSIPB200_ECUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+        double short_ranks = 0.0;
+        LCU(cudaMemcpy(&short_ranks, h->dPscal, sizeof(double), cudaMemcpyDeviceToHost));
+        const char* e = getenv("ENLSIP_TSQR_DIST");
+        h->tree_dist = short_ranks == 0.0 && !(e && e[0] == 's');
+    }
     {   // the T-factor buffer also serves the second-stage TSQR of the nranks stacked R factors: one 32 x 32 per subtile
         const long long nsub2 = ((long long)nranks * h->rr_rows / TS_B + TS_FAN - 1) / TS_FAN;
         if (nsub2 > h->dT_subtiles) {

@@ -1244,12 +1244,48 @@ __global__ void tsqr_colsq_finish_kernel(const double* __restrict__ part, int np
     }
 }
 
+// distributed variant of the last column: local sum of squares -> out[0] (all-reduced by the caller) -> sqrt into R
+__global__ void tsqr_colsq_partial_kernel(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nparts; ++i) s += part[i];
+        out[0] = s;
+    }
+}
+__global__ void tsqr_sqrt_store_kernel(const double* __restrict__ in, double* __restrict__ Rout, int ldr, int col) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) Rout[(long long)col * ldr + col] = sqrt(in[0]);
+}
+// rows 0..31 of the local matrix <- this rank's 32 rows of the cross-rank stage (columns left of c_from hold reflector
+// data there: they are zero in the matrix)
+__global__ void tsqr_copyback_kernel(double* __restrict__ A, const double* __restrict__ P, int ld, int c_from) {
+    const int r = blockIdx.x;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) A[(long long)r * ld + c] = (c >= c_from) ? P[(long long)r * ld + c] : 0.0;
+}
+
+// Row-sharded factorisation (one process per GPU): the cross-rank stage is ONE MORE LEVEL of every panel's tree.  After
+// the local levels of panel j each rank holds a 32-row R block (rows 0..31 of its matrix); the blocks are all-gathered
+// (32 x ld doubles per rank), every rank factors the stacked nranks x 32 rows (one subtile for up to 8 ranks) and
+// updates their trailing columns -- replicated, identical bits everywhere; rows 0..31 of the result are rows
+// 32 j .. 32 j + 31 of the global R, the other blocks are fill that goes back to rows 0..31 of their owners and takes part
+// in the next panel.  Against factoring locally, gathering the whole R factors and factoring the (nranks (n + 32)) x (n + 1)
+// stack again (~100 launches of latency-bound single-wave kernels): 8 small all-gathers + 8 x (one panel + one trailing
+// launch) at n = 256.
+struct TsqrDist {
+    int nranks = 1, rank = 0;
+    double* P = nullptr;         // max(nranks, 8) * 32 rows x ld, zero-initialised
+    double* scal = nullptr;      // one double
+    void* ctx = nullptr;
+    int (*allgather)(void* ctx, const double* send, double* recv, size_t count, cudaStream_t st) = nullptr;
+    int (*allreduce_sum)(void* ctx, double* buf, size_t count, cudaStream_t st) = nullptr;
+};
+
 // Host-side launcher.  A: rows_pad x ld row major, rows_pad a multiple of 32, pad rows zero.
 // ncols = n + 1 with n a multiple of 32 (columns n+1 .. ld-1 must be zero; ld = n + 8).
 // Rout: (n + 1) x ldr row major, zero-initialised by the caller.  Tbuf: ceil(nblk / 8) * 1024 doubles.
 // part: >= 512 doubles.  Returns the number of kernels launched.
+// dist (optional): row-sharded factorisation, see TsqrDist; returns -1 when a collective fails.
 inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rout, int ldr, double* Tbuf, double* part,
-                       cudaStream_t st) {
+                       cudaStream_t st, const TsqrDist* dist = nullptr) {
     const long long nblk = rows_pad / TS_B;
     const int npanels = n / TS_B;
     int launches = 0;
@@ -1272,7 +1308,11 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
     int trail_mode = trail_mode_env;
     CUtensorMap tmap;
     if (trail_mode == 4 && ((ld * (int)sizeof(double)) % 16 != 0 || !tsqr_make_tensor_map(&tmap, A, ld, rows_pad))) trail_mode = 2;
-    for (int j = 0; j < npanels; ++j) {
+    // all tree levels of panel j on the matrix M (nblk_m blocks of 32 rows)
+    auto panel_levels = [&](double* M, long long nblk_m, int j, int mode) {
+        const long long nblk = nblk_m;
+        double* A = M;
+        const int trail_mode = mode;
         const int col0 = j * TS_B;
         const int ncb32 = npanels - 1 - j;
         long long stride = 1;
@@ -1309,11 +1349,30 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             }
             stride *= TS_FAN;
         }
-        tsqr_extract_kernel<<<TS_B, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);
-        ++launches;
+    };
+    const bool sharded = dist && dist->nranks > 1;
+    for (int j = 0; j < npanels; ++j) {
+        const int col0 = j * TS_B;
+        panel_levels(A, nblk, j, trail_mode);
+        if (sharded) {
+            if (dist->allgather(dist->ctx, A, dist->P, (size_t)TS_B * ld, st) != 0) return -1;
+            panel_levels(dist->P, dist->nranks, j, trail_mode == 4 ? 2 : trail_mode);
+            tsqr_extract_kernel<<<TS_B, 256, 0, st>>>(dist->P, ld, col0, n + 1, Rout, ldr);
+            tsqr_copyback_kernel<<<TS_B, 256, 0, st>>>(A, dist->P + (size_t)TS_B * dist->rank * ld, ld, col0 + TS_B);
+            launches += 2;
+        } else {
+            tsqr_extract_kernel<<<TS_B, 256, 0, st>>>(A, ld, col0, n + 1, Rout, ldr);
+            ++launches;
+        }
     }
     const int nparts = 296;
     tsqr_colsq_kernel<<<nparts, 256, 0, st>>>(A, ld, rows_pad, n, part);
+    if (sharded) {
+        tsqr_colsq_partial_kernel<<<1, 32, 0, st>>>(part, nparts, dist->scal);
+        if (dist->allreduce_sum(dist->ctx, dist->scal, 1, st) != 0) return -1;
+        tsqr_sqrt_store_kernel<<<1, 32, 0, st>>>(dist->scal, Rout, ldr, n);
+        return launches + 3;
+    }
     tsqr_colsq_finish_kernel<<<1, 32, 0, st>>>(part, nparts, Rout, ldr, n);
     return launches + 2;
 }
