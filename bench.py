@@ -249,6 +249,46 @@ def c5_cpu_baseline(scale=2, passes_per_iteration=8.0 / 7.0, t_full=511):
                       "per reported iteration" % (n, m, nb, t, secs, ph[1], ph[2], ph[3], ph[4], ratio, t_full, passes_per_iteration)}
 
 
+def c2_arm(args, torch, dist, E, rank, world, local, dev):
+    """BASELINE.json config 2: B instances of Hock-Schittkowski 65 (n = 3, m = 3, 1 inequality + 6 bounds, analytic
+    Jacobians; test/problems/HS65.jl with perturbed starts) per GPU, one thread per problem.  Same timing rules as the
+    headline: warm-up, barrier + CUDA events, max over ranks."""
+    B = args.c2_problems
+    x0 = torch.from_numpy(np.ascontiguousarray(E.synth.gen_hs65_batch(B, start=rank * B))).to(dev)
+    mod = E.CnlsModel("hs65", x0, x_low=E.synth.HS65_LOW, x_upp=E.synth.HS65_UPP, device=local)
+    out = {"x": torch.empty(B, 3, dtype=torch.float64, device=dev), "f": torch.empty(B, dtype=torch.float64, device=dev)}
+    for k in ("exit_code", "status", "iters", "nact"):
+        out[k] = torch.empty(B, dtype=torch.int32, device=dev)
+    steps = max(3, args.steps // 4)
+    for _ in range(3):
+        E.solve(mod, want_active=False, want_counters=False, out=out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = mod.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        E.solve(mod, want_active=False, want_counters=False, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    st = out["status"].cpu().numpy()
+    ec = out["exit_code"].cpu().numpy()
+    res = {"metric": "batched CNLS solves/s (HS65: n=3, m=3)", "value": world * B / (ms * 1e-3), "unit": "solves/s", "n_gpus": world,
+           "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f64",
+           "config": {"workload": "C2 HS65 n=3 m=3, 1 inequality + 6 bounds, analytic Jacobians (BASELINE.json config 2)",
+                      "problems_per_gpu": B, "seed": 65, "l2": "inputs 24 B per problem: the state lives on chip, not an HBM workload"},
+           "gpu_launches": int(mod.launch_count() - l0),
+           "quality": {"converged_fraction": float(np.mean(st == 1)), "mean_iterations": float(out["iters"].float().mean().item()),
+                       "reference_would_hang_fraction": float(np.mean(ec == -98))}}
+    del mod
+    return res
+
+
 def c5_arm(args, torch, E, dev, local):
     """BASELINE.json config 5 (n = 4096, m = 16384, 1024 inequalities + 8192 bounds) on ONE GPU ("replicas only",
     SURVEY.md 8e): one step = one complete solve from x0."""
@@ -533,6 +573,8 @@ def main():
                     help="rows of the C4 problem the cpu_baseline leg of the default run times (scaled linearly to --large-rows)")
     ap.add_argument("--large-ref-rows", type=int, default=0, help="--impl reference: rows to time (0 = all rows if memory allows)")
     ap.add_argument("--skip-c5", action="store_true", help="skip BASELINE.json config 5 (one GPU, replicas only)")
+    ap.add_argument("--skip-c2", action="store_true", help="skip BASELINE.json config 2 (batched HS65)")
+    ap.add_argument("--c2-problems", type=int, default=1_000_000, help="HS65 instances per GPU (config 2)")
     ap.add_argument("--c5-steps", type=int, default=2)
     ap.add_argument("--c5-ref-full", action="store_true", help="--impl reference: time the C5 pass at the named size (minutes)")
     args = ap.parse_args()
@@ -692,6 +734,8 @@ def main():
     d2h = B * (6 * 8 + 8 + 4 * 4)
     same = bool(np.array_equal(hout["status"], status)) and bool(np.array_equal(hout["iters"], iters))
 
+    c2 = None if args.skip_c2 else c2_arm(args, torch, dist, E, rank, world, local, dev)
+
     # ---- the other half of the metric: GN iterations/s of the large-Jacobian regime (config 4) -------
     kernel_info = model.kernel_info()
     large = None
@@ -746,11 +790,14 @@ def main():
                                               "dgeqp3 (%s); Enlsip.jl itself needs Julia, absent from this image"
                                               % (args.cpu_sample, cpu_port.lapack),
                                     "mean_iterations": float(np.mean(cit))}
+        if c2 is not None:
+            line["batched_hs65"] = c2
+            line["gpu_launches"] += c2["gpu_launches"]
         if large is not None:
             if not args.skip_cpu and world == 1:
                 large["cpu_baseline"] = large_cpu_baseline(args.large_cpu_rows, args.large_rows)
             line["large"] = large
-            line["gpu_launches"] = int(launches) + large["gpu_launches"]
+            line["gpu_launches"] += large["gpu_launches"]
         if large5 is not None:
             if not args.skip_cpu:
                 large5["cpu_baseline"] = c5_cpu_baseline()
