@@ -300,7 +300,7 @@ int with_family(int family, int nt, F&& f) {
     return fail(ENLSIPB200_EINVAL, "this library was compiled for ENLSIPB200_FAMILY_USER only");
 #else
     switch (family) {
-        case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<64>{});
+        case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<80>{});
         case ENLSIPB200_FAMILY_GAUSS_PEAKS:
             switch (nt) {
                 case 64: return f(FamGaussPeaks{}, ic<32>{}, ic<64>{});
