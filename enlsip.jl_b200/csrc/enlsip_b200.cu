@@ -289,6 +289,19 @@ int flush_pending(enlsipb200_handle h, cudaStream_t st, long long B) {
 template <int V>
 using ic = std::integral_constant<int, V>;
 
+// One thread per problem (families with a handful of residuals): the CTA size that fills the shared memory of an SM.
+// These kernels are latency bound and gain with every resident problem (HS65: 6.6 / 7.8 / 8.4 M solves/s with 64 / 80 / 86
+// problems per SM); the whole state of a problem lives in shared memory (2.6 KB for HS65).
+template <class Fam>
+constexpr int nt_thread_per_problem() {
+    constexpr size_t cfg = ((sizeof(Options) + sizeof(Bounds) + 15) / 16) * 16;
+    constexpr size_t sd = ((sizeof(Solver<Fam, DevGroup<1>, 8>) + 7) / 8) | 1;
+    constexpr size_t per = Layout<Fam, 1, 8>::smem_bytes() / 8 + sd * 8;        // bytes per problem (smem_bytes is linear in NT)
+    constexpr size_t budget = 225 * 1024 - cfg;
+    constexpr int fit = (int)(budget / per) / 2 * 2;
+    return fit > 128 ? 128 : (fit < 32 ? 32 : fit);
+}
+
 // family id (+ CTA size for the tuned family) -> template instantiation
 template <class F>
 int with_family(int family, int nt, F&& f) {
@@ -296,11 +309,11 @@ int with_family(int family, int nt, F&& f) {
     // a user library holds the user's family only (compile time: one kernel instead of ten); few rows: one thread per
     // problem, otherwise one warp per problem
     (void)nt;
-    if (family == ENLSIPB200_FAMILY_USER) return f(FamUser{}, ic<(FamUser::M <= 8 ? 1 : 32)>{}, ic<(FamUser::M <= 8 ? 64 : 32)>{});
+    if (family == ENLSIPB200_FAMILY_USER) return f(FamUser{}, ic<(FamUser::M <= 8 ? 1 : 32)>{}, ic<(FamUser::M <= 8 ? nt_thread_per_problem<FamUser>() : 32)>{});
     return fail(ENLSIPB200_EINVAL, "this library was compiled for ENLSIPB200_FAMILY_USER only");
 #else
     switch (family) {
-        case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<80>{});
+        case ENLSIPB200_FAMILY_HS65: return f(FamHS65{}, ic<1>{}, ic<nt_thread_per_problem<FamHS65>()>{});
         case ENLSIPB200_FAMILY_GAUSS_PEAKS:
             switch (nt) {
                 case 64: return f(FamGaussPeaks{}, ic<32>{}, ic<64>{});
