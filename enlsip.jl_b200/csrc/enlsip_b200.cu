@@ -299,7 +299,7 @@ constexpr int nt_thread_per_problem() {
     constexpr size_t per = Layout<Fam, 1, 8>::smem_bytes() / 8 + sd * 8;        // bytes per problem (smem_bytes is linear in NT)
     constexpr size_t budget = 225 * 1024 - cfg;
     constexpr int fit = (int)(budget / per) / 2 * 2;
-    return fit > 128 ? 128 : (fit < 32 ? 32 : fit);
+    return fit > 128 ? 128 : (fit < 2 ? 1 : fit);      // (a family too large for 2 problems per SM still gets a kernel that fits)
 }
 
 // family id (+ CTA size for the tuned family) -> template instantiation
