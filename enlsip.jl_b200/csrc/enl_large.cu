@@ -916,8 +916,8 @@ struct LargeHandle : LargeOps, SmallBackend {
         const int mt = n + 1;
         sm_check(cudaMemcpyAsync(dJQ1, dJc, sizeof(double) * (size_t)mt * n, cudaMemcpyDeviceToDevice, st), "D2D");
         if (fa_k > 0) {
-            launches += enl_small::mulq_device(dJQ1, mt, n, dFA, n, fa_k, dtauA, ww, st, dTA, !ta_valid);
-            ta_valid = true;
+            double* TA = wy_t_of(dFA, n, fa_k, dtauA);        // all T factors of qr(C.A') at once; nullptr: per panel inside mulq_device
+            launches += enl_small::mulq_device(dJQ1, mt, n, dFA, n, fa_k, dtauA, ww, st, TA, false);
             ++n_dev_mulq;
         }
         jq1_valid = true;
