@@ -134,3 +134,21 @@ def test_trsv_coop_vs_dtrtrs(L, frows, k, kind):
     assert np.abs(out - ref[:, 0]).max() <= 1e-13 * cond * np.abs(ref).max()
     res = (R @ out - v) if kind == 2 else (R.T @ out - v)
     assert np.abs(res).max() <= 1e-12 * (np.abs(R).max() * np.abs(out).max() * k ** 0.5 + np.abs(v).max())
+
+
+@pytest.mark.parametrize("env", [{"ENLSIP_QR_PANEL": "graph"}, {"ENLSIP_QR_TRAIL": "dmma"}])
+def test_qrcp_alternative_paths_vs_dgeqp3(env):
+    """The selectable forms of the blocked QRCP stay correct: three kernels per column inside a CUDA graph (also the path
+    of matrices with more than 32768 rows) and the DMMA trailing update.  The switches are read once per process, so the
+    factorisation runs in a child process (tools/qrcp_time.py compares pivots, R and tau with LAPACK)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "qrcp_time.py"), "700", "450", "1"], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    m = re.search(r"pivots identical (\d+) / (\d+)\s+max \|R - R_lapack\| / max\|R\| = (\S+)\s+max \|tau diff\| = (\S+)", p.stdout)
+    assert m, p.stdout[-1500:]
+    assert m.group(1) == m.group(2) == "450" and float(m.group(3)) <= 1e-12 and float(m.group(4)) <= 1e-12
