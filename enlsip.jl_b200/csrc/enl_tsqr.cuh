@@ -1279,6 +1279,17 @@ struct TsqrDist {
     int (*allreduce_sum)(void* ctx, double* buf, size_t count, cudaStream_t st) = nullptr;
 };
 
+inline int tsqr_chunk_mode() {           // ENLSIP_TSQR_CHUNK=0: the first heuristic (halve the chunk until 296 CTAs exist)
+    static const int v = [] { const char* e = getenv("ENLSIP_TSQR_CHUNK"); return (e && e[0] == '0') ? 0 : 1; }();
+    return v;
+}
+
+inline int tsqr_chunk_prologue2() {     // twice the prologue of a chunk in units of one column block (ENLSIP_TSQR_CHUNK_P; measured
+                                        // at n = 4096, m = 16384: 48.7 / 49.1 / 49.5 / 50.4 ms per factorisation for 1 / 2 / 4 / 8)
+    static const int v = [] { const char* e = getenv("ENLSIP_TSQR_CHUNK_P"); const int x = e ? atoi(e) : 1; return x < 0 ? 0 : x; }();
+    return v;
+}
+
 // Host-side launcher.  A: rows_pad x ld row major, rows_pad a multiple of 32, pad rows zero.
 // ncols = n + 1 with n a multiple of 32 (columns n+1 .. ld-1 must be zero; ld = n + 8).
 // Rout: (n + 1) x ldr row major, zero-initialised by the caller.  Tbuf: ceil(nblk / 8) * 1024 doubles.
@@ -1324,9 +1335,24 @@ inline int tsqr_factor(double* A, int ld, long long rows_pad, int n, double* Rou
             else tsqr_panel_cg_kernel<<<(unsigned)nsub, 256, 0, st>>>(A, ld, nblk, stride, col0, level > 0, n, Tbuf);
             ++launches;
             if (ncb32 > 0 && trail_mode >= 2) {
-                // chunk = all column blocks of the subtile while there are enough subtiles to fill the machine
+                // Column blocks per CTA (chunk).  One CTA per SM is resident (registers, shared memory), so the launch runs
+                // in waves of 148 CTAs; a CTA costs a prologue (V and T staged once per chunk, about half a block's worth) plus
+                // its column blocks.  Pick the chunking with the fewest wave-units: with thousands of subtiles that is one
+                // chunk per subtile, with a few dozen subtiles (m = 4 n, upper tree levels) it avoids a mostly empty last
+                // wave.  The arithmetic of a column block does not depend on the chunk it is in.
                 int cbpc = ncb32;
-                while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
+                if (tsqr_chunk_mode() == 0) {
+                    while (cbpc > 1 && nsub * ((ncb32 + cbpc - 1) / cbpc) < 2 * 148) cbpc = (cbpc + 1) / 2;
+                } else {
+                    long long best_cost = -1;
+                    for (int c = ncb32; c >= 1; --c) {
+                        const long long chunks = (ncb32 + c - 1) / c;
+                        if (c < ncb32 && (ncb32 + c) / (c + 1) == chunks) continue;      // same chunk count as c + 1: larger CTAs for nothing
+                        const long long waves = (nsub * chunks + 147) / 148;
+                        const long long cost = waves * (tsqr_chunk_prologue2() + 2 * c);
+                        if (best_cost < 0 || cost < best_cost) { best_cost = cost; cbpc = c; }
+                    }
+                }
                 const int nchunks = (ncb32 + cbpc - 1) / cbpc;
                 if (trail_mode == 4 && tmap_nw == 16)
                     tsqr_trail_tmap_kernel<16><<<(unsigned)(nsub * nchunks), 32 * 17, tm_smem_bytes(16), st>>>(tmap, A, ld, nblk, stride, col0,
